@@ -1,0 +1,112 @@
+/*
+ * r3geo.h — C ABI of libr3geo.so: the B200 (sm_100a) rotated-geometry hot path of R3Det.
+ *
+ * Drop-in boundary: each entry point replaces one pybind11 function of the reference's native
+ * extensions (r3det/ops/<op>/src, cited per function).  Plain pointers and sizes only — no torch types.
+ * Conventions
+ *   - all pointers are DEVICE pointers on the current CUDA device unless the name ends in `_host`;
+ *   - the caller owns every buffer (inputs, outputs, workspace); the library never allocates, frees or
+ *     synchronises the device, and enqueues all work on `stream` (a cudaStream_t passed as void*);
+ *   - return value 0 = success, < 0 = error; r3g_last_error() returns a thread-local message;
+ *   - boxes are float32 rows <cx, cy, w, h, angle[rad]> with a row stride given in floats (5 or 6);
+ *   - variant: 1/2/3 = the reference's angle/geometry conventions v1/v2/v3;
+ *   - there is no CPU fallback: without a CUDA device every compute entry returns R3G_ERR_CUDA.
+ */
+#ifndef R3GEO_H_
+#define R3GEO_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define R3G_OK 0
+#define R3G_ERR_ARG (-1)       /* bad argument (null pointer, bad variant/mode, negative size ...) */
+#define R3G_ERR_WORKSPACE (-2) /* workspace too small */
+#define R3G_ERR_CUDA (-3)      /* CUDA runtime error (message has the cudaError string) */
+
+#define R3G_V1 1
+#define R3G_V2 2
+#define R3G_V3 3
+
+#define R3G_MODE_IOU 0
+#define R3G_MODE_IOF 1
+
+/* flags for the IoU entry points */
+#define R3G_FLAG_STRICT 1       /* re-evaluate degenerate pairs with the reference's own point-set algorithm */
+#define R3G_FLAG_SMALL_MASK 2   /* v3 wrapper: rows/cols with min(w,h) < 1e-3 are 0 (box_iou_rotated_wrapper.py:54-60) */
+
+/* flags for r3g_nms_f32 */
+#define R3G_NMS_INCLUSIVE 1     /* suppress when IoU >= thr (reference CPU rule); default IoU > thr (reference GPU rule) */
+#define R3G_NMS_ORDER_INDEX 2   /* keep list in ascending original index (rnms_kernel.cu:331-334); default descending score */
+#define R3G_NMS_DROP_SMALL 4    /* boxes with min(w,h) < 1e-3 take no part (nms_rotated_wrapper.py:40-46) */
+#define R3G_NMS_STRICT 8        /* decide near-threshold / degenerate pairs with the reference's own algorithm */
+
+const char* r3g_last_error(void);
+int r3g_version(void);
+
+/* ---- pairwise rotated IoU / IoF -------------------------------------------------------------------
+ * replaces  rbbox_geo_cuda.mat_iou_iof(rb1, rb2, iof)        r3det/ops/rbbox_geo/src/rbbox_geo_cuda.cpp:25-30   (variant 1)
+ *           box_iou_rotated_ext.overlaps(b1, b2, iou_or_iof)  r3det/ops/box_iou_rotated/src/box_iou_rotated_ext.cpp:36-38 (variant 3)
+ *           mmcv.ops.box_iou_rotated(b1, b2, mode)            call site rotate_iou2d_calculator.py:156          (variant 2)
+ * out is row-major (m, n).  Workspace holds the prepared boxes: r3g_iou_workspace_bytes(m, n). */
+int r3g_iou_workspace_bytes(int64_t m, int64_t n, size_t* bytes);
+int r3g_iou_matrix_f32(const float* boxes1, int64_t m, int64_t stride1,
+                       const float* boxes2, int64_t n, int64_t stride2,
+                       int variant, int mode, int flags, float* out,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* replaces rbbox_geo_cuda.vec_iou_iof (rbbox_geo_cuda.cpp:25-30): out has max(n1, n2) elements,
+ * element i pairs boxes1[i % n1] with boxes2[i % n2] (rbbox_geo_kernel.cu:278-281). */
+int r3g_iou_aligned_f32(const float* boxes1, int64_t n1, int64_t stride1,
+                        const float* boxes2, int64_t n2, int64_t stride2,
+                        int variant, int mode, int flags, float* out, void* stream);
+
+/* counters of the last r3g_iou_matrix_f32 launch on this workspace (device-side, 4 x uint64 at the
+ * start of the workspace): pairs passing the circumradius test, passing the separating-axis test,
+ * re-evaluated by the strict path, total pairs.  For roofline accounting (bench.py). */
+#define R3G_IOU_STATS_U64 4
+
+/* ---- rotated NMS ------------------------------------------------------------------------------------
+ * replaces  rnms_ext.rnms(dets[K,6], thr)                      r3det/ops/rnms/src/rnms_ext.cpp:11-20          (variant 1, ORDER_INDEX)
+ *           nms_rotated_ext.nms_rotated(dets, scores, thr)     r3det/ops/nms_rotated/src/nms_rotated_ext.cpp:53-56 (variant 3, ORDER_SCORE)
+ *           ml_nms_rotated(dets, scores, labels, thr)          r3det/ops/ml_nms_rotated/src/nms_rotated.h:23-38   (variant 2, labels)
+ * boxes: (K, stride) floats; scores: (K); labels: (K) int64 in [0, 2^31) or NULL (single class).  A box
+ * suppresses a lower-scored box of the same label when IoU > thr (>= with R3G_NMS_INCLUSIVE).
+ * keep_out: (K) int64 original indices, first *num_keep_out valid (both device memory).
+ * With labels, `class_offset` != NULL points to ONE device float: the reference's per-class coordinate
+ * offset scale (rnms_wrapper.py:61-64 / nms_rotated_wrapper.py:84-90); boxes are then evaluated at
+ * x + label*scale, y + label*scale in FP32 exactly as the reference's batched wrappers do. */
+int r3g_nms_workspace_bytes(int64_t K, size_t* bytes);
+int r3g_nms_f32(const float* boxes, int64_t stride, const float* scores, const int64_t* labels,
+                int64_t K, float thr, int variant, int flags, const float* class_offset,
+                int64_t* keep_out, int64_t* num_keep_out,
+                void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- FRM feature refinement ---------------------------------------------------------------------------
+ * replaces feature_refine_cuda.forward / .backward   r3det/ops/fr/src/feature_refine_cuda.cpp:24-67
+ * feat/out/grad: (N, C, H, W) float32 contiguous; boxes: (N*H*W, 5); points in {1, 5}.
+ * forward:  out = feat + sum_p bilinear(feat, y_p, x_p)   (out need not be pre-zeroed)
+ * backward: grad_in = grad_out + scatter of bilinear weights, atomic-free (sorted taps in workspace). */
+int r3g_frm_forward_f32(const float* feat, const float* boxes, int N, int C, int H, int W,
+                        float spatial_scale, int points, float* out, void* stream);
+int r3g_frm_backward_workspace_bytes(int N, int H, int W, int points, size_t* bytes);
+int r3g_frm_backward_f32(const float* grad_out, const float* boxes, int N, int C, int H, int W,
+                         float spatial_scale, int points, float* grad_in,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- box transforms (r3det/core/bbox/rtransforms.py) ---------------------------------------------------
+ * obb2poly :367-440, poly2obb :190-277, obb2hbb :443-537, hbb2obb :540-592, obb2xyxy :595-651.
+ * n boxes; version 1/2/3. */
+int r3g_obb2poly_f32(const float* obb, int64_t n, int version, float* poly, void* stream);
+int r3g_poly2obb_f32(const float* poly, int64_t n, int version, float* obb, void* stream);
+int r3g_obb2hbb_f32(const float* obb, int64_t n, int version, float* hbb, void* stream);
+int r3g_hbb2obb_f32(const float* hbb, int64_t n, int version, float* obb, void* stream);
+int r3g_obb2xyxy_f32(const float* obb, int64_t n, int version, float* xyxy, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* R3GEO_H_ */

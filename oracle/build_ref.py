@@ -8,6 +8,7 @@ cpu_baseline / ``--impl reference`` legs may load these libraries.
 
     python oracle/build_ref.py            # build what is missing / stale
     python oracle/build_ref.py --force
+    python oracle/build_ref.py --cuda     # also the reference CUDA kernels for sm_100 (minutes each)
 
 Exposed C entry points (see oracle/refshim/*.cpp):
     libref_v1.so     ref_v1_iou_matrix_f32/_f64, ref_v1_iou_aligned_f32, ref_v1_nms_f32
@@ -71,10 +72,47 @@ def build_one(name, force=False):
     return name, "built"
 
 
-def main(force=False):
+CUDA_TARGETS = {
+    # name: (shim, macro, reference .cu)  — the reference CUDA kernels, compiled unmodified for sm_100
+    "libref_cuda_v1iou.so": ("refcuda_v1iou.cu", "R3REF_RBBOX_GEO_KERNEL", f"{OPS}/rbbox_geo/src/rbbox_geo_kernel.cu"),
+    "libref_cuda_frm.so": ("refcuda_frm.cu", "R3REF_FEATURE_REFINE_KERNEL", f"{OPS}/fr/src/feature_refine_kernel.cu"),
+    "libref_cuda_v3iou.so": ("refcuda_v3iou.cu", "R3REF_BOX_IOU_ROTATED_CUDA",
+                             f"{OPS}/box_iou_rotated/src/box_iou_rotated_cuda.cu"),
+    "libref_cuda_v3nms.so": ("refcuda_v3nms.cu", "R3REF_NMS_ROTATED_CUDA",
+                             f"{OPS}/nms_rotated/src/nms_rotated_cuda.cu"),
+}
+
+
+def build_cuda_one(name, force=False):
+    """Reference CUDA kernels (rbbox_geo, fr, box_iou_rotated, nms_rotated) — the kernels to beat on B200."""
+    shim, macro, ref_file = CUDA_TARGETS[name]
+    out = os.path.join(OUT, name)
+    src = os.path.join(HERE, "refshim", shim)
+    if not os.path.exists(ref_file):
+        return name, "skipped (reference tree not present)"
+    if (not force and os.path.exists(out)
+            and os.path.getmtime(out) > max(os.path.getmtime(src), os.path.getmtime(ref_file))):
+        return name, "up to date"
+    c, l = _torch_flags()
+    # same defines the reference's setup.py passes (setup.py:33-37); arch = sm_100 (it ships no arch flags)
+    cmd = ["nvcc", "-std=c++17", "-O2", "-shared", "-Xcompiler", "-fPIC,-fvisibility=hidden", "-w",
+           "-gencode", "arch=compute_100,code=sm_100",
+           "-D__CUDA_NO_HALF_OPERATORS__", "-D__CUDA_NO_HALF_CONVERSIONS__", "-D__CUDA_NO_HALF2_OPERATORS__",
+           f"-D{macro}=\"{ref_file}\"", f"-I{os.path.dirname(ref_file)}", f"-I{os.path.join(HERE, 'refshim')}"]
+    cmd += c + [src, "-o", out] + [x.replace("-Wl,-rpath,", "-Xlinker=-rpath=") for x in l]
+    cmd += ["-ltorch_cuda", "-lc10_cuda", "-lcudart"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        return name, "FAILED\n" + r.stderr[-4000:]
+    return name, "built"
+
+
+def main(force=False, cuda=False):
     os.makedirs(OUT, exist_ok=True)
     with ThreadPoolExecutor(4) as ex:
         res = list(ex.map(lambda n: build_one(n, force), TARGETS))
+        if cuda:
+            res += list(ex.map(lambda n: build_cuda_one(n, force), CUDA_TARGETS))
     ok = True
     for n, s in res:
         print(f"[oracle/_ref] {n}: {s}")
@@ -83,4 +121,4 @@ def main(force=False):
 
 
 if __name__ == "__main__":
-    sys.exit(0 if main("--force" in sys.argv) else 1)
+    sys.exit(0 if main("--force" in sys.argv, "--cuda" in sys.argv) else 1)

@@ -1,0 +1,22 @@
+"""r3det_b200 — B200 (sm_100a) implementation of R3Det's rotated-geometry hot path behind the
+reference's own Python operator API (r3det/ops, r3det/core).  Hand-written CUDA kernels in csrc/,
+reached through the C ABI of include/r3geo.h; no CPU fallback.
+
+Module map (reference module -> here):
+  r3det/ops/rbbox_geo            -> rbbox_geo         rbbox_iou
+  r3det/ops/box_iou_rotated      -> box_iou_rotated   obb_overlaps
+  r3det/ops/rnms                 -> rnms              rnms, batched_rnms
+  r3det/ops/nms_rotated          -> nms_rotated       obb_nms, obb_batched_nms, poly_nms
+  r3det/ops/ml_nms_rotated       -> ml_nms_rotated    ml_nms_rotated
+  r3det/core/bbox/iou_calculators-> iou_calculators   RBboxOverlaps2D_v1/v2/v3, rbbox_overlaps_v1/v2/v3
+  r3det/core/post_processing     -> bbox_nms_rotated  multiclass_nms_rotated
+"""
+from . import _lib  # noqa: F401
+from .bbox_nms_rotated import multiclass_nms_rotated  # noqa: F401
+from .box_iou_rotated import obb_overlaps  # noqa: F401
+from .iou_calculators import (IOU_CALCULATORS, RBboxOverlaps2D_v1, RBboxOverlaps2D_v2,  # noqa: F401
+                              RBboxOverlaps2D_v3, rbbox_overlaps_v1, rbbox_overlaps_v2, rbbox_overlaps_v3)
+from .ml_nms_rotated import ml_nms_rotated  # noqa: F401
+from .nms_rotated import obb_batched_nms, obb_nms, poly_nms  # noqa: F401
+from .rbbox_geo import aligned_iou, pairwise_iou, rbbox_iou  # noqa: F401
+from .rnms import batched_rnms, rnms  # noqa: F401

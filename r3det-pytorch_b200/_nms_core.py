@@ -1,0 +1,56 @@
+"""Shared launcher for the rotated-NMS entry point r3g_nms_f32 (include/r3geo.h)."""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+
+def nms_device(boxes, scores, thr, variant, labels=None, class_offset=None, inclusive=False,
+               order_index=False, drop_small=False, strict=True):
+    """Rotated NMS on CUDA tensors.
+
+    boxes (K, >=5) f32, scores (K,) f32, labels (K,) int64 or None, class_offset: 0-dim CUDA f32 tensor or None.
+    Returns (keep, num_keep): keep is a (K,) int64 CUDA tensor whose first num_keep (0-dim int64 CUDA tensor)
+    entries are the kept original indices; no host synchronisation happens here.
+    """
+    L.require_cuda(boxes, scores)
+    boxes, stride = L.as_f32_rows(boxes)
+    scores = scores.float().contiguous()
+    K = boxes.size(0)
+    dev = boxes.device
+    keep = torch.empty((K,), dtype=torch.int64, device=dev)
+    num = torch.zeros((), dtype=torch.int64, device=dev)
+    if K == 0:
+        return keep, num
+    if labels is not None:
+        L.require_cuda(labels)
+        labels = labels.to(torch.int64).contiguous()
+    if class_offset is not None:
+        class_offset = class_offset.to(device=dev, dtype=torch.float32).reshape(1).contiguous()
+    flags = (L.NMS_INCLUSIVE if inclusive else 0) | (L.NMS_ORDER_INDEX if order_index else 0) | \
+            (L.NMS_DROP_SMALL if drop_small else 0) | (L.NMS_STRICT if strict else 0)
+    lib = L.lib()
+    nbytes = C.c_size_t(0)
+    L.check(lib.r3g_nms_workspace_bytes(K, C.byref(nbytes)))
+    ws = L.workspace(nbytes.value, dev)
+    with torch.cuda.device(dev):
+        L.check(lib.r3g_nms_f32(L.ptr(boxes), stride, L.ptr(scores), L.ptr(labels), K, float(thr), L.V[variant], flags,
+                                L.ptr(class_offset), L.ptr(keep), C.c_void_p(num.data_ptr()), L.ptr(ws), ws.numel(),
+                                L.stream_ptr(dev)))
+    return keep, num
+
+
+def to_cuda_input(x, device_id, what):
+    """numpy / CPU tensors are uploaded (the reference's convenience path, e.g. rnms_wrapper.py:11-15);
+    returns (cuda tensor, is_numpy, was_host).  Host inputs get the reference's CPU rule (IoU >= thr)."""
+    import numpy as np
+    if isinstance(x, torch.Tensor):
+        if x.is_cuda:
+            return x, False, False
+        dev = torch.device("cuda", torch.cuda.current_device() if device_id is None else device_id)
+        return x.to(dev), False, True
+    if isinstance(x, np.ndarray):
+        dev = torch.device("cuda", torch.cuda.current_device() if device_id is None else device_id)
+        return torch.from_numpy(x).to(dev), True, device_id is None
+    raise TypeError(f"{what} must be either a Tensor or numpy array, but got {type(x)}")

@@ -1,0 +1,32 @@
+// api.cu — error string, version and device queries of the C ABI (include/r3geo.h).
+#include <stdarg.h>
+#include <string.h>
+#include "common.cuh"
+
+namespace r3g {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int device_sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+}  // namespace r3g
+
+R3G_API const char* r3g_last_error(void) { return r3g::g_err; }
+R3G_API int r3g_version(void) { return 100; }

@@ -1,0 +1,223 @@
+// geom.cuh — rotated-box pair geometry shared by the IoU and NMS kernels (sm_100a product code).
+//
+// One FP32, register-only, branch-light core serves RBboxOverlaps2D_v1/v2/v3 and nms v1/v2/v3:
+//   * prepared boxes: per-box sincos, half extents, circumradius and area are computed ONCE per box
+//     (O(M+N)) with the same trig the reference variant uses, not once per pair as the reference does
+//     (rbbox_geo_kernel.cu:143-155, box_iou_rotated_utils.h:55-74);
+//   * pair test: circumradius reject -> separating-axis reject -> intersection area;
+//   * intersection area = closed line integral  ∮ X dY  of box B's boundary CLAMPED to box A
+//     (A axis-aligned in its own frame).  Clamping to a convex set preserves winding numbers, so the
+//     clamped boundary encloses exactly A∩B.  Each of B's 4 edges contributes
+//         (clampY(q) - clampY(p)) * mean_{x in [x0,x1]} clampX(x)
+//     — a fixed sequence of min/max/fma with no polygon storage, vertex counting or sorting.  It is
+//     the Sutherland–Hodgman clip + shoelace sum evaluated edge-by-edge in closed form, and it is
+//     continuous in its inputs (no topological decisions), unlike the reference's point-set
+//     algorithms (rbbox_geo_kernel.cu:193-228 de-dup + angular sort; box_iou_rotated_utils.h:157-289
+//     Graham scan).
+// Variant-specific behaviour that is not pure geometry (v1's 1e-2 vertex de-dup, NMS threshold ties)
+// is handled by the exact restatements in emu.cuh, invoked only for the rare flagged pairs.
+//
+// The header also compiles as plain C++ (R3G_HD empty) so tests can sweep 10^7 pairs on the CPU
+// against the oracle without a GPU (tests/hostgeom).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define R3G_HD __host__ __device__ __forceinline__
+#else
+#define R3G_HD inline
+#endif
+
+namespace r3g {
+
+enum Variant { V1 = 1, V2 = 2, V3 = 3 };
+enum Mode { MODE_IOU = 0, MODE_IOF = 1 };
+
+// Prepared box = two 16-byte records (kept as two planes so that lane-consecutive boxes are
+// conflict-free 128-bit shared-memory / global accesses).
+struct __attribute__((aligned(16))) BoxP0 { float cx, cy, r, area; };   // centre, safe circumradius, w*h
+struct __attribute__((aligned(16))) BoxP1 { float c, s, hw, hh; };      // unit w-axis (c,s), half extents
+
+// Per-box preparation with the variant's own trig:
+//   v1: cosf/sinf, rotation +a           (rbbox_geo_kernel.cu:143-155)
+//   v2: (float)cos/sin(double), +a       (ml_nms_rotated/src/box_iou_rotated_utils.h:60-77)
+//   v3: (float)cos/sin(double), -a       (box_iou_rotated/src/box_iou_rotated_utils.h:60-73)
+R3G_HD void prep_box(const float* b, int variant, BoxP0& p0, BoxP1& p1) {
+    float w = b[2], h = b[3], a = b[4];
+    float c, s;
+    if (variant == V1) {
+        c = cosf(a);
+        s = sinf(a);
+    } else {
+        double th = (double)a;
+        c = (float)cos(th);
+        s = (float)sin(th);
+        if (variant == V3) s = -s;
+    }
+    p1.c = c; p1.s = s;
+    p1.hw = 0.5f * w; p1.hh = 0.5f * h;
+    p0.cx = b[0]; p0.cy = b[1];
+    // conservative radius: never rejects a pair whose boxes touch
+    p0.r = sqrtf(p1.hw * p1.hw + p1.hh * p1.hh) * 1.00001f + 1e-6f;
+    p0.area = w * h;
+}
+
+R3G_HD bool circle_reject(const BoxP0& A, const BoxP0& B) {
+    float dx = B.cx - A.cx, dy = B.cy - A.cy, rr = A.r + B.r;
+    return dx * dx + dy * dy > rr * rr;
+}
+
+R3G_HD float clampf(float x, float lim) { return fminf(fmaxf(x, -lim), lim); }
+
+// 2-ulp division for the four per-edge weighted means (the result is a convex combination, so a relative
+// error of 2^-22 moves the area by < 3e-7 of area(A)); IEEE division is kept for the two edge slopes.
+#if defined(__CUDA_ARCH__)
+R3G_HD float fast_div(float a, float b) { return __fdividef(a, b); }
+#else
+R3G_HD float fast_div(float a, float b) { return a / b; }
+#endif
+
+// Corners of B and the frame quantities of the pair, in A's frame (A = [-a,a]x[-b,b]).
+struct PairFrame {
+    float qx[4], qy[4];   // B's corners, CCW for positive w,h
+    float su, sv;         // dx/dy of B's u-edges (q0->q1, q2->q3) and v-edges (q1->q2, q3->q0)
+    float a, b;
+};
+
+// Returns false when a separating axis exists (boxes disjoint -> intersection exactly 0).
+R3G_HD bool pair_frame(const BoxP0& A0, const BoxP1& A1, const BoxP0& B0, const BoxP1& B1, PairFrame& f) {
+    float dx = B0.cx - A0.cx, dy = B0.cy - A0.cy;
+    float a = A1.hw, b = A1.hh;
+    // relative rotation (cos, sin of thetaB - thetaA)
+    float cd = A1.c * B1.c + A1.s * B1.s;
+    float sd = A1.c * B1.s - A1.s * B1.c;
+    float acd = fabsf(cd), asd = fabsf(sd);
+    // centre offset in A's frame and in B's frame
+    float dlx = dx * A1.c + dy * A1.s, dly = dy * A1.c - dx * A1.s;
+    float dbx = dx * B1.c + dy * B1.s, dby = dy * B1.c - dx * B1.s;
+    // B's half-axis vectors in A's frame
+    float ux = B1.hw * cd, uy = B1.hw * sd;
+    float vx = -B1.hh * sd, vy = B1.hh * cd;
+    // separating axes: A's two, then B's two
+    bool sep = (fabsf(dlx) > a + fabsf(ux) + fabsf(vx)) | (fabsf(dly) > b + fabsf(uy) + fabsf(vy)) |
+               (fabsf(dbx) > B1.hw + a * acd + b * asd) | (fabsf(dby) > B1.hh + a * asd + b * acd);
+    if (sep) return false;
+    float ex = dlx - vx, ey = dly - vy, gx = dlx + vx, gy = dly + vy;
+    f.qx[0] = ex - ux; f.qy[0] = ey - uy;
+    f.qx[1] = ex + ux; f.qy[1] = ey + uy;
+    f.qx[2] = gx + ux; f.qy[2] = gy + uy;
+    f.qx[3] = gx - ux; f.qy[3] = gy - uy;
+    // an edge whose y-extent is below 1e-12*size contributes nothing: its slope is irrelevant
+    f.su = (asd > 1e-12f) ? cd / sd : 0.0f;
+    f.sv = (acd > 1e-12f) ? -sd / cd : 0.0f;
+    f.a = a; f.b = b;
+    return true;
+}
+
+// Separating-axis test alone (the cheap second-stage filter of the kernels): true = boxes overlap or touch.
+R3G_HD bool pair_sat(const BoxP0& A0, const BoxP1& A1, const BoxP0& B0, const BoxP1& B1) {
+    float dx = B0.cx - A0.cx, dy = B0.cy - A0.cy;
+    float cd = A1.c * B1.c + A1.s * B1.s;
+    float sd = A1.c * B1.s - A1.s * B1.c;
+    float acd = fabsf(cd), asd = fabsf(sd);
+    float dlx = dx * A1.c + dy * A1.s, dly = dy * A1.c - dx * A1.s;
+    float dbx = dx * B1.c + dy * B1.s, dby = dy * B1.c - dx * B1.s;
+    float aw = fabsf(A1.hw), ah = fabsf(A1.hh), bw = fabsf(B1.hw), bh = fabsf(B1.hh);
+    bool sep = (fabsf(dlx) > aw + bw * acd + bh * asd) | (fabsf(dly) > ah + bw * asd + bh * acd) |
+               (fabsf(dbx) > bw + aw * acd + ah * asd) | (fabsf(dby) > bh + aw * asd + ah * acd);
+    return !sep;
+}
+
+// One edge p->q of B: (clampY(q)-clampY(p)) * mean of clampX over the part of the edge inside |y|<=b.
+R3G_HD float edge_term(float px, float py, float Yp, float qx, float qy, float Yq, float slope, float a) {
+    float dY = Yq - Yp;
+    float x0 = fmaf(Yp - py, slope, px);      // x where the edge enters the slab (== px if p is inside)
+    float x1 = fmaf(Yq - qy, slope, qx);      // x where it leaves           (== qx if q is inside)
+    // integral of clamp(x,-a,a) from x0 to x1 via the three monotone pieces x = min(x,-a)+clamp(x)+max(x,a)
+    float l0 = fminf(x0, -a), l1 = fminf(x1, -a);
+    float m0 = clampf(x0, a), m1 = clampf(x1, a);
+    float h0 = fmaxf(x0, a), h1 = fmaxf(x1, a);
+    float d1 = l1 - l0, d2 = m1 - m0, d3 = h1 - h0;
+    float num = fmaf(a, d3 - d1, 0.5f * (m0 + m1) * d2);
+    float den = d1 + d2 + d3;
+    float mean = (den != 0.0f) ? fast_div(num, den) : m0;
+    return dY * mean;
+}
+
+R3G_HD float frame_area(const PairFrame& f) {
+    float Y0 = clampf(f.qy[0], f.b), Y1 = clampf(f.qy[1], f.b);
+    float Y2 = clampf(f.qy[2], f.b), Y3 = clampf(f.qy[3], f.b);
+    float t0 = edge_term(f.qx[0], f.qy[0], Y0, f.qx[1], f.qy[1], Y1, f.su, f.a);
+    float t1 = edge_term(f.qx[1], f.qy[1], Y1, f.qx[2], f.qy[2], Y2, f.sv, f.a);
+    float t2 = edge_term(f.qx[2], f.qy[2], Y2, f.qx[3], f.qy[3], Y3, f.su, f.a);
+    float t3 = edge_term(f.qx[3], f.qy[3], Y3, f.qx[0], f.qy[0], Y0, f.sv, f.a);
+    return fabsf((t0 + t2) + (t1 + t3));
+}
+
+// Intersection area of two prepared boxes (0 when disjoint).
+R3G_HD float pair_intersection(const BoxP0& A0, const BoxP1& A1, const BoxP0& B0, const BoxP1& B1) {
+    PairFrame f;
+    if (!pair_frame(A0, A1, B0, B1, f)) return 0.0f;
+    return frame_area(f);
+}
+
+// v1 only: true when some corner of one box lies within `tau` of the other's boundary — the only
+// configurations in which the reference's 1e-2 vertex de-dup / strict tests (rbbox_geo_kernel.cu:169-170,
+// 195-213) can change the polygon, i.e. where v1 departs from the geometric area.  Conservative.
+R3G_HD bool corner_near_boundary(const float* qx, const float* qy, float a, float b, float tau) {
+    bool near = false;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        float ex = fabsf(qx[k]) - a, ey = fabsf(qy[k]) - b;
+        near |= (fabsf(ex) < tau & ey < tau) | (fabsf(ey) < tau & ex < tau);
+    }
+    return near;
+}
+
+R3G_HD bool v1_dedup_risk(const BoxP0& A0, const BoxP1& A1, const BoxP0& B0, const BoxP1& B1,
+                          const PairFrame& f, float tau) {
+    if (corner_near_boundary(f.qx, f.qy, f.a, f.b, tau)) return true;
+    // A's corners in B's frame
+    float dx = A0.cx - B0.cx, dy = A0.cy - B0.cy;
+    float cd = B1.c * A1.c + B1.s * A1.s;
+    float sd = B1.c * A1.s - B1.s * A1.c;
+    float dlx = dx * B1.c + dy * B1.s, dly = dy * B1.c - dx * B1.s;
+    float ux = A1.hw * cd, uy = A1.hw * sd, vx = -A1.hh * sd, vy = A1.hh * cd;
+    float px[4], py[4];
+    px[0] = dlx - ux - vx; py[0] = dly - uy - vy;
+    px[1] = dlx + ux - vx; py[1] = dly + uy - vy;
+    px[2] = dlx + ux + vx; py[2] = dly + uy + vy;
+    px[3] = dlx - ux + vx; py[3] = dly - uy + vy;
+    return corner_near_boundary(px, py, B1.hw, B1.hh, tau);
+}
+
+// IoU / IoF from the intersection area under the variant's epilogue.
+//   v1: clamp to [0, min(s1,s2)] (rbbox_geo_kernel.cu:254-256), no small-area guard
+//   v2/v3: area < 1e-14 -> 0 (box_iou_rotated_utils.h:353-355)
+R3G_HD float overlap_ratio(float inter, float s1, float s2, int variant, int mode) {
+    if (variant == V1) {
+        inter = fmaxf(fminf(fminf(inter, s1), s2), 0.0f);
+    } else if (s1 < 1e-14f || s2 < 1e-14f) {
+        return 0.0f;
+    }
+    float den = (mode == MODE_IOF) ? s1 : (s1 + s2 - inter);
+    return (den > 0.0f) ? inter / den : 0.0f;
+}
+
+// Fast-path overlap of one prepared pair.  `risk` is set for pairs the caller must re-evaluate with the
+// variant's restatement in emu.cuh (strict reference parity); tau = 0 disables the test.
+R3G_HD float pair_overlap(const BoxP0& A0, const BoxP1& A1, const BoxP0& B0, const BoxP1& B1,
+                          int variant, int mode, float tau, bool& risk) {
+    risk = false;
+    PairFrame f;
+    if (!pair_frame(A0, A1, B0, B1, f)) return 0.0f;
+    float inter = frame_area(f);
+    if (tau > 0.0f) {
+        // thin boxes (< tau) make every vertex "near": hand them to the restatement as well
+        risk = (fminf(fminf(A1.hw, A1.hh), fminf(B1.hw, B1.hh)) < tau) || v1_dedup_risk(A0, A1, B0, B1, f, tau);
+    }
+    return overlap_ratio(inter, A0.area, B0.area, variant, mode);
+}
+
+}  // namespace r3g

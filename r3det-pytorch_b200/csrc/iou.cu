@@ -1,0 +1,336 @@
+// iou.cu — pairwise rotated IoU / IoF for RBboxOverlaps2D_v1/v2/v3 on sm_100a.
+//
+// Replaces (reference, relative to /root/reference):
+//   mat_iou_iof_kernel / vec_iou_iof_kernel       r3det/ops/rbbox_geo/src/rbbox_geo_kernel.cu:230-309
+//   box_iou_rotated_cuda_kernel                   r3det/ops/box_iou_rotated/src/box_iou_rotated_cuda.cu:13-63
+//
+// Design (B200-first):
+//   1. prep kernel: per-box trig/extent/radius ONCE (O(M+N)) into two float4 planes (workspace).
+//   2. matrix kernel: persistent warps, one (64 rows x 128 cols) item per warp at a time.
+//      stage 1 — every lane owns 4 adjacent columns (one 16-byte store per row) and walks the rows
+//                with a 7-flop circumradius test; the row's zeros are written with coalesced 512-byte
+//                streaming stores; surviving pairs (5-12 % on detection workloads) are compacted into a
+//                per-warp shared-memory queue with ballot + popc.
+//      stage 2 — whenever >= 32 survivors are queued the warp evaluates them at FULL lane occupancy:
+//                separating-axis reject, clamped-boundary area integral (geom.cuh), variant epilogue,
+//                4-byte scatter store over the zero already in L2.
+//      The reference runs its whole point-set algorithm in every thread of a warp as soon as one lane
+//      overlaps (~80 % of warps at 5 % overlap) and recomputes sinf/cosf per pair.
+//   Bound: HBM store (4 B/pair) on detection-like inputs, FP32 issue on dense-overlap inputs.
+#include "common.cuh"
+#include "emu.cuh"
+#include "geom.cuh"
+
+namespace r3g {
+
+constexpr int IOU_THREADS = 256;
+constexpr int IOU_WARPS = IOU_THREADS / 32;
+constexpr int IOU_CPL = 4;                 // columns per lane
+constexpr int IOU_TN = 32 * IOU_CPL;       // 128 columns per warp item
+constexpr int IOU_TM = 64;                 // rows per warp item
+constexpr int IOU_QCAP = 32 + IOU_TN;      // worst case: 31 queued + one full row of survivors
+
+__global__ void prep_boxes_kernel(const float* __restrict__ boxes, int64_t n, int64_t stride, int variant,
+                                  BoxP0* __restrict__ p0, BoxP1* __restrict__ p1) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* b = boxes + i * stride;
+    float raw[5] = { b[0], b[1], b[2], b[3], b[4] };
+    BoxP0 a; BoxP1 c;
+    emu::prep_box_strict(raw, variant, a, c);
+    p0[i] = a;
+    p1[i] = c;
+}
+
+__device__ __noinline__ float emu_pair_call(const float* b1, const float* b2, int variant, int mode) {
+    float x[5] = { b1[0], b1[1], b1[2], b1[3], b1[4] };
+    float y[5] = { b2[0], b2[1], b2[2], b2[3], b2[4] };
+    return emu::pair(x, y, variant, mode);
+}
+
+struct IouArgs {
+    const BoxP0* r0; const BoxP1* r1; int64_t m;
+    const BoxP0* c0; const BoxP1* c1; int64_t n;
+    const float* raw1; int64_t s1;
+    const float* raw2; int64_t s2;
+    int variant, mode, small_mask;
+    float tau;
+    float* out;
+    unsigned long long* stats;
+};
+
+__device__ __forceinline__ float4 ldg4(const void* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+struct PairBoxes { BoxP0 A0, B0; BoxP1 A1, B1; };
+__device__ __forceinline__ PairBoxes load_pair(const IouArgs& A, unsigned i, unsigned j) {
+    float4 a0 = ldg4(A.r0 + i), a1 = ldg4(A.r1 + i), b0 = ldg4(A.c0 + j), b1 = ldg4(A.c1 + j);
+    PairBoxes P;
+    P.A0 = { a0.x, a0.y, a0.z, a0.w }; P.A1 = { a1.x, a1.y, a1.z, a1.w };
+    P.B0 = { b0.x, b0.y, b0.z, b0.w }; P.B1 = { b1.x, b1.y, b1.z, b1.w };
+    return P;
+}
+
+// Three per-warp queues of (row, col) pairs, all persistent across the warp's items and flushed once at
+// kernel end, so every stage below runs with 32 active lanes:
+//   q1: passed the circumradius test      -> separating-axis test
+//   q2: passed the separating-axis test   -> area integral + epilogue + store
+//   q3: flagged degenerate (strict mode)  -> the reference's own point-set algorithm (emu.cuh)
+struct WarpQueues {
+    uint2* q1; uint2* q2; uint2* q3;
+    int c1, c2, c3;
+};
+
+template <bool VEC>
+__global__ void __launch_bounds__(IOU_THREADS, 3) iou_matrix_kernel(const IouArgs A) {
+    __shared__ uint2 q1_all[IOU_WARPS][IOU_QCAP];
+    __shared__ uint2 q2_all[IOU_WARPS][64];
+    __shared__ uint2 q3_all[IOU_WARPS][64];
+    const unsigned warp = threadIdx.x >> 5, lane = lane_id();
+    uint2* q1 = q1_all[warp];
+    uint2* q2 = q2_all[warp];
+    uint2* q3 = q3_all[warp];
+    int c1 = 0, c2 = 0, c3 = 0;
+    const unsigned lt = lanemask_lt();
+    const int64_t tiles_n = (A.n + IOU_TN - 1) / IOU_TN;
+    const int64_t tiles_m = (A.m + IOU_TM - 1) / IOU_TM;
+    const int64_t total = tiles_m * tiles_n;
+    unsigned n_circle = 0, n_sat = 0, n_emu = 0;
+
+    int64_t item = (int64_t)blockIdx.x * IOU_WARPS + warp;
+    int64_t i = 0, i1 = 0, jb = 0;
+    float bx[IOU_CPL], by[IOU_CPL], br[IOU_CPL];
+    bool bv[IOU_CPL];
+    bool full4 = false;
+    bool have_item = false, done = false;
+
+    while (true) {
+        // ---- drain stages (single copy of each): deepest first so queues never overflow ----
+        if (c3 >= 32 || (done && c3 > 0)) {
+            const int nb = min(32, c3);
+            __syncwarp();
+            if ((int)lane < nb) {
+                const uint2 e = q3[c3 - nb + lane];
+                float r = emu_pair_call(A.raw1 + (int64_t)e.x * A.s1, A.raw2 + (int64_t)e.y * A.s2, A.variant, A.mode);
+                if (A.small_mask) {
+                    const float4 a1 = ldg4(A.r1 + e.x), b1 = ldg4(A.c1 + e.y);
+                    if (fminf(a1.z, a1.w) * 2.0f < 0.001f || fminf(b1.z, b1.w) * 2.0f < 0.001f) r = 0.0f;
+                }
+                A.out[(int64_t)e.x * A.n + e.y] = r;
+            }
+            __syncwarp();
+            c3 -= nb;
+            n_emu += nb;
+            continue;
+        }
+        if (c2 >= 32 || (done && c1 == 0 && c2 > 0)) {
+            const int nb = min(32, c2);
+            __syncwarp();
+            bool risk = false;
+            uint2 e = make_uint2(0u, 0u);
+            if ((int)lane < nb) {
+                e = q2[c2 - nb + lane];
+                const PairBoxes P = load_pair(A, e.x, e.y);
+                float r = pair_overlap(P.A0, P.A1, P.B0, P.B1, A.variant, A.mode, A.tau, risk);
+                if (A.small_mask && (fminf(P.A1.hw, P.A1.hh) * 2.0f < 0.001f || fminf(P.B1.hw, P.B1.hh) * 2.0f < 0.001f)) r = 0.0f;
+                if (!risk && r != 0.0f) A.out[(int64_t)e.x * A.n + e.y] = r;
+            }
+            __syncwarp();
+            c2 -= nb;
+            const unsigned bal = __ballot_sync(0xffffffffu, risk);
+            if (risk) q3[c3 + __popc(bal & lt)] = e;
+            c3 += __popc(bal);
+            n_sat += nb;
+            continue;
+        }
+        if (c1 >= 32 || (done && c1 > 0)) {
+            const int nb = min(32, c1);
+            __syncwarp();
+            bool ok = false;
+            uint2 e = make_uint2(0u, 0u);
+            if ((int)lane < nb) {
+                e = q1[c1 - nb + lane];
+                const PairBoxes P = load_pair(A, e.x, e.y);
+                ok = pair_sat(P.A0, P.A1, P.B0, P.B1);
+            }
+            __syncwarp();
+            c1 -= nb;
+            const unsigned bal = __ballot_sync(0xffffffffu, ok);
+            if (ok) q2[c2 + __popc(bal & lt)] = e;
+            c2 += __popc(bal);
+            n_circle += nb;
+            continue;
+        }
+        if (done) break;
+
+        // ---- stage 1: one row of the current item (or fetch the next item) ----
+        if (!have_item || i >= i1) {
+            if (have_item) item += (int64_t)gridDim.x * IOU_WARPS;
+            if (item >= total) { done = true; continue; }
+            have_item = true;
+            const int64_t tm = item / tiles_n, tn = item - tm * tiles_n;
+            i = tm * IOU_TM; i1 = min(A.m, i + IOU_TM);
+            jb = tn * IOU_TN + lane * IOU_CPL;
+#pragma unroll
+            for (int k = 0; k < IOU_CPL; k++) {
+                bv[k] = (jb + k) < A.n;
+                float4 b = bv[k] ? ldg4(A.c0 + jb + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+                bx[k] = b.x; by[k] = b.y; br[k] = b.z;
+            }
+            full4 = VEC && (jb + IOU_CPL <= A.n);
+        }
+        {
+            const float4 a = ldg4(A.r0 + i);
+            bool pass[IOU_CPL];
+#pragma unroll
+            for (int k = 0; k < IOU_CPL; k++) {
+                float dx = bx[k] - a.x, dy = by[k] - a.y, rr = br[k] + a.z;
+                pass[k] = bv[k] && !(dx * dx + dy * dy > rr * rr);
+            }
+            float* orow = A.out + i * A.n + jb;
+            if (full4) {
+                st_cs_f4(orow, make_float4(0.f, 0.f, 0.f, 0.f));
+            } else {
+#pragma unroll
+                for (int k = 0; k < IOU_CPL; k++)
+                    if (bv[k]) st_cs_f1(orow + k, 0.f);
+            }
+#pragma unroll
+            for (int k = 0; k < IOU_CPL; k++) {
+                const unsigned bal = __ballot_sync(0xffffffffu, pass[k]);
+                if (pass[k]) q1[c1 + __popc(bal & lt)] = make_uint2((unsigned)i, (unsigned)(jb + k));
+                c1 += __popc(bal);
+            }
+            i++;
+        }
+    }
+
+    if (A.stats) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) A.stats[3] = (unsigned long long)A.m * (unsigned long long)A.n;
+        if (lane == 0) {
+            atomicAdd(A.stats + 0, (unsigned long long)n_circle);
+            atomicAdd(A.stats + 1, (unsigned long long)n_sat);
+            atomicAdd(A.stats + 2, (unsigned long long)n_emu);
+        }
+    }
+}
+
+__global__ void iou_aligned_kernel(const float* __restrict__ b1, int64_t n1, int64_t s1,
+                                   const float* __restrict__ b2, int64_t n2, int64_t s2,
+                                   int variant, int mode, float tau, int small_mask, float* __restrict__ out) {
+    const int64_t n = n1 > n2 ? n1 : n2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float* p = b1 + (i % n1) * s1;
+        const float* q = b2 + (i % n2) * s2;
+        float x[5] = { p[0], p[1], p[2], p[3], p[4] };
+        float y[5] = { q[0], q[1], q[2], q[3], q[4] };
+        BoxP0 A0, B0; BoxP1 A1, B1;
+        emu::prep_box_strict(x, variant, A0, A1);
+        emu::prep_box_strict(y, variant, B0, B1);
+        float r = 0.0f;
+        if (!circle_reject(A0, B0)) {
+            bool risk;
+            r = pair_overlap(A0, A1, B0, B1, variant, mode, tau, risk);
+            if (risk) r = emu_pair_call(p, q, variant, mode);
+        }
+        if (small_mask && (fminf(x[2], x[3]) < 0.001f || fminf(y[2], y[3]) < 0.001f)) r = 0.0f;
+        out[i] = r;
+    }
+}
+
+struct IouWorkspace {
+    unsigned long long* stats;
+    BoxP0 *r0, *c0;
+    BoxP1 *r1, *c1;
+    size_t bytes;
+};
+
+static IouWorkspace carve(void* ws, int64_t m, int64_t n) {
+    IouWorkspace w;
+    char* p = (char*)ws;
+    size_t off = 0;
+    w.stats = (unsigned long long*)(p + off); off += 256;
+    w.r0 = (BoxP0*)(p + off); off += align_up(sizeof(BoxP0) * (size_t)m, 256);
+    w.r1 = (BoxP1*)(p + off); off += align_up(sizeof(BoxP1) * (size_t)m, 256);
+    w.c0 = (BoxP0*)(p + off); off += align_up(sizeof(BoxP0) * (size_t)n, 256);
+    w.c1 = (BoxP1*)(p + off); off += align_up(sizeof(BoxP1) * (size_t)n, 256);
+    w.bytes = off;
+    return w;
+}
+
+}  // namespace r3g
+
+using namespace r3g;
+
+R3G_API int r3g_iou_workspace_bytes(int64_t m, int64_t n, size_t* bytes) {
+    R3G_REQUIRE(bytes != nullptr && m >= 0 && n >= 0, "r3g_iou_workspace_bytes: bad arguments");
+    *bytes = carve(nullptr, m, n).bytes;
+    return R3G_OK;
+}
+
+R3G_API int r3g_iou_matrix_f32(const float* boxes1, int64_t m, int64_t stride1,
+                               const float* boxes2, int64_t n, int64_t stride2,
+                               int variant, int mode, int flags, float* out,
+                               void* workspace, size_t workspace_bytes, void* stream) {
+    R3G_REQUIRE(m >= 0 && n >= 0, "r3g_iou_matrix_f32: negative size");
+    R3G_REQUIRE(variant >= 1 && variant <= 3, "r3g_iou_matrix_f32: variant must be 1, 2 or 3 (got %d)", variant);
+    R3G_REQUIRE(mode == R3G_MODE_IOU || mode == R3G_MODE_IOF, "r3g_iou_matrix_f32: mode must be iou(0) or iof(1)");
+    if (m == 0 || n == 0) return R3G_OK;
+    R3G_REQUIRE(boxes1 && boxes2 && out && workspace, "r3g_iou_matrix_f32: null pointer");
+    R3G_REQUIRE(stride1 >= 5 && stride2 >= 5, "r3g_iou_matrix_f32: box stride must be >= 5 floats");
+    R3G_REQUIRE(m < (1ll << 31) && n < (1ll << 31), "r3g_iou_matrix_f32: more than 2^31 boxes");
+    IouWorkspace w = carve(workspace, m, n);
+    if (workspace_bytes < w.bytes) {
+        set_error("r3g_iou_matrix_f32: workspace too small (%zu < %zu)", workspace_bytes, w.bytes);
+        return R3G_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    R3G_CUDA_OK(cudaMemsetAsync(w.stats, 0, 256, st));
+    prep_boxes_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(boxes1, m, stride1, variant, w.r0, w.r1);
+    prep_boxes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(boxes2, n, stride2, variant, w.c0, w.c1);
+    R3G_LAUNCH_OK("prep_boxes_kernel");
+
+    IouArgs a;
+    a.r0 = w.r0; a.r1 = w.r1; a.m = m; a.c0 = w.c0; a.c1 = w.c1; a.n = n;
+    a.raw1 = boxes1; a.s1 = stride1; a.raw2 = boxes2; a.s2 = stride2;
+    a.variant = variant; a.mode = mode;
+    a.small_mask = (variant == R3G_V3 && (flags & R3G_FLAG_SMALL_MASK)) ? 1 : 0;
+    a.tau = (flags & R3G_FLAG_STRICT) ? 2e-2f : 0.0f;
+    a.out = out; a.stats = w.stats;
+
+    const bool vec = (n % 4 == 0) && (((uintptr_t)out & 15u) == 0);
+    static int occ_vec = 0, occ_scl = 0;
+    int& occ = vec ? occ_vec : occ_scl;
+    if (occ == 0) {
+        if (vec) R3G_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, iou_matrix_kernel<true>, IOU_THREADS, 0));
+        else R3G_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, iou_matrix_kernel<false>, IOU_THREADS, 0));
+        if (occ < 1) occ = 1;
+    }
+    const int64_t items = ((m + IOU_TM - 1) / IOU_TM) * ((n + IOU_TN - 1) / IOU_TN);
+    int64_t grid = (items + IOU_WARPS - 1) / IOU_WARPS;
+    const int64_t cap = (int64_t)device_sm_count() * occ;
+    if (grid > cap) grid = cap;
+    if (vec) iou_matrix_kernel<true><<<(unsigned)grid, IOU_THREADS, 0, st>>>(a);
+    else iou_matrix_kernel<false><<<(unsigned)grid, IOU_THREADS, 0, st>>>(a);
+    R3G_LAUNCH_OK("iou_matrix_kernel");
+    return R3G_OK;
+}
+
+R3G_API int r3g_iou_aligned_f32(const float* boxes1, int64_t n1, int64_t stride1,
+                                const float* boxes2, int64_t n2, int64_t stride2,
+                                int variant, int mode, int flags, float* out, void* stream) {
+    R3G_REQUIRE(n1 >= 0 && n2 >= 0, "r3g_iou_aligned_f32: negative size");
+    R3G_REQUIRE(variant >= 1 && variant <= 3, "r3g_iou_aligned_f32: variant must be 1, 2 or 3 (got %d)", variant);
+    R3G_REQUIRE(mode == R3G_MODE_IOU || mode == R3G_MODE_IOF, "r3g_iou_aligned_f32: mode must be iou(0) or iof(1)");
+    if (n1 == 0 || n2 == 0) return R3G_OK;
+    R3G_REQUIRE(boxes1 && boxes2 && out, "r3g_iou_aligned_f32: null pointer");
+    R3G_REQUIRE(stride1 >= 5 && stride2 >= 5, "r3g_iou_aligned_f32: box stride must be >= 5 floats");
+    const int64_t n = n1 > n2 ? n1 : n2;
+    int64_t grid = (n + 255) / 256;
+    const int64_t cap = (int64_t)device_sm_count() * 8;
+    if (grid > cap) grid = cap;
+    iou_aligned_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(
+        boxes1, n1, stride1, boxes2, n2, stride2, variant, mode, (flags & R3G_FLAG_STRICT) ? 2e-2f : 0.0f,
+        (variant == R3G_V3 && (flags & R3G_FLAG_SMALL_MASK)) ? 1 : 0, out);
+    R3G_LAUNCH_OK("iou_aligned_kernel");
+    return R3G_OK;
+}

@@ -1,0 +1,459 @@
+// nms.cu — rotated NMS (single class and per-class segmented) entirely on the device, sm_100a.
+//
+// Replaces (reference, relative to /root/reference):
+//   nmsr_kernel + nmsr_cuda host scan            r3det/ops/rnms/src/rcuda/rnms_kernel.cu:229-335        (v1)
+//   nms_rotated_cuda_kernel + host scan          r3det/ops/nms_rotated/src/nms_rotated_cuda.cu:12-134    (v3)
+//   ml_nms_rotated                               r3det/ops/ml_nms_rotated/src/nms_rotated_cuda.cu:13-137 (v2)
+// The reference computes the FULL K x K bitmask (cross-class pairs included, via a coordinate offset
+// trick), copies it to the host and scans it serially on the CPU.  Here:
+//   1. radix sort by score (and a stable second pass by label) -> position space p = (label asc, score desc);
+//   2. boxes are gathered/prepared once in p-order (class offsets applied in FP32 exactly as the
+//      reference's batched wrappers do, so the geometry sees the same rounded coordinates);
+//   3. mask kernel: only upper-triangular 64x64 tiles INSIDE a class segment are visited; a warp owns a
+//      64-row x 256-column item, rejects pairs with the circumradius test at one lane per column,
+//      compacts the survivors with ballot/popc into a shared-memory queue and evaluates them 32 at a
+//      time with the clamped-boundary integral (geom.cuh); suppression bits are OR-ed into shared-memory
+//      64-bit words and written once;
+//   4. scan kernel: one CTA per class; per 64-row block the intra-block chain is resolved from the 64
+//      diagonal words with ffs-jumps over already-suppressed rows, then the kept rows' mask words are
+//      OR-ed into the shared-memory `removed` bit-vector by all threads (no host round trip);
+//   5. flags -> exclusive scan -> keep list in score order or index order.
+// Pairs whose IoU lies within `margin` of the threshold (or that trip the degeneracy test) are decided
+// by the reference's own algorithm (emu.cuh), which makes the keep set the reference's.
+#include <cub/cub.cuh>
+#include "common.cuh"
+#include "emu.cuh"
+#include "geom.cuh"
+
+namespace r3g {
+
+constexpr int NMS_THREADS = 256;
+constexpr int NMS_WARPS = NMS_THREADS / 32;
+constexpr int NMS_G = 4;                       // column blocks (of 64) per item
+constexpr int NMS_CPL = NMS_G * 64 / 32;       // 8 columns per lane
+constexpr int NMS_QCAP = 32 + NMS_G * 64;
+
+struct NmsWs {
+    unsigned *keyA, *keyA2, *keyB, *keyB2;
+    int *ord_rank, *ord_tmp, *pos_rank, *pos_tmp;   // ord_rank[r] = original index of rank r; pos_rank[p] = rank at position p
+    unsigned* pos_label;
+    BoxP0* p0; BoxP1* p1; float* raw; unsigned char* valid;
+    int* blk_end; long long *nw, *row_base, *ng, *item_base;
+    int* seg_list; int* counters;                   // counters[0] = nseg
+    int *flag, *pref;
+    void* cub_tmp; size_t cub_bytes;
+    unsigned long long* mask;
+    size_t bytes;
+};
+
+static size_t cub_temp_bytes(int64_t K, int64_t nblk) {
+    size_t a = 0, b = 0, c = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, a, (unsigned*)nullptr, (unsigned*)nullptr, (int*)nullptr, (int*)nullptr, (int)K);
+    cub::DeviceScan::ExclusiveSum(nullptr, b, (int*)nullptr, (int*)nullptr, (int)K);
+    cub::DeviceScan::ExclusiveSum(nullptr, c, (long long*)nullptr, (long long*)nullptr, (int)nblk + 1);
+    size_t m = a > b ? a : b;
+    return align_up(m > c ? m : c, 256);
+}
+
+static NmsWs carve_nms(void* ws, int64_t K) {
+    NmsWs w;
+    const int64_t nblk = (K + 63) / 64;
+    char* p = (char*)ws;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { char* r = p + off; off += align_up(bytes, 256); return (void*)r; };
+    w.counters = (int*)take(256);
+    w.keyA = (unsigned*)take(4 * K); w.keyA2 = (unsigned*)take(4 * K);
+    w.keyB = (unsigned*)take(4 * K); w.keyB2 = (unsigned*)take(4 * K);
+    w.ord_rank = (int*)take(4 * K); w.ord_tmp = (int*)take(4 * K);
+    w.pos_rank = (int*)take(4 * K); w.pos_tmp = (int*)take(4 * K);
+    w.pos_label = (unsigned*)take(4 * K);
+    w.p0 = (BoxP0*)take(16 * K); w.p1 = (BoxP1*)take(16 * K);
+    w.raw = (float*)take(20 * K); w.valid = (unsigned char*)take(K);
+    w.blk_end = (int*)take(4 * nblk);
+    w.nw = (long long*)take(8 * (nblk + 1)); w.row_base = (long long*)take(8 * (nblk + 1));
+    w.ng = (long long*)take(8 * (nblk + 1)); w.item_base = (long long*)take(8 * (nblk + 1));
+    w.seg_list = (int*)take(4 * K);
+    w.flag = (int*)take(4 * K); w.pref = (int*)take(4 * K);
+    w.cub_bytes = cub_temp_bytes(K, nblk);
+    w.cub_tmp = take(w.cub_bytes);
+    w.mask = (unsigned long long*)take((size_t)8 * 64 * (size_t)(nblk * (nblk + 1) / 2));
+    w.bytes = off;
+    return w;
+}
+
+__device__ __forceinline__ unsigned score_key_desc(float s) {
+    unsigned b = __float_as_uint(s);
+    unsigned asc = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+    return ~asc;
+}
+
+__global__ void nms_keys_kernel(const float* __restrict__ scores, int K, unsigned* keyA, int* idx) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < K) { keyA[i] = score_key_desc(scores[i]); idx[i] = i; }
+}
+
+__global__ void nms_label_keys_kernel(const int64_t* __restrict__ labels, const int* __restrict__ ord_rank, int K,
+                                      unsigned* keyB, int* rank_iota) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < K) {
+        keyB[r] = labels ? (unsigned)labels[ord_rank[r]] : 0u;
+        rank_iota[r] = r;
+    }
+}
+
+// Gather + prepare boxes in position order; class offsets in FP32 as the reference wrappers compute them:
+//   offsets = label.to(float) * scale ; box[:, :2] += offsets      (rnms_wrapper.py:61-64, nms_rotated_wrapper.py:84-90)
+__global__ void nms_gather_kernel(const float* __restrict__ boxes, int64_t stride, const int* __restrict__ ord_rank,
+                                  const int* __restrict__ pos_rank, const unsigned* __restrict__ pos_label, int K,
+                                  int variant, int drop_small, const float* __restrict__ class_offset, int has_labels,
+                                  BoxP0* p0, BoxP1* p1, float* raw, unsigned char* valid) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= K) return;
+    const int idx = ord_rank[pos_rank[p]];
+    const float* b = boxes + (int64_t)idx * stride;
+    float x[5] = { b[0], b[1], b[2], b[3], b[4] };
+    if (class_offset != nullptr && has_labels) {
+        float off = __fmul_rn((float)(int)pos_label[p], class_offset[0]);
+        x[0] = __fadd_rn(x[0], off);
+        x[1] = __fadd_rn(x[1], off);
+    }
+    BoxP0 a; BoxP1 c;
+    emu::prep_box_strict(x, variant, a, c);
+    p0[p] = a; p1[p] = c;
+#pragma unroll
+    for (int k = 0; k < 5; k++) raw[(int64_t)p * 5 + k] = x[k];
+    valid[p] = (drop_small && fminf(x[2], x[3]) < 0.001f) ? 0 : 1;    // nms_rotated_wrapper.py:40-46
+}
+
+// per 64-row block: last column block its rows can interact with (end of the class segment of its last row)
+__global__ void nms_blocks_kernel(const unsigned* __restrict__ pos_label, int K, int nblk,
+                                  int* blk_end, long long* nw, long long* ng) {
+    int rb = blockIdx.x * blockDim.x + threadIdx.x;
+    if (rb > nblk) return;
+    if (rb == nblk) { nw[rb] = 0; ng[rb] = 0; return; }
+    int last = min(K, rb * 64 + 64) - 1;
+    unsigned L = pos_label[last];
+    int lo = last, hi = K;                          // first p > last with label != L (labels sorted ascending)
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (pos_label[mid] == L) lo = mid; else hi = mid;
+    }
+    int be = lo >> 6;
+    blk_end[rb] = be;
+    long long w = be - rb + 1;
+    nw[rb] = w * 64;                                // words of this row block (64 rows x w words)
+    ng[rb] = (w + NMS_G - 1) / NMS_G;               // items of this row block
+}
+
+__global__ void nms_segments_kernel(const unsigned* __restrict__ pos_label, int K, int* seg_list, int* counters) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= K) return;
+    if (p == 0 || pos_label[p] != pos_label[p - 1]) seg_list[atomicAdd(&counters[0], 1)] = p;
+}
+
+__device__ __noinline__ float nms_emu_call(const float* b1, const float* b2, int variant) {
+    float x[5] = { b1[0], b1[1], b1[2], b1[3], b1[4] };
+    float y[5] = { b2[0], b2[1], b2[2], b2[3], b2[4] };
+    return emu::pair(x, y, variant, MODE_IOU);
+}
+
+struct MaskArgs {
+    const BoxP0* p0; const BoxP1* p1; const float* raw; const unsigned char* valid; const unsigned* label;
+    const int* blk_end; const long long* row_base; const long long* item_base;
+    unsigned long long* mask;
+    int K, nblk, variant, inclusive;
+    float thr, tau, margin;
+};
+
+__device__ __forceinline__ float4 nldg4(const void* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+__global__ void __launch_bounds__(NMS_THREADS) nms_mask_kernel(const MaskArgs A) {
+    __shared__ unsigned q_all[NMS_WARPS][NMS_QCAP];
+    __shared__ unsigned long long sm_all[NMS_WARPS][64 * NMS_G];
+    const unsigned warp = threadIdx.x >> 5, lane = lane_id(), lt = lanemask_lt();
+    unsigned* q = q_all[warp];
+    unsigned long long* sm = sm_all[warp];
+    const long long total = A.item_base[A.nblk];
+
+    for (long long item = (long long)blockIdx.x * NMS_WARPS + warp; item < total; item += (long long)gridDim.x * NMS_WARPS) {
+        // row block of this item: last rb with item_base[rb] <= item
+        int lo = 0, hi = A.nblk;
+        while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if (A.item_base[mid] <= item) lo = mid; else hi = mid;
+        }
+        const int rb = lo;
+        const int g = (int)(item - A.item_base[rb]);
+        const int be = A.blk_end[rb];
+        const int cb0 = rb + g * NMS_G;                       // first column block of the item
+        const int ncb = min(NMS_G, be - cb0 + 1);             // valid column blocks
+        const int i0 = rb * 64, i1 = min(A.K, i0 + 64);
+        const int j0 = cb0 * 64, j1 = min(A.K, j0 + ncb * 64);
+
+        for (int k = lane; k < 64 * NMS_G; k += 32) sm[k] = 0ull;
+        float bx[NMS_CPL], by[NMS_CPL], br[NMS_CPL];
+        unsigned bl[NMS_CPL];
+        bool bv[NMS_CPL];
+#pragma unroll
+        for (int k = 0; k < NMS_CPL; k++) {
+            const int j = j0 + lane + 32 * k;
+            bv[k] = j < j1;
+            float4 b = bv[k] ? nldg4(A.p0 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            bx[k] = b.x; by[k] = b.y; br[k] = b.z;
+            bl[k] = bv[k] ? A.label[j] : 0xffffffffu;
+            bv[k] = bv[k] && A.valid[j];
+        }
+        __syncwarp();
+        int count = 0;
+
+        auto drain = [&](int first, int nb) {
+            __syncwarp();
+            if ((int)lane < nb) {
+                const unsigned e = q[first + lane];
+                const int il = e >> 8, jl = e & 255u;
+                const int i = i0 + il, j = j0 + jl;
+                float4 a0 = nldg4(A.p0 + i), a1 = nldg4(A.p1 + i), b0 = nldg4(A.p0 + j), b1 = nldg4(A.p1 + j);
+                BoxP0 A0 = { a0.x, a0.y, a0.z, a0.w }; BoxP1 A1 = { a1.x, a1.y, a1.z, a1.w };
+                BoxP0 B0 = { b0.x, b0.y, b0.z, b0.w }; BoxP1 B1 = { b1.x, b1.y, b1.z, b1.w };
+                bool risk;
+                float r = pair_overlap(A0, A1, B0, B1, A.variant, MODE_IOU, A.tau, risk);
+                if (A.tau > 0.0f && (risk || fabsf(r - A.thr) < A.margin))
+                    r = nms_emu_call(A.raw + (int64_t)i * 5, A.raw + (int64_t)j * 5, A.variant);
+                const bool sup = A.inclusive ? (r >= A.thr) : (r > A.thr);
+                if (sup) atomicOr(&sm[il * NMS_G + (jl >> 6)], 1ull << (jl & 63));
+            }
+            __syncwarp();
+        };
+
+        for (int i = i0; i < i1; i++) {
+            const float4 a = nldg4(A.p0 + i);
+            const unsigned la = A.label[i];
+            const bool va = A.valid[i] != 0;
+            const unsigned rowbits = (unsigned)(i - i0) << 8;
+#pragma unroll
+            for (int k = 0; k < NMS_CPL; k++) {
+                const int jl = lane + 32 * k;
+                float dx = bx[k] - a.x, dy = by[k] - a.y, rr = br[k] + a.z;
+                const bool pass = va && bv[k] && (bl[k] == la) && (j0 + jl > i) && !(dx * dx + dy * dy > rr * rr);
+                const unsigned bal = __ballot_sync(0xffffffffu, pass);
+                if (pass) q[count + __popc(bal & lt)] = rowbits | (unsigned)jl;
+                count += __popc(bal);
+            }
+            while (count >= 32) { drain(count - 32, 32); count -= 32; }
+        }
+        if (count > 0) drain(0, count);
+        __syncwarp();
+        // write the item's words: row r of block rb holds (be - rb + 1) words, word index = cb - rb
+        const long long base = A.row_base[rb];
+        const int nwr = be - rb + 1;
+        for (int k = lane; k < 64 * NMS_G; k += 32) {
+            const int il = k / NMS_G, c = k % NMS_G;
+            if (c < ncb) A.mask[base + (long long)il * nwr + (cb0 - rb + c)] = sm[k];
+        }
+        __syncwarp();
+    }
+}
+
+struct ScanArgs {
+    const unsigned long long* mask; const unsigned char* valid; const unsigned* label;
+    const int* blk_end; const long long* row_base; const int* seg_list; const int* counters;
+    const int* pos_rank; const int* ord_rank;
+    int* flag;
+    int K, order_index, remv_cap;
+};
+
+__global__ void __launch_bounds__(NMS_THREADS) nms_scan_kernel(const ScanArgs A) {
+    extern __shared__ unsigned long long remv[];          // remv_cap words
+    __shared__ unsigned long long D[64];
+    __shared__ unsigned long long kept_s;
+    const int tid = threadIdx.x;
+    const int nseg = A.counters[0];
+    for (int s = blockIdx.x; s < nseg; s += gridDim.x) {
+        const int ps = A.seg_list[s];
+        const unsigned L = A.label[ps];
+        int lo = ps, hi = A.K;
+        while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if (A.label[mid] == L) lo = mid; else hi = mid;
+        }
+        const int pe = lo + 1;
+        const int bf = ps >> 6, bl = (pe - 1) >> 6;
+        const int nb = bl - bf + 1;
+        for (int w = tid; w < nb && w < A.remv_cap; w += NMS_THREADS) remv[w] = 0ull;
+        __syncthreads();
+        for (int b = bf; b <= bl; b++) {
+            const int r0 = max(ps, b * 64), r1 = min(pe, b * 64 + 64);
+            const long long base = A.row_base[b];
+            const int nwr = A.blk_end[b] - b + 1;
+            if (tid < 64) {
+                const int p = b * 64 + tid;
+                unsigned long long d = 0ull;
+                if (p >= r0 && p < r1 && A.valid[p]) d = A.mask[base + (long long)tid * nwr];
+                D[tid] = d;
+            }
+            __syncthreads();
+            if (tid < 32) {
+                // valid rows of this segment inside the block
+                unsigned long long vb = 0ull;
+                for (int t = (int)tid; t < 64; t += 32) {
+                    const int p = b * 64 + t;
+                    const bool ok = (p >= r0 && p < r1 && A.valid[p]);
+                    unsigned m = __ballot_sync(0xffffffffu, ok);
+                    vb |= (unsigned long long)m << (t & 32);
+                }
+                unsigned long long cur = remv[b - bf], kept = 0ull;
+                unsigned long long avail = vb & ~cur;
+                while (avail) {                               // warp-uniform loop, one kept row per trip
+                    const int t = __ffsll((long long)avail) - 1;
+                    kept |= 1ull << t;
+                    cur |= D[t];
+                    const unsigned long long above = (t == 63) ? 0ull : (~0ull << (t + 1));
+                    avail = vb & ~cur & above;
+                }
+                if (tid == 0) kept_s = kept;
+            }
+            __syncthreads();
+            const unsigned long long kept = kept_s;
+            // OR the kept rows' words for later blocks of this segment into remv (thread owns its words)
+            const int nlater = bl - b;                          // words b+1 .. bl
+            for (int w = tid; w < nlater; w += NMS_THREADS) {
+                unsigned long long acc = remv[b - bf + 1 + w];
+                unsigned long long kk = kept;
+                while (kk) {
+                    const int t = __ffsll((long long)kk) - 1;
+                    kk &= kk - 1;
+                    acc |= A.mask[base + (long long)t * nwr + 1 + w];
+                }
+                remv[b - bf + 1 + w] = acc;
+            }
+            if (tid < 64) {
+                const int p = b * 64 + tid;
+                if (p >= r0 && p < r1) {
+                    const int rank = A.pos_rank[p];
+                    const int slot = A.order_index ? A.ord_rank[rank] : rank;
+                    A.flag[slot] = (int)((kept >> tid) & 1ull);
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void nms_emit_kernel(const int* __restrict__ flag, const int* __restrict__ pref, const int* __restrict__ ord_rank,
+                                int K, int order_index, int64_t* keep_out, int64_t* num_keep) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= K) return;
+    if (flag[s]) keep_out[pref[s]] = order_index ? (int64_t)s : (int64_t)ord_rank[s];
+    if (s == K - 1) *num_keep = (int64_t)pref[s] + flag[s];
+}
+
+}  // namespace r3g
+
+using namespace r3g;
+
+R3G_API int r3g_nms_workspace_bytes(int64_t K, size_t* bytes) {
+    R3G_REQUIRE(bytes != nullptr && K >= 0, "r3g_nms_workspace_bytes: bad arguments");
+    R3G_REQUIRE(K < (1ll << 30), "r3g_nms_workspace_bytes: K too large");
+    *bytes = carve_nms(nullptr, K > 0 ? K : 1).bytes;
+    return R3G_OK;
+}
+
+R3G_API int r3g_nms_f32(const float* boxes, int64_t stride, const float* scores, const int64_t* labels,
+                        int64_t K, float thr, int variant, int flags, const float* class_offset,
+                        int64_t* keep_out, int64_t* num_keep_out,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+    R3G_REQUIRE(K >= 0 && K < (1ll << 30), "r3g_nms_f32: bad K");
+    R3G_REQUIRE(variant >= 1 && variant <= 3, "r3g_nms_f32: variant must be 1, 2 or 3 (got %d)", variant);
+    R3G_REQUIRE(num_keep_out != nullptr, "r3g_nms_f32: null num_keep_out");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (K == 0) {
+        R3G_CUDA_OK(cudaMemsetAsync(num_keep_out, 0, sizeof(int64_t), st));
+        return R3G_OK;
+    }
+    R3G_REQUIRE(boxes && scores && keep_out && workspace, "r3g_nms_f32: null pointer");
+    R3G_REQUIRE(stride >= 5, "r3g_nms_f32: box stride must be >= 5 floats");
+    NmsWs w = carve_nms(workspace, K);
+    if (workspace_bytes < w.bytes) {
+        set_error("r3g_nms_f32: workspace too small (%zu < %zu)", workspace_bytes, w.bytes);
+        return R3G_ERR_WORKSPACE;
+    }
+    const int Ki = (int)K;
+    const int nblk = (Ki + 63) / 64;
+    const int tpb = 256, gK = (Ki + tpb - 1) / tpb;
+    R3G_CUDA_OK(cudaMemsetAsync(w.counters, 0, 256, st));
+
+    // 1. rank order by descending score (stable: ties keep ascending index)
+    nms_keys_kernel<<<gK, tpb, 0, st>>>(scores, Ki, w.keyA, w.ord_tmp);
+    size_t tb = w.cub_bytes;
+    R3G_CUDA_OK(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, w.keyA, w.keyA2, w.ord_tmp, w.ord_rank, Ki, 0, 32, st));
+    // 2. position order: stable by label on top of the rank order
+    nms_label_keys_kernel<<<gK, tpb, 0, st>>>(labels, w.ord_rank, Ki, w.keyB, w.pos_tmp);
+    if (labels) {
+        tb = w.cub_bytes;
+        R3G_CUDA_OK(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, w.keyB, w.pos_label, w.pos_tmp, w.pos_rank, Ki, 0, 32, st));
+    } else {
+        R3G_CUDA_OK(cudaMemcpyAsync(w.pos_label, w.keyB, 4 * (size_t)Ki, cudaMemcpyDeviceToDevice, st));
+        R3G_CUDA_OK(cudaMemcpyAsync(w.pos_rank, w.pos_tmp, 4 * (size_t)Ki, cudaMemcpyDeviceToDevice, st));
+    }
+    // 3. gather + prepare
+    nms_gather_kernel<<<gK, tpb, 0, st>>>(boxes, stride, w.ord_rank, w.pos_rank, w.pos_label, Ki, variant,
+                                          (flags & R3G_NMS_DROP_SMALL) ? 1 : 0, class_offset, labels ? 1 : 0,
+                                          w.p0, w.p1, w.raw, w.valid);
+    // 4. block / segment structure
+    nms_blocks_kernel<<<(nblk + 1 + tpb - 1) / tpb, tpb, 0, st>>>(w.pos_label, Ki, nblk, w.blk_end, w.nw, w.ng);
+    tb = w.cub_bytes;
+    R3G_CUDA_OK(cub::DeviceScan::ExclusiveSum(w.cub_tmp, tb, w.nw, w.row_base, nblk + 1, st));
+    tb = w.cub_bytes;
+    R3G_CUDA_OK(cub::DeviceScan::ExclusiveSum(w.cub_tmp, tb, w.ng, w.item_base, nblk + 1, st));
+    nms_segments_kernel<<<gK, tpb, 0, st>>>(w.pos_label, Ki, w.seg_list, w.counters);
+    R3G_LAUNCH_OK("nms structure kernels");
+
+    // 5. suppression bitmask
+    MaskArgs ma;
+    ma.p0 = w.p0; ma.p1 = w.p1; ma.raw = w.raw; ma.valid = w.valid; ma.label = w.pos_label;
+    ma.blk_end = w.blk_end; ma.row_base = w.row_base; ma.item_base = w.item_base; ma.mask = w.mask;
+    ma.K = Ki; ma.nblk = nblk; ma.variant = variant; ma.inclusive = (flags & R3G_NMS_INCLUSIVE) ? 1 : 0;
+    ma.thr = thr;
+    ma.tau = (flags & R3G_NMS_STRICT) ? 2e-2f : 0.0f;
+    ma.margin = (variant == R3G_V1) ? 1e-3f : 5e-5f;
+    static int occ = 0;
+    if (occ == 0) {
+        R3G_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, nms_mask_kernel, NMS_THREADS, 0));
+        if (occ < 1) occ = 1;
+    }
+    // upper bound on items: triangular number of (row block, group) pairs
+    long long max_items = (long long)nblk * ((nblk + NMS_G - 1) / NMS_G + 1);
+    long long grid = (max_items + NMS_WARPS - 1) / NMS_WARPS;
+    const long long cap = (long long)device_sm_count() * occ;
+    if (grid > cap) grid = cap;
+    nms_mask_kernel<<<(unsigned)grid, NMS_THREADS, 0, st>>>(ma);
+    R3G_LAUNCH_OK("nms_mask_kernel");
+
+    // 6. greedy scan per class segment
+    ScanArgs sa;
+    sa.mask = w.mask; sa.valid = w.valid; sa.label = w.pos_label; sa.blk_end = w.blk_end; sa.row_base = w.row_base;
+    sa.seg_list = w.seg_list; sa.counters = w.counters; sa.pos_rank = w.pos_rank; sa.ord_rank = w.ord_rank;
+    sa.flag = w.flag; sa.K = Ki; sa.order_index = (flags & R3G_NMS_ORDER_INDEX) ? 1 : 0;
+    sa.remv_cap = nblk;
+    size_t smem = (size_t)nblk * 8;
+    if (smem > 200 * 1024) {
+        set_error("r3g_nms_f32: K=%lld exceeds the single-image limit of this build (%d boxes)", (long long)K, 200 * 1024 / 8 * 64);
+        return R3G_ERR_ARG;
+    }
+    static size_t smem_set = 0;
+    if (smem > 48 * 1024 && smem > smem_set) {
+        R3G_CUDA_OK(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        smem_set = 200 * 1024;
+    }
+    int sgrid = device_sm_count() * 2;
+    if (!labels) sgrid = 1;
+    nms_scan_kernel<<<sgrid, NMS_THREADS, smem, st>>>(sa);
+    R3G_LAUNCH_OK("nms_scan_kernel");
+
+    // 7. compaction in the requested order
+    tb = w.cub_bytes;
+    R3G_CUDA_OK(cub::DeviceScan::ExclusiveSum(w.cub_tmp, tb, w.flag, w.pref, Ki, st));
+    nms_emit_kernel<<<gK, tpb, 0, st>>>(w.flag, w.pref, w.ord_rank, Ki, sa.order_index, keep_out, num_keep_out);
+    R3G_LAUNCH_OK("nms_emit_kernel");
+    return R3G_OK;
+}

@@ -1,0 +1,60 @@
+"""v3 rotated NMS — host-side mirror of r3det/ops/nms_rotated/nms_rotated_wrapper.py
+(obb_nms :23-54, obb_batched_nms :79-98).  Keep lists are in descending-score order
+(nms_rotated_cuda.cu:131-133); boxes with min(w,h) < 1e-3 take no part (:40-46).  CUDA inputs use the
+reference GPU rule (IoU > thr), numpy / CPU inputs the reference CPU rule (IoU >= thr,
+nms_rotated_cpu.cpp:55); all compute is on the GPU."""
+import torch
+
+from ._nms_core import nms_device, to_cuda_input
+
+
+def obb2hbb(obboxes):
+    """[x_ctr,y_ctr,w,h,angle] -> [x_lt,y_lt,x_rb,y_rb] (nms_rotated_wrapper.py:7-20)."""
+    center, w, h, theta = torch.split(obboxes, [2, 1, 1, 1], dim=1)
+    Cos, Sin = torch.cos(theta), torch.sin(theta)
+    x_bias = torch.abs(w / 2 * Cos) + torch.abs(h / 2 * Sin)
+    y_bias = torch.abs(w / 2 * Sin) + torch.abs(h / 2 * Cos)
+    bias = torch.cat([x_bias, y_bias], dim=1)
+    return torch.cat([center - bias, center + bias], dim=1)
+
+
+def obb_nms(dets, iou_thr, device_id=None):
+    """Compute the NMS of oriented bboxes.  dets: (K, 6) <x, y, w, h, a, score>."""
+    dets_th, is_numpy, was_host = to_cuda_input(dets, device_id, "dets")
+    if dets_th.numel() == 0:
+        inds = dets_th.new_zeros(0, dtype=torch.int64)
+    else:
+        d = dets_th.float()
+        keep, num = nms_device(d[:, :5], d[:, 5], iou_thr, "v3", inclusive=was_host, drop_small=True)
+        inds = keep[:int(num.item())]
+    if is_numpy:
+        inds = inds.cpu().numpy()
+    elif was_host:
+        inds = inds.cpu()
+    return dets[inds, :], inds
+
+
+def poly_nms(dets, iou_thr, device_id=None):
+    """NMS of 8-point polygons (nms_rotated_wrapper.py:57-76) — a 'next' row of SURVEY.md §8f, not built yet."""
+    raise NotImplementedError("poly_nms is outside the round-1 hot path (SURVEY.md §8f rank 4)")
+
+
+def obb_batched_nms(bboxes, scores, inds, nms_thr, class_agnostic=False):
+    """Compute the NMS of oriented bboxes in batches (per class id `inds`)."""
+    if bboxes.size(-1) != 5:
+        raise NotImplementedError("obb_batched_nms: only (N, 5) oriented boxes are supported")
+    if class_agnostic or bboxes.shape[0] == 0:
+        dets, keep = obb_nms(torch.cat([bboxes, scores[:, None]], -1), nms_thr)
+        return torch.cat([bboxes[keep], dets[:, -1:]], -1), keep
+    b, _, was_host = to_cuda_input(bboxes, None, "bboxes")
+    s = scores.to(b.device)
+    lab = inds.to(b.device)
+    hbboxes = obb2hbb(b)
+    scale = (hbboxes.max() - hbboxes.min()) + 1              # nms_rotated_wrapper.py:85-86
+    keep, num = nms_device(b, s, nms_thr, "v3", labels=lab, class_offset=scale, inclusive=was_host, drop_small=True)
+    keep = keep[:int(num.item())]
+    if was_host:
+        keep = keep.cpu()
+    bboxes = bboxes[keep]
+    scores = scores[keep]
+    return torch.cat([bboxes, scores[:, None]], -1), keep
