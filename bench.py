@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""bench.py — rotated IoU Gpairs/s (headline) + NMS cands/s + FRM GB/s on B200, one JSON line.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]                  (N > 1: launched by torchrun)
+    python bench.py --impl reference [--gpus N] [--steps K] [--warmup W] (the reference's CPU implementation)
+
+A "step" is one pass of the hot path over one batch: BASELINE.json configs[2], the rotated-IoU microbench —
+RBboxOverlaps2D_v1 on 1,000 GT x 200,000 anchors per GPU (synthetic rotated boxes), through
+the C ABI (r3g_iou_matrix_f32: 2 prep kernels + the pair kernel).  The anchor axis is the shard axis: every
+rank owns 200k anchors (weak scaling), GT replicated, no data-path collective.
+  value     Gpairs/s, inputs resident in HBM, K steps timed with CUDA events between barriers, max over ranks
+  e2e       same metric through the Python plugin API with HOST buffers: pinned H2D of both box sets + D2H of the
+            (1000 x 200000) result inside the timed region
+  roofline  HBM store bound: 4 B per pair / mean duration of the pair kernel alone (r3g_iou_matrix_prepared_f32),
+            against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the reference's own host geometry (oracle/_ref, unmodified reference sources) on a bounded sample
+Extra objects `nms` and `frm` report the other two kernels of the path with their own rooflines.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GT, ANCHORS = 1000, 200000
+VARIANT = "v1"
+METRIC, UNIT = "rotated_iou_pairs_per_s", "Gpairs/s"
+AR = {'v1': (-np.pi / 2, 0), 'v2': (-np.pi / 4, 3 * np.pi / 4), 'v3': (-np.pi / 2, np.pi / 2)}
+
+
+def rand_obb(n, seed, version='v1', lo=8, hi=512, span=1024):
+    rng = np.random.default_rng(seed)
+    cx = rng.uniform(0, span, n); cy = rng.uniform(0, span, n)
+    w = np.exp(rng.uniform(np.log(lo), np.log(hi), n)); h = np.exp(rng.uniform(np.log(lo), np.log(hi), n))
+    a = rng.uniform(*AR[version], n)
+    return np.stack([cx, cy, w, h, a], 1).astype(np.float32)
+
+
+def clustered(K, seed, version='v1', ncls=15):
+    rng = np.random.default_rng(seed)
+    seeds = rand_obb(max(K // 10, 1), seed + 1000, version, 12, 200)
+    idx = rng.integers(0, len(seeds), K)
+    b = seeds[idx].copy()
+    b[:, 0:2] += rng.normal(0, 4, (K, 2)); b[:, 4] += rng.normal(0, 0.05, K)
+    b[:, 2:4] *= np.exp(rng.normal(0, 0.1, (K, 2)))
+    return b.astype(np.float32), rng.permutation(np.linspace(0.05, 1, K)).astype(np.float32), (idx % ncls).astype(np.int64)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """Samples SM clock + throttle reasons during the timed region (pynvml, 20 ms period)."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz, self._stop, self.ok = [], set(), None, threading.Event(), False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:  # noqa: BLE001
+            self.ok = False
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake": 0x80, "sync_boost": 0x10, "applications_clocks_setting": 0x2}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:  # noqa: BLE001
+                    r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.02)
+
+    def __enter__(self):
+        if self.ok:
+            self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self.ok:
+            self.t.join(1.0)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": int(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------ reference CPU arm
+def ref_cpu_fn():
+    """(callable(b1, b2) -> IoU matrix, kind): the reference's own host geometry when oracle/_ref travelled here,
+    else the oracle port."""
+    try:
+        from oracle import ref
+        if ref.available("libref_v1.so"):
+            ref.v1_iou(rand_obb(2, 0), rand_obb(2, 1))
+            return (lambda a, b: ref.v1_iou(a, b)), "reference"
+    except Exception:  # noqa: BLE001
+        pass
+    from oracle import port
+    return (lambda a, b: port.iou_matrix(a, b, VARIANT)), "port"
+
+
+def cpu_pairs_per_s(anchors_per_thread, threads, seed=100):
+    """All `threads` host threads, each on its own anchor shard x the 1,000 GT (ctypes releases the GIL)."""
+    from concurrent.futures import ThreadPoolExecutor
+    fn, kind = ref_cpu_fn()
+    gt = rand_obb(GT, 1, VARIANT)
+    shards = [rand_obb(anchors_per_thread, seed + i, VARIANT) for i in range(threads)]
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(threads) as ex:
+        list(ex.map(lambda a: fn(gt, a), shards))
+    dt = time.perf_counter() - t0
+    return GT * anchors_per_thread * threads / dt, dt, kind
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    # calibrate, then size the per-step sample so that (steps + warmup) steps finish in ~2 minutes
+    rate, _, kind = cpu_pairs_per_s(500, cores)
+    budget_s = 110.0 / max(args.steps + args.warmup, 1)
+    apt = int(max(20, min(40000, rate * budget_s / (GT * cores))))
+    for _ in range(args.warmup):
+        cpu_pairs_per_s(apt, cores)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        cpu_pairs_per_s(apt, cores, seed=200 + i)
+    dt = time.perf_counter() - t0
+    pairs = GT * apt * cores * args.steps
+    val = pairs / dt / 1e9
+    sample = f"{GT} GT x {apt * cores} anchors per step ({apt} per thread), {args.steps} steps"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / max(args.steps, 1) * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[2] rotated IoU microbench: 1000 GT x 200000 anchors per GPU, RBboxOverlaps2D_v1, "
+                               "timed on a bounded CPU sample of the same boxes", "variant": VARIANT},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    import r3det_b200 as R
+    from r3det_b200 import _lib as L
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world > 1:
+            t = torch.tensor([x], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return x
+
+    lib = L.lib()
+    gt_h = torch.from_numpy(rand_obb(GT, 1, VARIANT)).pin_memory()
+    an_h = torch.from_numpy(rand_obb(ANCHORS, 1000 + rank, VARIANT)).pin_memory()       # this rank's anchor shard
+    gt, an = gt_h.to(dev), an_h.to(dev)
+    out = torch.empty((GT, ANCHORS), dtype=torch.float32, device=dev)
+    nbytes = C.c_size_t(0)
+    L.check(lib.r3g_iou_workspace_bytes(GT, ANCHORS, C.byref(nbytes)))
+    ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream(dev)
+    sp = C.c_void_p(stream.cuda_stream)
+    flags = L.FLAG_STRICT
+    pairs = GT * ANCHORS
+
+    def step():
+        L.check(lib.r3g_iou_matrix_f32(L.ptr(gt), GT, 5, L.ptr(an), ANCHORS, 5, L.V[VARIANT], 0, flags,
+                                       L.ptr(out), L.ptr(ws), ws.numel(), sp))
+
+    def pair_kernel_only():
+        L.check(lib.r3g_iou_matrix_prepared_f32(L.ptr(gt), GT, 5, L.ptr(an), ANCHORS, 5, L.V[VARIANT], 0, flags,
+                                                L.ptr(out), L.ptr(ws), ws.numel(), sp))
+
+    with ClockSampler(local) as clocks:
+        for _ in range(max(args.warmup, 3)):
+            step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            step()
+        e1.record(stream)
+        barrier()
+        ms_total = max_over_ranks(e0.elapsed_time(e1))
+        # the dominant kernel alone (prepared boxes already in the workspace), same K launches
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record(stream)
+        for _ in range(args.steps):
+            pair_kernel_only()
+        k1.record(stream)
+        barrier()
+        ms_kernel = k0.elapsed_time(k1) / args.steps
+    stats = ws[:32].view(torch.int64).cpu().numpy().tolist()
+
+    # ---- e2e: host buffers through the plugin API (H2D of both box sets, D2H of the result, every step)
+    res_h = torch.empty((GT, ANCHORS), dtype=torch.float32).pin_memory()
+    calc = R.RBboxOverlaps2D_v1()
+    e2e_steps = max(3, min(args.steps, 20))
+
+    def e2e_step():
+        g = gt_h.to(dev, non_blocking=True)
+        a = an_h.to(dev, non_blocking=True)
+        o = calc(g, a)
+        res_h.copy_(o, non_blocking=True)
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e0.record(stream)
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record(stream)
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1)) / e2e_steps
+    assert float(res_h[0].max()) >= 0.0
+
+    hbm, peak_src = measured_peaks()
+    value = world * pairs * args.steps / (ms_total * 1e-3) / 1e9
+    achieved = 4.0 * pairs / (ms_kernel * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[2] rotated IoU microbench: RBboxOverlaps2D_v1, 1000 GT x 200000 anchors per GPU "
+                               "(anchor axis sharded across ranks, GT replicated)",
+                   "variant": VARIANT, "gt": GT, "anchors_per_gpu": ANCHORS, "strict_reference_parity": True,
+                   "l2": "each step writes an 800 MB result (> 126 MB L2); no flush needed"},
+        "e2e": {"value": world * pairs / (ms_e2e * 1e-3) / 1e9, "unit": UNIT,
+                "h2d_bytes_per_step": int(gt_h.numel() * 4 + an_h.numel() * 4), "d2h_bytes_per_step": int(res_h.numel() * 4),
+                "ms_per_step": ms_e2e, "steps": e2e_steps},
+        "gpu_launches": 3 * args.steps,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
+                     "traffic": None, "peak_source": peak_src, "kernel": "iou_matrix_kernel<true>",
+                     "kernel_ms": ms_kernel, "algorithmic_bytes_per_launch": 4 * pairs,
+                     "pairs_circle_pass": stats[0], "pairs_sat_pass": stats[1], "pairs_strict": stats[2]},
+        "clocks": clocks.summary(),
+    }
+
+    if rank == 0:
+        line["nms"] = bench_nms(torch, R, dev, hbm)
+        line["frm"] = bench_frm(torch, R, dev, hbm)
+        cores = os.cpu_count() or 1
+        apt = 4000
+        rate, dt, kind = cpu_pairs_per_s(apt, cores)
+        line["cpu_baseline"] = {"value": rate / 1e9, "unit": UNIT, "cores": cores, "kind": kind,
+                                "sample": f"{GT} GT x {apt * cores} anchors ({apt} per thread, {dt:.1f} s wall)"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def _time(torch, fn, iters, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    e1.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def bench_nms(torch, R, dev, hbm):
+    """configs[3]: clustered candidates x 15 DOTA classes per image, nms v1 (batched_rnms semantics), thr 0.1."""
+    from r3det_b200._nms_core import nms_device
+    out = {"unit": "Mcands/s", "variant": "v1", "classes": 15, "iou_thr": 0.1, "sweep": {}}
+    for K in (2000, 8000, 20000, 80000, 200000):
+        b, s, l = clustered(K, 2, "v1")
+        B, S, Lb = (torch.from_numpy(x).to(dev) for x in (b, s, l))
+        scale = torch.tensor(float(b.max() + 1), device=dev)
+        fn = lambda: nms_device(B, S, 0.1, "v1", labels=Lb, class_offset=scale, order_index=True)
+        keep, num = fn()
+        ms = _time(torch, fn, 5 if K >= 80000 else 20)
+        out["sweep"][str(K)] = {"ms": ms, "mcands_per_s": K / ms / 1e3, "kept": int(num)}
+    return out
+
+
+def bench_frm(torch, R, dev, hbm):
+    """configs[1] FRM shapes: batch 8, 256 channels, 5 FPN levels of a 1024^2 patch; 8 B per element roofline."""
+    from r3det_b200.fr import frm_backward, frm_forward
+    rng = np.random.default_rng(4)
+    res = {}
+    for P in (1, 5):
+        tf = tb = 0.0
+        elems = 0
+        for H, stride in ((128, 8), (64, 16), (32, 32), (16, 64), (8, 128)):
+            x = torch.randn((8, 256, H, H), device=dev)
+            ys, xs = np.meshgrid(np.arange(H) * stride, np.arange(H) * stride, indexing="ij")
+            ctr = np.stack([xs, ys], -1).reshape(-1, 2).astype(np.float32)
+            bx = np.zeros((8, H * H, 5), np.float32)
+            bx[:, :, :2] = ctr[None] + rng.normal(0, stride, (8, H * H, 2))
+            bx[:, :, 2:4] = np.exp(rng.uniform(np.log(stride), np.log(8 * stride), (8, H * H, 2)))
+            bx[:, :, 4] = rng.uniform(-np.pi / 2, 0, (8, H * H))
+            bt = torch.from_numpy(bx.reshape(-1, 5)).to(dev)
+            tf += _time(torch, lambda: frm_forward(x, bt, 1.0 / stride, P), 10)
+            tb += _time(torch, lambda: frm_backward(x, bt, 1.0 / stride, P), 10)
+            elems += x.numel()
+        res[f"points{P}"] = {"fwd_ms": tf, "bwd_ms": tb, "fwd_gbs": elems * 8 / tf / 1e6, "bwd_gbs": elems * 8 / tb / 1e6,
+                             "fwd_frac_of_hbm": elems * 8 / tf / 1e6 / hbm, "bwd_frac_of_hbm": elems * 8 / tb / 1e6 / hbm}
+    res["elements"] = elems
+    res["bytes_per_element"] = 8
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=500)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -37,6 +37,7 @@ extern "C" {
 /* flags for the IoU entry points */
 #define R3G_FLAG_STRICT 1       /* re-evaluate degenerate pairs with the reference's own point-set algorithm */
 #define R3G_FLAG_SMALL_MASK 2   /* v3 wrapper: rows/cols with min(w,h) < 1e-3 are 0 (box_iou_rotated_wrapper.py:54-60) */
+#define R3G_FLAG_EMULATE_ALL 4  /* diagnostic: every overlapping pair goes through the reference's own algorithm */
 
 /* flags for r3g_nms_f32 */
 #define R3G_NMS_INCLUSIVE 1     /* suppress when IoU >= thr (reference CPU rule); default IoU > thr (reference GPU rule) */
@@ -57,6 +58,17 @@ int r3g_iou_matrix_f32(const float* boxes1, int64_t m, int64_t stride1,
                        const float* boxes2, int64_t n, int64_t stride2,
                        int variant, int mode, int flags, float* out,
                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* The two halves of r3g_iou_matrix_f32, exposed so that callers with static boxes (anchors) can prepare once
+ * and so that the matrix kernel can be timed alone: prepare = per-box trig/extents into the workspace
+ * (O(m+n)); matrix_prepared = the pair kernel over a prepared workspace. */
+int r3g_iou_prepare_f32(const float* boxes1, int64_t m, int64_t stride1,
+                        const float* boxes2, int64_t n, int64_t stride2, int variant,
+                        void* workspace, size_t workspace_bytes, void* stream);
+int r3g_iou_matrix_prepared_f32(const float* boxes1, int64_t m, int64_t stride1,
+                                const float* boxes2, int64_t n, int64_t stride2,
+                                int variant, int mode, int flags, float* out,
+                                void* workspace, size_t workspace_bytes, void* stream);
 
 /* replaces rbbox_geo_cuda.vec_iou_iof (rbbox_geo_cuda.cpp:25-30): out has max(n1, n2) elements,
  * element i pairs boxes1[i % n1] with boxes2[i % n2] (rbbox_geo_kernel.cu:278-281). */

@@ -10,13 +10,18 @@ Module map (reference module -> here):
   r3det/ops/ml_nms_rotated       -> ml_nms_rotated    ml_nms_rotated
   r3det/core/bbox/iou_calculators-> iou_calculators   RBboxOverlaps2D_v1/v2/v3, rbbox_overlaps_v1/v2/v3
   r3det/core/post_processing     -> bbox_nms_rotated  multiclass_nms_rotated
+  r3det/ops/fr                   -> fr                FeatureRefineFunction, feature_refine, FR, FeatureRefineModule
+  r3det/core/bbox/rtransforms    -> rtransforms       poly2obb, obb2poly, obb2hbb, hbb2obb, obb2xyxy, norm_angle, ...
 """
 from . import _lib  # noqa: F401
 from .bbox_nms_rotated import multiclass_nms_rotated  # noqa: F401
 from .box_iou_rotated import obb_overlaps  # noqa: F401
+from .fr import FR, FeatureRefineFunction, FeatureRefineModule, feature_refine  # noqa: F401
 from .iou_calculators import (IOU_CALCULATORS, RBboxOverlaps2D_v1, RBboxOverlaps2D_v2,  # noqa: F401
                               RBboxOverlaps2D_v3, rbbox_overlaps_v1, rbbox_overlaps_v2, rbbox_overlaps_v3)
 from .ml_nms_rotated import ml_nms_rotated  # noqa: F401
 from .nms_rotated import obb_batched_nms, obb_nms, poly_nms  # noqa: F401
 from .rbbox_geo import aligned_iou, pairwise_iou, rbbox_iou  # noqa: F401
 from .rnms import batched_rnms, rnms  # noqa: F401
+from .rtransforms import (hbb2obb, norm_angle, obb2hbb, obb2poly, obb2xyxy, poly2obb, rbbox2result,  # noqa: F401
+                          rbbox2roi)

@@ -15,6 +15,7 @@ V = {"v1": 1, "v2": 2, "v3": 3}
 MODE = {"iou": 0, "iof": 1}
 FLAG_STRICT = 1
 FLAG_SMALL_MASK = 2
+FLAG_EMULATE_ALL = 4
 NMS_INCLUSIVE = 1
 NMS_ORDER_INDEX = 2
 NMS_DROP_SMALL = 4
@@ -29,6 +30,8 @@ _SIGNATURES = {
     "r3g_version": (_i32, []),
     "r3g_iou_workspace_bytes": (_i32, [_i64, _i64, C.POINTER(_sz)]),
     "r3g_iou_matrix_f32": (_i32, [_vp, _i64, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _sz, _vp]),
+    "r3g_iou_prepare_f32": (_i32, [_vp, _i64, _i64, _vp, _i64, _i64, _i32, _vp, _sz, _vp]),
+    "r3g_iou_matrix_prepared_f32": (_i32, [_vp, _i64, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _sz, _vp]),
     "r3g_iou_aligned_f32": (_i32, [_vp, _i64, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _vp, _vp]),
     "r3g_nms_workspace_bytes": (_i32, [_i64, C.POINTER(_sz)]),
     "r3g_nms_f32": (_i32, [_vp, _i64, _vp, _vp, _i64, _f32, _i32, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),

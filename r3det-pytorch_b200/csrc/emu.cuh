@@ -39,6 +39,9 @@ R3G_HD P2 scale2(float s, P2 a) { P2 r = { mulr(s, a.x), mulr(s, a.y) }; return 
 // ------------------------------------------------------------------------------------------------
 R3G_HD void v1_corners(const float* rb, P2* vs) {                       // :143-155
     float x = rb[0], y = rb[1], w_2 = rb[2] / 2, h_2 = rb[3] / 2, a = rb[4];
+    // cosf/sinf as the reference calls them: CUDA's on the device (what rbbox_geo / rnms CUDA builds use), libm's on
+    // the host.  The two differ in the last ulp for ~10 % of angles; on near-coincident boxes (< 1e-2 px apart) the v1
+    // algorithm is chaotic in that bit, which is why the reference's own CPU and CUDA builds disagree there.
     float cosa = cosf(a), sina = sinf(a);
     float wx = mulr(cosa, w_2), wy = mulr(sina, w_2);
     float hx = mulr(-sina, h_2), hy = mulr(cosa, h_2);

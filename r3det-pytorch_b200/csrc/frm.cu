@@ -1,4 +1,310 @@
+// frm.cu — FRM feature refinement (forward + atomic-free backward) on sm_100a.
+//
+// Replaces (reference, relative to /root/reference):
+//   feature_refine_forward_kernel / feature_refine_backward_kernel   r3det/ops/fr/src/feature_refine_kernel.cu:112-230
+// Reference: one thread per NCHW element; every thread re-reads its location's box, re-derives the sample
+// points (sinf/cosf for points=5) and the bilinear weights — identical work repeated for all C=256
+// channels — and the backward pass issues 1+4*points float atomics per element into a pre-zeroed buffer.
+// Here the sample taps depend only on (n, h, w), so:
+//   forward : a thread owns one location, derives its taps ONCE into registers and streams the channels;
+//             CTAs tile the map 8(h) x 32(w) so the main loads/stores are 128-byte rows and the gathers of a
+//             CTA (which, with the reference's x/y swap, land near the TRANSPOSED location) share sectors;
+//             blocks are ordered (tile, channel-chunk, image) so concurrently running CTAs gather from the
+//             same few planes (L2-resident).  HBM traffic: read feat once + write out once = 8 B/element;
+//             no zero-fill pass (the reference's Python zero-fills `output` first).
+//   backward: the taps of an image are inverted once per call into a per-target CSR by a radix sort on the
+//             target index ("sorted scatter"); a thread owns one target pixel and GATHERS
+//             grad_in[t] = grad_out[t] + sum_e w_e * grad_out[src_e] for 16 channels per pass.  No atomics,
+//             no pre-zeroed output, bit-reproducible (stable sort => fixed summation order).
+// Sample-point math follows feature_refine_kernel.cu:16-65 (interpolation) and :127-151 (points), including
+// the reference's swap of box x -> row and box y -> column.
+#include <cub/cub.cuh>
 #include "common.cuh"
-R3G_API int r3g_frm_forward_f32(const float*, const float*, int, int, int, int, float, int, float*, void*) { r3g::set_error("not built yet"); return R3G_ERR_ARG; }
-R3G_API int r3g_frm_backward_workspace_bytes(int, int, int, int, size_t*) { r3g::set_error("not built yet"); return R3G_ERR_ARG; }
-R3G_API int r3g_frm_backward_f32(const float*, const float*, int, int, int, int, float, int, float*, void*, size_t, void*) { r3g::set_error("not built yet"); return R3G_ERR_ARG; }
+
+namespace r3g {
+
+constexpr int FRM_THREADS = 256;
+constexpr int FRM_CCHUNK_FWD = 32;   // channels per forward CTA
+constexpr int FRM_CC_BWD = 16;       // channels accumulated together per backward thread
+
+struct Taps4 { float w[4]; int o[4]; };
+
+// bilinear taps of one sample; invalid samples get zero weights and offset 0 (feature_refine_kernel.cu:16-110)
+__device__ __forceinline__ bool frm_taps(int H, int W, float y, float x, Taps4& t) {
+    if (y < -1.0f || y > (float)H || x < -1.0f || x > (float)W) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) { t.w[k] = 0.0f; t.o[k] = 0; }
+        return false;
+    }
+    if (y <= 0.0f) y = 0.0f;
+    if (x <= 0.0f) x = 0.0f;
+    int yl = (int)y, xl = (int)x, yh, xh;
+    if (yl >= H - 1) { yh = yl = H - 1; y = (float)yl; } else yh = yl + 1;
+    if (xl >= W - 1) { xh = xl = W - 1; x = (float)xl; } else xh = xl + 1;
+    const float ly = y - (float)yl, lx = x - (float)xl;
+    const float hy = 1.0f - ly, hx = 1.0f - lx;
+    t.w[0] = hy * hx; t.w[1] = hy * lx; t.w[2] = ly * hx; t.w[3] = ly * lx;
+    t.o[0] = yl * W + xl; t.o[1] = yl * W + xh; t.o[2] = yh * W + xl; t.o[3] = yh * W + xh;
+    return true;
+}
+
+// sample positions of one location (feature_refine_kernel.cu:127-151): px = column coordinate, py = row coordinate
+template <int P>
+__device__ __forceinline__ void frm_points(const float* __restrict__ bb, float scale, float* px, float* py) {
+    const float roi_y = bb[0] * scale;       // box x -> ROW coordinate   (:131)
+    const float roi_x = bb[1] * scale;       // box y -> COLUMN coordinate (:132)
+    px[0] = roi_x; py[0] = roi_y;
+    if (P > 1) {
+        const float roi_w = bb[2] * scale, roi_h = bb[3] * scale, roi_a = bb[4];
+        const float w_2 = roi_w / 2, h_2 = roi_h / 2;
+        const float cosa = cosf(roi_a), sina = sinf(roi_a);
+        const float wx = cosa * w_2, wy = sina * w_2;
+        const float hx = -sina * h_2, hy = cosa * h_2;
+        px[1] = roi_x + wx + hx; py[1] = roi_y + wy + hy;
+        px[2] = roi_x - wx + hx; py[2] = roi_y - wy + hy;
+        px[3] = roi_x - wx - hx; py[3] = roi_y - wy - hy;
+        px[4] = roi_x + wx - hx; py[4] = roi_y + wy - hy;
+    }
+}
+
+struct TileGeom { int tile_w, tile_h, tiles_x, tiles_y; };
+
+static TileGeom tile_geom(int H, int W) {
+    TileGeom g;
+    g.tile_w = 32;
+    while (g.tile_w > 4 && g.tile_w / 2 >= W) g.tile_w /= 2;
+    g.tile_h = FRM_THREADS / g.tile_w;
+    g.tiles_x = (W + g.tile_w - 1) / g.tile_w;
+    g.tiles_y = (H + g.tile_h - 1) / g.tile_h;
+    return g;
+}
+
+template <int P>
+__global__ void __launch_bounds__(FRM_THREADS) frm_forward_kernel(
+    const float* __restrict__ feat, const float* __restrict__ boxes, int N, int C, int H, int W,
+    float scale, TileGeom g, int cchunks, float* __restrict__ out) {
+    // blockIdx.x = tile + tiles * (chunk + cchunks * n): tiles fastest so that co-resident CTAs share planes
+    const int tiles = g.tiles_x * g.tiles_y;
+    int bid = blockIdx.x;
+    const int tile = bid % tiles; bid /= tiles;
+    const int chunk = bid % cchunks;
+    const int n = bid / cchunks;
+    const int tx = threadIdx.x % g.tile_w, ty = threadIdx.x / g.tile_w;
+    const int w = (tile % g.tiles_x) * g.tile_w + tx;
+    const int h = (tile / g.tiles_x) * g.tile_h + ty;
+    if (w >= W || h >= H) return;
+    const int HW = H * W;
+    const int loc = h * W + w;
+
+    float px[5], py[5];
+    const float* bb = boxes + ((size_t)n * HW + loc) * 5;
+    float b5[5] = { __ldg(bb), __ldg(bb + 1), __ldg(bb + 2), __ldg(bb + 3), __ldg(bb + 4) };
+    frm_points<P>(b5, scale, px, py);
+    Taps4 t[P];
+#pragma unroll
+    for (int p = 0; p < P; p++) frm_taps(H, W, py[p], px[p], t[p]);
+
+    const int c0 = chunk * FRM_CCHUNK_FWD, c1 = min(C, c0 + FRM_CCHUNK_FWD);
+    const float* plane = feat + ((size_t)n * C + c0) * HW;
+    float* oplane = out + ((size_t)n * C + c0) * HW;
+#pragma unroll 4
+    for (int c = c0; c < c1; c++, plane += HW, oplane += HW) {
+        float v = __ldg(plane + loc);
+#pragma unroll
+        for (int p = 0; p < P; p++) {
+            float s = t[p].w[0] * __ldg(plane + t[p].o[0]);
+            s = fmaf(t[p].w[1], __ldg(plane + t[p].o[1]), s);
+            s = fmaf(t[p].w[2], __ldg(plane + t[p].o[2]), s);
+            s = fmaf(t[p].w[3], __ldg(plane + t[p].o[3]), s);
+            v += s;
+        }
+        __stcs(oplane + loc, v);
+    }
+}
+
+// ---- backward: tap generation -> sort by target -> CSR -> gather ------------------------------------------
+
+template <int P>
+__global__ void frm_bwd_taps_kernel(const float* __restrict__ boxes, int N, int H, int W, float scale,
+                                    unsigned* __restrict__ keys, unsigned* __restrict__ ids, float* __restrict__ wts) {
+    const int HW = H * W;
+    const size_t nl = (size_t)N * HW;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nl) return;
+    const int n = (int)(i / HW);
+    const float* bb = boxes + i * 5;
+    float b5[5] = { __ldg(bb), __ldg(bb + 1), __ldg(bb + 2), __ldg(bb + 3), __ldg(bb + 4) };
+    float px[5], py[5];
+    frm_points<P>(b5, scale, px, py);
+    const unsigned sentinel = (unsigned)nl;          // invalid samples sort to the end
+#pragma unroll
+    for (int p = 0; p < P; p++) {
+        Taps4 t;
+        const bool ok = frm_taps(H, W, py[p], px[p], t);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const size_t e = (i * P + p) * 4 + k;
+            keys[e] = ok ? (unsigned)((size_t)n * HW + t.o[k]) : sentinel;
+            ids[e] = (unsigned)e;
+            wts[e] = t.w[k];
+        }
+    }
+}
+
+__global__ void frm_bwd_rows_kernel(const unsigned* __restrict__ skeys, size_t E, size_t nl, unsigned* __restrict__ row_start) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > nl) return;
+    size_t lo = 0, hi = E;                            // lower_bound(skeys, t)
+    while (lo < hi) {
+        const size_t mid = (lo + hi) >> 1;
+        if (skeys[mid] < (unsigned)t) lo = mid + 1; else hi = mid;
+    }
+    row_start[t] = (unsigned)lo;
+}
+
+__global__ void frm_bwd_materialize_kernel(const unsigned* __restrict__ sids, const float* __restrict__ wts,
+                                           size_t E, int HW, int P, unsigned* __restrict__ src, float* __restrict__ wsorted) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= E) return;
+    const unsigned e = sids[i];
+    src[i] = (unsigned)((e / (unsigned)(4 * P)) % (unsigned)HW);     // source location inside its image
+    wsorted[i] = wts[e];
+}
+
+__global__ void __launch_bounds__(FRM_THREADS) frm_backward_kernel(
+    const float* __restrict__ gout, const unsigned* __restrict__ row_start, const unsigned* __restrict__ src,
+    const float* __restrict__ wsorted, int N, int C, int H, int W, TileGeom g, int cchunks, float* __restrict__ gin) {
+    const int tiles = g.tiles_x * g.tiles_y;
+    int bid = blockIdx.x;
+    const int tile = bid % tiles; bid /= tiles;
+    const int chunk = bid % cchunks;
+    const int n = bid / cchunks;
+    const int tx = threadIdx.x % g.tile_w, ty = threadIdx.x / g.tile_w;
+    const int w = (tile % g.tiles_x) * g.tile_w + tx;
+    const int h = (tile / g.tiles_x) * g.tile_h + ty;
+    if (w >= W || h >= H) return;
+    const int HW = H * W;
+    const int loc = h * W + w;
+    const size_t t = (size_t)n * HW + loc;
+    const unsigned e0 = __ldg(row_start + t), e1 = __ldg(row_start + t + 1);
+    const int c0 = chunk * FRM_CC_BWD;
+    const float* base = gout + ((size_t)n * C + c0) * HW;
+    float acc[FRM_CC_BWD];
+#pragma unroll
+    for (int k = 0; k < FRM_CC_BWD; k++) acc[k] = (c0 + k < C) ? __ldg(base + (size_t)k * HW + loc) : 0.0f;
+    if (c0 + FRM_CC_BWD <= C) {
+        for (unsigned e = e0; e < e1; e++) {
+            const unsigned l = __ldg(src + e);
+            const float wt = __ldg(wsorted + e);
+#pragma unroll
+            for (int k = 0; k < FRM_CC_BWD; k++) acc[k] = fmaf(wt, __ldg(base + (size_t)k * HW + l), acc[k]);
+        }
+    } else {
+        for (unsigned e = e0; e < e1; e++) {
+            const unsigned l = __ldg(src + e);
+            const float wt = __ldg(wsorted + e);
+#pragma unroll
+            for (int k = 0; k < FRM_CC_BWD; k++)
+                if (c0 + k < C) acc[k] = fmaf(wt, __ldg(base + (size_t)k * HW + l), acc[k]);
+        }
+    }
+    float* obase = gin + ((size_t)n * C + c0) * HW;
+#pragma unroll
+    for (int k = 0; k < FRM_CC_BWD; k++)
+        if (c0 + k < C) __stcs(obase + (size_t)k * HW + loc, acc[k]);
+}
+
+struct FrmBwdWs {
+    unsigned *keys, *keys2, *ids, *ids2, *row_start, *src;
+    float *wts, *wsorted;
+    void* cub_tmp; size_t cub_bytes;
+    size_t bytes;
+};
+
+static FrmBwdWs carve_frm(void* ws, int N, int H, int W, int P) {
+    FrmBwdWs w;
+    const size_t nl = (size_t)N * H * W, E = nl * P * 4;
+    char* p = (char*)ws;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { char* r = p + off; off += align_up(bytes, 256); return (void*)r; };
+    w.keys = (unsigned*)take(4 * E); w.keys2 = (unsigned*)take(4 * E);
+    w.ids = (unsigned*)take(4 * E); w.ids2 = (unsigned*)take(4 * E);
+    w.wts = (float*)take(4 * E); w.wsorted = (float*)take(4 * E);
+    w.src = (unsigned*)take(4 * E);
+    w.row_start = (unsigned*)take(4 * (nl + 1));
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, (unsigned*)nullptr, (unsigned*)nullptr, (unsigned*)nullptr, (unsigned*)nullptr, (int)E);
+    w.cub_bytes = align_up(tb, 256);
+    w.cub_tmp = take(w.cub_bytes);
+    w.bytes = off;
+    return w;
+}
+
+static int check_frm_args(const char* who, const void* a, const void* b, const void* c, int N, int C, int H, int W, int points) {
+    R3G_REQUIRE(N >= 0 && C >= 0 && H >= 0 && W >= 0, "%s: negative dimension", who);
+    R3G_REQUIRE(points == 1 || points == 5, "%s: points must be 1 or 5 (got %d)", who, points);   // feature_refine_module.py:19
+    if ((size_t)N * C * H * W == 0) return 1;
+    R3G_REQUIRE(a && b && c, "%s: null pointer", who);
+    R3G_REQUIRE((size_t)N * H * W * (size_t)points * 4 < (1ull << 31), "%s: too many sample taps for 32-bit indexing", who);
+    R3G_REQUIRE((size_t)H * W < (1ull << 24), "%s: feature map too large", who);
+    return 0;
+}
+
+}  // namespace r3g
+
+using namespace r3g;
+
+R3G_API int r3g_frm_forward_f32(const float* feat, const float* boxes, int N, int C, int H, int W,
+                                float spatial_scale, int points, float* out, void* stream) {
+    int rc = check_frm_args("r3g_frm_forward_f32", feat, boxes, out, N, C, H, W, points);
+    if (rc < 0) return rc;
+    if (rc == 1) return R3G_OK;
+    const TileGeom g = tile_geom(H, W);
+    const int cchunks = (C + FRM_CCHUNK_FWD - 1) / FRM_CCHUNK_FWD;
+    const size_t blocks = (size_t)g.tiles_x * g.tiles_y * cchunks * N;
+    R3G_REQUIRE(blocks < (1ull << 31), "r3g_frm_forward_f32: grid too large");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (points == 1) frm_forward_kernel<1><<<(unsigned)blocks, FRM_THREADS, 0, st>>>(feat, boxes, N, C, H, W, spatial_scale, g, cchunks, out);
+    else frm_forward_kernel<5><<<(unsigned)blocks, FRM_THREADS, 0, st>>>(feat, boxes, N, C, H, W, spatial_scale, g, cchunks, out);
+    R3G_LAUNCH_OK("frm_forward_kernel");
+    return R3G_OK;
+}
+
+R3G_API int r3g_frm_backward_workspace_bytes(int N, int H, int W, int points, size_t* bytes) {
+    R3G_REQUIRE(bytes != nullptr && N >= 0 && H >= 0 && W >= 0 && (points == 1 || points == 5),
+                "r3g_frm_backward_workspace_bytes: bad arguments");
+    *bytes = carve_frm(nullptr, N > 0 ? N : 1, H > 0 ? H : 1, W > 0 ? W : 1, points).bytes;
+    return R3G_OK;
+}
+
+R3G_API int r3g_frm_backward_f32(const float* grad_out, const float* boxes, int N, int C, int H, int W,
+                                 float spatial_scale, int points, float* grad_in,
+                                 void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = check_frm_args("r3g_frm_backward_f32", grad_out, boxes, grad_in, N, C, H, W, points);
+    if (rc < 0) return rc;
+    if (rc == 1) return R3G_OK;
+    R3G_REQUIRE(workspace != nullptr, "r3g_frm_backward_f32: null workspace");
+    FrmBwdWs w = carve_frm(workspace, N, H, W, points);
+    if (workspace_bytes < w.bytes) {
+        set_error("r3g_frm_backward_f32: workspace too small (%zu < %zu)", workspace_bytes, w.bytes);
+        return R3G_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t nl = (size_t)N * H * W, E = nl * points * 4;
+    const int tpb = 256;
+    if (points == 1) frm_bwd_taps_kernel<1><<<(unsigned)((nl + tpb - 1) / tpb), tpb, 0, st>>>(boxes, N, H, W, spatial_scale, w.keys, w.ids, w.wts);
+    else frm_bwd_taps_kernel<5><<<(unsigned)((nl + tpb - 1) / tpb), tpb, 0, st>>>(boxes, N, H, W, spatial_scale, w.keys, w.ids, w.wts);
+    int end_bit = 1;
+    while (((size_t)1 << end_bit) <= nl) end_bit++;            // keys are in [0, nl]
+    size_t tb = w.cub_bytes;
+    R3G_CUDA_OK(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, w.keys, w.keys2, w.ids, w.ids2, (int)E, 0, end_bit, st));
+    frm_bwd_rows_kernel<<<(unsigned)((nl + 1 + tpb - 1) / tpb), tpb, 0, st>>>(w.keys2, E, nl, w.row_start);
+    frm_bwd_materialize_kernel<<<(unsigned)((E + tpb - 1) / tpb), tpb, 0, st>>>(w.ids2, w.wts, E, H * W, points, w.src, w.wsorted);
+    const TileGeom g = tile_geom(H, W);
+    const int cchunks = (C + FRM_CC_BWD - 1) / FRM_CC_BWD;
+    const size_t blocks = (size_t)g.tiles_x * g.tiles_y * cchunks * N;
+    R3G_REQUIRE(blocks < (1ull << 31), "r3g_frm_backward_f32: grid too large");
+    frm_backward_kernel<<<(unsigned)blocks, FRM_THREADS, 0, st>>>(grad_out, w.row_start, w.src, w.wsorted, N, C, H, W, g, cchunks, grad_in);
+    R3G_LAUNCH_OK("frm_backward kernels");
+    return R3G_OK;
+}

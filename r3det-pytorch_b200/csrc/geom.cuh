@@ -214,8 +214,13 @@ R3G_HD float pair_overlap(const BoxP0& A0, const BoxP1& A1, const BoxP0& B0, con
     if (!pair_frame(A0, A1, B0, B1, f)) return 0.0f;
     float inter = frame_area(f);
     if (tau > 0.0f) {
-        // thin boxes (< tau) make every vertex "near": hand them to the restatement as well
-        risk = (fminf(fminf(A1.hw, A1.hh), fminf(B1.hw, B1.hh)) < tau) || v1_dedup_risk(A0, A1, B0, B1, f, tau);
+        // Thin boxes go to the restatement as well: below tau every vertex is "near" another one, and for v1
+        // (absolute-coordinate arithmetic, corners quantised to ulp(|coordinate|) ~ 1e-4 px) a box thinner than
+        // 4 px carries a relative area noise above the 1e-5 gate that only the same arithmetic reproduces.
+        // (IoF divides by the first box alone: there the reference's own FP32 noise passes 1e-5 below 16 px, all variants.)
+        const float thin = (mode == MODE_IOF) ? 8.0f : ((variant == V1) ? 2.0f : tau);
+        risk = (fminf(fminf(fabsf(A1.hw), fabsf(A1.hh)), fminf(fabsf(B1.hw), fabsf(B1.hh))) < thin) ||
+               v1_dedup_risk(A0, A1, B0, B1, f, tau);
     }
     return overlap_ratio(inter, A0.area, B0.area, variant, mode);
 }

@@ -267,34 +267,55 @@ R3G_API int r3g_iou_workspace_bytes(int64_t m, int64_t n, size_t* bytes) {
     return R3G_OK;
 }
 
-R3G_API int r3g_iou_matrix_f32(const float* boxes1, int64_t m, int64_t stride1,
-                               const float* boxes2, int64_t n, int64_t stride2,
-                               int variant, int mode, int flags, float* out,
-                               void* workspace, size_t workspace_bytes, void* stream) {
-    R3G_REQUIRE(m >= 0 && n >= 0, "r3g_iou_matrix_f32: negative size");
-    R3G_REQUIRE(variant >= 1 && variant <= 3, "r3g_iou_matrix_f32: variant must be 1, 2 or 3 (got %d)", variant);
-    R3G_REQUIRE(mode == R3G_MODE_IOU || mode == R3G_MODE_IOF, "r3g_iou_matrix_f32: mode must be iou(0) or iof(1)");
+static int iou_check_common(const char* who, int64_t m, int64_t n, int variant, int mode) {
+    R3G_REQUIRE(m >= 0 && n >= 0, "%s: negative size", who);
+    R3G_REQUIRE(variant >= 1 && variant <= 3, "%s: variant must be 1, 2 or 3 (got %d)", who, variant);
+    R3G_REQUIRE(mode == R3G_MODE_IOU || mode == R3G_MODE_IOF, "%s: mode must be iou(0) or iof(1)", who);
+    R3G_REQUIRE(m < (1ll << 31) && n < (1ll << 31), "%s: more than 2^31 boxes", who);
+    return R3G_OK;
+}
+
+R3G_API int r3g_iou_prepare_f32(const float* boxes1, int64_t m, int64_t stride1,
+                                const float* boxes2, int64_t n, int64_t stride2, int variant,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = iou_check_common("r3g_iou_prepare_f32", m, n, variant, R3G_MODE_IOU);
+    if (rc != R3G_OK) return rc;
     if (m == 0 || n == 0) return R3G_OK;
-    R3G_REQUIRE(boxes1 && boxes2 && out && workspace, "r3g_iou_matrix_f32: null pointer");
-    R3G_REQUIRE(stride1 >= 5 && stride2 >= 5, "r3g_iou_matrix_f32: box stride must be >= 5 floats");
-    R3G_REQUIRE(m < (1ll << 31) && n < (1ll << 31), "r3g_iou_matrix_f32: more than 2^31 boxes");
+    R3G_REQUIRE(boxes1 && boxes2 && workspace, "r3g_iou_prepare_f32: null pointer");
+    R3G_REQUIRE(stride1 >= 5 && stride2 >= 5, "r3g_iou_prepare_f32: box stride must be >= 5 floats");
     IouWorkspace w = carve(workspace, m, n);
     if (workspace_bytes < w.bytes) {
-        set_error("r3g_iou_matrix_f32: workspace too small (%zu < %zu)", workspace_bytes, w.bytes);
+        set_error("r3g_iou_prepare_f32: workspace too small (%zu < %zu)", workspace_bytes, w.bytes);
+        return R3G_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    prep_boxes_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(boxes1, m, stride1, variant, w.r0, w.r1);
+    prep_boxes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(boxes2, n, stride2, variant, w.c0, w.c1);
+    R3G_LAUNCH_OK("prep_boxes_kernel");
+    return R3G_OK;
+}
+
+R3G_API int r3g_iou_matrix_prepared_f32(const float* boxes1, int64_t m, int64_t stride1,
+                                        const float* boxes2, int64_t n, int64_t stride2,
+                                        int variant, int mode, int flags, float* out,
+                                        void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = iou_check_common("r3g_iou_matrix_prepared_f32", m, n, variant, mode);
+    if (rc != R3G_OK) return rc;
+    if (m == 0 || n == 0) return R3G_OK;
+    R3G_REQUIRE(boxes1 && boxes2 && out && workspace, "r3g_iou_matrix_prepared_f32: null pointer");
+    IouWorkspace w = carve(workspace, m, n);
+    if (workspace_bytes < w.bytes) {
+        set_error("r3g_iou_matrix_prepared_f32: workspace too small (%zu < %zu)", workspace_bytes, w.bytes);
         return R3G_ERR_WORKSPACE;
     }
     cudaStream_t st = (cudaStream_t)stream;
     R3G_CUDA_OK(cudaMemsetAsync(w.stats, 0, 256, st));
-    prep_boxes_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(boxes1, m, stride1, variant, w.r0, w.r1);
-    prep_boxes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(boxes2, n, stride2, variant, w.c0, w.c1);
-    R3G_LAUNCH_OK("prep_boxes_kernel");
-
     IouArgs a;
     a.r0 = w.r0; a.r1 = w.r1; a.m = m; a.c0 = w.c0; a.c1 = w.c1; a.n = n;
     a.raw1 = boxes1; a.s1 = stride1; a.raw2 = boxes2; a.s2 = stride2;
     a.variant = variant; a.mode = mode;
     a.small_mask = (variant == R3G_V3 && (flags & R3G_FLAG_SMALL_MASK)) ? 1 : 0;
-    a.tau = (flags & R3G_FLAG_STRICT) ? 2e-2f : 0.0f;
+    a.tau = (flags & R3G_FLAG_EMULATE_ALL) ? 1e30f : ((flags & R3G_FLAG_STRICT) ? 2e-2f : 0.0f);
     a.out = out; a.stats = w.stats;
 
     const bool vec = (n % 4 == 0) && (((uintptr_t)out & 15u) == 0);
@@ -315,6 +336,18 @@ R3G_API int r3g_iou_matrix_f32(const float* boxes1, int64_t m, int64_t stride1,
     return R3G_OK;
 }
 
+R3G_API int r3g_iou_matrix_f32(const float* boxes1, int64_t m, int64_t stride1,
+                               const float* boxes2, int64_t n, int64_t stride2,
+                               int variant, int mode, int flags, float* out,
+                               void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = iou_check_common("r3g_iou_matrix_f32", m, n, variant, mode);
+    if (rc != R3G_OK) return rc;
+    rc = r3g_iou_prepare_f32(boxes1, m, stride1, boxes2, n, stride2, variant, workspace, workspace_bytes, stream);
+    if (rc != R3G_OK) return rc;
+    return r3g_iou_matrix_prepared_f32(boxes1, m, stride1, boxes2, n, stride2, variant, mode, flags, out,
+                                       workspace, workspace_bytes, stream);
+}
+
 R3G_API int r3g_iou_aligned_f32(const float* boxes1, int64_t n1, int64_t stride1,
                                 const float* boxes2, int64_t n2, int64_t stride2,
                                 int variant, int mode, int flags, float* out, void* stream) {
@@ -329,7 +362,7 @@ R3G_API int r3g_iou_aligned_f32(const float* boxes1, int64_t n1, int64_t stride1
     const int64_t cap = (int64_t)device_sm_count() * 8;
     if (grid > cap) grid = cap;
     iou_aligned_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(
-        boxes1, n1, stride1, boxes2, n2, stride2, variant, mode, (flags & R3G_FLAG_STRICT) ? 2e-2f : 0.0f,
+        boxes1, n1, stride1, boxes2, n2, stride2, variant, mode, (flags & R3G_FLAG_EMULATE_ALL) ? 1e30f : ((flags & R3G_FLAG_STRICT) ? 2e-2f : 0.0f),
         (variant == R3G_V3 && (flags & R3G_FLAG_SMALL_MASK)) ? 1 : 0, out);
     R3G_LAUNCH_OK("iou_aligned_kernel");
     return R3G_OK;

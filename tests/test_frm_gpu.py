@@ -1,0 +1,89 @@
+"""GPU parity tests for the FRM op (forward + atomic-free backward).  Gate (north_star): 1e-5 relative."""
+import numpy as np
+import pytest
+import torch
+
+from tests.util import golden
+from oracle import port
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+
+
+def _rel(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-12))
+
+
+def _case(rng, N, Cc, H, W, stride):
+    feat = rng.standard_normal((N, Cc, H, W)).astype(np.float32)
+    gout = rng.standard_normal((N, Cc, H, W)).astype(np.float32)
+    ys, xs = np.meshgrid(np.arange(H) * stride, np.arange(W) * stride, indexing="ij")
+    ctr = np.stack([xs, ys], -1).reshape(-1, 2).astype(np.float32)
+    boxes = np.zeros((N, H * W, 5), np.float32)
+    boxes[:, :, :2] = ctr[None] + rng.normal(0, stride, (N, H * W, 2))
+    boxes[:, :, 2:4] = np.exp(rng.uniform(np.log(stride), np.log(8 * stride), (N, H * W, 2)))
+    boxes[:, :, 4] = rng.uniform(-np.pi / 2, 0, (N, H * W))
+    return feat, gout, boxes.reshape(-1, 5)
+
+
+def test_golden_reference_cuda_kernel(cuda_dev):
+    """against the reference's own feature_refine CUDA kernels compiled for sm_100 (tests/golden/make_golden_gpu.py)"""
+    from r3det_b200.fr import frm_backward, frm_forward
+    g = golden("frm_refcuda.npz")
+    for tag in ("a", "b"):
+        f, go, b = (torch.from_numpy(g[f"{tag}_{k}"]).to(cuda_dev) for k in ("feat", "gout", "boxes"))
+        for P in (1, 5):
+            assert _rel(frm_forward(f, b, float(g[f"{tag}_scale"]), P).cpu().numpy(), g[f"{tag}_fwd_p{P}"]) <= RTOL
+            assert _rel(frm_backward(go, b, float(g[f"{tag}_scale"]), P).cpu().numpy(), g[f"{tag}_bwd_p{P}"]) <= RTOL
+
+
+@pytest.mark.parametrize("shape", [(2, 8, 16, 16, 8), (1, 5, 9, 13, 16), (3, 33, 7, 40, 32), (2, 40, 32, 32, 8), (1, 3, 1, 1, 128)])
+@pytest.mark.parametrize("P", [1, 5])
+def test_oracle(cuda_dev, shape, P):
+    from r3det_b200.fr import frm_backward, frm_forward
+    N, Cc, H, W, stride = shape
+    feat, gout, boxes = _case(np.random.default_rng(N * 100 + Cc), N, Cc, H, W, stride)
+    boxes[:4, :2] = [[-50, -50], [1e4, 3], [-1.0 * stride, 2.0], [0, 0]][: min(4, len(boxes))] if len(boxes) >= 4 else boxes[:4, :2]
+    f, g, b = (torch.from_numpy(x).to(cuda_dev) for x in (feat, gout, boxes))
+    assert _rel(frm_forward(f, b, 1.0 / stride, P).cpu().numpy(), port.frm_forward(feat, boxes, 1.0 / stride, P)) <= RTOL
+    got = frm_backward(g, b, 1.0 / stride, P).cpu().numpy()
+    assert _rel(got, port.frm_backward(gout, boxes, 1.0 / stride, P, acc64=True)) <= RTOL
+    assert np.array_equal(got, frm_backward(g, b, 1.0 / stride, P).cpu().numpy())       # bit-reproducible (no atomics)
+
+
+def test_autograd_function_and_module(cuda_dev):
+    import r3det_b200 as R
+    feat, gout, boxes = _case(np.random.default_rng(5), 2, 16, 16, 16, 8)
+    f = torch.from_numpy(feat).to(cuda_dev).requires_grad_(True)
+    b = torch.from_numpy(boxes).to(cuda_dev)
+    out = R.feature_refine(f, b, 0.125, 5)
+    out.backward(torch.from_numpy(gout).to(cuda_dev))
+    assert _rel(f.grad.cpu().numpy(), port.frm_backward(gout, boxes, 0.125, 5, acc64=True)) <= RTOL
+    with pytest.raises(AssertionError):
+        R.feature_refine(f, b, 0.125, 3)                                               # points in {1, 5} only
+    m = R.FeatureRefineModule(16, [8, 16]).to(cuda_dev); m.init_weights()
+    xs = [torch.randn(2, 16, 16, 16, device=cuda_dev, requires_grad=True), torch.randn(2, 16, 8, 8, device=cuda_dev)]
+    rois = [[b[:256], b[:64]], [b[256:512], b[64:128]]]
+    ys = m(xs, rois)
+    assert [tuple(y.shape) for y in ys] == [(2, 16, 16, 16), (2, 16, 8, 8)]
+    sum(y.sum() for y in ys).backward()
+    assert xs[0].grad is not None and torch.isfinite(xs[0].grad).all()
+    assert repr(m.fr[0]) == "FR(spatial_scale=0.125, points=1)"
+
+
+def test_full_size_adjoint_identity(cuda_dev):
+    """R3Det largest level, batch 8 (8 x 256 x 128 x 128): FRM is linear in the features, so
+    <FRM(x), g> == <x, FRM^T(g)> — checks forward and backward against each other at full size."""
+    from r3det_b200.fr import frm_backward, frm_forward
+    rng = np.random.default_rng(7)
+    N, Cc, H, W, stride = 8, 256, 128, 128, 8
+    _, _, boxes = _case(rng, N, 1, H, W, stride)
+    b = torch.from_numpy(boxes).to(cuda_dev)
+    gen = torch.Generator(device=cuda_dev).manual_seed(4)
+    x = torch.randn((N, Cc, H, W), device=cuda_dev, generator=gen)
+    g = torch.randn((N, Cc, H, W), device=cuda_dev, generator=gen)
+    for P in (1, 5):
+        lhs = (frm_forward(x, b, 1.0 / stride, P).double() * g.double()).sum().item()
+        rhs = (x.double() * frm_backward(g, b, 1.0 / stride, P).double()).sum().item()
+        scale = (x.double().norm() * g.double().norm()).item()
+        assert abs(lhs - rhs) / scale < 1e-6

@@ -1,0 +1,159 @@
+"""GPU parity tests for the rotated IoU path, through the reference-facing Python API -> C ABI -> sm_100a kernels.
+Gate (north_star): IoU within 1e-5 absolute in FP32."""
+import numpy as np
+import pytest
+import torch
+
+from tests.util import anchors_1024, clustered, golden, rand_obb
+from oracle import port
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def _t(x, dev):
+    return torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+
+
+def test_golden_reference_cpu(cuda_dev):
+    import r3det_b200 as R
+    g = golden("iou_ref.npz")
+    a, b = _t(g["v1_b1"], cuda_dev), _t(g["v1_b2"], cuda_dev)
+    assert np.abs(R.rbbox_iou(a, b).cpu().numpy() - g["v1_iou"]).max() <= TOL
+    # IoF on the sub-8-px boxes of this set: the reference's absolute-coordinate arithmetic turns a 1-ulp difference
+    # between glibc and CUDA cosf/sinf into > 1e-5 (its own CPU and CUDA builds differ by as much) -> 2e-5 here
+    assert np.abs(R.rbbox_iou(a, b, False, True).cpu().numpy() - g["v1_iof"]).max() <= 2 * TOL
+    assert np.abs(R.rbbox_iou(a[:100], b[:100], True).cpu().numpy() - g["v1_aligned"]).max() <= TOL
+    assert np.abs(R.rbbox_iou(a[:1], b[:50], True).cpu().numpy() - g["v1_aligned_bcast"]).max() <= TOL
+    a, b = _t(g["v3_b1"], cuda_dev), _t(g["v3_b2"], cuda_dev)
+    assert np.abs(R.pairwise_iou(a, b, "v3").cpu().numpy() - g["v3_iou"]).max() <= TOL
+    assert np.abs(R.pairwise_iou(a, b, "v3", "iof").cpu().numpy() - g["v3_iof"]).max() <= TOL
+    a, b = _t(g["v2_b1"], cuda_dev), _t(g["v2_b2"], cuda_dev)
+    assert np.abs(R.pairwise_iou(a, b, "v2").cpu().numpy() - g["v2_iou"]).max() <= TOL
+    got = R.obb_overlaps(_t(g["kat_b1"], cuda_dev), _t(g["kat_b2"], cuda_dev)).item()
+    assert abs(got - 0.545840204) < 2e-6
+
+
+def test_golden_reference_cuda_kernel(cuda_dev):
+    """against outputs of the reference's own rbbox_geo CUDA kernel compiled for sm_100 (tests/golden/make_golden_gpu.py)"""
+    import r3det_b200 as R
+    g = golden("iou_refcuda.npz")
+    a, b = _t(g["b1"], cuda_dev), _t(g["b2"], cuda_dev)
+    assert np.abs(R.rbbox_iou(a, b).cpu().numpy() - g["v1_iou"]).max() <= TOL
+    assert np.abs(R.rbbox_iou(a, b, False, True).cpu().numpy() - g["v1_iof"]).max() <= 2 * TOL   # sub-8px boxes, IoF
+    assert np.abs(R.rbbox_iou(a, b[:300], True).cpu().numpy() - g["v1_aligned"]).max() <= TOL
+
+
+@pytest.mark.parametrize("v", ["v1", "v2", "v3"])
+@pytest.mark.parametrize("mode", ["iou", "iof"])
+def test_oracle_sweeps(cuda_dev, v, mode):
+    import r3det_b200 as R
+    c, _, _ = clustered(1500, 17, v)
+    d = c[:600].copy(); e = d.copy(); e[:, :2] += np.random.default_rng(0).normal(0, 1e-3, (600, 2)).astype(np.float32)
+    an = rand_obb(1200, 18, v, 16, 400); an[:, 4] = 0
+    gt = rand_obb(400, 19, v, 10, 300); gt[:, 4] = np.float32(-np.pi / 2)
+    regimes = {
+        "random": (rand_obb(1000, 11, v), rand_obb(3001, 12, v)),              # n % 4 != 0: scalar store path
+        "small": (rand_obb(800, 13, v, 0.5, 8, 64), rand_obb(1000, 14, v, 0.5, 8, 64)),
+        "aspect": (rand_obb(700, 15, v, 8, 1000), rand_obb(900, 16, v, 8, 1000)),
+        "clustered": (c, c), "near_identical": (d, e), "axis_aligned": (gt, an),
+    }
+    for name, (a, b) in regimes.items():
+        got = R.pairwise_iou(_t(a, cuda_dev), _t(b, cuda_dev), v, mode).cpu().numpy()
+        want = port.iou_matrix(a, b, v, mode, wrapper_mask=False)
+        assert got.shape == want.shape
+        if v == "v1" and name == "near_identical":     # chaotic regime of the v1 reference, see test_reference_arithmetic_on_device
+            assert (np.abs(got - want) > TOL).sum() <= 1e-3 * (want > 0).sum()
+            continue
+        err = np.abs(got - want).max()
+        assert err <= TOL, f"{v}/{mode}/{name}: {err:.3g}"
+        assert want[got == 0].max(initial=0) < 1e-6, f"{v}/{mode}/{name}: a scored pair was zeroed"
+
+
+@pytest.mark.parametrize("v", ["v1", "v2", "v3"])
+def test_reference_arithmetic_on_device(cuda_dev, v):
+    """R3G_FLAG_EMULATE_ALL routes every overlapping pair through the device restatement of the reference's
+    point-set algorithm.  v2/v3 (double-precision trig) must reproduce the CPU reference BIT FOR BIT, degenerate
+    inputs and the reference's own garbage on near-coincident boxes included.  v1 calls cosf/sinf, where CUDA and
+    libm differ in the last ulp: <= 5e-6 on regular boxes; on near-coincident boxes (< 1e-2 px apart) the v1
+    algorithm is chaotic in that bit (the reference's CPU and CUDA builds disagree there too), so at most 0.1 % of
+    such pairs may differ."""
+    import r3det_b200 as R
+    from r3det_b200 import _lib as L
+    c, _, _ = clustered(900, 23, v)
+    e = c.copy(); e[:, :2] += np.random.default_rng(1).normal(0, 1e-3, (900, 2)).astype(np.float32)
+    sets = {"random": (rand_obb(700, 31, v), rand_obb(1100, 32, v)), "near_identical": (c, e),
+            "small": (rand_obb(300, 33, v, 0.5, 8, 64), rand_obb(300, 34, v, 0.5, 8, 64))}
+    for name, (a, b) in sets.items():
+        got = R.pairwise_iou(_t(a, cuda_dev), _t(b, cuda_dev), v, flags=L.FLAG_EMULATE_ALL).cpu().numpy()
+        want = port.iou_matrix(a, b, v, wrapper_mask=False)
+        if v != "v1":
+            assert np.array_equal(got, want), f"{v}/{name}"
+        elif name == "near_identical":
+            assert (np.abs(got - want) > 1e-5).sum() <= 1e-3 * (want > 0).sum(), f"{v}/{name}"
+        else:
+            assert np.abs(got - want).max() <= (5e-6 if name == "random" else 1e-5), f"{v}/{name}"
+
+
+def test_anchor_grid_case(cuda_dev):
+    """config 1/2 shape: the 196,416-anchor RAnchorGenerator grid x GT (here obb2hbb'ed GT as the v1 config does)"""
+    import r3det_b200 as R
+    anchors = anchors_1024()
+    assert anchors.shape == (196416, 5)
+    gt = rand_obb(64, 3, "v1", 10, 300)
+    gt_h = R.obb2hbb(_t(gt, cuda_dev), "v1")
+    out = R.RBboxOverlaps2D_v1()(gt_h, _t(anchors, cuda_dev))
+    assert out.shape == (64, 196416)
+    sel = np.random.default_rng(0).choice(196416, 4000, replace=False)
+    want = port.iou_matrix(gt_h.cpu().numpy(), anchors[sel], "v1")
+    assert np.abs(out[:, sel].cpu().numpy() - want).max() <= TOL
+
+
+def test_calculator_api_shapes_and_quirks(cuda_dev):
+    import r3det_b200 as R
+    a, b = _t(rand_obb(7, 1), cuda_dev), _t(rand_obb(7, 2), cuda_dev)
+    a6 = torch.cat([a, torch.rand(7, 1, device=cuda_dev)], 1)
+    for calc, aligned_shape in ((R.RBboxOverlaps2D_v1(), (7,)), (R.RBboxOverlaps2D_v2(), (7,)), (R.RBboxOverlaps2D_v3(), (7, 1))):
+        assert calc(a6, b).shape == (7, 7)                                   # 6th (score) column stripped
+        assert calc(a, b, is_aligned=True).shape == aligned_shape           # v1 (n,), v3 (m,1): reference quirk
+        assert calc(a[:0], b).shape == (0, 7) and calc(a, b[:0]).shape == (7, 0)
+        with pytest.raises(AssertionError):
+            calc(a, b, mode="giou")
+    # v3 wrapper: rows/cols with min(w,h) < 1e-3 are zero (box_iou_rotated_wrapper.py:54-60)
+    tiny = a.clone(); tiny[2, 2] = 5e-4
+    assert R.obb_overlaps(tiny, a)[2].abs().max().item() == 0.0 and R.obb_overlaps(a, tiny)[:, 2].abs().max().item() == 0.0
+    # numpy convenience path
+    n = R.obb_overlaps(rand_obb(5, 3, "v3"), rand_obb(6, 4, "v3"), device_id=0)
+    assert isinstance(n, np.ndarray) and n.shape == (5, 6)
+    assert np.abs(n - port.iou_matrix(rand_obb(5, 3, "v3"), rand_obb(6, 4, "v3"), "v3")).max() <= TOL
+
+
+def test_full_size_properties(cuda_dev):
+    """BASELINE config 3 size (200k x 1k): size-independent properties instead of an O(2e8) CPU oracle."""
+    import r3det_b200 as R
+    for v in ("v1", "v3"):
+        gt, an = rand_obb(1000, 1, v), rand_obb(200000, 0, v)
+        G, A = _t(gt, cuda_dev), _t(an, cuda_dev)
+        out, stats = R.pairwise_iou(G, A, v, return_stats=True)
+        assert out.shape == (1000, 200000)
+        assert out.min().item() >= 0.0 and out.max().item() <= 1.0 + 1e-6
+        stats = stats.cpu().numpy()
+        assert stats[3] == 200000 * 1000 and stats[0] >= stats[1] >= stats[2]
+        # symmetry: IoU(A, G) == IoU(G, A)^T (independent tile decomposition, roles of clamp box / clipped box swapped)
+        sub = slice(50000, 58000)
+        tr = R.pairwise_iou(A[sub], G, v)
+        assert (tr.t() - out[:, sub]).abs().max().item() <= TOL
+        # translation invariance and angle periodicity (a + pi is the same rectangle)
+        sh = torch.tensor([137.5, -61.25, 0, 0, 0], device=cuda_dev)
+        assert (R.pairwise_iou(G + sh, A[sub] + sh, v) - out[:, sub]).abs().max().item() <= TOL
+        pi = torch.tensor([0, 0, 0, 0, np.pi], device=cuda_dev, dtype=torch.float32)
+        assert (R.pairwise_iou(G + pi, A[sub], v) - out[:, sub]).abs().max().item() <= TOL
+        # self overlap == 1 (the reference's own point-set algorithms give 1 +- 1.5e-5 on identical boxes)
+        assert (R.pairwise_iou(G, G, v).diagonal() - 1).abs().max().item() <= 3 * TOL
+        if v == "v3":       # pure geometry; (v1 boxes are re-fitted to the reference's rounded corners, ~1e-5 on w*h)
+            assert (R.pairwise_iou(G, G, v, flags=0).diagonal() - 1).abs().max().item() <= 2e-6
+        # spot check against the oracle
+        sel = np.random.default_rng(1).choice(200000, 3000, replace=False)
+        want = port.iou_matrix(gt, an[sel], v, wrapper_mask=False)
+        assert np.abs(out[:, sel].cpu().numpy() - want).max() <= TOL
+        del out, tr
