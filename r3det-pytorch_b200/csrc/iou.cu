@@ -4,18 +4,23 @@
 //   mat_iou_iof_kernel / vec_iou_iof_kernel       r3det/ops/rbbox_geo/src/rbbox_geo_kernel.cu:230-309
 //   box_iou_rotated_cuda_kernel                   r3det/ops/box_iou_rotated/src/box_iou_rotated_cuda.cu:13-63
 //
-// Design (B200-first, see DESIGN.md §IoU):
-//   1. prep kernel: per-box trig/extent/radius ONCE (O(M+N)) into two float4 planes (workspace).
-//   2. matrix kernel: persistent warps, one (64 rows x 128 cols) item per warp at a time.
-//      stage 1 — every lane owns 4 adjacent columns (one 16-byte store per row) and walks the rows
-//                with a 7-flop circumradius test; the row's zeros are written with coalesced 512-byte
-//                streaming stores; surviving pairs (5-12 % on detection workloads) are compacted into a
-//                per-warp shared-memory queue with ballot + popc.
-//      stage 2 — whenever >= 32 survivors are queued the warp evaluates them at FULL lane occupancy:
-//                separating-axis reject, clamped-boundary area integral (geom.cuh), variant epilogue,
-//                4-byte scatter store over the zero already in L2.
-//      The reference runs its whole point-set algorithm in every thread of a warp as soon as one lane
-//      overlaps (~80 % of warps at 5 % overlap) and recomputes sinf/cosf per pair.
+// Design (B200-first, see DESIGN.md §4.1):
+//   1. prep kernels: per-box trig/extent/radius ONCE (O(M+N)) into float4 planes in the workspace.
+//   2. matrix kernel: persistent warps pull (64 rows x 128 cols) items from an atomic counter.
+//      stage 1 — a lane owns 4 adjacent columns (one 16-byte store per row).  The circumradius test is evaluated in
+//                its expanded form  |c|^2 - r^2 + |a|^2 - ra^2 - 2(a.c + ra r) - slack < 0 : three FFMA + one FADD per
+//                pair on per-row / per-column constants, and the SIGN BIT is shifted straight into a 32-bit mask
+//                (8 rows x 4 columns per lane) — no predicates, no branches.  Each row's zeros leave as one coalesced
+//                512-byte streaming store per warp.  Every 8 rows the masks are compacted (warp scan of popc) into a
+//                shared-memory queue of 16-bit (row, col) entries.
+//      stage 2 — whenever >= 32 entries are queued the warp runs the separating-axis test at FULL lane occupancy;
+//      stage 3 — the truly overlapping pairs (5 % on detection workloads) are queued again and evaluated 32 at a time
+//                with the clamped-boundary area integral (geom.cuh) + variant epilogue, 4-byte store over the zero
+//                already in L2;
+//      stage 4 — strict mode: flagged degenerate pairs are queued a third time and re-evaluated with the reference's
+//                own point-set algorithm (emu.cuh), again 32 at a time.
+//      The reference runs its whole point-set algorithm in every thread of a warp as soon as one lane overlaps
+//      (~80 % of warps at 5 % overlap) and recomputes sinf/cosf per pair.
 //   Bound: HBM store (4 B/pair) on detection-like inputs, FP32 issue on dense-overlap inputs.
 #include "common.cuh"
 #include "emu.cuh"
@@ -25,13 +30,20 @@ namespace r3g {
 
 constexpr int IOU_THREADS = 256;
 constexpr int IOU_WARPS = IOU_THREADS / 32;
-constexpr int IOU_CPL = 4;                 // columns per lane
-constexpr int IOU_TN = 32 * IOU_CPL;       // 128 columns per warp item
-constexpr int IOU_TM = 64;                 // rows per warp item
-constexpr int IOU_QCAP = 32 + IOU_TN;      // worst case: 31 queued + one full row of survivors
+constexpr int IOU_CPL = 4;                  // columns per lane
+constexpr int IOU_TN = 32 * IOU_CPL;        // 128 columns per warp item
+constexpr int IOU_TM = 64;                  // rows per warp item
+constexpr int IOU_RG = 8;                   // rows per mask group (8 rows x 4 columns = 32 mask bits per lane)
+constexpr int IOU_Q1CAP = 32 + IOU_RG * IOU_TN;   // worst case: 31 queued + one full group of survivors
+constexpr float IOU_SLACK = 1.0f / 262144.0f;     // 2^-18 relative slack of the expanded circle test (conservative)
+
+// Row plane for the expanded circumradius test, relative to the origin (ox, oy):
+//   {-2(ax-ox), -2(ay-oy), -2 ra, |a-o|^2 - ra^2 - slack_a}
+struct __attribute__((aligned(16))) RowP2 { float mx, my, mr, k; };
 
 __global__ void prep_boxes_kernel(const float* __restrict__ boxes, int64_t n, int64_t stride, int variant,
-                                  BoxP0* __restrict__ p0, BoxP1* __restrict__ p1) {
+                                  const float* __restrict__ origin_box,
+                                  BoxP0* __restrict__ p0, BoxP1* __restrict__ p1, RowP2* __restrict__ p2) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float* b = boxes + i * stride;
@@ -40,6 +52,14 @@ __global__ void prep_boxes_kernel(const float* __restrict__ boxes, int64_t n, in
     emu::prep_box_strict(raw, variant, a, c);
     p0[i] = a;
     p1[i] = c;
+    if (p2 != nullptr) {
+        const float x = a.cx - origin_box[0], y = a.cy - origin_box[1];
+        const float q = x * x + y * y, rr = a.r * a.r;
+        RowP2 r;
+        r.mx = -2.0f * x; r.my = -2.0f * y; r.mr = -2.0f * a.r;
+        r.k = (q - rr) - IOU_SLACK * (q + rr) - 1e-6f;
+        p2[i] = r;
+    }
 }
 
 __device__ __noinline__ float emu_pair_call(const float* b1, const float* b2, int variant, int mode) {
@@ -49,20 +69,21 @@ __device__ __noinline__ float emu_pair_call(const float* b1, const float* b2, in
 }
 
 struct IouArgs {
-    const BoxP0* r0; const BoxP1* r1; int64_t m;
-    const BoxP0* c0; const BoxP1* c1; int64_t n;
+    const BoxP0* r0; const BoxP1* r1; const RowP2* r2; int m;
+    const BoxP0* c0; const BoxP1* c1; int n;
     const float* raw1; int64_t s1;
     const float* raw2; int64_t s2;
+    const float* origin_box;
     int variant, mode, small_mask;
     float tau;
     float* out;
-    unsigned long long* stats;
+    unsigned long long* stats;      // [0..3] counters, [4] item ticket
 };
 
 __device__ __forceinline__ float4 ldg4(const void* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
 struct PairBoxes { BoxP0 A0, B0; BoxP1 A1, B1; };
-__device__ __forceinline__ PairBoxes load_pair(const IouArgs& A, unsigned i, unsigned j) {
+__device__ __forceinline__ PairBoxes load_pair(const IouArgs& A, int i, int j) {
     float4 a0 = ldg4(A.r0 + i), a1 = ldg4(A.r1 + i), b0 = ldg4(A.c0 + j), b1 = ldg4(A.c1 + j);
     PairBoxes P;
     P.A0 = { a0.x, a0.y, a0.z, a0.w }; P.A1 = { a1.x, a1.y, a1.z, a1.w };
@@ -70,139 +91,163 @@ __device__ __forceinline__ PairBoxes load_pair(const IouArgs& A, unsigned i, uns
     return P;
 }
 
-// Three per-warp queues of (row, col) pairs, all persistent across the warp's items and flushed once at
-// kernel end, so every stage below runs with 32 active lanes:
-//   q1: passed the circumradius test      -> separating-axis test
-//   q2: passed the separating-axis test   -> area integral + epilogue + store
-//   q3: flagged degenerate (strict mode)  -> the reference's own point-set algorithm (emu.cuh)
-struct WarpQueues {
-    uint2* q1; uint2* q2; uint2* q3;
-    int c1, c2, c3;
-};
-
 template <bool VEC>
 __global__ void __launch_bounds__(IOU_THREADS, 3) iou_matrix_kernel(const IouArgs A) {
-    __shared__ uint2 q1_all[IOU_WARPS][IOU_QCAP];
-    __shared__ uint2 q2_all[IOU_WARPS][64];
+    // per-warp queues: q1/q2 hold item-relative 16-bit (row << 7 | col) entries and are flushed at item end;
+    // q3 holds absolute (row, col) pairs and persists across items (flagged pairs are rare)
+    __shared__ unsigned short q1_all[IOU_WARPS][IOU_Q1CAP];
+    __shared__ unsigned short q2_all[IOU_WARPS][64];
     __shared__ uint2 q3_all[IOU_WARPS][64];
     const unsigned warp = threadIdx.x >> 5, lane = lane_id();
-    uint2* q1 = q1_all[warp];
-    uint2* q2 = q2_all[warp];
+    unsigned short* q1 = q1_all[warp];
+    unsigned short* q2 = q2_all[warp];
     uint2* q3 = q3_all[warp];
     int c1 = 0, c2 = 0, c3 = 0;
     const unsigned lt = lanemask_lt();
-    const int64_t tiles_n = (A.n + IOU_TN - 1) / IOU_TN;
-    const int64_t tiles_m = (A.m + IOU_TM - 1) / IOU_TM;
-    const int64_t total = tiles_m * tiles_n;
+    const int tiles_n = (A.n + IOU_TN - 1) / IOU_TN;
+    const int tiles_m = (A.m + IOU_TM - 1) / IOU_TM;
+    const long long total = (long long)tiles_m * tiles_n;
     unsigned n_circle = 0, n_sat = 0, n_emu = 0;
+    const float ox = __ldg(A.origin_box), oy = __ldg(A.origin_box + 1);
+    int i0 = 0, j0 = 0;
 
-    int64_t item = (int64_t)blockIdx.x * IOU_WARPS + warp;
-    int64_t i = 0, i1 = 0, jb = 0;
-    float bx[IOU_CPL], by[IOU_CPL], br[IOU_CPL];
-    bool bv[IOU_CPL];
-    bool full4 = false;
-    bool have_item = false, done = false;
+    // ---- drains (called with warp-uniform arguments) -------------------------------------------------------------
+    auto drain_emu = [&](int nb) {
+        __syncwarp();
+        if ((int)lane < nb) {
+            const uint2 e = q3[c3 - nb + lane];
+            float r = emu_pair_call(A.raw1 + (int64_t)e.x * A.s1, A.raw2 + (int64_t)e.y * A.s2, A.variant, A.mode);
+            if (A.small_mask) {
+                const float4 a1 = ldg4(A.r1 + e.x), b1 = ldg4(A.c1 + e.y);
+                if (fminf(a1.z, a1.w) * 2.0f < 0.001f || fminf(b1.z, b1.w) * 2.0f < 0.001f) r = 0.0f;
+            }
+            A.out[(int64_t)e.x * A.n + e.y] = r;
+        }
+        __syncwarp();
+        c3 -= nb;
+        n_emu += nb;
+    };
+    auto drain_area = [&](int nb) {
+        __syncwarp();
+        bool risk = false;
+        int i = 0, j = 0;
+        if ((int)lane < nb) {
+            const unsigned e = q2[c2 - nb + lane];
+            i = i0 + (int)(e >> 7); j = j0 + (int)(e & 127u);
+            const PairBoxes P = load_pair(A, i, j);
+            float r = pair_overlap(P.A0, P.A1, P.B0, P.B1, A.variant, A.mode, A.tau, risk);
+            if (A.small_mask && (fminf(P.A1.hw, P.A1.hh) * 2.0f < 0.001f || fminf(P.B1.hw, P.B1.hh) * 2.0f < 0.001f)) r = 0.0f;
+            if (!risk && r != 0.0f) A.out[(int64_t)i * A.n + j] = r;
+        }
+        __syncwarp();
+        c2 -= nb;
+        n_sat += nb;
+        const unsigned bal = __ballot_sync(0xffffffffu, risk);
+        if (bal) {
+            if (risk) q3[c3 + __popc(bal & lt)] = make_uint2((unsigned)i, (unsigned)j);
+            c3 += __popc(bal);
+            if (c3 >= 32) drain_emu(32);
+        }
+    };
+    auto drain_sat = [&](int nb) {
+        __syncwarp();
+        bool ok = false;
+        unsigned e = 0;
+        if ((int)lane < nb) {
+            e = q1[c1 - nb + lane];
+            const PairBoxes P = load_pair(A, i0 + (int)(e >> 7), j0 + (int)(e & 127u));
+            ok = pair_sat(P.A0, P.A1, P.B0, P.B1);
+        }
+        __syncwarp();
+        c1 -= nb;
+        n_circle += nb;
+        const unsigned bal = __ballot_sync(0xffffffffu, ok);
+        if (ok) q2[c2 + __popc(bal & lt)] = (unsigned short)e;
+        c2 += __popc(bal);
+        if (c2 >= 32) drain_area(32);
+    };
 
     while (true) {
-        // ---- drain stages (single copy of each): deepest first so queues never overflow ----
-        if (c3 >= 32 || (done && c3 > 0)) {
-            const int nb = min(32, c3);
-            __syncwarp();
-            if ((int)lane < nb) {
-                const uint2 e = q3[c3 - nb + lane];
-                float r = emu_pair_call(A.raw1 + (int64_t)e.x * A.s1, A.raw2 + (int64_t)e.y * A.s2, A.variant, A.mode);
-                if (A.small_mask) {
-                    const float4 a1 = ldg4(A.r1 + e.x), b1 = ldg4(A.c1 + e.y);
-                    if (fminf(a1.z, a1.w) * 2.0f < 0.001f || fminf(b1.z, b1.w) * 2.0f < 0.001f) r = 0.0f;
-                }
-                A.out[(int64_t)e.x * A.n + e.y] = r;
-            }
-            __syncwarp();
-            c3 -= nb;
-            n_emu += nb;
-            continue;
-        }
-        if (c2 >= 32 || (done && c1 == 0 && c2 > 0)) {
-            const int nb = min(32, c2);
-            __syncwarp();
-            bool risk = false;
-            uint2 e = make_uint2(0u, 0u);
-            if ((int)lane < nb) {
-                e = q2[c2 - nb + lane];
-                const PairBoxes P = load_pair(A, e.x, e.y);
-                float r = pair_overlap(P.A0, P.A1, P.B0, P.B1, A.variant, A.mode, A.tau, risk);
-                if (A.small_mask && (fminf(P.A1.hw, P.A1.hh) * 2.0f < 0.001f || fminf(P.B1.hw, P.B1.hh) * 2.0f < 0.001f)) r = 0.0f;
-                if (!risk && r != 0.0f) A.out[(int64_t)e.x * A.n + e.y] = r;
-            }
-            __syncwarp();
-            c2 -= nb;
-            const unsigned bal = __ballot_sync(0xffffffffu, risk);
-            if (risk) q3[c3 + __popc(bal & lt)] = e;
-            c3 += __popc(bal);
-            n_sat += nb;
-            continue;
-        }
-        if (c1 >= 32 || (done && c1 > 0)) {
-            const int nb = min(32, c1);
-            __syncwarp();
-            bool ok = false;
-            uint2 e = make_uint2(0u, 0u);
-            if ((int)lane < nb) {
-                e = q1[c1 - nb + lane];
-                const PairBoxes P = load_pair(A, e.x, e.y);
-                ok = pair_sat(P.A0, P.A1, P.B0, P.B1);
-            }
-            __syncwarp();
-            c1 -= nb;
-            const unsigned bal = __ballot_sync(0xffffffffu, ok);
-            if (ok) q2[c2 + __popc(bal & lt)] = e;
-            c2 += __popc(bal);
-            n_circle += nb;
-            continue;
-        }
-        if (done) break;
+        // next item (dynamic: the ticket counter is zeroed by the launcher)
+        long long item = 0;
+        if (lane == 0) item = (long long)atomicAdd(A.stats + 4, 1ull);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= total) break;
+        const int tm = (int)(item / tiles_n), tn = (int)(item - (long long)tm * tiles_n);
+        i0 = tm * IOU_TM;
+        j0 = tn * IOU_TN;
+        const int i1 = min(A.m, i0 + IOU_TM);
+        const int jb = j0 + (int)lane * IOU_CPL;
 
-        // ---- stage 1: one row of the current item (or fetch the next item) ----
-        if (!have_item || i >= i1) {
-            if (have_item) item += (int64_t)gridDim.x * IOU_WARPS;
-            if (item >= total) { done = true; continue; }
-            have_item = true;
-            const int64_t tm = item / tiles_n, tn = item - tm * tiles_n;
-            i = tm * IOU_TM; i1 = min(A.m, i + IOU_TM);
-            jb = tn * IOU_TN + lane * IOU_CPL;
+        // this lane's 4 columns, relative to the origin; invalid columns are pushed to infinity (always rejected)
+        float cx[IOU_CPL], cy[IOU_CPL], cr[IOU_CPL], ck[IOU_CPL];
 #pragma unroll
-            for (int k = 0; k < IOU_CPL; k++) {
-                bv[k] = (jb + k) < A.n;
-                float4 b = bv[k] ? ldg4(A.c0 + jb + k) : make_float4(0.f, 0.f, 0.f, 0.f);
-                bx[k] = b.x; by[k] = b.y; br[k] = b.z;
-            }
-            full4 = VEC && (jb + IOU_CPL <= A.n);
-        }
-        {
-            const float4 a = ldg4(A.r0 + i);
-            bool pass[IOU_CPL];
-#pragma unroll
-            for (int k = 0; k < IOU_CPL; k++) {
-                float dx = bx[k] - a.x, dy = by[k] - a.y, rr = br[k] + a.z;
-                pass[k] = bv[k] && !(dx * dx + dy * dy > rr * rr);
-            }
-            float* orow = A.out + i * A.n + jb;
-            if (full4) {
-                st_cs_f4(orow, make_float4(0.f, 0.f, 0.f, 0.f));
+        for (int k = 0; k < IOU_CPL; k++) {
+            if (jb + k < A.n) {
+                const float4 b = ldg4(A.c0 + jb + k);
+                cx[k] = b.x - ox; cy[k] = b.y - oy; cr[k] = b.z;
+                const float q = cx[k] * cx[k] + cy[k] * cy[k], rr = b.z * b.z;
+                ck[k] = (q - rr) - IOU_SLACK * (q + rr);
             } else {
-#pragma unroll
-                for (int k = 0; k < IOU_CPL; k++)
-                    if (bv[k]) st_cs_f1(orow + k, 0.f);
+                cx[k] = 0.0f; cy[k] = 0.0f; cr[k] = 0.0f; ck[k] = 3.0e38f;
             }
-#pragma unroll
-            for (int k = 0; k < IOU_CPL; k++) {
-                const unsigned bal = __ballot_sync(0xffffffffu, pass[k]);
-                if (pass[k]) q1[c1 + __popc(bal & lt)] = make_uint2((unsigned)i, (unsigned)(jb + k));
-                c1 += __popc(bal);
-            }
-            i++;
         }
+        const bool full4 = VEC && (jb + IOU_CPL <= A.n);
+        float* orow = A.out + (int64_t)i0 * A.n + jb;
+
+        for (int ig = i0; ig < i1; ig += IOU_RG) {
+            const int nr = min(IOU_RG, i1 - ig);
+            unsigned m = 0;
+#pragma unroll
+            for (int r = 0; r < IOU_RG; r++) {
+                if (r < nr) {
+                    const float4 a = ldg4(A.r2 + ig + r);
+#pragma unroll
+                    for (int k = 0; k < IOU_CPL; k++) {
+                        // s < 0  <=>  centres closer than the sum of the (conservative) circumradii
+                        float s = fmaf(a.x, cx[k], ck[k] + a.w);
+                        s = fmaf(a.y, cy[k], s);
+                        s = fmaf(a.z, cr[k], s);
+                        m = __funnelshift_l(__float_as_uint(s), m, 1);
+                    }
+                    if (full4) {
+                        st_cs_f4(orow, make_float4(0.f, 0.f, 0.f, 0.f));
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < IOU_CPL; k++)
+                            if (jb + k < A.n) st_cs_f1(orow + k, 0.f);
+                    }
+                    orow += A.n;
+                }
+            }
+            // compact the group's survivors: warp scan of popc, then each lane emits its own bits (row-major order)
+            const int cnt = __popc(m);
+            int incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, d);
+                if ((int)lane >= d) incl += t;
+            }
+            const int tot = __shfl_sync(0xffffffffu, incl, 31);
+            if (tot) {
+                int pos = c1 + incl - cnt;
+                const int nbits = nr * IOU_CPL;
+                const unsigned rowbase = (unsigned)(ig - i0);
+                while (m) {
+                    const int b = 31 - __clz(m);
+                    m ^= 1u << b;
+                    const unsigned idx = (unsigned)(nbits - 1 - b);
+                    q1[pos++] = (unsigned short)(((rowbase + (idx >> 2)) << 7) | (lane * IOU_CPL + (idx & 3u)));
+                }
+                c1 += tot;
+                while (c1 >= 32) drain_sat(32);
+            }
+        }
+        // item end: flush the item-relative queues
+        if (c1 > 0) drain_sat(c1);
+        if (c2 > 0) drain_area(c2);
     }
+    if (c3 > 0) drain_emu(c3);
 
     if (A.stats) {
         if (blockIdx.x == 0 && threadIdx.x == 0) A.stats[3] = (unsigned long long)A.m * (unsigned long long)A.n;
@@ -241,6 +286,7 @@ struct IouWorkspace {
     unsigned long long* stats;
     BoxP0 *r0, *c0;
     BoxP1 *r1, *c1;
+    RowP2* r2;
     size_t bytes;
 };
 
@@ -253,6 +299,7 @@ static IouWorkspace carve(void* ws, int64_t m, int64_t n) {
     w.r1 = (BoxP1*)(p + off); off += align_up(sizeof(BoxP1) * (size_t)m, 256);
     w.c0 = (BoxP0*)(p + off); off += align_up(sizeof(BoxP0) * (size_t)n, 256);
     w.c1 = (BoxP1*)(p + off); off += align_up(sizeof(BoxP1) * (size_t)n, 256);
+    w.r2 = (RowP2*)(p + off); off += align_up(sizeof(RowP2) * (size_t)m, 256);
     w.bytes = off;
     return w;
 }
@@ -271,7 +318,7 @@ static int iou_check_common(const char* who, int64_t m, int64_t n, int variant, 
     R3G_REQUIRE(m >= 0 && n >= 0, "%s: negative size", who);
     R3G_REQUIRE(variant >= 1 && variant <= 3, "%s: variant must be 1, 2 or 3 (got %d)", who, variant);
     R3G_REQUIRE(mode == R3G_MODE_IOU || mode == R3G_MODE_IOF, "%s: mode must be iou(0) or iof(1)", who);
-    R3G_REQUIRE(m < (1ll << 31) && n < (1ll << 31), "%s: more than 2^31 boxes", who);
+    R3G_REQUIRE(m < (1ll << 30) && n < (1ll << 30), "%s: more than 2^30 boxes", who);
     return R3G_OK;
 }
 
@@ -289,8 +336,8 @@ R3G_API int r3g_iou_prepare_f32(const float* boxes1, int64_t m, int64_t stride1,
         return R3G_ERR_WORKSPACE;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    prep_boxes_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(boxes1, m, stride1, variant, w.r0, w.r1);
-    prep_boxes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(boxes2, n, stride2, variant, w.c0, w.c1);
+    prep_boxes_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(boxes1, m, stride1, variant, boxes1, w.r0, w.r1, w.r2);
+    prep_boxes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(boxes2, n, stride2, variant, boxes1, w.c0, w.c1, nullptr);
     R3G_LAUNCH_OK("prep_boxes_kernel");
     return R3G_OK;
 }
@@ -311,8 +358,8 @@ R3G_API int r3g_iou_matrix_prepared_f32(const float* boxes1, int64_t m, int64_t 
     cudaStream_t st = (cudaStream_t)stream;
     R3G_CUDA_OK(cudaMemsetAsync(w.stats, 0, 256, st));
     IouArgs a;
-    a.r0 = w.r0; a.r1 = w.r1; a.m = m; a.c0 = w.c0; a.c1 = w.c1; a.n = n;
-    a.raw1 = boxes1; a.s1 = stride1; a.raw2 = boxes2; a.s2 = stride2;
+    a.r0 = w.r0; a.r1 = w.r1; a.r2 = w.r2; a.m = (int)m; a.c0 = w.c0; a.c1 = w.c1; a.n = (int)n;
+    a.raw1 = boxes1; a.s1 = stride1; a.raw2 = boxes2; a.s2 = stride2; a.origin_box = boxes1;
     a.variant = variant; a.mode = mode;
     a.small_mask = (variant == R3G_V3 && (flags & R3G_FLAG_SMALL_MASK)) ? 1 : 0;
     a.tau = (flags & R3G_FLAG_EMULATE_ALL) ? 1e30f : ((flags & R3G_FLAG_STRICT) ? 2e-2f : 0.0f);
