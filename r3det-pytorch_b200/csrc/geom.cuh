@@ -73,9 +73,22 @@ R3G_HD float clampf(float x, float lim) { return fminf(fmaxf(x, -lim), lim); }
 // 2-ulp division for the four per-edge weighted means (the result is a convex combination, so a relative
 // error of 2^-22 moves the area by < 3e-7 of area(A)); IEEE division is kept for the two edge slopes.
 #if defined(__CUDA_ARCH__)
-R3G_HD float fast_div(float a, float b) { return __fdividef(a, b); }
+R3G_HD float fast_div(float a, float b) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b));      // 1 ulp; b is a sum of edge-length pieces, far from the ftz range
+    return a * r;
+}
+// ~1-ulp quotient without the IEEE slow path: approximate reciprocal + one Newton step + residual correction
+R3G_HD float nr_div(float a, float b) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b));
+    r = fmaf(fmaf(-b, r, 1.0f), r, r);
+    float q = a * r;
+    return fmaf(fmaf(-b, q, a), r, q);
+}
 #else
 R3G_HD float fast_div(float a, float b) { return a / b; }
+R3G_HD float nr_div(float a, float b) { return a / b; }
 #endif
 
 // Corners of B and the frame quantities of the pair, in A's frame (A = [-a,a]x[-b,b]).
@@ -83,6 +96,7 @@ struct PairFrame {
     float qx[4], qy[4];   // B's corners, CCW for positive w,h
     float su, sv;         // dx/dy of B's u-edges (q0->q1, q2->q3) and v-edges (q1->q2, q3->q0)
     float a, b;
+    float cd, sd, dbx, dby;   // relative rotation and centre offset in B's frame (for the degeneracy test)
 };
 
 // Returns false when a separating axis exists (boxes disjoint -> intersection exactly 0).
@@ -109,9 +123,10 @@ R3G_HD bool pair_frame(const BoxP0& A0, const BoxP1& A1, const BoxP0& B0, const 
     f.qx[2] = gx + ux; f.qy[2] = gy + uy;
     f.qx[3] = gx - ux; f.qy[3] = gy - uy;
     // an edge whose y-extent is below 1e-12*size contributes nothing: its slope is irrelevant
-    f.su = (asd > 1e-12f) ? cd / sd : 0.0f;
-    f.sv = (acd > 1e-12f) ? -sd / cd : 0.0f;
+    f.su = (asd > 1e-12f) ? nr_div(cd, sd) : 0.0f;
+    f.sv = (acd > 1e-12f) ? nr_div(-sd, cd) : 0.0f;
     f.a = a; f.b = b;
+    f.cd = cd; f.sd = sd; f.dbx = dbx; f.dby = dby;
     return true;
 }
 
@@ -177,19 +192,17 @@ R3G_HD bool corner_near_boundary(const float* qx, const float* qy, float a, floa
 
 R3G_HD bool v1_dedup_risk(const BoxP0& A0, const BoxP1& A1, const BoxP0& B0, const BoxP1& B1,
                           const PairFrame& f, float tau) {
+    (void)A0; (void)B0;
     if (corner_near_boundary(f.qx, f.qy, f.a, f.b, tau)) return true;
-    // A's corners in B's frame
-    float dx = A0.cx - B0.cx, dy = A0.cy - B0.cy;
-    float cd = B1.c * A1.c + B1.s * A1.s;
-    float sd = B1.c * A1.s - B1.s * A1.c;
-    float dlx = dx * B1.c + dy * B1.s, dly = dy * B1.c - dx * B1.s;
-    float ux = A1.hw * cd, uy = A1.hw * sd, vx = -A1.hh * sd, vy = A1.hh * cd;
+    // A's corners in B's frame: -db +- a*(cd,-sd) +- b*(sd,cd)
+    const float P = f.a * f.cd, Q = f.b * f.sd, R = f.a * f.sd, S = f.b * f.cd;
+    const float x0 = -f.dbx + P, x1 = -f.dbx - P, y0 = -f.dby - R, y1 = -f.dby + R;
     float px[4], py[4];
-    px[0] = dlx - ux - vx; py[0] = dly - uy - vy;
-    px[1] = dlx + ux - vx; py[1] = dly + uy - vy;
-    px[2] = dlx + ux + vx; py[2] = dly + uy + vy;
-    px[3] = dlx - ux + vx; py[3] = dly - uy + vy;
-    return corner_near_boundary(px, py, B1.hw, B1.hh, tau);
+    px[0] = x0 + Q; py[0] = y0 + S;
+    px[1] = x0 - Q; py[1] = y0 - S;
+    px[2] = x1 + Q; py[2] = y1 + S;
+    px[3] = x1 - Q; py[3] = y1 - S;
+    return corner_near_boundary(px, py, fabsf(B1.hw), fabsf(B1.hh), tau);
 }
 
 // IoU / IoF from the intersection area under the variant's epilogue.
@@ -202,7 +215,7 @@ R3G_HD float overlap_ratio(float inter, float s1, float s2, int variant, int mod
         return 0.0f;
     }
     float den = (mode == MODE_IOF) ? s1 : (s1 + s2 - inter);
-    return (den > 0.0f) ? inter / den : 0.0f;
+    return (den > 0.0f) ? nr_div(inter, den) : 0.0f;
 }
 
 // Fast-path overlap of one prepared pair.  `risk` is set for pairs the caller must re-evaluate with the

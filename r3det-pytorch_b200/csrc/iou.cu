@@ -91,17 +91,29 @@ __device__ __forceinline__ PairBoxes load_pair(const IouArgs& A, int i, int j) {
     return P;
 }
 
+// Per-warp shared-memory working set: the item's prepared boxes (staged with cp.async) and the queues.
+struct __attribute__((aligned(16))) WarpSmem {
+    float4 r0[IOU_TM], r1[IOU_TM];                 // rows of the item: BoxP0, BoxP1 (RowP2 is read by broadcast LDG)
+    float4 c0[IOU_TN], c1[IOU_TN];                 // columns of the item: BoxP0, BoxP1
+    uint2 q3[64];                                  // flagged pairs (absolute row, col); persists across items
+    unsigned short q1[IOU_Q1CAP];                  // circumradius survivors, item-relative (row << 7 | col)
+    unsigned short q2[64];                         // separating-axis survivors
+};
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+__device__ __forceinline__ BoxP0 as_p0(float4 v) { BoxP0 b = { v.x, v.y, v.z, v.w }; return b; }
+__device__ __forceinline__ BoxP1 as_p1(float4 v) { BoxP1 b = { v.x, v.y, v.z, v.w }; return b; }
+
 template <bool VEC>
 __global__ void __launch_bounds__(IOU_THREADS, 3) iou_matrix_kernel(const IouArgs A) {
-    // per-warp queues: q1/q2 hold item-relative 16-bit (row << 7 | col) entries and are flushed at item end;
-    // q3 holds absolute (row, col) pairs and persists across items (flagged pairs are rare)
-    __shared__ unsigned short q1_all[IOU_WARPS][IOU_Q1CAP];
-    __shared__ unsigned short q2_all[IOU_WARPS][64];
-    __shared__ uint2 q3_all[IOU_WARPS][64];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     const unsigned warp = threadIdx.x >> 5, lane = lane_id();
-    unsigned short* q1 = q1_all[warp];
-    unsigned short* q2 = q2_all[warp];
-    uint2* q3 = q3_all[warp];
+    WarpSmem& W = reinterpret_cast<WarpSmem*>(smem_raw)[warp];
     int c1 = 0, c2 = 0, c3 = 0;
     const unsigned lt = lanemask_lt();
     const int tiles_n = (A.n + IOU_TN - 1) / IOU_TN;
@@ -109,93 +121,121 @@ __global__ void __launch_bounds__(IOU_THREADS, 3) iou_matrix_kernel(const IouArg
     const long long total = (long long)tiles_m * tiles_n;
     unsigned n_circle = 0, n_sat = 0, n_emu = 0;
     const float ox = __ldg(A.origin_box), oy = __ldg(A.origin_box + 1);
-    int i0 = 0, j0 = 0;
 
-    // ---- drains (called with warp-uniform arguments) -------------------------------------------------------------
-    auto drain_emu = [&](int nb) {
-        __syncwarp();
-        if ((int)lane < nb) {
-            const uint2 e = q3[c3 - nb + lane];
-            float r = emu_pair_call(A.raw1 + (int64_t)e.x * A.s1, A.raw2 + (int64_t)e.y * A.s2, A.variant, A.mode);
-            if (A.small_mask) {
-                const float4 a1 = ldg4(A.r1 + e.x), b1 = ldg4(A.c1 + e.y);
-                if (fminf(a1.z, a1.w) * 2.0f < 0.001f || fminf(b1.z, b1.w) * 2.0f < 0.001f) r = 0.0f;
-            }
-            A.out[(int64_t)e.x * A.n + e.y] = r;
-        }
-        __syncwarp();
-        c3 -= nb;
-        n_emu += nb;
-    };
-    auto drain_area = [&](int nb) {
-        __syncwarp();
-        bool risk = false;
-        int i = 0, j = 0;
-        if ((int)lane < nb) {
-            const unsigned e = q2[c2 - nb + lane];
-            i = i0 + (int)(e >> 7); j = j0 + (int)(e & 127u);
-            const PairBoxes P = load_pair(A, i, j);
-            float r = pair_overlap(P.A0, P.A1, P.B0, P.B1, A.variant, A.mode, A.tau, risk);
-            if (A.small_mask && (fminf(P.A1.hw, P.A1.hh) * 2.0f < 0.001f || fminf(P.B1.hw, P.B1.hh) * 2.0f < 0.001f)) r = 0.0f;
-            if (!risk && r != 0.0f) A.out[(int64_t)i * A.n + j] = r;
-        }
-        __syncwarp();
-        c2 -= nb;
-        n_sat += nb;
-        const unsigned bal = __ballot_sync(0xffffffffu, risk);
-        if (bal) {
-            if (risk) q3[c3 + __popc(bal & lt)] = make_uint2((unsigned)i, (unsigned)j);
-            c3 += __popc(bal);
-            if (c3 >= 32) drain_emu(32);
-        }
-    };
-    auto drain_sat = [&](int nb) {
-        __syncwarp();
-        bool ok = false;
-        unsigned e = 0;
-        if ((int)lane < nb) {
-            e = q1[c1 - nb + lane];
-            const PairBoxes P = load_pair(A, i0 + (int)(e >> 7), j0 + (int)(e & 127u));
-            ok = pair_sat(P.A0, P.A1, P.B0, P.B1);
-        }
-        __syncwarp();
-        c1 -= nb;
-        n_circle += nb;
-        const unsigned bal = __ballot_sync(0xffffffffu, ok);
-        if (ok) q2[c2 + __popc(bal & lt)] = (unsigned short)e;
-        c2 += __popc(bal);
-        if (c2 >= 32) drain_area(32);
-    };
+    int i0 = 0, j0 = 0, i1 = 0, ig = 0, jb = 0;
+    float cx[IOU_CPL], cy[IOU_CPL], cr[IOU_CPL], ck[IOU_CPL];
+    bool full4 = false;
+    float* orow = A.out;
+    bool flush = true, done = false;       // start by fetching an item
 
+    // One state loop; every stage body exists exactly once in the instruction stream (I-cache), deepest stage first.
     while (true) {
-        // next item (dynamic: the ticket counter is zeroed by the launcher)
-        long long item = 0;
-        if (lane == 0) item = (long long)atomicAdd(A.stats + 4, 1ull);
-        item = __shfl_sync(0xffffffffu, item, 0);
-        if (item >= total) break;
-        const int tm = (int)(item / tiles_n), tn = (int)(item - (long long)tm * tiles_n);
-        i0 = tm * IOU_TM;
-        j0 = tn * IOU_TN;
-        const int i1 = min(A.m, i0 + IOU_TM);
-        const int jb = j0 + (int)lane * IOU_CPL;
-
-        // this lane's 4 columns, relative to the origin; invalid columns are pushed to infinity (always rejected)
-        float cx[IOU_CPL], cy[IOU_CPL], cr[IOU_CPL], ck[IOU_CPL];
-#pragma unroll
-        for (int k = 0; k < IOU_CPL; k++) {
-            if (jb + k < A.n) {
-                const float4 b = ldg4(A.c0 + jb + k);
-                cx[k] = b.x - ox; cy[k] = b.y - oy; cr[k] = b.z;
-                const float q = cx[k] * cx[k] + cy[k] * cy[k], rr = b.z * b.z;
-                ck[k] = (q - rr) - IOU_SLACK * (q + rr);
-            } else {
-                cx[k] = 0.0f; cy[k] = 0.0f; cr[k] = 0.0f; ck[k] = 3.0e38f;
+        if (c3 >= 32 || (done && c3 > 0)) {
+            // ---- stage 4: reference restatement for flagged pairs ----
+            const int nb = min(32, c3);
+            __syncwarp();
+            if ((int)lane < nb) {
+                const uint2 e = W.q3[c3 - nb + lane];
+                float r = emu_pair_call(A.raw1 + (int64_t)e.x * A.s1, A.raw2 + (int64_t)e.y * A.s2, A.variant, A.mode);
+                if (A.small_mask) {
+                    const float4 a1 = ldg4(A.r1 + e.x), b1 = ldg4(A.c1 + e.y);
+                    if (fminf(a1.z, a1.w) * 2.0f < 0.001f || fminf(b1.z, b1.w) * 2.0f < 0.001f) r = 0.0f;
+                }
+                A.out[(int64_t)e.x * A.n + e.y] = r;
             }
+            __syncwarp();
+            c3 -= nb;
+            n_emu += nb;
+            continue;
         }
-        const bool full4 = VEC && (jb + IOU_CPL <= A.n);
-        float* orow = A.out + (int64_t)i0 * A.n + jb;
+        if (done) break;
+        if (c2 >= 32 || (flush && c1 == 0 && c2 > 0)) {
+            // ---- stage 3: area integral + epilogue for truly overlapping pairs ----
+            const int nb = min(32, c2);
+            __syncwarp();
+            bool risk = false;
+            int i = 0, j = 0;
+            if ((int)lane < nb) {
+                const unsigned e = W.q2[c2 - nb + lane];
+                const int il = (int)(e >> 7), jl = (int)(e & 127u);
+                i = i0 + il; j = j0 + jl;
+                const BoxP0 A0 = as_p0(W.r0[il]), B0 = as_p0(W.c0[jl]);
+                const BoxP1 A1 = as_p1(W.r1[il]), B1 = as_p1(W.c1[jl]);
+                float r = pair_overlap(A0, A1, B0, B1, A.variant, A.mode, A.tau, risk);
+                if (A.small_mask && (fminf(A1.hw, A1.hh) * 2.0f < 0.001f || fminf(B1.hw, B1.hh) * 2.0f < 0.001f)) r = 0.0f;
+                if (!risk && r != 0.0f) A.out[(int64_t)i * A.n + j] = r;
+            }
+            __syncwarp();
+            c2 -= nb;
+            n_sat += nb;
+            const unsigned bal = __ballot_sync(0xffffffffu, risk);
+            if (risk) W.q3[c3 + __popc(bal & lt)] = make_uint2((unsigned)i, (unsigned)j);
+            c3 += __popc(bal);
+            continue;
+        }
+        if (c1 >= 32 || (flush && c1 > 0)) {
+            // ---- stage 2: separating-axis test ----
+            const int nb = min(32, c1);
+            __syncwarp();
+            bool ok = false;
+            unsigned e = 0;
+            if ((int)lane < nb) {
+                e = W.q1[c1 - nb + lane];
+                const int il = (int)(e >> 7), jl = (int)(e & 127u);
+                ok = pair_sat(as_p0(W.r0[il]), as_p1(W.r1[il]), as_p0(W.c0[jl]), as_p1(W.c1[jl]));
+            }
+            __syncwarp();
+            c1 -= nb;
+            n_circle += nb;
+            const unsigned bal = __ballot_sync(0xffffffffu, ok);
+            if (ok) W.q2[c2 + __popc(bal & lt)] = (unsigned short)e;
+            c2 += __popc(bal);
+            continue;
+        }
+        if (flush) {
+            // ---- next item (dynamic ticket; the counter is zeroed by the launcher) ----
+            long long item = 0;
+            if (lane == 0) item = (long long)atomicAdd(A.stats + 4, 1ull);
+            item = __shfl_sync(0xffffffffu, item, 0);
+            if (item >= total) { done = true; continue; }
+            const int tm = (int)(item / tiles_n), tn = (int)(item - (long long)tm * tiles_n);
+            i0 = tm * IOU_TM; j0 = tn * IOU_TN;
+            i1 = min(A.m, i0 + IOU_TM);
+            ig = i0;
+            jb = j0 + (int)lane * IOU_CPL;
+            __syncwarp();
+            // stage the item's prepared boxes: 2 x 64 row records + 2 x 128 column records, 16 bytes each
+            for (int t = lane; t < IOU_TM; t += 32) {
+                const int i = min(i0 + t, A.m - 1);
+                cp_async16(&W.r0[t], A.r0 + i); cp_async16(&W.r1[t], A.r1 + i);
+            }
+            for (int t = lane; t < IOU_TN; t += 32) {
+                const int j = min(j0 + t, A.n - 1);
+                cp_async16(&W.c0[t], A.c0 + j); cp_async16(&W.c1[t], A.c1 + j);
+            }
+            cp_async_wait_all();
+            __syncwarp();
+            // this lane's 4 columns relative to the origin; invalid columns are pushed to +inf (always rejected)
+#pragma unroll
+            for (int k = 0; k < IOU_CPL; k++) {
+                if (jb + k < A.n) {
+                    const float4 b = W.c0[lane * IOU_CPL + k];
+                    cx[k] = b.x - ox; cy[k] = b.y - oy; cr[k] = b.z;
+                    const float q = cx[k] * cx[k] + cy[k] * cy[k], rr = b.z * b.z;
+                    ck[k] = (q - rr) - IOU_SLACK * (q + rr);
+                } else {
+                    cx[k] = 0.0f; cy[k] = 0.0f; cr[k] = 0.0f; ck[k] = 3.0e38f;
+                }
+            }
+            full4 = VEC && (jb + IOU_CPL <= A.n);
+            orow = A.out + (int64_t)i0 * A.n + jb;
+            flush = false;
+            continue;
+        }
+        if (ig >= i1) { flush = true; continue; }
 
-        for (int ig = i0; ig < i1; ig += IOU_RG) {
+        // ---- stage 1: one group of 8 rows x (4 columns per lane) ----
+        {
             const int nr = min(IOU_RG, i1 - ig);
             unsigned m = 0;
 #pragma unroll
@@ -237,17 +277,13 @@ __global__ void __launch_bounds__(IOU_THREADS, 3) iou_matrix_kernel(const IouArg
                     const int b = 31 - __clz(m);
                     m ^= 1u << b;
                     const unsigned idx = (unsigned)(nbits - 1 - b);
-                    q1[pos++] = (unsigned short)(((rowbase + (idx >> 2)) << 7) | (lane * IOU_CPL + (idx & 3u)));
+                    W.q1[pos++] = (unsigned short)(((rowbase + (idx >> 2)) << 7) | (lane * IOU_CPL + (idx & 3u)));
                 }
                 c1 += tot;
-                while (c1 >= 32) drain_sat(32);
             }
+            ig += IOU_RG;
         }
-        // item end: flush the item-relative queues
-        if (c1 > 0) drain_sat(c1);
-        if (c2 > 0) drain_area(c2);
     }
-    if (c3 > 0) drain_emu(c3);
 
     if (A.stats) {
         if (blockIdx.x == 0 && threadIdx.x == 0) A.stats[3] = (unsigned long long)A.m * (unsigned long long)A.n;
@@ -366,19 +402,25 @@ R3G_API int r3g_iou_matrix_prepared_f32(const float* boxes1, int64_t m, int64_t 
     a.out = out; a.stats = w.stats;
 
     const bool vec = (n % 4 == 0) && (((uintptr_t)out & 15u) == 0);
+    const size_t smem = sizeof(WarpSmem) * IOU_WARPS;
     static int occ_vec = 0, occ_scl = 0;
     int& occ = vec ? occ_vec : occ_scl;
     if (occ == 0) {
-        if (vec) R3G_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, iou_matrix_kernel<true>, IOU_THREADS, 0));
-        else R3G_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, iou_matrix_kernel<false>, IOU_THREADS, 0));
+        if (vec) {
+            R3G_CUDA_OK(cudaFuncSetAttribute(iou_matrix_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            R3G_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, iou_matrix_kernel<true>, IOU_THREADS, smem));
+        } else {
+            R3G_CUDA_OK(cudaFuncSetAttribute(iou_matrix_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            R3G_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, iou_matrix_kernel<false>, IOU_THREADS, smem));
+        }
         if (occ < 1) occ = 1;
     }
     const int64_t items = ((m + IOU_TM - 1) / IOU_TM) * ((n + IOU_TN - 1) / IOU_TN);
     int64_t grid = (items + IOU_WARPS - 1) / IOU_WARPS;
     const int64_t cap = (int64_t)device_sm_count() * occ;
     if (grid > cap) grid = cap;
-    if (vec) iou_matrix_kernel<true><<<(unsigned)grid, IOU_THREADS, 0, st>>>(a);
-    else iou_matrix_kernel<false><<<(unsigned)grid, IOU_THREADS, 0, st>>>(a);
+    if (vec) iou_matrix_kernel<true><<<(unsigned)grid, IOU_THREADS, smem, st>>>(a);
+    else iou_matrix_kernel<false><<<(unsigned)grid, IOU_THREADS, smem, st>>>(a);
     R3G_LAUNCH_OK("iou_matrix_kernel");
     return R3G_OK;
 }
