@@ -29,15 +29,18 @@ namespace r3g {
 
 constexpr int NMS_THREADS = 256;
 constexpr int NMS_WARPS = NMS_THREADS / 32;
-constexpr int NMS_G = 4;                       // column blocks (of 64) per item
-constexpr int NMS_CPL = NMS_G * 64 / 32;       // 8 columns per lane
-constexpr int NMS_QCAP = 32 + NMS_G * 64;
+constexpr int NMS_G = 2;                       // column blocks (of 64) per item
+constexpr int NMS_TN = NMS_G * 64;             // 128 columns per item
+constexpr int NMS_CPL = NMS_TN / 32;           // 4 adjacent columns per lane
+constexpr int NMS_RG = 8;                      // rows per mask group (8 rows x 4 columns = 32 mask bits per lane)
+constexpr int NMS_Q1CAP = 32 + NMS_RG * NMS_TN;
+constexpr float NMS_SLACK = 1.0f / 262144.0f;  // 2^-18 relative slack of the expanded circumradius test
 
 struct NmsWs {
     unsigned *keyA, *keyA2, *keyB, *keyB2;
     int *ord_rank, *ord_tmp, *pos_rank, *pos_tmp;   // ord_rank[r] = original index of rank r; pos_rank[p] = rank at position p
     unsigned* pos_label;
-    BoxP0* p0; BoxP1* p1; float* raw; unsigned char* valid;
+    BoxP0* p0; BoxP1* p1; float4* p2r; float4* p2c; float* raw; unsigned char* valid;
     int* blk_end; long long *nw, *row_base, *ng, *item_base;
     int* seg_list; int* counters;                   // counters[0] = nseg
     int *flag, *pref;
@@ -68,6 +71,7 @@ static NmsWs carve_nms(void* ws, int64_t K) {
     w.pos_rank = (int*)take(4 * K); w.pos_tmp = (int*)take(4 * K);
     w.pos_label = (unsigned*)take(4 * K);
     w.p0 = (BoxP0*)take(16 * K); w.p1 = (BoxP1*)take(16 * K);
+    w.p2r = (float4*)take(16 * K); w.p2c = (float4*)take(16 * K);
     w.raw = (float*)take(20 * K); w.valid = (unsigned char*)take(K);
     w.blk_end = (int*)take(4 * nblk);
     w.nw = (long long*)take(8 * (nblk + 1)); w.row_base = (long long*)take(8 * (nblk + 1));
@@ -106,14 +110,15 @@ __global__ void nms_label_keys_kernel(const int64_t* __restrict__ labels, const 
 __global__ void nms_gather_kernel(const float* __restrict__ boxes, int64_t stride, const int* __restrict__ ord_rank,
                                   const int* __restrict__ pos_rank, const unsigned* __restrict__ pos_label, int K,
                                   int variant, int drop_small, const float* __restrict__ class_offset, int has_labels,
-                                  BoxP0* p0, BoxP1* p1, float* raw, unsigned char* valid) {
+                                  BoxP0* p0, BoxP1* p1, float4* p2r, float4* p2c, float* raw, unsigned char* valid) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= K) return;
     const int idx = ord_rank[pos_rank[p]];
     const float* b = boxes + (int64_t)idx * stride;
     float x[5] = { b[0], b[1], b[2], b[3], b[4] };
+    float off = 0.0f;
     if (class_offset != nullptr && has_labels) {
-        float off = __fmul_rn((float)(int)pos_label[p], class_offset[0]);
+        off = __fmul_rn((float)(int)pos_label[p], class_offset[0]);
         x[0] = __fadd_rn(x[0], off);
         x[1] = __fadd_rn(x[1], off);
     }
@@ -122,7 +127,16 @@ __global__ void nms_gather_kernel(const float* __restrict__ boxes, int64_t strid
     p0[p] = a; p1[p] = c;
 #pragma unroll
     for (int k = 0; k < 5; k++) raw[(int64_t)p * 5 + k] = x[k];
-    valid[p] = (drop_small && fminf(x[2], x[3]) < 0.001f) ? 0 : 1;    // nms_rotated_wrapper.py:40-46
+    const bool ok = !(drop_small && fminf(x[2], x[3]) < 0.001f);      // nms_rotated_wrapper.py:40-46
+    valid[p] = ok ? 1 : 0;
+    // expanded circumradius test planes, in class-local coordinates (the class offset is removed again so that the
+    // squares stay small): row form {-2X, -2Y, -2r, |X|^2 - r^2 - slack}, column form {X, Y, r, |X|^2 - r^2 - slack};
+    // boxes that take no part are pushed to +inf (never pass)
+    const float X = a.cx - off, Y = a.cy - off;
+    const float q = X * X + Y * Y, rr = a.r * a.r;
+    const float kk = ok ? (q - rr) - NMS_SLACK * (q + rr) - 1e-6f : 3.0e38f;
+    p2r[p] = make_float4(-2.0f * X, -2.0f * Y, -2.0f * a.r, kk);
+    p2c[p] = make_float4(X, Y, a.r, kk);
 }
 
 // per 64-row block: last column block its rows can interact with (end of the class segment of its last row)
@@ -158,7 +172,8 @@ __device__ __noinline__ float nms_emu_call(const float* b1, const float* b2, int
 }
 
 struct MaskArgs {
-    const BoxP0* p0; const BoxP1* p1; const float* raw; const unsigned char* valid; const unsigned* label;
+    const BoxP0* p0; const BoxP1* p1; const float4* p2r; const float4* p2c; const float* raw; const unsigned char* valid;
+    const unsigned* label; unsigned long long* ticket;
     const int* blk_end; const long long* row_base; const long long* item_base;
     unsigned long long* mask;
     int K, nblk, variant, inclusive;
@@ -167,81 +182,184 @@ struct MaskArgs {
 
 __device__ __forceinline__ float4 nldg4(const void* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
-__global__ void __launch_bounds__(NMS_THREADS) nms_mask_kernel(const MaskArgs A) {
-    __shared__ unsigned q_all[NMS_WARPS][NMS_QCAP];
+__global__ void __launch_bounds__(NMS_THREADS, 3) nms_mask_kernel(const MaskArgs A) {
+    // per-warp: q1 circumradius survivors -> q2 separating-axis survivors -> (q3 near-threshold / degenerate pairs);
+    // q1/q2 entries are item-relative (row << 7 | col); all queues are flushed at item end (bits land in `sm`)
+    __shared__ unsigned short q1_all[NMS_WARPS][NMS_Q1CAP];
+    __shared__ unsigned short q2_all[NMS_WARPS][64];
+    __shared__ uint2 q3_all[NMS_WARPS][96];          // (row, col) positions of pairs left to the reference restatement; persists across items
     __shared__ unsigned long long sm_all[NMS_WARPS][64 * NMS_G];
     const unsigned warp = threadIdx.x >> 5, lane = lane_id(), lt = lanemask_lt();
-    unsigned* q = q_all[warp];
+    unsigned short* q1 = q1_all[warp];
+    unsigned short* q2 = q2_all[warp];
+    uint2* q3 = q3_all[warp];
     unsigned long long* sm = sm_all[warp];
     const long long total = A.item_base[A.nblk];
+    int c1 = 0, c2 = 0, c3 = 0;
+    int i0 = 0, j0 = 0;
 
-    for (long long item = (long long)blockIdx.x * NMS_WARPS + warp; item < total; item += (long long)gridDim.x * NMS_WARPS) {
+    int rb = -1, cb0 = 0, ncb = 0;
+    auto decide = [&](int il, int jl, float r) {
+        const bool sup = A.inclusive ? (r >= A.thr) : (r > A.thr);
+        if (sup) atomicOr(&sm[il * NMS_G + (jl >> 6)], 1ull << (jl & 63));
+    };
+    // Pairs decided by the reference's own algorithm.  Entries of the item in flight go to its shared-memory words;
+    // entries of finished items (their words are already in global memory) are OR-ed into the global mask.
+    auto drain_emu = [&](int nb) {
+        __syncwarp();
+        if ((int)lane < nb) {
+            const uint2 e = q3[c3 - nb + lane];
+            const int i = (int)e.x, j = (int)e.y;
+            const float r = nms_emu_call(A.raw + (int64_t)i * 5, A.raw + (int64_t)j * 5, A.variant);
+            const bool sup = A.inclusive ? (r >= A.thr) : (r > A.thr);
+            if (sup) {
+                const int rbi = i >> 6, cbj = j >> 6;
+                if (rbi == rb && cbj >= cb0 && cbj < cb0 + ncb) {
+                    atomicOr(&sm[(i & 63) * NMS_G + (cbj - cb0)], 1ull << (j & 63));
+                } else {
+                    const long long base = A.row_base[rbi];
+                    const int nwr = A.blk_end[rbi] - rbi + 1;
+                    atomicOr(A.mask + base + (long long)(i & 63) * nwr + (cbj - rbi), 1ull << (j & 63));
+                }
+            }
+        }
+        __syncwarp();
+        c3 -= nb;
+    };
+    auto drain_area = [&](int nb) {
+        __syncwarp();
+        bool emu = false;
+        unsigned e = 0;
+        if ((int)lane < nb) {
+            e = q2[c2 - nb + lane];
+            const int il = (int)(e >> 7), jl = (int)(e & 127u);
+            const int i = i0 + il, j = j0 + jl;
+            float4 a0 = nldg4(A.p0 + i), a1 = nldg4(A.p1 + i), b0 = nldg4(A.p0 + j), b1 = nldg4(A.p1 + j);
+            BoxP0 A0 = { a0.x, a0.y, a0.z, a0.w }; BoxP1 A1 = { a1.x, a1.y, a1.z, a1.w };
+            BoxP0 B0 = { b0.x, b0.y, b0.z, b0.w }; BoxP1 B1 = { b1.x, b1.y, b1.z, b1.w };
+            bool risk;
+            const float r = pair_overlap(A0, A1, B0, B1, A.variant, MODE_IOU, A.tau, risk);
+            emu = A.tau > 0.0f && (risk || fabsf(r - A.thr) < A.margin);
+            if (!emu) decide(il, jl, r);
+        }
+        __syncwarp();
+        c2 -= nb;
+        const unsigned bal = __ballot_sync(0xffffffffu, emu);
+        if (bal) {
+            if (emu) q3[c3 + __popc(bal & lt)] = make_uint2((unsigned)(i0 + (int)(e >> 7)), (unsigned)(j0 + (int)(e & 127u)));
+            c3 += __popc(bal);
+            if (c3 >= 64) drain_emu(32);
+        }
+    };
+    auto drain_sat = [&](int nb) {
+        __syncwarp();
+        bool ok = false;
+        unsigned e = 0;
+        if ((int)lane < nb) {
+            e = q1[c1 - nb + lane];
+            const int i = i0 + (int)(e >> 7), j = j0 + (int)(e & 127u);
+            float4 a0 = nldg4(A.p0 + i), a1 = nldg4(A.p1 + i), b0 = nldg4(A.p0 + j), b1 = nldg4(A.p1 + j);
+            BoxP0 A0 = { a0.x, a0.y, a0.z, a0.w }; BoxP1 A1 = { a1.x, a1.y, a1.z, a1.w };
+            BoxP0 B0 = { b0.x, b0.y, b0.z, b0.w }; BoxP1 B1 = { b1.x, b1.y, b1.z, b1.w };
+            ok = pair_sat(A0, A1, B0, B1);
+        }
+        __syncwarp();
+        c1 -= nb;
+        const unsigned bal = __ballot_sync(0xffffffffu, ok);
+        if (ok) q2[c2 + __popc(bal & lt)] = (unsigned short)e;
+        c2 += __popc(bal);
+        if (c2 >= 32) drain_area(32);
+    };
+
+    while (true) {
+        long long item = 0;
+        if (lane == 0) item = (long long)atomicAdd(A.ticket, 1ull);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= total) break;
         // row block of this item: last rb with item_base[rb] <= item
         int lo = 0, hi = A.nblk;
         while (hi - lo > 1) {
             int mid = (lo + hi) >> 1;
             if (A.item_base[mid] <= item) lo = mid; else hi = mid;
         }
-        const int rb = lo;
+        rb = lo;
         const int g = (int)(item - A.item_base[rb]);
         const int be = A.blk_end[rb];
-        const int cb0 = rb + g * NMS_G;                       // first column block of the item
-        const int ncb = min(NMS_G, be - cb0 + 1);             // valid column blocks
-        const int i0 = rb * 64, i1 = min(A.K, i0 + 64);
-        const int j0 = cb0 * 64, j1 = min(A.K, j0 + ncb * 64);
+        cb0 = rb + g * NMS_G;                                 // first column block of the item
+        ncb = min(NMS_G, be - cb0 + 1);                       // valid column blocks
+        i0 = rb * 64;
+        j0 = cb0 * 64;
+        const int i1 = min(A.K, i0 + 64);
+        const int j1 = min(A.K, j0 + ncb * 64);
+        const int jb = j0 + (int)lane * NMS_CPL;
 
         for (int k = lane; k < 64 * NMS_G; k += 32) sm[k] = 0ull;
-        float bx[NMS_CPL], by[NMS_CPL], br[NMS_CPL];
-        unsigned bl[NMS_CPL];
-        bool bv[NMS_CPL];
+        float cx[NMS_CPL], cy[NMS_CPL], cr[NMS_CPL], ck[NMS_CPL];
+        unsigned cl[NMS_CPL];
 #pragma unroll
         for (int k = 0; k < NMS_CPL; k++) {
-            const int j = j0 + lane + 32 * k;
-            bv[k] = j < j1;
-            float4 b = bv[k] ? nldg4(A.p0 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-            bx[k] = b.x; by[k] = b.y; br[k] = b.z;
-            bl[k] = bv[k] ? A.label[j] : 0xffffffffu;
-            bv[k] = bv[k] && A.valid[j];
+            if (jb + k < j1) {
+                const float4 b = nldg4(A.p2c + jb + k);
+                cx[k] = b.x; cy[k] = b.y; cr[k] = b.z; ck[k] = b.w;
+                cl[k] = A.label[jb + k];
+            } else {
+                cx[k] = 0.0f; cy[k] = 0.0f; cr[k] = 0.0f; ck[k] = 3.0e38f; cl[k] = 0xffffffffu;
+            }
         }
+        // interior items (one label throughout, all columns after all rows) need no per-pair label / order test
+        const bool interior = (cb0 > rb) && (A.label[i0] == A.label[j1 - 1]);
         __syncwarp();
-        int count = 0;
 
-        auto drain = [&](int first, int nb) {
-            __syncwarp();
-            if ((int)lane < nb) {
-                const unsigned e = q[first + lane];
-                const int il = e >> 8, jl = e & 255u;
-                const int i = i0 + il, j = j0 + jl;
-                float4 a0 = nldg4(A.p0 + i), a1 = nldg4(A.p1 + i), b0 = nldg4(A.p0 + j), b1 = nldg4(A.p1 + j);
-                BoxP0 A0 = { a0.x, a0.y, a0.z, a0.w }; BoxP1 A1 = { a1.x, a1.y, a1.z, a1.w };
-                BoxP0 B0 = { b0.x, b0.y, b0.z, b0.w }; BoxP1 B1 = { b1.x, b1.y, b1.z, b1.w };
-                bool risk;
-                float r = pair_overlap(A0, A1, B0, B1, A.variant, MODE_IOU, A.tau, risk);
-                if (A.tau > 0.0f && (risk || fabsf(r - A.thr) < A.margin))
-                    r = nms_emu_call(A.raw + (int64_t)i * 5, A.raw + (int64_t)j * 5, A.variant);
-                const bool sup = A.inclusive ? (r >= A.thr) : (r > A.thr);
-                if (sup) atomicOr(&sm[il * NMS_G + (jl >> 6)], 1ull << (jl & 63));
-            }
-            __syncwarp();
-        };
-
-        for (int i = i0; i < i1; i++) {
-            const float4 a = nldg4(A.p0 + i);
-            const unsigned la = A.label[i];
-            const bool va = A.valid[i] != 0;
-            const unsigned rowbits = (unsigned)(i - i0) << 8;
+        for (int ig = i0; ig < i1; ig += NMS_RG) {
+            const int nr = min(NMS_RG, i1 - ig);
+            unsigned m = 0;
 #pragma unroll
-            for (int k = 0; k < NMS_CPL; k++) {
-                const int jl = lane + 32 * k;
-                float dx = bx[k] - a.x, dy = by[k] - a.y, rr = br[k] + a.z;
-                const bool pass = va && bv[k] && (bl[k] == la) && (j0 + jl > i) && !(dx * dx + dy * dy > rr * rr);
-                const unsigned bal = __ballot_sync(0xffffffffu, pass);
-                if (pass) q[count + __popc(bal & lt)] = rowbits | (unsigned)jl;
-                count += __popc(bal);
+            for (int r = 0; r < NMS_RG; r++) {
+                if (r < nr) {
+                    const float4 a = nldg4(A.p2r + ig + r);
+#pragma unroll
+                    for (int k = 0; k < NMS_CPL; k++) {
+                        float s = fmaf(a.x, cx[k], ck[k] + a.w);
+                        s = fmaf(a.y, cy[k], s);
+                        s = fmaf(a.z, cr[k], s);
+                        m = __funnelshift_l(__float_as_uint(s), m, 1);
+                    }
+                }
             }
-            while (count >= 32) { drain(count - 32, 32); count -= 32; }
+            if (!interior && m != 0) {      // boundary items only (diagonal block / class boundary): label and order per pair
+                unsigned allow = 0;
+                for (int r = 0; r < nr; r++) {
+                    const unsigned la = A.label[ig + r];
+#pragma unroll
+                    for (int k = 0; k < NMS_CPL; k++)
+                        allow = (allow << 1) | ((cl[k] == la && jb + k > ig + r) ? 1u : 0u);
+                }
+                m &= allow;
+            }
+            const int cnt = __popc(m);
+            int incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, d);
+                if ((int)lane >= d) incl += t;
+            }
+            const int tot = __shfl_sync(0xffffffffu, incl, 31);
+            if (tot) {
+                int pos = c1 + incl - cnt;
+                const int nbits = nr * NMS_CPL;
+                const unsigned rowbase = (unsigned)(ig - i0);
+                while (m) {
+                    const int b = 31 - __clz(m);
+                    m ^= 1u << b;
+                    const unsigned idx = (unsigned)(nbits - 1 - b);
+                    q1[pos++] = (unsigned short)(((rowbase + (idx >> 2)) << 7) | (lane * NMS_CPL + (idx & 3u)));
+                }
+                c1 += tot;
+                while (c1 >= 32) drain_sat(32);
+            }
         }
-        if (count > 0) drain(0, count);
+        if (c1 > 0) drain_sat(c1);
+        if (c2 > 0) drain_area(c2);
         __syncwarp();
         // write the item's words: row r of block rb holds (be - rb + 1) words, word index = cb - rb
         const long long base = A.row_base[rb];
@@ -251,7 +369,11 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_mask_kernel(const MaskArgs A)
             if (c < ncb) A.mask[base + (long long)il * nwr + (cb0 - rb + c)] = sm[k];
         }
         __syncwarp();
+        rb = -1;                               // the item's words are in global memory now
+        while (c3 >= 32) drain_emu(32);
     }
+    rb = -1;
+    if (c3 > 0) drain_emu(c3);
 }
 
 struct ScanArgs {
@@ -262,11 +384,19 @@ struct ScanArgs {
     int K, order_index, remv_cap;
 };
 
+// Greedy scan, one CTA per class segment, software-pipelined so that no global-memory latency sits on the serial
+// chain.  For the 64-row block b of a segment:
+//   warp 0      : chain over the 64 diagonal words D_b (shared memory) with ffs jumps -> kept_b; ORs the kept rows'
+//                 next-column words N_b (prefetched for ALL 64 rows) into removed[b+1]; writes the keep flags;
+//   warps 1..7  : prefetch D_{b+1}, N_{b+1} and the valid bits of block b+1 into the other buffer, and apply the
+//                 kept rows of block b-1 to removed[b+1 ..] (their words two and more columns ahead).
+// One __syncthreads per block; removed[] lives in shared memory and is updated with atomicOr.
 __global__ void __launch_bounds__(NMS_THREADS) nms_scan_kernel(const ScanArgs A) {
     extern __shared__ unsigned long long remv[];          // remv_cap words
-    __shared__ unsigned long long D[64];
-    __shared__ unsigned long long kept_s;
-    const int tid = threadIdx.x;
+    __shared__ unsigned long long D[2][64], N[2][64];
+    __shared__ unsigned vbits[2][2];
+    __shared__ unsigned long long kept_s[2];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nseg = A.counters[0];
     for (int s = blockIdx.x; s < nseg; s += gridDim.x) {
         const int ps = A.seg_list[s];
@@ -279,62 +409,79 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_scan_kernel(const ScanArgs A)
         const int pe = lo + 1;
         const int bf = ps >> 6, bl = (pe - 1) >> 6;
         const int nb = bl - bf + 1;
-        for (int w = tid; w < nb && w < A.remv_cap; w += NMS_THREADS) remv[w] = 0ull;
-        __syncthreads();
-        for (int b = bf; b <= bl; b++) {
-            const int r0 = max(ps, b * 64), r1 = min(pe, b * 64 + 64);
-            const long long base = A.row_base[b];
-            const int nwr = A.blk_end[b] - b + 1;
-            if (tid < 64) {
-                const int p = b * 64 + tid;
-                unsigned long long d = 0ull;
-                if (p >= r0 && p < r1 && A.valid[p]) d = A.mask[base + (long long)tid * nwr];
-                D[tid] = d;
+        __syncthreads();                                   // previous segment fully done with shared memory
+        for (int w = tid; w < nb; w += NMS_THREADS) remv[w] = 0ull;
+        if (tid < 2) kept_s[tid] = 0ull;
+
+        // loads D / N / valid bits of block b into buffer `buf`; executed by two full warps (t = 0..63)
+        auto prefetch = [&](int b, int buf, int t) {
+            const int p = b * 64 + t;
+            const bool in = (p >= ps && p < pe);
+            const bool ok = in && A.valid[p];
+            unsigned long long d = 0ull, n = 0ull;
+            if (ok) {
+                const long long base = A.row_base[b];
+                const int nwr = A.blk_end[b] - b + 1;
+                d = A.mask[base + (long long)t * nwr];
+                if (b + 1 <= bl) n = A.mask[base + (long long)t * nwr + 1];
             }
+            D[buf][t] = d;
+            N[buf][t] = n;
+            const unsigned bal = __ballot_sync(0xffffffffu, ok);
+            if ((t & 31) == 0) vbits[buf][t >> 5] = bal;
+        };
+        if (tid < 64) prefetch(bf, 0, tid);
+
+        for (int b = bf; b <= bl; b++) {
+            const int buf = (b - bf) & 1;
             __syncthreads();
-            if (tid < 32) {
-                // valid rows of this segment inside the block
-                unsigned long long vb = 0ull;
-                for (int t = (int)tid; t < 64; t += 32) {
-                    const int p = b * 64 + t;
-                    const bool ok = (p >= r0 && p < r1 && A.valid[p]);
-                    unsigned m = __ballot_sync(0xffffffffu, ok);
-                    vb |= (unsigned long long)m << (t & 32);
-                }
-                unsigned long long cur = remv[b - bf], kept = 0ull;
+            if (warp == 0) {
+                const unsigned long long vb = ((unsigned long long)vbits[buf][1] << 32) | vbits[buf][0];
+                unsigned long long cur = remv[b - bf], kept = 0ull, nxt = 0ull;
                 unsigned long long avail = vb & ~cur;
-                while (avail) {                               // warp-uniform loop, one kept row per trip
+                while (avail) {                               // warp-uniform; one kept row per trip
                     const int t = __ffsll((long long)avail) - 1;
                     kept |= 1ull << t;
-                    cur |= D[t];
+                    cur |= D[buf][t];
+                    nxt |= N[buf][t];
                     const unsigned long long above = (t == 63) ? 0ull : (~0ull << (t + 1));
                     avail = vb & ~cur & above;
                 }
-                if (tid == 0) kept_s = kept;
-            }
-            __syncthreads();
-            const unsigned long long kept = kept_s;
-            // OR the kept rows' words for later blocks of this segment into remv (thread owns its words)
-            const int nlater = bl - b;                          // words b+1 .. bl
-            for (int w = tid; w < nlater; w += NMS_THREADS) {
-                unsigned long long acc = remv[b - bf + 1 + w];
-                unsigned long long kk = kept;
-                while (kk) {
-                    const int t = __ffsll((long long)kk) - 1;
-                    kk &= kk - 1;
-                    acc |= A.mask[base + (long long)t * nwr + 1 + w];
+                if (lane == 0) {
+                    kept_s[buf] = kept;
+                    if (b < bl && nxt) atomicOr(&remv[b + 1 - bf], nxt);
                 }
-                remv[b - bf + 1 + w] = acc;
-            }
-            if (tid < 64) {
-                const int p = b * 64 + tid;
-                if (p >= r0 && p < r1) {
-                    const int rank = A.pos_rank[p];
-                    const int slot = A.order_index ? A.ord_rank[rank] : rank;
-                    A.flag[slot] = (int)((kept >> tid) & 1ull);
+                for (int t = lane; t < 64; t += 32) {
+                    const int p = b * 64 + t;
+                    if (p >= ps && p < pe) {
+                        const int rank = A.pos_rank[p];
+                        const int slot = A.order_index ? A.ord_rank[rank] : rank;
+                        A.flag[slot] = (int)((kept >> t) & 1ull);
+                    }
+                }
+            } else {
+                const int u = tid - 32;                        // 0 .. 223
+                if (u < 64 && b + 1 <= bl) prefetch(b + 1, buf ^ 1, u);
+                if (u >= 64 && b > bf) {
+                    // kept rows of block b-1 -> removed[b+1 ..] (their words 2, 3, ... ; word 1 went through N)
+                    const unsigned long long kp = kept_s[buf ^ 1];
+                    if (kp) {
+                        const int pb = b - 1;
+                        const long long base = A.row_base[pb];
+                        const int nwr = A.blk_end[pb] - pb + 1;
+                        const int nlater = bl - pb - 1;          // columns pb+2 .. bl
+                        for (int w = u - 64; w < nlater; w += NMS_THREADS - 96) {
+                            unsigned long long acc = 0ull, kk = kp;
+                            while (kk) {
+                                const int t = __ffsll((long long)kk) - 1;
+                                kk &= kk - 1;
+                                acc |= A.mask[base + (long long)t * nwr + 2 + w];
+                            }
+                            if (acc) atomicOr(&remv[pb + 2 + w - bf], acc);
+                        }
+                    }
                 }
             }
-            __syncthreads();
         }
     }
 }
@@ -398,7 +545,7 @@ R3G_API int r3g_nms_f32(const float* boxes, int64_t stride, const float* scores,
     // 3. gather + prepare
     nms_gather_kernel<<<gK, tpb, 0, st>>>(boxes, stride, w.ord_rank, w.pos_rank, w.pos_label, Ki, variant,
                                           (flags & R3G_NMS_DROP_SMALL) ? 1 : 0, class_offset, labels ? 1 : 0,
-                                          w.p0, w.p1, w.raw, w.valid);
+                                          w.p0, w.p1, w.p2r, w.p2c, w.raw, w.valid);
     // 4. block / segment structure
     nms_blocks_kernel<<<(nblk + 1 + tpb - 1) / tpb, tpb, 0, st>>>(w.pos_label, Ki, nblk, w.blk_end, w.nw, w.ng);
     tb = w.cub_bytes;
@@ -410,7 +557,8 @@ R3G_API int r3g_nms_f32(const float* boxes, int64_t stride, const float* scores,
 
     // 5. suppression bitmask
     MaskArgs ma;
-    ma.p0 = w.p0; ma.p1 = w.p1; ma.raw = w.raw; ma.valid = w.valid; ma.label = w.pos_label;
+    ma.p0 = w.p0; ma.p1 = w.p1; ma.p2r = w.p2r; ma.p2c = w.p2c; ma.raw = w.raw; ma.valid = w.valid; ma.label = w.pos_label;
+    ma.ticket = (unsigned long long*)(w.counters + 8);
     ma.blk_end = w.blk_end; ma.row_base = w.row_base; ma.item_base = w.item_base; ma.mask = w.mask;
     ma.K = Ki; ma.nblk = nblk; ma.variant = variant; ma.inclusive = (flags & R3G_NMS_INCLUSIVE) ? 1 : 0;
     ma.thr = thr;
@@ -421,6 +569,7 @@ R3G_API int r3g_nms_f32(const float* boxes, int64_t stride, const float* scores,
         R3G_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, nms_mask_kernel, NMS_THREADS, 0));
         if (occ < 1) occ = 1;
     }
+    // persistent warps pulling items from a ticket counter (zeroed with the other counters above);
     // upper bound on items: triangular number of (row block, group) pairs
     long long max_items = (long long)nblk * ((nblk + NMS_G - 1) / NMS_G + 1);
     long long grid = (max_items + NMS_WARPS - 1) / NMS_WARPS;
