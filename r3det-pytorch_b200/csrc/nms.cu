@@ -396,6 +396,8 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_scan_kernel(const ScanArgs A)
     __shared__ unsigned long long D[2][64], N[2][64];
     __shared__ unsigned vbits[2][2];
     __shared__ unsigned long long kept_s[2];
+    __shared__ long long mbase[4];                        // row_base / words-per-row of blocks b-1 .. b+2 (ring by b & 3)
+    __shared__ int mnwr[4];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nseg = A.counters[0];
     for (int s = blockIdx.x; s < nseg; s += gridDim.x) {
@@ -411,7 +413,12 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_scan_kernel(const ScanArgs A)
         const int nb = bl - bf + 1;
         __syncthreads();                                   // previous segment fully done with shared memory
         for (int w = tid; w < nb; w += NMS_THREADS) remv[w] = 0ull;
-        if (tid < 2) kept_s[tid] = 0ull;
+        if (tid < 2) {
+            kept_s[tid] = 0ull;
+            const int b = bf + tid;
+            if (b <= bl) { mbase[b & 3] = A.row_base[b]; mnwr[b & 3] = A.blk_end[b] - b + 1; }
+        }
+        __syncthreads();
 
         // loads D / N / valid bits of block b into buffer `buf`; executed by two full warps (t = 0..63)
         auto prefetch = [&](int b, int buf, int t) {
@@ -420,8 +427,8 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_scan_kernel(const ScanArgs A)
             const bool ok = in && A.valid[p];
             unsigned long long d = 0ull, n = 0ull;
             if (ok) {
-                const long long base = A.row_base[b];
-                const int nwr = A.blk_end[b] - b + 1;
+                const long long base = mbase[b & 3];
+                const int nwr = mnwr[b & 3];
                 d = A.mask[base + (long long)t * nwr];
                 if (b + 1 <= bl) n = A.mask[base + (long long)t * nwr + 1];
             }
@@ -451,36 +458,60 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_scan_kernel(const ScanArgs A)
                     kept_s[buf] = kept;
                     if (b < bl && nxt) atomicOr(&remv[b + 1 - bf], nxt);
                 }
-                for (int t = lane; t < 64; t += 32) {
-                    const int p = b * 64 + t;
-                    if (p >= ps && p < pe) {
-                        const int rank = A.pos_rank[p];
-                        const int slot = A.order_index ? A.ord_rank[rank] : rank;
-                        A.flag[slot] = (int)((kept >> t) & 1ull);
-                    }
-                }
             } else {
                 const int u = tid - 32;                        // 0 .. 223
                 if (u < 64 && b + 1 <= bl) prefetch(b + 1, buf ^ 1, u);
                 if (u >= 64 && b > bf) {
                     // kept rows of block b-1 -> removed[b+1 ..] (their words 2, 3, ... ; word 1 went through N)
                     const unsigned long long kp = kept_s[buf ^ 1];
+                    if (u < 128) {                             // keep flags of block b-1 (off the resolver's critical path)
+                        const int t = u - 64, p = (b - 1) * 64 + t;
+                        if (p >= ps && p < pe) {
+                            const int rank = A.pos_rank[p];
+                            const int slot = A.order_index ? A.ord_rank[rank] : rank;
+                            A.flag[slot] = (int)((kp >> t) & 1ull);
+                        }
+                    }
+                    if (u == 223 && b + 2 <= bl) {             // meta of block b+2 for the next iteration's prefetch
+                        mbase[(b + 2) & 3] = A.row_base[b + 2];
+                        mnwr[(b + 2) & 3] = A.blk_end[b + 2] - (b + 2) + 1;
+                    }
                     if (kp) {
                         const int pb = b - 1;
-                        const long long base = A.row_base[pb];
-                        const int nwr = A.blk_end[pb] - pb + 1;
+                        const long long base = mbase[pb & 3];
+                        const int nwr = mnwr[pb & 3];
                         const int nlater = bl - pb - 1;          // columns pb+2 .. bl
                         for (int w = u - 64; w < nlater; w += NMS_THREADS - 96) {
                             unsigned long long acc = 0ull, kk = kp;
-                            while (kk) {
-                                const int t = __ffsll((long long)kk) - 1;
-                                kk &= kk - 1;
-                                acc |= A.mask[base + (long long)t * nwr + 2 + w];
+                            const unsigned long long* col = A.mask + base + 2 + w;
+                            while (kk) {                         // four independent loads in flight per trip
+                                int t[4];
+#pragma unroll
+                                for (int q = 0; q < 4; q++) {
+                                    t[q] = kk ? __ffsll((long long)kk) - 1 : -1;
+                                    kk &= kk - 1;
+                                }
+                                unsigned long long v[4];
+#pragma unroll
+                                for (int q = 0; q < 4; q++) v[q] = (t[q] >= 0) ? col[(long long)t[q] * nwr] : 0ull;
+                                acc |= (v[0] | v[1]) | (v[2] | v[3]);
                             }
                             if (acc) atomicOr(&remv[pb + 2 + w - bf], acc);
                         }
                     }
+                } else if (u == 223 && b + 2 <= bl) {          // first block of the segment: no block b-1 yet
+                    mbase[(b + 2) & 3] = A.row_base[b + 2];
+                    mnwr[(b + 2) & 3] = A.blk_end[b + 2] - (b + 2) + 1;
                 }
+            }
+        }
+        __syncthreads();
+        if (tid < 64) {                                        // keep flags of the segment's last block
+            const int t = tid, p = bl * 64 + t;
+            if (p >= ps && p < pe) {
+                const int rank = A.pos_rank[p];
+                const int slot = A.order_index ? A.ord_rank[rank] : rank;
+                A.flag[slot] = (int)((kept_s[(bl - bf) & 1] >> t) & 1ull);
             }
         }
     }
