@@ -6,12 +6,13 @@
 // points (sinf/cosf for points=5) and the bilinear weights — identical work repeated for all C=256
 // channels — and the backward pass issues 1+4*points float atomics per element into a pre-zeroed buffer.
 // Here the sample taps depend only on (n, h, w), so:
-//   forward : a thread owns one location, derives its taps ONCE into registers and streams the channels;
-//             CTAs tile the map 8(h) x 32(w) so the main loads/stores are 128-byte rows and the gathers of a
-//             CTA (which, with the reference's x/y swap, land near the TRANSPOSED location) share sectors;
-//             blocks are ordered (tile, channel-chunk, image) so concurrently running CTAs gather from the
-//             same few planes (L2-resident).  HBM traffic: read feat once + write out once = 8 B/element;
-//             no zero-fill pass (the reference's Python zero-fills `output` first).
+//   forward : a thread owns one location, derives its taps ONCE into registers and streams the channels.  Lanes run
+//             along h: with the reference's x/y swap the taps of h-adjacent locations are adjacent in memory, so
+//             the gathers coalesce; the location's own element / the output go through a padded shared-memory
+//             tile with a row-oriented mapping, software-pipelined one round (8 channels) ahead in registers.
+//             Blocks are ordered (tile, channel-chunk, image) so concurrently running CTAs gather from the same
+//             few planes (L2-resident).  HBM traffic: read feat once + write out once = 8 B/element; no zero-fill
+//             pass (the reference's Python zero-fills `output` first).
 //   backward: the taps of an image are inverted once per call into a per-target CSR by a radix sort on the
 //             target index ("sorted scatter"); a thread owns one target pixel and GATHERS
 //             grad_in[t] = grad_out[t] + sum_e w_e * grad_out[src_e] for 16 channels per pass.  No atomics,
@@ -67,58 +68,114 @@ __device__ __forceinline__ void frm_points(const float* __restrict__ bb, float s
     }
 }
 
+// Location tile of a CTA: tile_h consecutive rows (h) x tile_w consecutive columns (w), tile_h * tile_w = 256.
+// Compute mapping: thread t owns location (h0 + t % tile_h, w0 + t / tile_h) — LANES RUN ALONG h.  The reference
+// samples box x as the ROW coordinate and box y as the COLUMN coordinate (feature_refine_kernel.cu:131-132), so for
+// refined boxes near their own location the taps of lane-adjacent locations (h, h+1, ...) are adjacent in memory and
+// every gather is a handful of coalesced sectors instead of 32 scattered ones.  The location's own element (and the
+// output) would be strided by W in that mapping, so they are moved through a padded shared-memory tile with a
+// row-oriented mapping (t / tile_w, t % tile_w): global traffic stays fully coalesced in both directions.
 struct TileGeom { int tile_w, tile_h, tiles_x, tiles_y; };
 
 static TileGeom tile_geom(int H, int W) {
     TileGeom g;
-    g.tile_w = 32;
-    while (g.tile_w > 4 && g.tile_w / 2 >= W) g.tile_w /= 2;
-    g.tile_h = FRM_THREADS / g.tile_w;
+    g.tile_h = 32;
+    while (g.tile_h > 4 && g.tile_h / 2 >= H) g.tile_h /= 2;
+    g.tile_w = FRM_THREADS / g.tile_h;
+    (void)W;
     g.tiles_x = (W + g.tile_w - 1) / g.tile_w;
     g.tiles_y = (H + g.tile_h - 1) / g.tile_h;
     return g;
 }
 
+constexpr int FRM_TILE_PITCH = 296;      // >= tile_h * (tile_w + 1) for every geometry (32x9, 16x17, 8x33, 4x65)
+constexpr int FRM_CH_FWD = 8;            // channels per shared-memory round (forward)
+
 template <int P>
-__global__ void __launch_bounds__(FRM_THREADS) frm_forward_kernel(
+__global__ void __launch_bounds__(FRM_THREADS, (P == 1) ? 4 : 2) frm_forward_kernel(
     const float* __restrict__ feat, const float* __restrict__ boxes, int N, int C, int H, int W,
     float scale, TileGeom g, int cchunks, float* __restrict__ out) {
+    __shared__ float tile[FRM_CH_FWD][FRM_TILE_PITCH];
     // blockIdx.x = tile + tiles * (chunk + cchunks * n): tiles fastest so that co-resident CTAs share planes
     const int tiles = g.tiles_x * g.tiles_y;
     int bid = blockIdx.x;
-    const int tile = bid % tiles; bid /= tiles;
+    const int tl = bid % tiles; bid /= tiles;
     const int chunk = bid % cchunks;
     const int n = bid / cchunks;
-    const int tx = threadIdx.x % g.tile_w, ty = threadIdx.x / g.tile_w;
-    const int w = (tile % g.tiles_x) * g.tile_w + tx;
-    const int h = (tile / g.tiles_x) * g.tile_h + ty;
-    if (w >= W || h >= H) return;
+    const int h0 = (tl / g.tiles_x) * g.tile_h, w0 = (tl % g.tiles_x) * g.tile_w;
+    const int pitch = g.tile_w + 1;
+    // compute mapping (lanes along h)
+    const int ch = threadIdx.x % g.tile_h, cw = threadIdx.x / g.tile_h;
+    const int h = h0 + ch, w = w0 + cw;
+    const bool cvalid = (h < H) && (w < W);
+    // row-oriented mapping for the coalesced global load / store of the tile
+    const int rh = threadIdx.x / g.tile_w, rw = threadIdx.x % g.tile_w;
+    const bool rvalid = (h0 + rh < H) && (w0 + rw < W);
     const int HW = H * W;
-    const int loc = h * W + w;
+    const int rloc = (h0 + rh) * W + (w0 + rw);
+    const int cslot = ch * pitch + cw, rslot = rh * pitch + rw;
 
-    float px[5], py[5];
-    const float* bb = boxes + ((size_t)n * HW + loc) * 5;
-    float b5[5] = { __ldg(bb), __ldg(bb + 1), __ldg(bb + 2), __ldg(bb + 3), __ldg(bb + 4) };
-    frm_points<P>(b5, scale, px, py);
     Taps4 t[P];
+    if (cvalid) {
+        float px[5], py[5];
+        const float* bb = boxes + ((size_t)n * HW + (size_t)h * W + w) * 5;
+        float b5[5] = { __ldg(bb), __ldg(bb + 1), __ldg(bb + 2), __ldg(bb + 3), __ldg(bb + 4) };
+        frm_points<P>(b5, scale, px, py);
 #pragma unroll
-    for (int p = 0; p < P; p++) frm_taps(H, W, py[p], px[p], t[p]);
+        for (int p = 0; p < P; p++) frm_taps(H, W, py[p], px[p], t[p]);
+    } else {
+#pragma unroll
+        for (int p = 0; p < P; p++)
+#pragma unroll
+            for (int k = 0; k < 4; k++) { t[p].w[k] = 0.0f; t[p].o[k] = 0; }
+    }
 
     const int c0 = chunk * FRM_CCHUNK_FWD, c1 = min(C, c0 + FRM_CCHUNK_FWD);
-    const float* plane = feat + ((size_t)n * C + c0) * HW;
-    float* oplane = out + ((size_t)n * C + c0) * HW;
-#pragma unroll 4
-    for (int c = c0; c < c1; c++, plane += HW, oplane += HW) {
-        float v = __ldg(plane + loc);
+    // software pipeline: the next round's own-elements are in flight (registers) while this round gathers
+    float nxt[FRM_CH_FWD];
+    {
+        const float* plane = feat + ((size_t)n * C + c0) * HW + rloc;
 #pragma unroll
-        for (int p = 0; p < P; p++) {
-            float s = t[p].w[0] * __ldg(plane + t[p].o[0]);
-            s = fmaf(t[p].w[1], __ldg(plane + t[p].o[1]), s);
-            s = fmaf(t[p].w[2], __ldg(plane + t[p].o[2]), s);
-            s = fmaf(t[p].w[3], __ldg(plane + t[p].o[3]), s);
-            v += s;
+        for (int cc = 0; cc < FRM_CH_FWD; cc++) nxt[cc] = (rvalid && c0 + cc < c1) ? __ldg(plane + (size_t)cc * HW) : 0.0f;
+    }
+    for (int cb = c0; cb < c1; cb += FRM_CH_FWD) {
+        const float* plane = feat + ((size_t)n * C + cb) * HW;
+        float* oplane = out + ((size_t)n * C + cb) * HW + rloc;
+#pragma unroll
+        for (int cc = 0; cc < FRM_CH_FWD; cc++) tile[cc][rslot] = nxt[cc];
+        __syncthreads();
+        if (cb + FRM_CH_FWD < c1) {
+            const float* np = plane + (size_t)FRM_CH_FWD * HW + rloc;
+#pragma unroll
+            for (int cc = 0; cc < FRM_CH_FWD; cc++)
+                nxt[cc] = (rvalid && cb + FRM_CH_FWD + cc < c1) ? __ldg(np + (size_t)cc * HW) : 0.0f;
         }
-        __stcs(oplane + loc, v);
+        if (cvalid) {
+#pragma unroll
+            for (int cc = 0; cc < FRM_CH_FWD; cc++) {
+                if (cb + cc < c1) {
+                    const float* pl = plane + (size_t)cc * HW;
+                    float v = tile[cc][cslot];
+#pragma unroll
+                    for (int p = 0; p < P; p++) {
+                        float sacc = t[p].w[0] * __ldg(pl + t[p].o[0]);
+                        sacc = fmaf(t[p].w[1], __ldg(pl + t[p].o[1]), sacc);
+                        sacc = fmaf(t[p].w[2], __ldg(pl + t[p].o[2]), sacc);
+                        sacc = fmaf(t[p].w[3], __ldg(pl + t[p].o[3]), sacc);
+                        v += sacc;
+                    }
+                    tile[cc][cslot] = v;
+                }
+            }
+        }
+        __syncthreads();
+        // each thread re-reads only its own row-oriented slot here and overwrites only that slot at the top of the
+        // next round, and every compute-mapped read of this round happened before the barrier above: no third barrier
+        if (rvalid) {
+#pragma unroll
+            for (int cc = 0; cc < FRM_CH_FWD; cc++)
+                if (cb + cc < c1) __stcs(oplane + (size_t)cc * HW, tile[cc][rslot]);
+        }
     }
 }
 
@@ -174,44 +231,59 @@ __global__ void frm_bwd_materialize_kernel(const unsigned* __restrict__ sids, co
 __global__ void __launch_bounds__(FRM_THREADS) frm_backward_kernel(
     const float* __restrict__ gout, const unsigned* __restrict__ row_start, const unsigned* __restrict__ src,
     const float* __restrict__ wsorted, int N, int C, int H, int W, TileGeom g, int cchunks, float* __restrict__ gin) {
+    __shared__ float tile[FRM_CC_BWD][FRM_TILE_PITCH];
     const int tiles = g.tiles_x * g.tiles_y;
     int bid = blockIdx.x;
-    const int tile = bid % tiles; bid /= tiles;
+    const int tl = bid % tiles; bid /= tiles;
     const int chunk = bid % cchunks;
     const int n = bid / cchunks;
-    const int tx = threadIdx.x % g.tile_w, ty = threadIdx.x / g.tile_w;
-    const int w = (tile % g.tiles_x) * g.tile_w + tx;
-    const int h = (tile / g.tiles_x) * g.tile_h + ty;
-    if (w >= W || h >= H) return;
+    const int h0 = (tl / g.tiles_x) * g.tile_h, w0 = (tl % g.tiles_x) * g.tile_w;
+    const int pitch = g.tile_w + 1;
+    const int ch = threadIdx.x % g.tile_h, cw = threadIdx.x / g.tile_h;     // lanes along h: the sources of
+    const int h = h0 + ch, w = w0 + cw;                                     // lane-adjacent targets are adjacent
+    const bool cvalid = (h < H) && (w < W);
+    const int rh = threadIdx.x / g.tile_w, rw = threadIdx.x % g.tile_w;
+    const bool rvalid = (h0 + rh < H) && (w0 + rw < W);
     const int HW = H * W;
-    const int loc = h * W + w;
-    const size_t t = (size_t)n * HW + loc;
-    const unsigned e0 = __ldg(row_start + t), e1 = __ldg(row_start + t + 1);
+    const int rloc = (h0 + rh) * W + (w0 + rw);
+    const int cslot = ch * pitch + cw, rslot = rh * pitch + rw;
     const int c0 = chunk * FRM_CC_BWD;
     const float* base = gout + ((size_t)n * C + c0) * HW;
-    float acc[FRM_CC_BWD];
-#pragma unroll
-    for (int k = 0; k < FRM_CC_BWD; k++) acc[k] = (c0 + k < C) ? __ldg(base + (size_t)k * HW + loc) : 0.0f;
-    if (c0 + FRM_CC_BWD <= C) {
-        for (unsigned e = e0; e < e1; e++) {
-            const unsigned l = __ldg(src + e);
-            const float wt = __ldg(wsorted + e);
-#pragma unroll
-            for (int k = 0; k < FRM_CC_BWD; k++) acc[k] = fmaf(wt, __ldg(base + (size_t)k * HW + l), acc[k]);
-        }
-    } else {
-        for (unsigned e = e0; e < e1; e++) {
-            const unsigned l = __ldg(src + e);
-            const float wt = __ldg(wsorted + e);
-#pragma unroll
-            for (int k = 0; k < FRM_CC_BWD; k++)
-                if (c0 + k < C) acc[k] = fmaf(wt, __ldg(base + (size_t)k * HW + l), acc[k]);
-        }
-    }
     float* obase = gin + ((size_t)n * C + c0) * HW;
+
 #pragma unroll
     for (int k = 0; k < FRM_CC_BWD; k++)
-        if (c0 + k < C) __stcs(obase + (size_t)k * HW + loc, acc[k]);
+        if (rvalid && c0 + k < C) tile[k][rslot] = __ldg(base + (size_t)k * HW + rloc);
+    __syncthreads();
+    if (cvalid) {
+        const size_t t = (size_t)n * HW + (size_t)h * W + w;
+        const unsigned e0 = __ldg(row_start + t), e1 = __ldg(row_start + t + 1);
+        float acc[FRM_CC_BWD];
+#pragma unroll
+        for (int k = 0; k < FRM_CC_BWD; k++) acc[k] = tile[k][cslot];
+        if (c0 + FRM_CC_BWD <= C) {
+            for (unsigned e = e0; e < e1; e++) {
+                const unsigned l = __ldg(src + e);
+                const float wt = __ldg(wsorted + e);
+#pragma unroll
+                for (int k = 0; k < FRM_CC_BWD; k++) acc[k] = fmaf(wt, __ldg(base + (size_t)k * HW + l), acc[k]);
+            }
+        } else {
+            for (unsigned e = e0; e < e1; e++) {
+                const unsigned l = __ldg(src + e);
+                const float wt = __ldg(wsorted + e);
+#pragma unroll
+                for (int k = 0; k < FRM_CC_BWD; k++)
+                    if (c0 + k < C) acc[k] = fmaf(wt, __ldg(base + (size_t)k * HW + l), acc[k]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < FRM_CC_BWD; k++) tile[k][cslot] = acc[k];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < FRM_CC_BWD; k++)
+        if (rvalid && c0 + k < C) __stcs(obase + (size_t)k * HW + rloc, tile[k][rslot]);
 }
 
 struct FrmBwdWs {
