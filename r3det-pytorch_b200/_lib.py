@@ -79,6 +79,23 @@ def require_cuda(*tensors):
             raise RuntimeError("r3det_b200 ops run on CUDA tensors only (no CPU fallback); got a CPU tensor")
 
 
+class device_guard:
+    """`with device_guard(dev):` — like torch.cuda.device(dev) but free when dev is already current."""
+    __slots__ = ("ctx",)
+
+    def __init__(self, device):
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        self.ctx = None if idx == torch.cuda.current_device() else torch.cuda.device(idx)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *a):
+        if self.ctx is not None:
+            self.ctx.__exit__(*a)
+
+
 def stream_ptr(device):
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 

@@ -34,7 +34,7 @@ def nms_device(boxes, scores, thr, variant, labels=None, class_offset=None, incl
     nbytes = C.c_size_t(0)
     L.check(lib.r3g_nms_workspace_bytes(K, C.byref(nbytes)))
     ws = L.workspace(nbytes.value, dev)
-    with torch.cuda.device(dev):
+    with L.device_guard(dev):
         L.check(lib.r3g_nms_f32(L.ptr(boxes), stride, L.ptr(scores), L.ptr(labels), K, float(thr), L.V[variant], flags,
                                 L.ptr(class_offset), L.ptr(keep), C.c_void_p(num.data_ptr()), L.ptr(ws), ws.numel(),
                                 L.stream_ptr(dev)))

@@ -28,11 +28,20 @@
 
 namespace r3g {
 
-constexpr int IOU_THREADS = 256;
+#ifndef R3G_IOU_THREADS
+#define R3G_IOU_THREADS 256
+#endif
+#ifndef R3G_IOU_MINB
+#define R3G_IOU_MINB 3
+#endif
+#ifndef R3G_IOU_TM
+#define R3G_IOU_TM 64
+#endif
+constexpr int IOU_THREADS = R3G_IOU_THREADS;
 constexpr int IOU_WARPS = IOU_THREADS / 32;
 constexpr int IOU_CPL = 4;                  // columns per lane
 constexpr int IOU_TN = 32 * IOU_CPL;        // 128 columns per warp item
-constexpr int IOU_TM = 64;                  // rows per warp item
+constexpr int IOU_TM = R3G_IOU_TM;          // rows per warp item
 constexpr int IOU_RG = 8;                   // rows per mask group (8 rows x 4 columns = 32 mask bits per lane)
 constexpr int IOU_Q1CAP = 32 + IOU_RG * IOU_TN;   // worst case: 31 queued + one full group of survivors
 constexpr float IOU_SLACK = 1.0f / 262144.0f;     // 2^-18 relative slack of the expanded circle test (conservative)
@@ -110,7 +119,7 @@ __device__ __forceinline__ BoxP0 as_p0(float4 v) { BoxP0 b = { v.x, v.y, v.z, v.
 __device__ __forceinline__ BoxP1 as_p1(float4 v) { BoxP1 b = { v.x, v.y, v.z, v.w }; return b; }
 
 template <bool VEC>
-__global__ void __launch_bounds__(IOU_THREADS, 3) iou_matrix_kernel(const IouArgs A) {
+__global__ void __launch_bounds__(IOU_THREADS, R3G_IOU_MINB) iou_matrix_kernel(const IouArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const unsigned warp = threadIdx.x >> 5, lane = lane_id();
     WarpSmem& W = reinterpret_cast<WarpSmem*>(smem_raw)[warp];

@@ -24,7 +24,7 @@ def frm_forward(features, best_rbboxes, spatial_scale, points=1):
     N, Cc, H, W = feats.shape
     assert boxes.numel() == N * H * W * 5, 'best_rbboxes must hold one 5-tuple per location'
     out = torch.empty_like(feats)
-    with torch.cuda.device(feats.device):
+    with L.device_guard(feats.device):
         L.check(L.lib().r3g_frm_forward_f32(L.ptr(feats), L.ptr(boxes), N, Cc, H, W, float(spatial_scale), int(points),
                                             L.ptr(out), L.stream_ptr(feats.device)))
     return out.to(features.dtype)
@@ -42,7 +42,7 @@ def frm_backward(grad_output, best_rbboxes, spatial_scale, points=1):
     nbytes = C.c_size_t(0)
     L.check(lib.r3g_frm_backward_workspace_bytes(N, H, W, int(points), C.byref(nbytes)))
     ws = L.workspace(nbytes.value, g.device)
-    with torch.cuda.device(g.device):
+    with L.device_guard(g.device):
         L.check(lib.r3g_frm_backward_f32(L.ptr(g), L.ptr(boxes), N, Cc, H, W, float(spatial_scale), int(points),
                                          L.ptr(gin), L.ptr(ws), ws.numel(), L.stream_ptr(g.device)))
     return gin.to(grad_output.dtype)

@@ -24,7 +24,7 @@ def pairwise_iou(b1, b2, variant, mode="iou", flags=L.FLAG_STRICT, return_stats=
     nbytes = C.c_size_t(0)
     L.check(lib.r3g_iou_workspace_bytes(m, n, C.byref(nbytes)))
     ws = L.workspace(nbytes.value, b1.device)
-    with torch.cuda.device(b1.device):
+    with L.device_guard(b1.device):
         L.check(lib.r3g_iou_matrix_f32(L.ptr(b1), m, s1, L.ptr(b2), n, s2, L.V[variant], L.MODE[mode], flags,
                                        L.ptr(out), L.ptr(ws), ws.numel(), L.stream_ptr(b1.device)))
     if return_stats:
@@ -41,7 +41,7 @@ def aligned_iou(b1, b2, variant, mode="iou", flags=L.FLAG_STRICT):
     out = torch.empty((max(n1, n2),), dtype=torch.float32, device=b1.device)
     if n1 == 0 or n2 == 0:
         return out
-    with torch.cuda.device(b1.device):
+    with L.device_guard(b1.device):
         L.check(L.lib().r3g_iou_aligned_f32(L.ptr(b1), n1, s1, L.ptr(b2), n2, s2, L.V[variant], L.MODE[mode],
                                             flags, L.ptr(out), L.stream_ptr(b1.device)))
     return out

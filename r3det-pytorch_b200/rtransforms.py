@@ -23,7 +23,7 @@ def _run(fn_name, x, version, in_cols, out_cols):
     n = xin.size(0)
     out = torch.empty((n, out_cols), dtype=torch.float32, device=x.device)
     if n:
-        with torch.cuda.device(x.device):
+        with L.device_guard(x.device):
             L.check(getattr(L.lib(), fn_name)(L.ptr(xin), n, _VER[version], L.ptr(out), L.stream_ptr(x.device)))
     return out.reshape(*lead, out_cols).to(x.dtype) if x.dtype != torch.float32 else out.reshape(*lead, out_cols)
 
