@@ -285,6 +285,8 @@ def run_gpu(args):
         "clocks": clocks.summary(),
     }
 
+    if world > 1:
+        line["collectives"] = exercise_collectives(torch, dist, R, dev, rank, world)
     if rank == 0:
         line["nms"] = bench_nms(torch, R, dev, hbm)
         line["frm"] = bench_frm(torch, R, dev, hbm)
@@ -297,6 +299,46 @@ def run_gpu(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def exercise_collectives(torch, dist, R, dev, rank, world):
+    """N > 1 only: the two harness-level exchanges of the path over NCCL — per-GT assigner statistics
+    from the row-sharded IoU (all_reduce MAX of a packed int64 + all_reduce SUM) and ONE all_gather of padded keep
+    lists from image-sharded NMS.  Checked for consistency across ranks; timed with CUDA events (not in `value`)."""
+    from r3det_b200 import sharding
+    gt = torch.from_numpy(rand_obb(GT, 1, VARIANT)).to(dev)
+    anchors = torch.from_numpy(rand_obb(ANCHORS, 7, VARIANT)).to(dev)          # same anchors everywhere; each rank takes its rows
+    iou_fn = lambda g, a: R.pairwise_iou(g, a, VARIANT)
+    e0, ea, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
+    local, lo, hi = sharding.sharded_pairwise_iou(gt, anchors, iou_fn)
+    torch.cuda.synchronize(); dist.barrier()
+    e0.record()
+    gmax, garg, npos, nneg = sharding.assigner_stats(local, lo, 0.5, 0.4)
+    ea.record(); ea.synchronize()
+    stats_ms = e0.elapsed_time(ea)
+    images = 8 * world
+    ilo, ihi = sharding.shard_range(images, rank, world)
+    dets, labels = [], []
+    for i in range(ilo, ihi):
+        b, s, l = clustered(2000, 50 + i, VARIANT)
+        B, S, Lb = (torch.from_numpy(x).to(dev) for x in (b, s, l))
+        d, keep = R.batched_rnms(B, S, Lb, 0.1)
+        dets.append(d[:2000]); labels.append(Lb[keep][:2000])
+    torch.cuda.synchronize(); dist.barrier()
+    e1.record()
+    all_dets, all_labels = sharding.gather_keep_lists(dets, labels, 2000, images)
+    e2.record(); e2.synchronize()
+    # every rank must hold the same global view
+    chk = torch.tensor([float(gmax.double().sum()), float(garg.double().sum()), float(npos), float(nneg),
+                        float(sum(d.double().sum() for d in all_dets))], dtype=torch.float64, device=dev)
+    ref = chk.clone(); dist.broadcast(ref, 0)
+    ok = bool(torch.equal(chk, ref)) and len(all_dets) == images
+    full = R.pairwise_iou(gt, anchors, VARIANT) if rank == 0 else None
+    if rank == 0:
+        ok = ok and bool(torch.equal(gmax, full.max(dim=1)[0])) and bool(torch.equal(garg, full.max(dim=1)[1]))
+    return {"consistent": ok, "images": images, "num_pos": npos, "num_neg": nneg,
+            "note": "first call of each collective: includes NCCL communicator warm-up",
+            "assigner_stats_first_call_ms": stats_ms, "gather_keep_lists_first_call_ms": e1.elapsed_time(e2)}
 
 
 def _time(torch, fn, iters, warm=3):

@@ -97,6 +97,18 @@ int r3g_nms_f32(const float* boxes, int64_t stride, const float* scores, const i
                 int64_t* keep_out, int64_t* num_keep_out,
                 void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- multiclass candidate extraction -----------------------------------------------------------------------
+ * replaces the torch prologue of multiclass_nms_rotated (r3det/core/post_processing/bbox_nms_rotated.py:34-41,
+ * 98-103): candidates = (box, class) pairs with multi_scores[i, c] > score_thr for c < C (the last, background,
+ * column is never read), enumerated row-major.  multi_bboxes is (n, 5) or (n, 5*C) (box_cols); score rows have
+ * `score_stride` floats.  Outputs are sized for n*C candidates; *count_out (device) receives K.
+ * out_src[k] = i*C + c.  score_factors (n) or NULL multiplies the emitted score (:100-101). */
+int r3g_mc_candidates_workspace_bytes(int64_t n, int C, size_t* bytes);
+int r3g_mc_candidates_f32(const float* multi_bboxes, int box_cols, const float* multi_scores, int64_t score_stride,
+                          const float* score_factors, int64_t n, int C, float score_thr,
+                          float* out_boxes, float* out_scores, int64_t* out_labels, int64_t* out_src,
+                          int64_t* count_out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- FRM feature refinement ---------------------------------------------------------------------------
  * replaces feature_refine_cuda.forward / .backward   r3det/ops/fr/src/feature_refine_cuda.cpp:24-67
  * feat/out/grad: (N, C, H, W) float32 contiguous; boxes: (N*H*W, 5); points in {1, 5}.

@@ -1,92 +1,103 @@
-"""multiclass_nms_rotated — mirror of r3det/core/post_processing/bbox_nms_rotated.py:7-131.
+"""multiclass_nms_rotated — same call surface and results as
+r3det/core/post_processing/bbox_nms_rotated.py:7-131, different machinery.
 
-Same signature, same candidate order (row-major over (box, class) of scores > score_thr, :98-103), same
-per-variant output order and truncation:
-  v1   batched_rnms      keep in ascending candidate index, dets[:max_num] in that order (:111,127-129)
-  v3   obb_batched_nms   keep in descending score, dets[:max_num] = top scores (:113)
-  v2   ml_nms_rotated    keep in score order; `keep.size(0) > max_num` re-sort and slice (:115-125), including
-                         the reference's max_num=-1 quirk that drops the lowest-scoring detection
-  mmcv mmcv.ops.nms_rotated(bboxes, scores, iou_thr, labels) — third-party; served by the v2 geometry with
-                         labels (same lineage, +a rotation), dets/keep in score order, `return_inds` honoured.
-`nms` is an mmcv ConfigDict or dict with `iou_thr` and optional `type` (default 'v1', :43)."""
+The reference expands the boxes to (n, C, 5), boolean-masks them, calls `nonzero` (host sync) and then one of four
+NMS back ends.  Here one CUDA pass (`r3g_mc_candidates_f32`) emits the candidate list in the same row-major
+(box, class) order, the per-class segmented NMS kernel does the rest, and a small table carries what differs between
+the four `nms.type` values:
+
+  type    geometry  class offset scale (reference wrapper)           keep order        after NMS
+  'v1'    v1        bboxes.max() + 1                (rnms_wrapper.py:61-64)   candidate index   dets[:max_num]
+  'v3'    v3        hbb.max() - hbb.min() + 1       (nms_rotated_wrapper.py:84-90)  score      dets[:max_num]
+  'v2'    v2        none (labels compared)          (ml_nms_rotated)          score             re-sort + slice if k > max_num
+  'mmcv'  v2        none (mmcv.ops.nms_rotated with labels; third-party)      score             dets[:max_num], return_inds
+
+Quirks kept on purpose: 'v1' truncates in candidate-index order; 'v2' with the default max_num=-1 drops the
+lowest-scoring detection (`keep.size(0) > -1` → `inds[:-1]`, :119-121); `score_factors` are applied after the
+threshold test; empty input returns ((0, 6), (0,)) int64 labels."""
+import ctypes as C
+
 import torch
 
-from .ml_nms_rotated import ml_nms_rotated
-from .nms_rotated import obb_batched_nms
-from .rnms import batched_rnms
+from . import _lib as L
+from ._nms_core import nms_device
+from .nms_rotated import obb2hbb as _obb2xyxy_v3
+
+#            geometry, ordered by index, drop tiny boxes, offset rule
+_SPEC = {
+    'v1':   ('v1', True,  False, 'max'),
+    'v3':   ('v3', False, True,  'hbb_span'),
+    'v2':   ('v2', False, False, None),
+    'mmcv': ('v2', False, False, None),
+}
 
 
-def _get(nms, key, default=None):
-    if isinstance(nms, dict):
-        return nms.get(key, default)
-    return getattr(nms, key, default)
+def _cfg(nms, key, default=None):
+    return nms.get(key, default) if isinstance(nms, dict) else getattr(nms, key, default)
+
+
+def _candidates(multi_bboxes, multi_scores, score_thr, score_factors):
+    """Device-side candidate list: boxes (K,5), scores (K,), labels (K,), flat (box*C + class) index (K,)."""
+    n, C1 = multi_scores.shape
+    nc = C1 - 1
+    dev = multi_scores.device
+    mb = multi_bboxes.float().contiguous()
+    ms = multi_scores.float().contiguous()
+    sf = None if score_factors is None else score_factors.float().contiguous()
+    T = n * nc
+    boxes = torch.empty((T, 5), dtype=torch.float32, device=dev)
+    scores = torch.empty((T,), dtype=torch.float32, device=dev)
+    labels = torch.empty((T,), dtype=torch.int64, device=dev)
+    src = torch.empty((T,), dtype=torch.int64, device=dev)
+    count = torch.zeros((), dtype=torch.int64, device=dev)
+    if T:
+        lib = L.lib()
+        nbytes = C.c_size_t(0)
+        L.check(lib.r3g_mc_candidates_workspace_bytes(n, nc, C.byref(nbytes)))
+        ws = L.workspace(nbytes.value, dev)
+        with L.device_guard(dev):
+            L.check(lib.r3g_mc_candidates_f32(L.ptr(mb), mb.size(1), L.ptr(ms), C1, L.ptr(sf), n, nc, float(score_thr),
+                                              L.ptr(boxes), L.ptr(scores), L.ptr(labels), L.ptr(src),
+                                              C.c_void_p(count.data_ptr()), L.ptr(ws), ws.numel(), L.stream_ptr(dev)))
+    K = int(count.item())
+    return boxes[:K], scores[:K], labels[:K], src[:K]
 
 
 def multiclass_nms_rotated(multi_bboxes, multi_scores, score_thr, nms, max_num=-1, score_factors=None,
                            return_inds=False):
-    num_classes = multi_scores.size(1) - 1
-    if multi_bboxes.shape[1] > 5:
-        bboxes = multi_bboxes.view(multi_scores.size(0), -1, 5)
-    else:
-        bboxes = multi_bboxes[:, None].expand(multi_scores.size(0), num_classes, 5)
-    scores = multi_scores[:, :-1]
-    nms_version = _get(nms, 'type', 'v1')
-    iou_thr = _get(nms, 'iou_thr')
+    """NMS for multi-class rotated bboxes: (dets (k, 6), labels (k,)[, flat indices (k,)])."""
+    kind = _cfg(nms, 'type', 'v1')
+    if kind not in _SPEC:
+        raise KeyError(f'unknown rotated nms type {kind!r}')
+    geometry, by_index, drop_small, offset_rule = _SPEC[kind]
+    iou_thr = _cfg(nms, 'iou_thr')
+    host_in = not multi_scores.is_cuda                  # CPU tensors: upload, reference CPU rule (>=), results back on CPU
+    dev = multi_scores.device if not host_in else torch.device('cuda', torch.cuda.current_device())
+    back = (lambda t: t.cpu()) if host_in else (lambda t: t)
 
-    if nms_version == 'mmcv':
-        labels = torch.arange(num_classes, dtype=torch.long, device=scores.device)
-        labels = labels.view(1, -1).expand_as(scores)
-        bboxes = bboxes.reshape(-1, 5)
-        scores = scores.reshape(-1)
-        labels = labels.reshape(-1)
-        valid_mask = scores > score_thr
-        if score_factors is not None:
-            score_factors = score_factors.view(-1, 1).expand(multi_scores.size(0), num_classes)
-            scores = scores * score_factors.reshape(-1)
-        inds = valid_mask.nonzero(as_tuple=False).squeeze(1)
-        bboxes, scores, labels = bboxes[inds], scores[inds], labels[inds]
-        if bboxes.numel() == 0:
-            dets = torch.cat([bboxes, scores[:, None]], -1)
-            return (dets, labels, inds) if return_inds else (dets, labels)
-        keep = ml_nms_rotated(bboxes, scores, labels, iou_thr)
-        dets = torch.cat([bboxes[keep], scores[keep][:, None]], -1)
-        if max_num > 0:
-            dets = dets[:max_num]
-            keep = keep[:max_num]
-        return (dets, labels[keep], keep) if return_inds else (dets, labels[keep])
+    boxes, scores, labels, src = _candidates(multi_bboxes.to(dev), multi_scores.to(dev), score_thr,
+                                             None if score_factors is None else score_factors.to(dev))
+    if boxes.size(0) == 0:
+        if kind == 'mmcv':
+            dets = torch.cat([boxes, scores[:, None]], -1)
+            return (back(dets), back(labels), back(src)) if return_inds else (back(dets), back(labels))
+        return multi_bboxes.new_zeros((0, 6)), multi_bboxes.new_zeros((0, ), dtype=torch.long)
 
-    valid_mask = scores > score_thr
-    bboxes = bboxes[valid_mask]
-    if score_factors is not None:
-        scores = scores * score_factors[:, None]
-    scores = scores[valid_mask]
-    labels = valid_mask.nonzero(as_tuple=False)[:, 1]
+    scale = None
+    if offset_rule == 'max':
+        scale = boxes.max() + 1
+    elif offset_rule == 'hbb_span':
+        hb = _obb2xyxy_v3(boxes)
+        scale = (hb.max() - hb.min()) + 1
+    keep, num = nms_device(boxes, scores, iou_thr, geometry, labels=labels, class_offset=scale, inclusive=host_in,
+                           order_index=by_index, drop_small=drop_small)
+    keep = keep[:int(num.item())]
 
-    if bboxes.numel() == 0:
-        bboxes = multi_bboxes.new_zeros((0, 6))
-        labels = multi_bboxes.new_zeros((0, ), dtype=torch.long)
-        return bboxes, labels
-
-    if nms_version == 'v1':
-        dets, keep = batched_rnms(bboxes, scores, labels, iou_thr)
-    elif nms_version == 'v3':
-        dets, keep = obb_batched_nms(bboxes, scores, labels, iou_thr)
-    elif nms_version == 'v2':
-        keep = ml_nms_rotated(bboxes, scores, labels, iou_thr)
-        bboxes = bboxes[keep]
-        scores = scores[keep]
-        labels = labels[keep]
-        if keep.size(0) > max_num:
-            _, inds = scores.sort(descending=True)
-            inds = inds[:max_num]
-            bboxes = bboxes[inds]
-            scores = scores[inds]
-            labels = labels[inds]
-        return torch.cat([bboxes, scores[:, None]], 1), labels
-    else:
-        raise KeyError(f'unknown rotated nms type {nms_version!r}')
-
-    if max_num > 0:
-        dets = dets[:max_num]
+    if kind == 'v2' and keep.size(0) > max_num:          # reference :119-124 (also fires for max_num = -1)
+        keep = keep[:max_num]                            # keep is already in descending-score order
+    elif kind != 'v2' and max_num > 0:
         keep = keep[:max_num]
-    return dets, labels[keep]
+    dets = torch.cat([boxes[keep], scores[keep][:, None]], 1)
+    if kind == 'mmcv' and return_inds:
+        return back(dets), back(labels[keep]), back(keep)
+    return back(dets), back(labels[keep])

@@ -637,3 +637,84 @@ R3G_API int r3g_nms_f32(const float* boxes, int64_t stride, const float* scores,
     R3G_LAUNCH_OK("nms_emit_kernel");
     return R3G_OK;
 }
+
+// ---- multiclass candidate extraction --------------------------------------------------------------------------------
+// replaces the torch prologue of multiclass_nms_rotated (r3det/core/post_processing/bbox_nms_rotated.py:34-41, 98-103:
+// expand / boolean-mask / nonzero, five kernels and a sync) with ONE pass: candidate k enumerates the (box, class)
+// pairs with score > score_thr in row-major order — exactly the order `bboxes[valid_mask]` / `nonzero()[:, 1]` produce.
+namespace r3g {
+
+__global__ void mc_flags_kernel(const float* __restrict__ scores, int64_t n, int C, int64_t score_stride, float thr,
+                                int* __restrict__ flag) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * C) return;
+    const int64_t i = t / C;
+    const int c = (int)(t - i * C);
+    flag[t] = (scores[i * score_stride + c] > thr) ? 1 : 0;
+}
+
+__global__ void mc_emit_kernel(const float* __restrict__ boxes, int box_cols, const float* __restrict__ scores,
+                               const float* __restrict__ factors, int64_t n, int C, int64_t score_stride,
+                               const int* __restrict__ flag, const int* __restrict__ pref,
+                               float* __restrict__ out_boxes, float* __restrict__ out_scores,
+                               int64_t* __restrict__ out_labels, int64_t* __restrict__ out_src, int64_t* __restrict__ count) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * C) return;
+    if (t == n * C - 1) *count = (int64_t)pref[t] + flag[t];
+    if (!flag[t]) return;
+    const int64_t i = t / C;
+    const int c = (int)(t - i * C);
+    const int64_t k = pref[t];
+    const float* b = boxes + i * box_cols + (box_cols > 5 ? (int64_t)c * 5 : 0);
+#pragma unroll
+    for (int q = 0; q < 5; q++) out_boxes[k * 5 + q] = b[q];
+    float s = scores[i * score_stride + c];
+    if (factors) s = s * factors[i];
+    out_scores[k] = s;
+    out_labels[k] = c;
+    out_src[k] = t;
+}
+
+}  // namespace r3g
+
+R3G_API int r3g_mc_candidates_workspace_bytes(int64_t n, int C, size_t* bytes) {
+    R3G_REQUIRE(bytes && n >= 0 && C >= 0 && n * (int64_t)C < (1ll << 31), "r3g_mc_candidates_workspace_bytes: bad arguments");
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, (int*)nullptr, (int*)nullptr, (int)(n * C > 0 ? n * C : 1));
+    *bytes = align_up(tb, 256) + 2 * align_up(4 * (size_t)(n * C > 0 ? n * C : 1), 256);
+    return R3G_OK;
+}
+
+R3G_API int r3g_mc_candidates_f32(const float* multi_bboxes, int box_cols, const float* multi_scores, int64_t score_stride,
+                                  const float* score_factors, int64_t n, int C, float score_thr,
+                                  float* out_boxes, float* out_scores, int64_t* out_labels, int64_t* out_src,
+                                  int64_t* count_out, void* workspace, size_t workspace_bytes, void* stream) {
+    R3G_REQUIRE(n >= 0 && C >= 0 && n * (int64_t)C < (1ll << 31), "r3g_mc_candidates_f32: bad sizes");
+    R3G_REQUIRE(count_out != nullptr, "r3g_mc_candidates_f32: null count_out");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t T = n * C;
+    if (T == 0) {
+        R3G_CUDA_OK(cudaMemsetAsync(count_out, 0, sizeof(int64_t), st));
+        return R3G_OK;
+    }
+    R3G_REQUIRE(box_cols == 5 || box_cols == 5 * C, "r3g_mc_candidates_f32: boxes must be (n, 5) or (n, 5*C)");
+    R3G_REQUIRE(multi_bboxes && multi_scores && out_boxes && out_scores && out_labels && out_src && workspace,
+                "r3g_mc_candidates_f32: null pointer");
+    size_t need = 0;
+    r3g_mc_candidates_workspace_bytes(n, C, &need);
+    if (workspace_bytes < need) {
+        set_error("r3g_mc_candidates_f32: workspace too small (%zu < %zu)", workspace_bytes, need);
+        return R3G_ERR_WORKSPACE;
+    }
+    char* p = (char*)workspace;
+    int* flag = (int*)p; p += align_up(4 * (size_t)T, 256);
+    int* pref = (int*)p; p += align_up(4 * (size_t)T, 256);
+    size_t tb = need - 2 * align_up(4 * (size_t)T, 256);
+    const unsigned grid = (unsigned)((T + 255) / 256);
+    mc_flags_kernel<<<grid, 256, 0, st>>>(multi_scores, n, C, score_stride, score_thr, flag);
+    R3G_CUDA_OK(cub::DeviceScan::ExclusiveSum(p, tb, flag, pref, (int)T, st));
+    mc_emit_kernel<<<grid, 256, 0, st>>>(multi_bboxes, box_cols, multi_scores, score_factors, n, C, score_stride, flag, pref,
+                                         out_boxes, out_scores, out_labels, out_src, count_out);
+    R3G_LAUNCH_OK("mc candidate kernels");
+    return R3G_OK;
+}
