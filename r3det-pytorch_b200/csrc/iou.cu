@@ -62,7 +62,8 @@ __global__ void prep_boxes_kernel(const float* __restrict__ boxes, int64_t n, in
     p0[i] = a;
     p1[i] = c;
     if (p2 != nullptr) {
-        const float x = a.cx - origin_box[0], y = a.cy - origin_box[1];
+        const float ox = isfinite(origin_box[0]) ? origin_box[0] : 0.0f, oy = isfinite(origin_box[1]) ? origin_box[1] : 0.0f;
+        const float x = a.cx - ox, y = a.cy - oy;
         const float q = x * x + y * y, rr = a.r * a.r;
         RowP2 r;
         r.mx = -2.0f * x; r.my = -2.0f * y; r.mr = -2.0f * a.r;
@@ -129,7 +130,9 @@ __global__ void __launch_bounds__(IOU_THREADS, R3G_IOU_MINB) iou_matrix_kernel(c
     const int tiles_m = (A.m + IOU_TM - 1) / IOU_TM;
     const long long total = (long long)tiles_m * tiles_n;
     unsigned n_circle = 0, n_sat = 0, n_emu = 0;
-    const float ox = __ldg(A.origin_box), oy = __ldg(A.origin_box + 1);
+    float ox = __ldg(A.origin_box), oy = __ldg(A.origin_box + 1);     // common origin of the expanded circle test
+    if (!isfinite(ox)) ox = 0.0f;
+    if (!isfinite(oy)) oy = 0.0f;
 
     int i0 = 0, j0 = 0, i1 = 0, ig = 0, jb = 0;
     float cx[IOU_CPL], cy[IOU_CPL], cr[IOU_CPL], ck[IOU_CPL];
