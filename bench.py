@@ -290,6 +290,7 @@ def run_gpu(args):
     if rank == 0:
         line["nms"] = bench_nms(torch, R, dev, hbm)
         line["frm"] = bench_frm(torch, R, dev, hbm)
+        line["fused_assign"] = bench_assign(torch, R, dev, gt_h, an_h)
         cores = os.cpu_count() or 1
         apt = 4000
         rate, dt, kind = cpu_pairs_per_s(apt, cores)
@@ -352,6 +353,27 @@ def _time(torch, fn, iters, warm=3):
     e1.record()
     e1.synchronize()
     return e0.elapsed_time(e1) / iters
+
+
+def bench_assign(torch, R, dev, gt_h, an_h):
+    """the same 1000 x 200000 pairs consumed by the fused MaxIoUAssigner (pos 0.5 / neg 0.4 /
+    min_pos 0, gt_max_assign_all): no (G, A) matrix is stored.  `e2e` = pinned host boxes in, assignment (int64 per
+    anchor) + max overlaps back on the host."""
+    gt, an = gt_h.to(dev), an_h.to(dev)
+    fn = lambda: R.max_iou_assign(gt, an, 0.5, 0.4, 0.0, True, True, VARIANT)
+    ms = _time(torch, fn, 50)
+    res_i = torch.empty((ANCHORS,), dtype=torch.int64).pin_memory()
+    res_f = torch.empty((ANCHORS,), dtype=torch.float32).pin_memory()
+
+    def e2e():
+        o = R.max_iou_assign(gt_h.to(dev, non_blocking=True), an_h.to(dev, non_blocking=True), 0.5, 0.4, 0.0, True, True, VARIANT)
+        res_i.copy_(o.gt_inds, non_blocking=True); res_f.copy_(o.max_overlaps, non_blocking=True)
+
+    ms_e2e = _time(torch, e2e, 20)
+    pairs = GT * ANCHORS
+    return {"ms": ms, "gpairs_per_s": pairs / ms / 1e6, "e2e_ms": ms_e2e, "e2e_gpairs_per_s": pairs / ms_e2e / 1e6,
+            "d2h_bytes_per_step": int(res_i.numel() * 8 + res_f.numel() * 4), "passes": 2,
+            "num_pos": int((res_i > 0).sum())}
 
 
 def bench_nms(torch, R, dev, hbm):

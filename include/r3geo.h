@@ -76,6 +76,21 @@ int r3g_iou_aligned_f32(const float* boxes1, int64_t n1, int64_t stride1,
                         const float* boxes2, int64_t n2, int64_t stride2,
                         int variant, int mode, int flags, float* out, void* stream);
 
+/* ---- fused max-IoU assignment ----------------------------------------------------------
+ * mmdet-2.19 MaxIoUAssigner.assign_wrt_overlaps over overlaps = calculator(gt, anchors) WITHOUT materialising the
+ * (G, A) matrix (the reference path stores it: rotate_anchor_head.py:220-228 -> rotate_iou2d_calculator.py:42-43).
+ * Outputs (device): assigned_gt_inds (A) int64 [-1 ignore, 0 background, i+1 = GT i]; optional (may be NULL)
+ * max_overlaps (A), argmax_overlaps (A), gt_max_overlaps (G), gt_argmax_overlaps (G).  Ties resolve to the lowest
+ * index like torch.max; with gt_max_assign_all every anchor whose overlap equals a GT's maximum is assigned to it. */
+int r3g_assign_workspace_bytes(int64_t G, int64_t A, size_t* bytes);
+int r3g_max_iou_assign_f32(const float* gt, int64_t G, int64_t gt_stride,
+                           const float* anchors, int64_t A, int64_t anchor_stride,
+                           int variant, int flags, float pos_iou_thr, float neg_iou_thr, float min_pos_iou,
+                           int match_low_quality, int gt_max_assign_all,
+                           int64_t* assigned_gt_inds, float* max_overlaps, int64_t* argmax_overlaps,
+                           float* gt_max_overlaps, int64_t* gt_argmax_overlaps,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
 /* counters of the last r3g_iou_matrix_f32 launch on this workspace (device-side, 4 x uint64 at the
  * start of the workspace): pairs passing the circumradius test, passing the separating-axis test,
  * re-evaluated by the strict path, total pairs.  For roofline accounting (bench.py). */

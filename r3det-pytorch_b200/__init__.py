@@ -11,9 +11,11 @@ Module map (reference module -> here):
   r3det/core/bbox/iou_calculators-> iou_calculators   RBboxOverlaps2D_v1/v2/v3, rbbox_overlaps_v1/v2/v3
   r3det/core/post_processing     -> bbox_nms_rotated  multiclass_nms_rotated
   r3det/ops/fr                   -> fr                FeatureRefineFunction, feature_refine, FR, FeatureRefineModule
+  (mmdet MaxIoUAssigner + calculator, fused; §8f) -> assign   max_iou_assign, FusedMaxIoUAssigner
   r3det/core/bbox/rtransforms    -> rtransforms       poly2obb, obb2poly, obb2hbb, hbb2obb, obb2xyxy, norm_angle, ...
 """
 from . import _lib  # noqa: F401
+from .assign import FusedMaxIoUAssigner, max_iou_assign  # noqa: F401
 from .bbox_nms_rotated import multiclass_nms_rotated  # noqa: F401
 from .box_iou_rotated import obb_overlaps  # noqa: F401
 from .fr import FR, FeatureRefineFunction, FeatureRefineModule, feature_refine  # noqa: F401

@@ -33,6 +33,9 @@ _SIGNATURES = {
     "r3g_iou_prepare_f32": (_i32, [_vp, _i64, _i64, _vp, _i64, _i64, _i32, _vp, _sz, _vp]),
     "r3g_iou_matrix_prepared_f32": (_i32, [_vp, _i64, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _sz, _vp]),
     "r3g_iou_aligned_f32": (_i32, [_vp, _i64, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _vp, _vp]),
+    "r3g_assign_workspace_bytes": (_i32, [_i64, _i64, C.POINTER(_sz)]),
+    "r3g_max_iou_assign_f32": (_i32, [_vp, _i64, _i64, _vp, _i64, _i64, _i32, _i32, _f32, _f32, _f32, _i32, _i32,
+                                      _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "r3g_nms_workspace_bytes": (_i32, [_i64, C.POINTER(_sz)]),
     "r3g_nms_f32": (_i32, [_vp, _i64, _vp, _vp, _i64, _f32, _i32, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
     "r3g_mc_candidates_workspace_bytes": (_i32, [_i64, _i32, C.POINTER(_sz)]),

@@ -1,0 +1,93 @@
+"""Fused max-IoU assignment — the consumer side of the IoU calculators.
+
+In the reference, mmdet-2.19's ``MaxIoUAssigner`` calls ``RBboxOverlaps2D_v*`` for the full (G, A) matrix
+(800 MB for 1000 x 200k) and then reduces it with ``max`` over both axes
+(caller: r3det/models/dense_heads/rotate_anchor_head.py:220-228; assign_wrt_overlaps semantics recalled in SURVEY.md A6).
+``max_iou_assign`` does the same assignment in one C call without materialising the matrix; the overlaps it reduces
+are the matrix kernel's values bit for bit.  ``FusedMaxIoUAssigner`` wraps it behind MaxIoUAssigner's constructor and
+``assign`` signature and registers itself in mmdet's BBOX_ASSIGNERS when mmdet is importable.
+Not supported (raise): ``ignore_iof_thr >= 0`` with gt_bboxes_ignore, tuple ``neg_iou_thr``, ``gpu_assign_thr``."""
+import ctypes as C
+from collections import namedtuple
+
+import torch
+
+from . import _lib as L
+
+AssignOutput = namedtuple('AssignOutput', 'num_gts gt_inds max_overlaps labels argmax_overlaps gt_max_overlaps gt_argmax_overlaps')
+
+
+def max_iou_assign(gt_bboxes, bboxes, pos_iou_thr, neg_iou_thr, min_pos_iou=0.0, match_low_quality=True,
+                   gt_max_assign_all=True, variant='v1', gt_labels=None, flags=L.FLAG_STRICT):
+    """Assign each of the A `bboxes` (anchors) to a GT index + 1, 0 (background) or -1 (ignore).
+
+    Returns AssignOutput(num_gts, gt_inds (A,) int64, max_overlaps (A,), labels (A,) or None,
+    argmax_overlaps (A,), gt_max_overlaps (G,), gt_argmax_overlaps (G,))."""
+    L.require_cuda(bboxes)
+    anchors, sa = L.as_f32_rows(bboxes)
+    A = anchors.size(0)
+    dev = anchors.device
+    if gt_bboxes is None or gt_bboxes.numel() == 0:
+        gt, sg, G = None, 5, 0
+    else:
+        L.require_cuda(gt_bboxes)
+        gt, sg = L.as_f32_rows(gt_bboxes)
+        G = gt.size(0)
+    assigned = torch.empty((A,), dtype=torch.int64, device=dev)
+    max_ov = torch.empty((A,), dtype=torch.float32, device=dev)
+    argmax = torch.empty((A,), dtype=torch.int64, device=dev)
+    gt_max = torch.empty((G,), dtype=torch.float32, device=dev)
+    gt_arg = torch.empty((G,), dtype=torch.int64, device=dev)
+    if A:
+        lib = L.lib()
+        need = C.c_size_t(0)
+        L.check(lib.r3g_assign_workspace_bytes(G, A, C.byref(need)))
+        ws = L.workspace(need.value, dev)
+        with L.device_guard(dev):
+            L.check(lib.r3g_max_iou_assign_f32(L.ptr(gt), G, sg, L.ptr(anchors), A, sa, L.V[variant], flags,
+                                               float(pos_iou_thr), float(neg_iou_thr), float(min_pos_iou),
+                                               int(bool(match_low_quality)), int(bool(gt_max_assign_all)),
+                                               L.ptr(assigned), L.ptr(max_ov), L.ptr(argmax), L.ptr(gt_max), L.ptr(gt_arg),
+                                               L.ptr(ws), ws.numel(), L.stream_ptr(dev)))
+    labels = None
+    if gt_labels is not None:
+        labels = assigned.new_full((A,), -1)
+        pos = assigned > 0
+        if G:
+            labels[pos] = gt_labels.to(dev)[assigned[pos] - 1]
+    return AssignOutput(G, assigned, max_ov, labels, argmax, gt_max, gt_arg)
+
+
+class FusedMaxIoUAssigner(object):
+    """MaxIoUAssigner with the IoU calculator fused in (same constructor arguments; `iou_calculator` selects the variant)."""
+
+    def __init__(self, pos_iou_thr, neg_iou_thr, min_pos_iou=.0, gt_max_assign_all=True, ignore_iof_thr=-1,
+                 ignore_wrt_candidates=True, match_low_quality=True, gpu_assign_thr=-1,
+                 iou_calculator=dict(type='RBboxOverlaps2D_v1')):
+        if isinstance(neg_iou_thr, (tuple, list)):
+            raise NotImplementedError('FusedMaxIoUAssigner: tuple neg_iou_thr is not supported')
+        kind = iou_calculator['type'] if isinstance(iou_calculator, dict) else type(iou_calculator).__name__
+        self.variant = {'RBboxOverlaps2D_v1': 'v1', 'RBboxOverlaps2D_v2': 'v2', 'RBboxOverlaps2D_v3': 'v3'}[kind]
+        self.pos_iou_thr, self.neg_iou_thr, self.min_pos_iou = pos_iou_thr, neg_iou_thr, min_pos_iou
+        self.gt_max_assign_all, self.match_low_quality = gt_max_assign_all, match_low_quality
+        self.ignore_iof_thr = ignore_iof_thr
+
+    def assign(self, bboxes, gt_bboxes, gt_bboxes_ignore=None, gt_labels=None):
+        if self.ignore_iof_thr > 0 and gt_bboxes_ignore is not None and gt_bboxes_ignore.numel() > 0:
+            raise NotImplementedError('FusedMaxIoUAssigner: ignore regions are not supported')
+        strip = lambda b: b[..., :5] if b is not None and b.size(-1) == 6 else b
+        flags = L.FLAG_STRICT | (L.FLAG_SMALL_MASK if self.variant == 'v3' else 0)
+        out = max_iou_assign(strip(gt_bboxes), strip(bboxes), self.pos_iou_thr, self.neg_iou_thr, self.min_pos_iou,
+                             self.match_low_quality, self.gt_max_assign_all, self.variant, gt_labels, flags)
+        try:  # pragma: no cover - mmdet is not installed in the build image
+            from mmdet.core.bbox.assigners import AssignResult
+            return AssignResult(out.num_gts, out.gt_inds, out.max_overlaps, labels=out.labels)
+        except Exception:  # noqa: BLE001
+            return out
+
+
+try:  # pragma: no cover
+    from mmdet.core.bbox.builder import BBOX_ASSIGNERS
+    BBOX_ASSIGNERS.register_module(name='FusedMaxIoUAssigner', force=True)(FusedMaxIoUAssigner)
+except Exception:  # noqa: BLE001
+    pass

@@ -88,7 +88,41 @@ struct IouArgs {
     float tau;
     float* out;
     unsigned long long* stats;      // [0..3] counters, [4] item ticket
+    // fused assigner (OUT = 1, 2): packed (iou bits << 32 | ~index) running maxima, and the low-quality match table
+    unsigned long long* col_best;   // per column (anchor): best row (GT)
+    unsigned long long* row_best;   // per row (GT): best column (anchor)
+    int* lowq;                      // per column: largest (row + 1) whose overlap equals that row's maximum
+    float min_pos_iou;
 };
+
+// OUT selects what the kernel does with the overlaps it computes:
+//   0  store the (M, N) matrix                                         (RBboxOverlaps2D_v*)
+//   1  fused assigner pass 1: per-column and per-row max / argmax, no matrix (MaxIoUAssigner's two reductions)
+//   2  fused assigner pass 2: columns whose overlap with a row EQUALS that row's maximum (gt_max_assign_all)
+enum { OUT_MATRIX = 0, OUT_ASSIGN_MAX = 1, OUT_ASSIGN_TIES = 2 };
+
+__device__ __forceinline__ unsigned long long pack_best(float v, int idx) {
+    return ((unsigned long long)__float_as_uint(fmaxf(v, 0.0f)) << 32) | (unsigned)(0xFFFFFFFFu - (unsigned)idx);
+}
+__device__ __forceinline__ void update_best(unsigned long long* slot, unsigned long long cand) {
+    // the maxima settle after a few updates: read first (L2), issue the atomic only when it would change the slot
+    if (cand > __ldcg(slot)) atomicMax(slot, cand);
+}
+
+template <int OUT>
+__device__ __forceinline__ void emit_overlap(const IouArgs& A, int i, int j, float r) {
+    if (OUT == OUT_MATRIX) {
+        A.out[(int64_t)i * A.n + j] = r;
+    } else if (OUT == OUT_ASSIGN_MAX) {
+        if (r > 0.0f) {
+            update_best(A.col_best + j, pack_best(r, i));
+            update_best(A.row_best + i, pack_best(r, j));
+        }
+    } else {
+        const float gm = __uint_as_float((unsigned)(__ldcg(A.row_best + i) >> 32));
+        if (r == gm && gm >= A.min_pos_iou) atomicMax(A.lowq + j, i + 1);
+    }
+}
 
 __device__ __forceinline__ float4 ldg4(const void* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
@@ -119,7 +153,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 __device__ __forceinline__ BoxP0 as_p0(float4 v) { BoxP0 b = { v.x, v.y, v.z, v.w }; return b; }
 __device__ __forceinline__ BoxP1 as_p1(float4 v) { BoxP1 b = { v.x, v.y, v.z, v.w }; return b; }
 
-template <bool VEC>
+template <bool VEC, int OUT>
 __global__ void __launch_bounds__(IOU_THREADS, R3G_IOU_MINB) iou_matrix_kernel(const IouArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const unsigned warp = threadIdx.x >> 5, lane = lane_id();
@@ -136,6 +170,7 @@ __global__ void __launch_bounds__(IOU_THREADS, R3G_IOU_MINB) iou_matrix_kernel(c
 
     int i0 = 0, j0 = 0, i1 = 0, ig = 0, jb = 0;
     float cx[IOU_CPL], cy[IOU_CPL], cr[IOU_CPL], ck[IOU_CPL];
+    float cm[IOU_CPL] = { 0.f, 0.f, 0.f, 0.f };     // OUT_ASSIGN_TIES: the columns' best overlap (from pass 1)
     bool full4 = false;
     float* orow = A.out;
     bool flush = true, done = false;       // start by fetching an item
@@ -153,7 +188,7 @@ __global__ void __launch_bounds__(IOU_THREADS, R3G_IOU_MINB) iou_matrix_kernel(c
                     const float4 a1 = ldg4(A.r1 + e.x), b1 = ldg4(A.c1 + e.y);
                     if (fminf(a1.z, a1.w) * 2.0f < 0.001f || fminf(b1.z, b1.w) * 2.0f < 0.001f) r = 0.0f;
                 }
-                A.out[(int64_t)e.x * A.n + e.y] = r;
+                emit_overlap<OUT>(A, (int)e.x, (int)e.y, r);
             }
             __syncwarp();
             c3 -= nb;
@@ -175,7 +210,7 @@ __global__ void __launch_bounds__(IOU_THREADS, R3G_IOU_MINB) iou_matrix_kernel(c
                 const BoxP1 A1 = as_p1(W.r1[il]), B1 = as_p1(W.c1[jl]);
                 float r = pair_overlap(A0, A1, B0, B1, A.variant, A.mode, A.tau, risk);
                 if (A.small_mask && (fminf(A1.hw, A1.hh) * 2.0f < 0.001f || fminf(B1.hw, B1.hh) * 2.0f < 0.001f)) r = 0.0f;
-                if (!risk && r != 0.0f) A.out[(int64_t)i * A.n + j] = r;
+                if (!risk && r != 0.0f) emit_overlap<OUT>(A, i, j, r);
             }
             __syncwarp();
             c2 -= nb;
@@ -240,7 +275,12 @@ __global__ void __launch_bounds__(IOU_THREADS, R3G_IOU_MINB) iou_matrix_kernel(c
                 }
             }
             full4 = VEC && (jb + IOU_CPL <= A.n);
-            orow = A.out + (int64_t)i0 * A.n + jb;
+            if (OUT == OUT_MATRIX) orow = A.out + (int64_t)i0 * A.n + jb;
+            if (OUT == OUT_ASSIGN_TIES) {
+#pragma unroll
+                for (int k = 0; k < IOU_CPL; k++)
+                    cm[k] = (jb + k < A.n) ? __uint_as_float((unsigned)(__ldcg(A.col_best + jb + k) >> 32)) : -1.0f;
+            }
             flush = false;
             continue;
         }
@@ -262,15 +302,27 @@ __global__ void __launch_bounds__(IOU_THREADS, R3G_IOU_MINB) iou_matrix_kernel(c
                         s = fmaf(a.z, cr[k], s);
                         m = __funnelshift_l(__float_as_uint(s), m, 1);
                     }
-                    if (full4) {
-                        st_cs_f4(orow, make_float4(0.f, 0.f, 0.f, 0.f));
-                    } else {
+                    if (OUT == OUT_MATRIX) {
+                        if (full4) {
+                            st_cs_f4(orow, make_float4(0.f, 0.f, 0.f, 0.f));
+                        } else {
 #pragma unroll
-                        for (int k = 0; k < IOU_CPL; k++)
-                            if (jb + k < A.n) st_cs_f1(orow + k, 0.f);
+                            for (int k = 0; k < IOU_CPL; k++)
+                                if (jb + k < A.n) st_cs_f1(orow + k, 0.f);
+                        }
+                        orow += A.n;
                     }
-                    orow += A.n;
                 }
+            }
+            if (OUT == OUT_ASSIGN_TIES && m != 0) {
+                // a pair can equal its row's maximum only if the column's own maximum reaches it: prunes almost everything
+                unsigned allow = 0;
+                for (int r = 0; r < nr; r++) {
+                    const float gm = __uint_as_float((unsigned)(__ldcg(A.row_best + ig + r) >> 32));
+#pragma unroll
+                    for (int k = 0; k < IOU_CPL; k++) allow = (allow << 1) | ((cm[k] >= gm && gm > 0.0f) ? 1u : 0u);
+                }
+                m &= allow;
             }
             // compact the group's survivors: warp scan of popc, then each lane emits its own bits (row-major order)
             const int cnt = __popc(m);
@@ -362,6 +414,25 @@ R3G_API int r3g_iou_workspace_bytes(int64_t m, int64_t n, size_t* bytes) {
     return R3G_OK;
 }
 
+// Launch the pair sweep in one of its output modes (persistent grid = SMs x occupancy, dynamic item tickets).
+template <bool VEC, int OUT>
+static int launch_sweep(const IouArgs& a, cudaStream_t st) {
+    const size_t smem = sizeof(WarpSmem) * IOU_WARPS;
+    static int occ = 0;
+    if (occ == 0) {
+        R3G_CUDA_OK(cudaFuncSetAttribute(iou_matrix_kernel<VEC, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        R3G_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, iou_matrix_kernel<VEC, OUT>, IOU_THREADS, smem));
+        if (occ < 1) occ = 1;
+    }
+    const int64_t items = (((int64_t)a.m + IOU_TM - 1) / IOU_TM) * (((int64_t)a.n + IOU_TN - 1) / IOU_TN);
+    int64_t grid = (items + IOU_WARPS - 1) / IOU_WARPS;
+    const int64_t cap = (int64_t)device_sm_count() * occ;
+    if (grid > cap) grid = cap;
+    iou_matrix_kernel<VEC, OUT><<<(unsigned)grid, IOU_THREADS, smem, st>>>(a);
+    R3G_LAUNCH_OK("iou_matrix_kernel");
+    return R3G_OK;
+}
+
 static int iou_check_common(const char* who, int64_t m, int64_t n, int variant, int mode) {
     R3G_REQUIRE(m >= 0 && n >= 0, "%s: negative size", who);
     R3G_REQUIRE(variant >= 1 && variant <= 3, "%s: variant must be 1, 2 or 3 (got %d)", who, variant);
@@ -413,27 +484,10 @@ R3G_API int r3g_iou_matrix_prepared_f32(const float* boxes1, int64_t m, int64_t 
     a.tau = (flags & R3G_FLAG_EMULATE_ALL) ? 1e30f : ((flags & R3G_FLAG_STRICT) ? 2e-2f : 0.0f);
     a.out = out; a.stats = w.stats;
 
+    a.col_best = nullptr; a.row_best = nullptr; a.lowq = nullptr; a.min_pos_iou = 0.0f;
     const bool vec = (n % 4 == 0) && (((uintptr_t)out & 15u) == 0);
-    const size_t smem = sizeof(WarpSmem) * IOU_WARPS;
-    static int occ_vec = 0, occ_scl = 0;
-    int& occ = vec ? occ_vec : occ_scl;
-    if (occ == 0) {
-        if (vec) {
-            R3G_CUDA_OK(cudaFuncSetAttribute(iou_matrix_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            R3G_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, iou_matrix_kernel<true>, IOU_THREADS, smem));
-        } else {
-            R3G_CUDA_OK(cudaFuncSetAttribute(iou_matrix_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            R3G_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, iou_matrix_kernel<false>, IOU_THREADS, smem));
-        }
-        if (occ < 1) occ = 1;
-    }
-    const int64_t items = ((m + IOU_TM - 1) / IOU_TM) * ((n + IOU_TN - 1) / IOU_TN);
-    int64_t grid = (items + IOU_WARPS - 1) / IOU_WARPS;
-    const int64_t cap = (int64_t)device_sm_count() * occ;
-    if (grid > cap) grid = cap;
-    if (vec) iou_matrix_kernel<true><<<(unsigned)grid, IOU_THREADS, smem, st>>>(a);
-    else iou_matrix_kernel<false><<<(unsigned)grid, IOU_THREADS, smem, st>>>(a);
-    R3G_LAUNCH_OK("iou_matrix_kernel");
+    rc = vec ? launch_sweep<true, OUT_MATRIX>(a, st) : launch_sweep<false, OUT_MATRIX>(a, st);
+    if (rc != R3G_OK) return rc;
     return R3G_OK;
 }
 
@@ -466,5 +520,136 @@ R3G_API int r3g_iou_aligned_f32(const float* boxes1, int64_t n1, int64_t stride1
         boxes1, n1, stride1, boxes2, n2, stride2, variant, mode, (flags & R3G_FLAG_EMULATE_ALL) ? 1e30f : ((flags & R3G_FLAG_STRICT) ? 2e-2f : 0.0f),
         (variant == R3G_V3 && (flags & R3G_FLAG_SMALL_MASK)) ? 1 : 0, out);
     R3G_LAUNCH_OK("iou_aligned_kernel");
+    return R3G_OK;
+}
+
+// ---- fused assigner --------------------------------------------------------------------------------------------------
+// mmdet-2.19 MaxIoUAssigner.assign_wrt_overlaps around the reference's calculator call (caller:
+// r3det/models/dense_heads/rotate_anchor_head.py:220-228; semantics recalled in SURVEY.md A6) without materialising the
+// (G, A) overlap matrix: pass 1 keeps the per-anchor and per-GT max/argmax as packed 64-bit atomics, pass 2 (only for
+// gt_max_assign_all) re-visits the few pairs whose column maximum reaches their row maximum to find exact ties, and a
+// finalize kernel applies the thresholds.  The IoU values are the matrix kernel's, bit for bit (same code path).
+namespace r3g {
+
+__global__ void assign_init_kernel(unsigned long long* col_best, int64_t A, unsigned long long* row_best, int64_t G, int* lowq) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long zero_first = 0xFFFFFFFFull;            // overlap 0, index 0 (torch.max returns the first maximum)
+    if (t < A) { col_best[t] = zero_first; lowq[t] = 0; }
+    if (t < G) row_best[t] = zero_first;
+}
+
+// per GT: low-quality matching that does not need the tie pass
+//   gt_max_assign_all == 0: assigned[gt_argmax[i]] = i + 1 for gt_max[i] >= min_pos_iou        (later GTs win)
+//   gt_max[i] == 0 with min_pos_iou <= 0: `overlaps[i, :] == gt_max[i]` holds for EVERY anchor (mmdet quirk)
+__global__ void assign_gt_kernel(const unsigned long long* __restrict__ row_best, int64_t G, float min_pos_iou,
+                                 int assign_all, int* lowq, int* zero_gt, float* gt_max, int64_t* gt_argmax) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= G) return;
+    const unsigned long long b = row_best[i];
+    const float v = __uint_as_float((unsigned)(b >> 32));
+    const int arg = (int)(0xFFFFFFFFu - (unsigned)(b & 0xFFFFFFFFull));
+    if (gt_max) gt_max[i] = v;
+    if (gt_argmax) gt_argmax[i] = arg;
+    if (v >= min_pos_iou) {
+        if (!assign_all) atomicMax(lowq + arg, (int)i + 1);
+        else if (v == 0.0f) atomicMax(zero_gt, (int)i + 1);
+    }
+}
+
+__global__ void assign_finalize_kernel(const unsigned long long* __restrict__ col_best, const int* __restrict__ lowq,
+                                       const int* __restrict__ zero_gt, int64_t A, int64_t G, float pos_thr, float neg_thr,
+                                       int match_low_quality, int64_t* assigned, float* max_overlaps, int64_t* argmax) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= A) return;
+    if (G == 0) {                                                    // no GT: everything is background
+        assigned[j] = 0; if (max_overlaps) max_overlaps[j] = 0.0f; if (argmax) argmax[j] = 0;
+        return;
+    }
+    const unsigned long long b = col_best[j];
+    const float v = __uint_as_float((unsigned)(b >> 32));
+    const int arg = (int)(0xFFFFFFFFu - (unsigned)(b & 0xFFFFFFFFull));
+    int64_t a = -1;
+    if (v >= 0.0f && v < neg_thr) a = 0;
+    if (v >= pos_thr) a = arg + 1;
+    if (match_low_quality) {
+        const int lq = max(lowq[j], zero_gt[0]);
+        if (lq > 0) a = lq;
+    }
+    assigned[j] = a;
+    if (max_overlaps) max_overlaps[j] = v;
+    if (argmax) argmax[j] = arg;
+}
+
+struct AssignWs { IouWorkspace iou; unsigned long long *col_best, *row_best; int *lowq, *zero_gt; size_t bytes; };
+
+static AssignWs carve_assign(void* ws, int64_t G, int64_t A) {
+    AssignWs w;
+    w.iou = carve(ws, G, A);
+    char* p = (char*)ws;
+    size_t off = w.iou.bytes;
+    w.col_best = (unsigned long long*)(p + off); off += align_up(8 * (size_t)(A > 0 ? A : 1), 256);
+    w.row_best = (unsigned long long*)(p + off); off += align_up(8 * (size_t)(G > 0 ? G : 1), 256);
+    w.lowq = (int*)(p + off); off += align_up(4 * (size_t)(A > 0 ? A : 1), 256);
+    w.zero_gt = (int*)(p + off); off += 256;
+    w.bytes = off;
+    return w;
+}
+
+}  // namespace r3g
+
+R3G_API int r3g_assign_workspace_bytes(int64_t G, int64_t A, size_t* bytes) {
+    R3G_REQUIRE(bytes != nullptr && G >= 0 && A >= 0, "r3g_assign_workspace_bytes: bad arguments");
+    *bytes = carve_assign(nullptr, G, A).bytes;
+    return R3G_OK;
+}
+
+R3G_API int r3g_max_iou_assign_f32(const float* gt, int64_t G, int64_t gt_stride,
+                                   const float* anchors, int64_t A, int64_t anchor_stride,
+                                   int variant, int flags, float pos_iou_thr, float neg_iou_thr, float min_pos_iou,
+                                   int match_low_quality, int gt_max_assign_all,
+                                   int64_t* assigned_gt_inds, float* max_overlaps, int64_t* argmax_overlaps,
+                                   float* gt_max_overlaps, int64_t* gt_argmax_overlaps,
+                                   void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = iou_check_common("r3g_max_iou_assign_f32", G, A, variant, R3G_MODE_IOU);
+    if (rc != R3G_OK) return rc;
+    if (A == 0) return R3G_OK;
+    R3G_REQUIRE(anchors && assigned_gt_inds && workspace, "r3g_max_iou_assign_f32: null pointer");
+    R3G_REQUIRE(G == 0 || gt != nullptr, "r3g_max_iou_assign_f32: null gt");
+    AssignWs w = carve_assign(workspace, G, A);
+    if (workspace_bytes < w.bytes) {
+        set_error("r3g_max_iou_assign_f32: workspace too small (%zu < %zu)", workspace_bytes, w.bytes);
+        return R3G_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int tpb = 256;
+    const int64_t mx = A > G ? A : G;
+    assign_init_kernel<<<(unsigned)((mx + tpb - 1) / tpb), tpb, 0, st>>>(w.col_best, A, w.row_best, G, w.lowq);
+    R3G_CUDA_OK(cudaMemsetAsync(w.zero_gt, 0, 256, st));
+    if (G > 0) {
+        rc = r3g_iou_prepare_f32(gt, G, gt_stride, anchors, A, anchor_stride, variant, workspace, w.iou.bytes, stream);
+        if (rc != R3G_OK) return rc;
+        IouArgs a;
+        a.r0 = w.iou.r0; a.r1 = w.iou.r1; a.r2 = w.iou.r2; a.m = (int)G; a.c0 = w.iou.c0; a.c1 = w.iou.c1; a.n = (int)A;
+        a.raw1 = gt; a.s1 = gt_stride; a.raw2 = anchors; a.s2 = anchor_stride; a.origin_box = gt;
+        a.variant = variant; a.mode = R3G_MODE_IOU;
+        a.small_mask = (variant == R3G_V3 && (flags & R3G_FLAG_SMALL_MASK)) ? 1 : 0;
+        a.tau = (flags & R3G_FLAG_EMULATE_ALL) ? 1e30f : ((flags & R3G_FLAG_STRICT) ? 2e-2f : 0.0f);
+        a.out = nullptr; a.stats = w.iou.stats;
+        a.col_best = w.col_best; a.row_best = w.row_best; a.lowq = w.lowq; a.min_pos_iou = min_pos_iou;
+        R3G_CUDA_OK(cudaMemsetAsync(w.iou.stats, 0, 256, st));
+        rc = launch_sweep<false, OUT_ASSIGN_MAX>(a, st);
+        if (rc != R3G_OK) return rc;
+        assign_gt_kernel<<<(unsigned)((G + tpb - 1) / tpb), tpb, 0, st>>>(w.row_best, G, min_pos_iou, gt_max_assign_all,
+                                                                        w.lowq, w.zero_gt, gt_max_overlaps, gt_argmax_overlaps);
+        if (match_low_quality && gt_max_assign_all) {
+            R3G_CUDA_OK(cudaMemsetAsync(w.iou.stats, 0, 256, st));
+            rc = launch_sweep<false, OUT_ASSIGN_TIES>(a, st);
+            if (rc != R3G_OK) return rc;
+        }
+    }
+    assign_finalize_kernel<<<(unsigned)((A + tpb - 1) / tpb), tpb, 0, st>>>(w.col_best, w.lowq, w.zero_gt, A, G, pos_iou_thr,
+                                                                         neg_iou_thr, match_low_quality, assigned_gt_inds,
+                                                                         max_overlaps, argmax_overlaps);
+    R3G_LAUNCH_OK("assign kernels");
     return R3G_OK;
 }

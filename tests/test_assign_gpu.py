@@ -1,0 +1,73 @@
+"""Fused max-IoU assignment vs a torch restatement of mmdet-2.19 MaxIoUAssigner.assign_wrt_overlaps applied to OUR
+overlap matrix (the fused kernel reduces the very same values, so equality is exact, ties included)."""
+import numpy as np
+import pytest
+import torch
+
+from tests.util import anchors_1024, rand_obb
+
+pytestmark = pytest.mark.gpu
+
+
+def assign_wrt_overlaps(overlaps, pos_iou_thr, neg_iou_thr, min_pos_iou, match_low_quality, gt_max_assign_all):
+    """mmdet/core/bbox/assigners/max_iou_assigner.py (2.19) — recalled; SURVEY.md A6."""
+    G, A = overlaps.shape
+    assigned = overlaps.new_full((A,), -1, dtype=torch.long)
+    if G == 0:
+        assigned[:] = 0
+        return assigned, overlaps.new_zeros((A,))
+    max_ov, argmax = overlaps.max(dim=0)
+    gt_max, gt_argmax = overlaps.max(dim=1)
+    assigned[(max_ov >= 0) & (max_ov < neg_iou_thr)] = 0
+    pos = max_ov >= pos_iou_thr
+    assigned[pos] = argmax[pos] + 1
+    if match_low_quality:
+        for i in range(G):
+            if gt_max[i] >= min_pos_iou:
+                if gt_max_assign_all:
+                    assigned[overlaps[i, :] == gt_max[i]] = i + 1
+                else:
+                    assigned[gt_argmax[i]] = i + 1
+    return assigned, max_ov
+
+
+@pytest.mark.parametrize("v", ["v1", "v3"])
+@pytest.mark.parametrize("assign_all", [True, False])
+def test_against_matrix_reduction(cuda_dev, v, assign_all):
+    import r3det_b200 as R
+    t = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(cuda_dev)
+    cases = [(rand_obb(60, 1, v, 10, 300), anchors_1024(), 0.5, 0.4, 0.0),
+             (rand_obb(200, 2, v), rand_obb(5003, 3, v), 0.6, 0.5, 0.3),
+             (rand_obb(3, 4, v, 8, 16), rand_obb(1000, 5, v, 8, 16), 0.5, 0.4, 0.0)]      # GTs that overlap nothing
+    # a symmetric set: exact ties between anchors
+    g = np.array([[100, 100, 40, 40, 0.0]], np.float32)
+    an = np.array([[90, 100, 40, 40, 0.0], [110, 100, 40, 40, 0.0], [100, 90, 40, 40, 0.0], [300, 300, 10, 10, 0.0]], np.float32)
+    cases.append((g, an, 0.9, 0.4, 0.0))
+    for gt, an, pos, neg, minpos in cases:
+        G_, A_ = t(gt), t(an)
+        if v == "v1":
+            G_ = R.obb2hbb(G_, "v1") if gt.shape[0] > 3 else G_
+        ov = R.pairwise_iou(G_, A_, v)
+        want, want_max = assign_wrt_overlaps(ov, pos, neg, minpos, True, assign_all)
+        out = R.max_iou_assign(G_, A_, pos, neg, minpos, True, assign_all, v)
+        assert torch.equal(out.max_overlaps, want_max)
+        assert torch.equal(out.argmax_overlaps, ov.max(dim=0)[1])
+        assert torch.equal(out.gt_max_overlaps, ov.max(dim=1)[0]) and torch.equal(out.gt_argmax_overlaps, ov.max(dim=1)[1])
+        assert torch.equal(out.gt_inds, want), (v, assign_all, gt.shape, int((out.gt_inds != want).sum()))
+        nolq = R.max_iou_assign(G_, A_, pos, neg, minpos, False, assign_all, v)
+        assert torch.equal(nolq.gt_inds, assign_wrt_overlaps(ov, pos, neg, minpos, False, assign_all)[0])
+
+
+def test_edge_cases_and_class(cuda_dev):
+    import r3det_b200 as R
+    an = torch.from_numpy(rand_obb(500, 1)).to(cuda_dev)
+    out = R.max_iou_assign(an[:0], an, 0.5, 0.4)
+    assert out.num_gts == 0 and (out.gt_inds == 0).all() and (out.max_overlaps == 0).all()
+    gt = torch.from_numpy(rand_obb(20, 2)).to(cuda_dev)
+    labels = torch.arange(20, device=cuda_dev) % 15
+    a = R.FusedMaxIoUAssigner(0.5, 0.4, min_pos_iou=0, iou_calculator=dict(type='RBboxOverlaps2D_v1'))
+    res = a.assign(an, gt, gt_labels=labels)
+    pos = res.gt_inds > 0
+    assert pos.any() and torch.equal(res.labels[pos], labels[res.gt_inds[pos] - 1]) and (res.labels[~pos] == -1).all()
+    with pytest.raises(NotImplementedError):
+        R.FusedMaxIoUAssigner(0.5, (0.1, 0.4))
