@@ -171,6 +171,7 @@ __global__ void __launch_bounds__(IOU_THREADS, R3G_IOU_MINB) iou_matrix_kernel(c
     int i0 = 0, j0 = 0, i1 = 0, ig = 0, jb = 0;
     float cx[IOU_CPL], cy[IOU_CPL], cr[IOU_CPL], ck[IOU_CPL];
     float cm[IOU_CPL] = { 0.f, 0.f, 0.f, 0.f };     // OUT_ASSIGN_TIES: the columns' best overlap (from pass 1)
+    float gm_lo = 0.f, gm_hi = 0.f, cmax_item = 0.f;  // OUT_ASSIGN_TIES: row maxima of the item, best column maximum
     bool full4 = false;
     float* orow = A.out;
     bool flush = true, done = false;       // start by fetching an item
@@ -280,6 +281,13 @@ __global__ void __launch_bounds__(IOU_THREADS, R3G_IOU_MINB) iou_matrix_kernel(c
 #pragma unroll
                 for (int k = 0; k < IOU_CPL; k++)
                     cm[k] = (jb + k < A.n) ? __uint_as_float((unsigned)(__ldcg(A.col_best + jb + k) >> 32)) : -1.0f;
+                // row maxima of the item (lane t holds rows t and t+32) and the best column maximum of the item:
+                // a row whose maximum exceeds every column maximum of the item cannot tie here and is skipped whole
+                gm_lo = (i0 + (int)lane < i1) ? __uint_as_float((unsigned)(__ldcg(A.row_best + i0 + lane) >> 32)) : 0.0f;
+                gm_hi = (i0 + 32 + (int)lane < i1) ? __uint_as_float((unsigned)(__ldcg(A.row_best + i0 + 32 + lane) >> 32)) : 0.0f;
+                cmax_item = fmaxf(fmaxf(cm[0], cm[1]), fmaxf(cm[2], cm[3]));
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) cmax_item = fmaxf(cmax_item, __shfl_xor_sync(0xffffffffu, cmax_item, o));
             }
             flush = false;
             continue;
@@ -293,6 +301,21 @@ __global__ void __launch_bounds__(IOU_THREADS, R3G_IOU_MINB) iou_matrix_kernel(c
 #pragma unroll
             for (int r = 0; r < IOU_RG; r++) {
                 if (r < nr) {
+                    if (OUT == OUT_ASSIGN_TIES) {
+                        static_assert(IOU_TM <= 64, "row maxima are cached two per lane");
+                        const int rl = ig - i0 + r;
+                        const float gm = __shfl_sync(0xffffffffu, rl < 32 ? gm_lo : gm_hi, rl & 31);
+                        if (!(gm > 0.0f) || gm > cmax_item) { m <<= IOU_CPL; continue; }      // warp-uniform skip
+                        const float4 a = ldg4(A.r2 + ig + r);
+#pragma unroll
+                        for (int k = 0; k < IOU_CPL; k++) {
+                            float s = fmaf(a.x, cx[k], ck[k] + a.w);
+                            s = fmaf(a.y, cy[k], s);
+                            s = fmaf(a.z, cr[k], s);
+                            m = (m << 1) | ((s < 0.0f && cm[k] >= gm) ? 1u : 0u);
+                        }
+                        continue;
+                    }
                     const float4 a = ldg4(A.r2 + ig + r);
 #pragma unroll
                     for (int k = 0; k < IOU_CPL; k++) {
@@ -313,16 +336,6 @@ __global__ void __launch_bounds__(IOU_THREADS, R3G_IOU_MINB) iou_matrix_kernel(c
                         orow += A.n;
                     }
                 }
-            }
-            if (OUT == OUT_ASSIGN_TIES && m != 0) {
-                // a pair can equal its row's maximum only if the column's own maximum reaches it: prunes almost everything
-                unsigned allow = 0;
-                for (int r = 0; r < nr; r++) {
-                    const float gm = __uint_as_float((unsigned)(__ldcg(A.row_best + ig + r) >> 32));
-#pragma unroll
-                    for (int k = 0; k < IOU_CPL; k++) allow = (allow << 1) | ((cm[k] >= gm && gm > 0.0f) ? 1u : 0u);
-                }
-                m &= allow;
             }
             // compact the group's survivors: warp scan of popc, then each lane emits its own bits (row-major order)
             const int cnt = __popc(m);
