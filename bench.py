@@ -388,6 +388,19 @@ def bench_nms(torch, R, dev, hbm):
         keep, num = fn()
         ms = _time(torch, fn, 5 if K >= 80000 else 20)
         out["sweep"][str(K)] = {"ms": ms, "mcands_per_s": K / ms / 1e3, "kept": int(num)}
+    # configs[3] per-GPU batch: 8 images x K candidates in ONE launch sequence ((image, class) pairs are segments)
+    out["batch8"] = {}
+    for K in (2000, 8000, 20000):
+        imgs = [clustered(K, 100 + i, "v1") for i in range(8)]
+        B = torch.from_numpy(np.concatenate([x[0] for x in imgs])).to(dev)
+        S = torch.from_numpy(np.concatenate([x[1] for x in imgs])).to(dev)
+        Lb = torch.from_numpy(np.concatenate([x[2] for x in imgs])).to(dev)
+        bid = torch.arange(8, device=dev).repeat_interleave(K)
+        scales = torch.tensor([float(x[0].max() + 1) for x in imgs], device=dev)
+        fn = lambda: nms_device(B, S, 0.1, "v1", labels=Lb, class_offset=scales, order_index=True, batch_ids=bid, n_batches=8)
+        keep, num = fn()
+        ms = _time(torch, fn, 10)
+        out["batch8"][str(K)] = {"ms": ms, "mcands_per_s": 8 * K / ms / 1e3, "kept": int(num.sum())}
     return out
 
 

@@ -112,6 +112,17 @@ int r3g_nms_f32(const float* boxes, int64_t stride, const float* scores, const i
                 int64_t* keep_out, int64_t* num_keep_out,
                 void* workspace, size_t workspace_bytes, void* stream);
 
+/* Multi-image form of r3g_nms_f32: one launch sequence for a whole batch of images (BASELINE configs[3]: images are
+ * independent, so (image, class) pairs are simply more segments).  batch_ids: (K) int64 in [0, n_batches) or NULL
+ * (n_batches = 1); labels < 65536 when batch_ids is given; class_offset: n_batches device floats (per-image scale) or
+ * NULL.  keep_out: kept original indices grouped by image — ascending index (R3G_NMS_ORDER_INDEX; candidates are
+ * expected to be concatenated image by image) or descending score within each image; num_keep_out: n_batches int64. */
+int r3g_nms_batched_f32(const float* boxes, int64_t stride, const float* scores, const int64_t* labels,
+                        const int64_t* batch_ids, int n_batches,
+                        int64_t K, float thr, int variant, int flags, const float* class_offset,
+                        int64_t* keep_out, int64_t* num_keep_out,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- multiclass candidate extraction -----------------------------------------------------------------------
  * replaces the torch prologue of multiclass_nms_rotated (r3det/core/post_processing/bbox_nms_rotated.py:34-41,
  * 98-103): candidates = (box, class) pairs with multi_scores[i, c] > score_thr for c < C (the last, background,

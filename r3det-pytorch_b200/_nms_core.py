@@ -7,12 +7,16 @@ from . import _lib as L
 
 
 def nms_device(boxes, scores, thr, variant, labels=None, class_offset=None, inclusive=False,
-               order_index=False, drop_small=False, strict=True):
+               order_index=False, drop_small=False, strict=True, batch_ids=None, n_batches=1):
     """Rotated NMS on CUDA tensors.
 
     boxes (K, >=5) f32, scores (K,) f32, labels (K,) int64 or None, class_offset: 0-dim CUDA f32 tensor or None.
     Returns (keep, num_keep): keep is a (K,) int64 CUDA tensor whose first num_keep (0-dim int64 CUDA tensor)
     entries are the kept original indices; no host synchronisation happens here.
+
+    Multi-image batches (one launch sequence for many images): batch_ids (K,) int64 in [0, n_batches) with the
+    candidates concatenated image by image, class_offset a (n_batches,) tensor of per-image scales; num_keep is then a
+    (n_batches,) int64 tensor and keep is grouped by image (index order or per-image score order).
     """
     L.require_cuda(boxes, scores)
     boxes, stride = L.as_f32_rows(boxes)
@@ -20,14 +24,19 @@ def nms_device(boxes, scores, thr, variant, labels=None, class_offset=None, incl
     K = boxes.size(0)
     dev = boxes.device
     keep = torch.empty((K,), dtype=torch.int64, device=dev)
-    num = torch.zeros((), dtype=torch.int64, device=dev)
+    num = torch.zeros((n_batches,) if batch_ids is not None else (), dtype=torch.int64, device=dev)
     if K == 0:
         return keep, num
+    if batch_ids is not None:
+        L.require_cuda(batch_ids)
+        batch_ids = batch_ids.to(torch.int64).contiguous()
     if labels is not None:
         L.require_cuda(labels)
         labels = labels.to(torch.int64).contiguous()
     if class_offset is not None:
-        class_offset = class_offset.to(device=dev, dtype=torch.float32).reshape(1).contiguous()
+        class_offset = class_offset.to(device=dev, dtype=torch.float32).reshape(-1).contiguous()
+        if class_offset.numel() != (n_batches if batch_ids is not None else 1):
+            raise ValueError('class_offset must hold one scale per image')
     flags = (L.NMS_INCLUSIVE if inclusive else 0) | (L.NMS_ORDER_INDEX if order_index else 0) | \
             (L.NMS_DROP_SMALL if drop_small else 0) | (L.NMS_STRICT if strict else 0)
     lib = L.lib()
@@ -35,9 +44,9 @@ def nms_device(boxes, scores, thr, variant, labels=None, class_offset=None, incl
     L.check(lib.r3g_nms_workspace_bytes(K, C.byref(nbytes)))
     ws = L.workspace(nbytes.value, dev)
     with L.device_guard(dev):
-        L.check(lib.r3g_nms_f32(L.ptr(boxes), stride, L.ptr(scores), L.ptr(labels), K, float(thr), L.V[variant], flags,
-                                L.ptr(class_offset), L.ptr(keep), C.c_void_p(num.data_ptr()), L.ptr(ws), ws.numel(),
-                                L.stream_ptr(dev)))
+        L.check(lib.r3g_nms_batched_f32(L.ptr(boxes), stride, L.ptr(scores), L.ptr(labels), L.ptr(batch_ids),
+                                        int(n_batches), K, float(thr), L.V[variant], flags, L.ptr(class_offset),
+                                        L.ptr(keep), C.c_void_p(num.data_ptr()), L.ptr(ws), ws.numel(), L.stream_ptr(dev)))
     return keep, num
 
 

@@ -96,13 +96,22 @@ __global__ void nms_keys_kernel(const float* __restrict__ scores, int K, unsigne
     if (i < K) { keyA[i] = score_key_desc(scores[i]); idx[i] = i; }
 }
 
-__global__ void nms_label_keys_kernel(const int64_t* __restrict__ labels, const int* __restrict__ ord_rank, int K,
-                                      unsigned* keyB, int* rank_iota) {
+// segment key of rank r: the label, or (label << 16 | image) for multi-image batches
+__global__ void nms_label_keys_kernel(const int64_t* __restrict__ labels, const int64_t* __restrict__ batch_ids,
+                                      const int* __restrict__ ord_rank, int K, unsigned* keyB, int* rank_iota) {
     int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r < K) {
-        keyB[r] = labels ? (unsigned)labels[ord_rank[r]] : 0u;
+        const int idx = ord_rank[r];
+        unsigned key = labels ? (unsigned)labels[idx] : 0u;
+        if (batch_ids) key = (key << 16) | ((unsigned)batch_ids[idx] & 0xffffu);
+        keyB[r] = key;
         rank_iota[r] = r;
     }
+}
+
+__global__ void nms_batch_keys_kernel(const int64_t* __restrict__ batch_ids, const int* __restrict__ order, int K, unsigned* key) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < K) key[r] = (unsigned)batch_ids[order[r]] & 0xffffu;
 }
 
 // Gather + prepare boxes in position order; class offsets in FP32 as the reference wrappers compute them:
@@ -110,6 +119,7 @@ __global__ void nms_label_keys_kernel(const int64_t* __restrict__ labels, const 
 __global__ void nms_gather_kernel(const float* __restrict__ boxes, int64_t stride, const int* __restrict__ ord_rank,
                                   const int* __restrict__ pos_rank, const unsigned* __restrict__ pos_label, int K,
                                   int variant, int drop_small, const float* __restrict__ class_offset, int has_labels,
+                                  int batched,
                                   BoxP0* p0, BoxP1* p1, float4* p2r, float4* p2c, float* raw, unsigned char* valid) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= K) return;
@@ -118,7 +128,9 @@ __global__ void nms_gather_kernel(const float* __restrict__ boxes, int64_t strid
     float x[5] = { b[0], b[1], b[2], b[3], b[4] };
     float off = 0.0f;
     if (class_offset != nullptr && has_labels) {
-        off = __fmul_rn((float)(int)pos_label[p], class_offset[0]);
+        const unsigned key = pos_label[p];
+        const float scale = batched ? class_offset[key & 0xffffu] : class_offset[0];       // per-image offset scale
+        off = __fmul_rn((float)(int)(batched ? (key >> 16) : key), scale);
         x[0] = __fadd_rn(x[0], off);
         x[1] = __fadd_rn(x[1], off);
     }
@@ -518,11 +530,16 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_scan_kernel(const ScanArgs A)
 }
 
 __global__ void nms_emit_kernel(const int* __restrict__ flag, const int* __restrict__ pref, const int* __restrict__ ord_rank,
-                                int K, int order_index, int64_t* keep_out, int64_t* num_keep) {
+                                const int64_t* __restrict__ batch_ids, int K, int order_index, int64_t* keep_out,
+                                unsigned long long* num_keep) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= K) return;
-    if (flag[s]) keep_out[pref[s]] = order_index ? (int64_t)s : (int64_t)ord_rank[s];
-    if (s == K - 1) *num_keep = (int64_t)pref[s] + flag[s];
+    if (flag[s]) {
+        const int idx = order_index ? s : ord_rank[s];
+        keep_out[pref[s]] = (int64_t)idx;
+        if (batch_ids) atomicAdd(num_keep + batch_ids[idx], 1ull);       // per-image counts (zeroed by the launcher)
+    }
+    if (!batch_ids && s == K - 1) *num_keep = (unsigned long long)(pref[s] + flag[s]);
 }
 
 }  // namespace r3g
@@ -540,14 +557,23 @@ R3G_API int r3g_nms_f32(const float* boxes, int64_t stride, const float* scores,
                         int64_t K, float thr, int variant, int flags, const float* class_offset,
                         int64_t* keep_out, int64_t* num_keep_out,
                         void* workspace, size_t workspace_bytes, void* stream) {
+    return r3g_nms_batched_f32(boxes, stride, scores, labels, nullptr, 1, K, thr, variant, flags, class_offset,
+                               keep_out, num_keep_out, workspace, workspace_bytes, stream);
+}
+
+R3G_API int r3g_nms_batched_f32(const float* boxes, int64_t stride, const float* scores, const int64_t* labels,
+                                const int64_t* batch_ids, int n_batches,
+                                int64_t K, float thr, int variant, int flags, const float* class_offset,
+                                int64_t* keep_out, int64_t* num_keep_out,
+                                void* workspace, size_t workspace_bytes, void* stream) {
     R3G_REQUIRE(K >= 0 && K < (1ll << 30), "r3g_nms_f32: bad K");
+    R3G_REQUIRE(n_batches >= 1 && n_batches <= 65535, "r3g_nms_batched_f32: n_batches must be in [1, 65535]");
+    R3G_REQUIRE(batch_ids != nullptr || n_batches == 1, "r3g_nms_batched_f32: n_batches > 1 needs batch_ids");
     R3G_REQUIRE(variant >= 1 && variant <= 3, "r3g_nms_f32: variant must be 1, 2 or 3 (got %d)", variant);
     R3G_REQUIRE(num_keep_out != nullptr, "r3g_nms_f32: null num_keep_out");
     cudaStream_t st = (cudaStream_t)stream;
-    if (K == 0) {
-        R3G_CUDA_OK(cudaMemsetAsync(num_keep_out, 0, sizeof(int64_t), st));
-        return R3G_OK;
-    }
+    R3G_CUDA_OK(cudaMemsetAsync(num_keep_out, 0, sizeof(int64_t) * (size_t)n_batches, st));
+    if (K == 0) return R3G_OK;
     R3G_REQUIRE(boxes && scores && keep_out && workspace, "r3g_nms_f32: null pointer");
     R3G_REQUIRE(stride >= 5, "r3g_nms_f32: box stride must be >= 5 floats");
     NmsWs w = carve_nms(workspace, K);
@@ -564,9 +590,16 @@ R3G_API int r3g_nms_f32(const float* boxes, int64_t stride, const float* scores,
     nms_keys_kernel<<<gK, tpb, 0, st>>>(scores, Ki, w.keyA, w.ord_tmp);
     size_t tb = w.cub_bytes;
     R3G_CUDA_OK(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, w.keyA, w.keyA2, w.ord_tmp, w.ord_rank, Ki, 0, 32, st));
-    // 2. position order: stable by label on top of the rank order
-    nms_label_keys_kernel<<<gK, tpb, 0, st>>>(labels, w.ord_rank, Ki, w.keyB, w.pos_tmp);
-    if (labels) {
+    if (batch_ids) {
+        // multi-image batch: rank order becomes (image asc, score desc) by a stable 16-bit pass over the image id
+        nms_batch_keys_kernel<<<gK, tpb, 0, st>>>(batch_ids, w.ord_rank, Ki, w.keyA);
+        R3G_CUDA_OK(cudaMemcpyAsync(w.ord_tmp, w.ord_rank, 4 * (size_t)Ki, cudaMemcpyDeviceToDevice, st));
+        tb = w.cub_bytes;
+        R3G_CUDA_OK(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, w.keyA, w.keyA2, w.ord_tmp, w.ord_rank, Ki, 0, 16, st));
+    }
+    // 2. position order: stable by segment key (label, or label and image) on top of the rank order
+    nms_label_keys_kernel<<<gK, tpb, 0, st>>>(labels, batch_ids, w.ord_rank, Ki, w.keyB, w.pos_tmp);
+    if (labels || batch_ids) {
         tb = w.cub_bytes;
         R3G_CUDA_OK(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, w.keyB, w.pos_label, w.pos_tmp, w.pos_rank, Ki, 0, 32, st));
     } else {
@@ -576,7 +609,7 @@ R3G_API int r3g_nms_f32(const float* boxes, int64_t stride, const float* scores,
     // 3. gather + prepare
     nms_gather_kernel<<<gK, tpb, 0, st>>>(boxes, stride, w.ord_rank, w.pos_rank, w.pos_label, Ki, variant,
                                           (flags & R3G_NMS_DROP_SMALL) ? 1 : 0, class_offset, labels ? 1 : 0,
-                                          w.p0, w.p1, w.p2r, w.p2c, w.raw, w.valid);
+                                          batch_ids ? 1 : 0, w.p0, w.p1, w.p2r, w.p2c, w.raw, w.valid);
     // 4. block / segment structure
     nms_blocks_kernel<<<(nblk + 1 + tpb - 1) / tpb, tpb, 0, st>>>(w.pos_label, Ki, nblk, w.blk_end, w.nw, w.ng);
     tb = w.cub_bytes;
@@ -626,14 +659,15 @@ R3G_API int r3g_nms_f32(const float* boxes, int64_t stride, const float* scores,
         smem_set = 200 * 1024;
     }
     int sgrid = device_sm_count() * 2;
-    if (!labels) sgrid = 1;
+    if (!labels && !batch_ids) sgrid = 1;
     nms_scan_kernel<<<sgrid, NMS_THREADS, smem, st>>>(sa);
     R3G_LAUNCH_OK("nms_scan_kernel");
 
     // 7. compaction in the requested order
     tb = w.cub_bytes;
     R3G_CUDA_OK(cub::DeviceScan::ExclusiveSum(w.cub_tmp, tb, w.flag, w.pref, Ki, st));
-    nms_emit_kernel<<<gK, tpb, 0, st>>>(w.flag, w.pref, w.ord_rank, Ki, sa.order_index, keep_out, num_keep_out);
+    nms_emit_kernel<<<gK, tpb, 0, st>>>(w.flag, w.pref, w.ord_rank, batch_ids, Ki, sa.order_index, keep_out,
+                                        (unsigned long long*)num_keep_out);
     R3G_LAUNCH_OK("nms_emit_kernel");
     return R3G_OK;
 }

@@ -81,6 +81,29 @@ def test_multiclass_nms_rotated_golden(cuda_dev, v):
     assert tuple(d.shape) == tuple(g["empty_dets_shape"]) and tuple(l.shape) == tuple(g["empty_labels_shape"]) and l.dtype == torch.int64
 
 
+@pytest.mark.parametrize("v", ["v1", "v3"])
+def test_multi_image_batch_equals_per_image_calls(cuda_dev, v):
+    """one launch sequence for a batch of images == the per-image calls (BASELINE configs[3]: images are independent)"""
+    from r3det_b200._nms_core import nms_device
+    imgs = [clustered(K, 40 + i, v) for i, K in enumerate((700, 1, 1500, 64, 333))]
+    boxes = np.concatenate([b for b, _, _ in imgs]); scores = np.concatenate([s for _, s, _ in imgs])
+    labels = np.concatenate([l for _, _, l in imgs])
+    bid = np.concatenate([np.full(len(b), i, np.int64) for i, (b, _, _) in enumerate(imgs)])
+    scales = np.array([b.max() + 1 for b, _, _ in imgs], np.float32)
+    by_index = (v == "v1")
+    keep, num = nms_device(_t(boxes, cuda_dev), _t(scores, cuda_dev), 0.1, v, labels=_t(labels, cuda_dev),
+                           class_offset=_t(scales, cuda_dev), order_index=by_index, drop_small=(v == "v3"),
+                           batch_ids=_t(bid, cuda_dev), n_batches=len(imgs))
+    num = num.cpu().numpy(); keep = keep.cpu().numpy()
+    start, off = 0, 0
+    for i, (b, s, l) in enumerate(imgs):
+        k1, n1 = nms_device(_t(b, cuda_dev), _t(s, cuda_dev), 0.1, v, labels=_t(l, cuda_dev),
+                            class_offset=torch.tensor(scales[i], device=cuda_dev), order_index=by_index, drop_small=(v == "v3"))
+        want = k1[:int(n1)].cpu().numpy() + off
+        assert num[i] == len(want) and np.array_equal(keep[start:start + num[i]], want), i
+        start += num[i]; off += len(b)
+
+
 def test_edge_cases(cuda_dev):
     import r3det_b200 as R
     from r3det_b200._nms_core import nms_device
