@@ -43,7 +43,7 @@ struct NmsWs {
     BoxP0* p0; BoxP1* p1; float4* p2r; float4* p2c; float* raw; unsigned char* valid;
     int* blk_end; long long *nw, *row_base, *ng, *item_base;
     int* seg_list; int* counters;                   // counters[0] = nseg
-    int *flag, *pref;
+    int *flag, *pref, *keep_p;
     void* cub_tmp; size_t cub_bytes;
     unsigned long long* mask;
     size_t bytes;
@@ -77,7 +77,7 @@ static NmsWs carve_nms(void* ws, int64_t K) {
     w.nw = (long long*)take(8 * (nblk + 1)); w.row_base = (long long*)take(8 * (nblk + 1));
     w.ng = (long long*)take(8 * (nblk + 1)); w.item_base = (long long*)take(8 * (nblk + 1));
     w.seg_list = (int*)take(4 * K);
-    w.flag = (int*)take(4 * K); w.pref = (int*)take(4 * K);
+    w.flag = (int*)take(4 * K); w.pref = (int*)take(4 * K); w.keep_p = (int*)take(4 * K);
     w.cub_bytes = cub_temp_bytes(K, nblk);
     w.cub_tmp = take(w.cub_bytes);
     w.mask = (unsigned long long*)take((size_t)8 * 64 * (size_t)(nblk * (nblk + 1) / 2));
@@ -392,24 +392,29 @@ struct ScanArgs {
     const unsigned long long* mask; const unsigned char* valid; const unsigned* label;
     const int* blk_end; const long long* row_base; const int* seg_list; const int* counters;
     const int* pos_rank; const int* ord_rank;
-    int* flag;
-    int K, order_index, remv_cap;
+    int* keep_p;                                       // per position: 1 = kept
+    int K, remv_cap;
 };
 
-// Greedy scan, one CTA per class segment, software-pipelined so that no global-memory latency sits on the serial
-// chain.  For the 64-row block b of a segment:
-//   warp 0      : chain over the 64 diagonal words D_b (shared memory) with ffs jumps -> kept_b; ORs the kept rows'
-//                 next-column words N_b (prefetched for ALL 64 rows) into removed[b+1]; writes the keep flags;
-//   warps 1..7  : prefetch D_{b+1}, N_{b+1} and the valid bits of block b+1 into the other buffer, and apply the
-//                 kept rows of block b-1 to removed[b+1 ..] (their words two and more columns ahead).
-// One __syncthreads per block; removed[] lives in shared memory and is updated with atomicOr.
-__global__ void __launch_bounds__(NMS_THREADS) nms_scan_kernel(const ScanArgs A) {
+// Greedy scan, one CTA per class segment, software-pipelined in SUPERBLOCKS of 4 x 64 rows so that one barrier and one
+// global-memory round trip are paid per 256 rows and none of it sits on the serial chain.  For superblock S (column
+// window = its own 4 blocks + the next 4):
+//   warp 0      : for each of the 4 blocks: chain over the 64 diagonal words (shared memory) with ffs jumps -> kept;
+//                 lanes 0..7 OR the kept rows' window words into removed[] so the next block / superblock sees them;
+//   warps 1..7  : prefetch the 256 x 8 window words + valid bits of superblock S+1 into the other buffer, apply the
+//                 kept rows of superblock S-1 to removed[] beyond its window (global mask words, 4 loads in flight),
+//                 and write the keep flags of S-1.
+// removed[] lives in shared memory and is updated with atomicOr.
+constexpr int NMS_SB = 4;                       // blocks per superblock
+constexpr int NMS_WIN = 2 * NMS_SB;             // window words per row
+constexpr int SCAN_THREADS = 512;               // 1 resolver warp + 15 warps of prefetch / apply work
+
+__global__ void __launch_bounds__(SCAN_THREADS) nms_scan_kernel(const ScanArgs A) {
     extern __shared__ unsigned long long remv[];          // remv_cap words
-    __shared__ unsigned long long D[2][64], N[2][64];
-    __shared__ unsigned vbits[2][2];
-    __shared__ unsigned long long kept_s[2];
-    __shared__ long long mbase[4];                        // row_base / words-per-row of blocks b-1 .. b+2 (ring by b & 3)
-    __shared__ int mnwr[4];
+    __shared__ unsigned long long Wd[2][64 * NMS_SB][NMS_WIN];
+    __shared__ unsigned long long vbits[2][NMS_SB], kept_s[2][NMS_SB];
+    __shared__ long long mbase[4][NMS_SB];                // row_base / words-per-row, ring over superblocks S-1 .. S+2
+    __shared__ int mnwr[4][NMS_SB];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nseg = A.counters[0];
     for (int s = blockIdx.x; s < nseg; s += gridDim.x) {
@@ -423,110 +428,140 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_scan_kernel(const ScanArgs A)
         const int pe = lo + 1;
         const int bf = ps >> 6, bl = (pe - 1) >> 6;
         const int nb = bl - bf + 1;
+        const int nsb = (nb + NMS_SB - 1) / NMS_SB;
         __syncthreads();                                   // previous segment fully done with shared memory
-        for (int w = tid; w < nb; w += NMS_THREADS) remv[w] = 0ull;
-        if (tid < 2) {
-            kept_s[tid] = 0ull;
-            const int b = bf + tid;
-            if (b <= bl) { mbase[b & 3] = A.row_base[b]; mnwr[b & 3] = A.blk_end[b] - b + 1; }
-        }
+        for (int w = tid; w < nb; w += SCAN_THREADS) remv[w] = 0ull;
+        auto load_meta = [&](int S) {                      // one thread per block of superblock S
+            const int q = tid & (NMS_SB - 1), b = bf + S * NMS_SB + q;
+            if (b <= bl) { mbase[S & 3][q] = A.row_base[b]; mnwr[S & 3][q] = A.blk_end[b] - b + 1; }
+        };
+        if (tid < NMS_SB) { load_meta(0); kept_s[0][tid] = 0ull; kept_s[1][tid] = 0ull; }
+        else if (tid < 2 * NMS_SB && nsb > 1) load_meta(1);
         __syncthreads();
 
-        // loads D / N / valid bits of block b into buffer `buf`; executed by two full warps (t = 0..63)
-        auto prefetch = [&](int b, int buf, int t) {
-            const int p = b * 64 + t;
-            const bool in = (p >= ps && p < pe);
-            const bool ok = in && A.valid[p];
-            unsigned long long d = 0ull, n = 0ull;
-            if (ok) {
-                const long long base = mbase[b & 3];
-                const int nwr = mnwr[b & 3];
-                d = A.mask[base + (long long)t * nwr];
-                if (b + 1 <= bl) n = A.mask[base + (long long)t * nwr + 1];
+        // window words + valid bits of superblock S into buffer `buf`.  `nt` threads (rank `u`) share the 256 x 8 words as
+        // flattened (row, word) pairs so that every thread has ~9 independent loads in flight; the valid bits are ballots
+        // over whole warps (callers pass warp-aligned thread ranges).
+        auto prefetch = [&](int S, int buf, int u, int nt) {
+            const int b0 = bf + S * NMS_SB;
+            constexpr int PAIRS = 64 * NMS_SB * NMS_WIN;
+            constexpr int PER = (PAIRS + (SCAN_THREADS - 32) - 1) / (SCAN_THREADS - 32);
+            unsigned long long v[PER];
+#pragma unroll
+            for (int j = 0; j < PER; j++) {
+                const int idx = u + j * nt;
+                unsigned long long x = 0ull;
+                if (idx < PAIRS) {
+                    const int r = idx >> 3, k = idx & (NMS_WIN - 1), q = r >> 6, t = r & 63, b = b0 + q, col = b0 + k;
+                    const int p = b * 64 + t;
+                    if (b <= bl && col >= b && col <= bl && p >= ps && p < pe)
+                        x = A.mask[mbase[S & 3][q] + (long long)t * mnwr[S & 3][q] + (col - b)];
+                }
+                v[j] = x;
             }
-            D[buf][t] = d;
-            N[buf][t] = n;
-            const unsigned bal = __ballot_sync(0xffffffffu, ok);
-            if ((t & 31) == 0) vbits[buf][t >> 5] = bal;
+            for (int r0 = 0; r0 < 64 * NMS_SB; r0 += nt) {             // valid bits (rows of other segments / dropped boxes = 0)
+                const int r = r0 + u;
+                bool ok = false;
+                if (r < 64 * NMS_SB) {
+                    const int p = (b0 + (r >> 6)) * 64 + (r & 63);
+                    ok = (b0 + (r >> 6) <= bl) && p >= ps && p < pe && A.valid[p];
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, ok);
+                if (r < 64 * NMS_SB && (r & 31) == 0) reinterpret_cast<unsigned*>(&vbits[buf][r >> 6])[(r >> 5) & 1] = bal;
+            }
+#pragma unroll
+            for (int j = 0; j < PER; j++) {
+                const int idx = u + j * nt;
+                if (idx < PAIRS) Wd[buf][idx >> 3][idx & (NMS_WIN - 1)] = v[j];
+            }
         };
-        if (tid < 64) prefetch(bf, 0, tid);
+        prefetch(0, 0, tid, SCAN_THREADS);
 
-        for (int b = bf; b <= bl; b++) {
-            const int buf = (b - bf) & 1;
+        for (int S = 0; S < nsb; S++) {
+            const int buf = S & 1;
+            const int b0 = bf + S * NMS_SB;
             __syncthreads();
             if (warp == 0) {
-                const unsigned long long vb = ((unsigned long long)vbits[buf][1] << 32) | vbits[buf][0];
-                unsigned long long cur = remv[b - bf], kept = 0ull, nxt = 0ull;
-                unsigned long long avail = vb & ~cur;
-                while (avail) {                               // warp-uniform; one kept row per trip
-                    const int t = __ffsll((long long)avail) - 1;
-                    kept |= 1ull << t;
-                    cur |= D[buf][t];
-                    nxt |= N[buf][t];
-                    const unsigned long long above = (t == 63) ? 0ull : (~0ull << (t + 1));
-                    avail = vb & ~cur & above;
-                }
-                if (lane == 0) {
-                    kept_s[buf] = kept;
-                    if (b < bl && nxt) atomicOr(&remv[b + 1 - bf], nxt);
+                for (int q = 0; q < NMS_SB; q++) {
+                    const int b = b0 + q;
+                    if (b > bl) break;
+                    const unsigned long long vb = vbits[buf][q];
+                    unsigned long long cur = remv[b - bf], kept = 0ull, acc = 0ull;
+                    unsigned long long avail = vb & ~cur;
+                    while (avail) {                           // warp-uniform; one kept row per trip
+                        const int t = __ffsll((long long)avail) - 1;
+                        kept |= 1ull << t;
+                        cur |= Wd[buf][q * 64 + t][q];
+                        if (lane < NMS_WIN) acc |= Wd[buf][q * 64 + t][lane];
+                        const unsigned long long above = (t == 63) ? 0ull : (~0ull << (t + 1));
+                        avail = vb & ~cur & above;
+                    }
+                    if (lane < NMS_WIN && lane > q && b0 + lane <= bl && acc) atomicOr(&remv[b0 + lane - bf], acc);
+                    if (lane == 0) kept_s[buf][q] = kept;
+                    __syncwarp();
                 }
             } else {
-                const int u = tid - 32;                        // 0 .. 223
-                if (u < 64 && b + 1 <= bl) prefetch(b + 1, buf ^ 1, u);
-                if (u >= 64 && b > bf) {
-                    // kept rows of block b-1 -> removed[b+1 ..] (their words 2, 3, ... ; word 1 went through N)
-                    const unsigned long long kp = kept_s[buf ^ 1];
-                    if (u < 128) {                             // keep flags of block b-1 (off the resolver's critical path)
-                        const int t = u - 64, p = (b - 1) * 64 + t;
-                        if (p >= ps && p < pe) {
-                            const int rank = A.pos_rank[p];
-                            const int slot = A.order_index ? A.ord_rank[rank] : rank;
-                            A.flag[slot] = (int)((kp >> t) & 1ull);
-                        }
+                const int u = tid - 32;                        // 0 .. SCAN_THREADS - 33
+                const int nw_threads = SCAN_THREADS - 32;
+                if (S + 1 < nsb) prefetch(S + 1, buf ^ 1, u, nw_threads);
+                if (u < NMS_SB && S + 2 < nsb) load_meta(S + 2);
+                if (S > 0) {
+                    const int pb0 = b0 - NMS_SB;                 // previous superblock
+                    for (int r = u; r < 64 * NMS_SB; r += nw_threads) {      // its keep bits, by position (store only)
+                        const int q = r >> 6, t = r & 63, p = (pb0 + q) * 64 + t;
+                        if (pb0 + q <= bl && p >= ps && p < pe) A.keep_p[p] = (int)((kept_s[buf ^ 1][q] >> t) & 1ull);
                     }
-                    if (u == 223 && b + 2 <= bl) {             // meta of block b+2 for the next iteration's prefetch
-                        mbase[(b + 2) & 3] = A.row_base[b + 2];
-                        mnwr[(b + 2) & 3] = A.blk_end[b + 2] - (b + 2) + 1;
-                    }
-                    if (kp) {
-                        const int pb = b - 1;
-                        const long long base = mbase[pb & 3];
-                        const int nwr = mnwr[pb & 3];
-                        const int nlater = bl - pb - 1;          // columns pb+2 .. bl
-                        for (int w = u - 64; w < nlater; w += NMS_THREADS - 96) {
-                            unsigned long long acc = 0ull, kk = kp;
-                            const unsigned long long* col = A.mask + base + 2 + w;
-                            while (kk) {                         // four independent loads in flight per trip
-                                int t[4];
+                    // its kept rows -> removed[] beyond its window (columns pb0 + NMS_WIN .. bl): the first four kept rows
+                    // of each of the four blocks are fetched together (16 independent loads), the rest in a tail loop
+                    const int first = pb0 + NMS_WIN;
+                    unsigned long long kq[NMS_SB];
 #pragma unroll
-                                for (int q = 0; q < 4; q++) {
-                                    t[q] = kk ? __ffsll((long long)kk) - 1 : -1;
-                                    kk &= kk - 1;
+                    for (int q = 0; q < NMS_SB; q++) kq[q] = (pb0 + q <= bl) ? kept_s[buf ^ 1][q] : 0ull;
+                    if (kq[0] | kq[1] | kq[2] | kq[3]) {
+                        for (int col = first + u; col <= bl; col += nw_threads) {
+                            unsigned long long kk[NMS_SB], acc = 0ull;
+#pragma unroll
+                            for (int q = 0; q < NMS_SB; q++) kk[q] = kq[q];
+                            while (kk[0] | kk[1] | kk[2] | kk[3]) {                 // 16 independent loads per trip
+                                unsigned long long v[NMS_SB * 4];
+#pragma unroll
+                                for (int q = 0; q < NMS_SB; q++) {
+                                    const unsigned long long* cp = A.mask + mbase[(S - 1) & 3][q] + (col - (pb0 + q));
+                                    const int nwr = mnwr[(S - 1) & 3][q];
+#pragma unroll
+                                    for (int j = 0; j < 4; j++) {
+                                        const int t = kk[q] ? __ffsll((long long)kk[q]) - 1 : -1;
+                                        kk[q] &= kk[q] - 1;
+                                        v[q * 4 + j] = (t >= 0) ? cp[(long long)t * nwr] : 0ull;
+                                    }
                                 }
-                                unsigned long long v[4];
 #pragma unroll
-                                for (int q = 0; q < 4; q++) v[q] = (t[q] >= 0) ? col[(long long)t[q] * nwr] : 0ull;
-                                acc |= (v[0] | v[1]) | (v[2] | v[3]);
+                                for (int j = 0; j < NMS_SB * 4; j++) acc |= v[j];
                             }
-                            if (acc) atomicOr(&remv[pb + 2 + w - bf], acc);
+                            if (acc) atomicOr(&remv[col - bf], acc);
                         }
                     }
-                } else if (u == 223 && b + 2 <= bl) {          // first block of the segment: no block b-1 yet
-                    mbase[(b + 2) & 3] = A.row_base[b + 2];
-                    mnwr[(b + 2) & 3] = A.blk_end[b + 2] - (b + 2) + 1;
                 }
             }
         }
         __syncthreads();
-        if (tid < 64) {                                        // keep flags of the segment's last block
-            const int t = tid, p = bl * 64 + t;
-            if (p >= ps && p < pe) {
-                const int rank = A.pos_rank[p];
-                const int slot = A.order_index ? A.ord_rank[rank] : rank;
-                A.flag[slot] = (int)((kept_s[(bl - bf) & 1] >> t) & 1ull);
+        {   // keep bits of the segment's last superblock
+            const int S = nsb - 1, pb0 = bf + S * NMS_SB;
+            for (int r = tid; r < 64 * NMS_SB; r += SCAN_THREADS) {
+                const int q = r >> 6, t = r & 63, p = (pb0 + q) * 64 + t;
+                if (pb0 + q <= bl && p >= ps && p < pe) A.keep_p[p] = (int)((kept_s[S & 1][q] >> t) & 1ull);
             }
         }
     }
+}
+
+// keep bits by position -> flags in output-slot order (rank order, or original index for R3G_NMS_ORDER_INDEX)
+__global__ void nms_flags_kernel(const int* __restrict__ keep_p, const int* __restrict__ pos_rank,
+                                 const int* __restrict__ ord_rank, int K, int order_index, int* __restrict__ flag) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= K) return;
+    const int rank = pos_rank[p];
+    flag[order_index ? ord_rank[rank] : rank] = keep_p[p];
 }
 
 __global__ void nms_emit_kernel(const int* __restrict__ flag, const int* __restrict__ pref, const int* __restrict__ ord_rank,
@@ -646,27 +681,29 @@ R3G_API int r3g_nms_batched_f32(const float* boxes, int64_t stride, const float*
     ScanArgs sa;
     sa.mask = w.mask; sa.valid = w.valid; sa.label = w.pos_label; sa.blk_end = w.blk_end; sa.row_base = w.row_base;
     sa.seg_list = w.seg_list; sa.counters = w.counters; sa.pos_rank = w.pos_rank; sa.ord_rank = w.ord_rank;
-    sa.flag = w.flag; sa.K = Ki; sa.order_index = (flags & R3G_NMS_ORDER_INDEX) ? 1 : 0;
+    sa.keep_p = w.keep_p; sa.K = Ki;
+    const int order_index = (flags & R3G_NMS_ORDER_INDEX) ? 1 : 0;
     sa.remv_cap = nblk;
     size_t smem = (size_t)nblk * 8;
-    if (smem > 200 * 1024) {
-        set_error("r3g_nms_f32: K=%lld exceeds the single-image limit of this build (%d boxes)", (long long)K, 200 * 1024 / 8 * 64);
+    if (smem > 190 * 1024) {
+        set_error("r3g_nms_f32: K=%lld exceeds the single-image limit of this build (%d boxes)", (long long)K, 190 * 1024 / 8 * 64);
         return R3G_ERR_ARG;
     }
-    static size_t smem_set = 0;
-    if (smem > 48 * 1024 && smem > smem_set) {
-        R3G_CUDA_OK(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        smem_set = 200 * 1024;
+    static bool smem_set = false;
+    if (!smem_set) {      // static (window buffers) + dynamic (removed[]) shared memory may exceed the 48 KB default
+        R3G_CUDA_OK(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 190 * 1024));
+        smem_set = true;
     }
     int sgrid = device_sm_count() * 2;
     if (!labels && !batch_ids) sgrid = 1;
-    nms_scan_kernel<<<sgrid, NMS_THREADS, smem, st>>>(sa);
+    nms_scan_kernel<<<sgrid, SCAN_THREADS, smem, st>>>(sa);
     R3G_LAUNCH_OK("nms_scan_kernel");
+    nms_flags_kernel<<<gK, tpb, 0, st>>>(w.keep_p, w.pos_rank, w.ord_rank, Ki, order_index, w.flag);
 
     // 7. compaction in the requested order
     tb = w.cub_bytes;
     R3G_CUDA_OK(cub::DeviceScan::ExclusiveSum(w.cub_tmp, tb, w.flag, w.pref, Ki, st));
-    nms_emit_kernel<<<gK, tpb, 0, st>>>(w.flag, w.pref, w.ord_rank, batch_ids, Ki, sa.order_index, keep_out,
+    nms_emit_kernel<<<gK, tpb, 0, st>>>(w.flag, w.pref, w.ord_rank, batch_ids, Ki, order_index, keep_out,
                                         (unsigned long long*)num_keep_out);
     R3G_LAUNCH_OK("nms_emit_kernel");
     return R3G_OK;
