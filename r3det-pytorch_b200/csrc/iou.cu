@@ -78,6 +78,8 @@ __device__ __noinline__ float emu_pair_call(const float* b1, const float* b2, in
     return emu::pair(x, y, variant, mode);
 }
 
+struct __attribute__((aligned(16))) TieRec { int row, col; float iou; int pad; };
+
 struct IouArgs {
     const BoxP0* r0; const BoxP1* r1; const RowP2* r2; int m;
     const BoxP0* c0; const BoxP1* c1; int n;
@@ -93,6 +95,9 @@ struct IouArgs {
     unsigned long long* row_best;   // per row (GT): best column (anchor)
     int* lowq;                      // per column: largest (row + 1) whose overlap equals that row's maximum
     float min_pos_iou;
+    // tie candidates of pass 1 (gt_max_assign_all): pairs whose overlap reached their row's running maximum when they
+    // were evaluated.  The running maximum only grows, so every pair that equals the FINAL maximum is in the list.
+    TieRec* ties; unsigned tie_cap;  // stats[5] counts the records (may exceed tie_cap: then pass 2 sweeps instead)
 };
 
 // OUT selects what the kernel does with the overlaps it computes:
@@ -116,7 +121,12 @@ __device__ __forceinline__ void emit_overlap(const IouArgs& A, int i, int j, flo
     } else if (OUT == OUT_ASSIGN_MAX) {
         if (r > 0.0f) {
             update_best(A.col_best + j, pack_best(r, i));
-            update_best(A.row_best + i, pack_best(r, j));
+            const unsigned long long cand = pack_best(r, j), cur = __ldcg(A.row_best + i);
+            if (cand > cur) atomicMax(A.row_best + i, cand);
+            if (A.ties != nullptr && r >= __uint_as_float((unsigned)(cur >> 32)) && r >= A.min_pos_iou) {
+                const unsigned long long t = atomicAdd(A.stats + 5, 1ull);
+                if (t < A.tie_cap) { TieRec e = { i, j, r, 0 }; A.ties[t] = e; }
+            }
         }
     } else {
         const float gm = __uint_as_float((unsigned)(__ldcg(A.row_best + i) >> 32));
@@ -164,6 +174,7 @@ __global__ void __launch_bounds__(IOU_THREADS, R3G_IOU_MINB) iou_matrix_kernel(c
     const int tiles_m = (A.m + IOU_TM - 1) / IOU_TM;
     const long long total = (long long)tiles_m * tiles_n;
     unsigned n_circle = 0, n_sat = 0, n_emu = 0;
+    if (OUT == OUT_ASSIGN_TIES && A.ties != nullptr && __ldcg(A.stats + 5) <= A.tie_cap) return;   // the list was complete
     float ox = __ldg(A.origin_box), oy = __ldg(A.origin_box + 1);     // common origin of the expanded circle test
     if (!isfinite(ox)) ox = 0.0f;
     if (!isfinite(oy)) oy = 0.0f;
@@ -489,7 +500,7 @@ R3G_API int r3g_iou_matrix_prepared_f32(const float* boxes1, int64_t m, int64_t 
     }
     cudaStream_t st = (cudaStream_t)stream;
     R3G_CUDA_OK(cudaMemsetAsync(w.stats, 0, 256, st));
-    IouArgs a;
+    IouArgs a = {};
     a.r0 = w.r0; a.r1 = w.r1; a.r2 = w.r2; a.m = (int)m; a.c0 = w.c0; a.c1 = w.c1; a.n = (int)n;
     a.raw1 = boxes1; a.s1 = stride1; a.raw2 = boxes2; a.s2 = stride2; a.origin_box = boxes1;
     a.variant = variant; a.mode = mode;
@@ -569,6 +580,18 @@ __global__ void assign_gt_kernel(const unsigned long long* __restrict__ row_best
     }
 }
 
+// gt_max_assign_all from the tie list of pass 1: a recorded pair matches when its overlap equals the row's final maximum
+__global__ void assign_ties_kernel(const TieRec* __restrict__ ties, const unsigned long long* __restrict__ count, unsigned cap,
+                                   const unsigned long long* __restrict__ row_best, float min_pos_iou, int* lowq) {
+    const unsigned long long n = *count;
+    if (n > cap) return;                                             // overflow: the sweep (OUT_ASSIGN_TIES) does it
+    for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (unsigned long long)gridDim.x * blockDim.x) {
+        const TieRec e = ties[t];
+        const float gm = __uint_as_float((unsigned)(row_best[e.row] >> 32));
+        if (e.iou == gm && gm >= min_pos_iou) atomicMax(lowq + e.col, e.row + 1);
+    }
+}
+
 __global__ void assign_finalize_kernel(const unsigned long long* __restrict__ col_best, const int* __restrict__ lowq,
                                        const int* __restrict__ zero_gt, int64_t A, int64_t G, float pos_thr, float neg_thr,
                                        int match_low_quality, int64_t* assigned, float* max_overlaps, int64_t* argmax) {
@@ -593,7 +616,7 @@ __global__ void assign_finalize_kernel(const unsigned long long* __restrict__ co
     if (argmax) argmax[j] = arg;
 }
 
-struct AssignWs { IouWorkspace iou; unsigned long long *col_best, *row_best; int *lowq, *zero_gt; size_t bytes; };
+struct AssignWs { IouWorkspace iou; unsigned long long *col_best, *row_best; int *lowq, *zero_gt; TieRec* ties; unsigned tie_cap; size_t bytes; };
 
 static AssignWs carve_assign(void* ws, int64_t G, int64_t A) {
     AssignWs w;
@@ -604,6 +627,9 @@ static AssignWs carve_assign(void* ws, int64_t G, int64_t A) {
     w.row_best = (unsigned long long*)(p + off); off += align_up(8 * (size_t)(G > 0 ? G : 1), 256);
     w.lowq = (int*)(p + off); off += align_up(4 * (size_t)(A > 0 ? A : 1), 256);
     w.zero_gt = (int*)(p + off); off += 256;
+    // expected records: a few (~ln of the overlapping columns) per row; far above that the list gives way to the sweep
+    w.tie_cap = (unsigned)(65536 + 64 * (size_t)(G > 0 ? G : 0));
+    w.ties = (TieRec*)(p + off); off += align_up(sizeof(TieRec) * (size_t)w.tie_cap, 256);
     w.bytes = off;
     return w;
 }
@@ -641,7 +667,7 @@ R3G_API int r3g_max_iou_assign_f32(const float* gt, int64_t G, int64_t gt_stride
     if (G > 0) {
         rc = r3g_iou_prepare_f32(gt, G, gt_stride, anchors, A, anchor_stride, variant, workspace, w.iou.bytes, stream);
         if (rc != R3G_OK) return rc;
-        IouArgs a;
+        IouArgs a = {};
         a.r0 = w.iou.r0; a.r1 = w.iou.r1; a.r2 = w.iou.r2; a.m = (int)G; a.c0 = w.iou.c0; a.c1 = w.iou.c1; a.n = (int)A;
         a.raw1 = gt; a.s1 = gt_stride; a.raw2 = anchors; a.s2 = anchor_stride; a.origin_box = gt;
         a.variant = variant; a.mode = R3G_MODE_IOU;
@@ -649,13 +675,19 @@ R3G_API int r3g_max_iou_assign_f32(const float* gt, int64_t G, int64_t gt_stride
         a.tau = (flags & R3G_FLAG_EMULATE_ALL) ? 1e30f : ((flags & R3G_FLAG_STRICT) ? 2e-2f : 0.0f);
         a.out = nullptr; a.stats = w.iou.stats;
         a.col_best = w.col_best; a.row_best = w.row_best; a.lowq = w.lowq; a.min_pos_iou = min_pos_iou;
+        const bool want_ties = match_low_quality && gt_max_assign_all;
+        a.ties = want_ties ? w.ties : nullptr; a.tie_cap = w.tie_cap;
         R3G_CUDA_OK(cudaMemsetAsync(w.iou.stats, 0, 256, st));
         rc = launch_sweep<false, OUT_ASSIGN_MAX>(a, st);
         if (rc != R3G_OK) return rc;
         assign_gt_kernel<<<(unsigned)((G + tpb - 1) / tpb), tpb, 0, st>>>(w.row_best, G, min_pos_iou, gt_max_assign_all,
                                                                         w.lowq, w.zero_gt, gt_max_overlaps, gt_argmax_overlaps);
-        if (match_low_quality && gt_max_assign_all) {
-            R3G_CUDA_OK(cudaMemsetAsync(w.iou.stats, 0, 256, st));
+        if (want_ties) {
+            assign_ties_kernel<<<(unsigned)((w.tie_cap + 4 * tpb - 1) / (4 * tpb)), tpb, 0, st>>>(w.ties, w.iou.stats + 5, w.tie_cap,
+                                                                                            w.row_best, min_pos_iou, w.lowq);
+            // list overflow (massive ties, e.g. many identical anchors): exact sweep; its warps return at once otherwise.
+            // stats[5] must survive the reset of the item ticket, so only the ticket is cleared.
+            R3G_CUDA_OK(cudaMemsetAsync(w.iou.stats + 4, 0, 8, st));
             rc = launch_sweep<false, OUT_ASSIGN_TIES>(a, st);
             if (rc != R3G_OK) return rc;
         }

@@ -71,3 +71,19 @@ def test_edge_cases_and_class(cuda_dev):
     assert pos.any() and torch.equal(res.labels[pos], labels[res.gt_inds[pos] - 1]) and (res.labels[~pos] == -1).all()
     with pytest.raises(NotImplementedError):
         R.FusedMaxIoUAssigner(0.5, (0.1, 0.4))
+
+
+def test_massive_ties_take_the_sweep(cuda_dev):
+    """More exact ties than the tie list of pass 1 can hold: the library must fall back to the exact tie sweep."""
+    import r3det_b200 as R
+    rng = np.random.default_rng(7)
+    gt = rand_obb(6, 11, "v1", 30, 200)
+    reps = 40000                                              # 6 x 40000 tie candidates > list capacity (65536 + 64 G)
+    an = np.concatenate([np.repeat(gt, reps, axis=0), rand_obb(5000, 12, "v1")]).astype(np.float32)
+    an = an[rng.permutation(len(an))]
+    G_, A_ = torch.from_numpy(gt).to(cuda_dev), torch.from_numpy(an).to(cuda_dev)
+    ov = R.pairwise_iou(G_, A_, "v1")
+    for pos, minpos in ((0.5, 0.0), (1.5, 0.3)):              # pos 1.5: only low-quality matching assigns positives
+        want, _ = assign_wrt_overlaps(ov, pos, 0.4, minpos, True, True)
+        out = R.max_iou_assign(G_, A_, pos, 0.4, minpos, True, True, "v1")
+        assert torch.equal(out.gt_inds, want), int((out.gt_inds != want).sum())
