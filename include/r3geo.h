@@ -156,6 +156,45 @@ int r3g_obb2hbb_f32(const float* obb, int64_t n, int version, float* hbb, void* 
 int r3g_hbb2obb_f32(const float* hbb, int64_t n, int version, float* obb, void* stream);
 int r3g_obb2xyxy_f32(const float* obb, int64_t n, int version, float* xyxy, void* stream);
 
+/* ---- rotated box coder and the steps around NMS / FRM that use it -------------------
+ * replaces DeltaXYWHAOBBoxCoder.encode / .decode   r3det/core/bbox/coder/delta_xywha_rbbox_coder.py:46-101
+ *   (bbox2delta_v1/v2/v3 :104-139 / :214-252 / :314-360, delta2bbox_v1/v2/v3 :142-211 / :255-311 / :363-423)
+ * means / stds: 5 floats each in HOST memory.  deltas: (n, 5*groups), rois: n rows of `roi_stride` floats, out like
+ * deltas.  max_shape_hw: HOST {H, W} or NULL; honoured by v1 only, exactly as in the reference (:97-99). */
+int r3g_delta2bbox_f32(const float* rois, int64_t n, int64_t roi_stride, const float* deltas, int64_t groups,
+                       const float* means, const float* stds, int variant, const int* max_shape_hw,
+                       double wh_ratio_clip, int add_ctr_clamp, float ctr_clamp, float* out, void* stream);
+int r3g_bbox2delta_f32(const float* proposals, int64_t proposal_stride, const float* gt, int64_t gt_stride, int64_t n,
+                       const float* means, const float* stds, int variant, float* out, void* stream);
+/* replaces RRetinaHead.filter_bboxes   r3det/models/dense_heads/rotate_retina_head.py:117-179   for one level:
+ * cls_score (B, A*C, H, W), bbox_pred (B, A*5, H, W), anchors (H*W*A, 5) -> out (B, H*W, 5): per location the anchor
+ * with the largest class logit (first maximum), decoded.  Network outputs are read in NCHW, no permuted copies. */
+int r3g_filter_bboxes_f32(const float* cls_score, const float* bbox_pred, const float* anchors, int64_t B, int64_t A,
+                          int64_t C, int64_t H, int64_t W, const float* means, const float* stds, int variant,
+                          double wh_ratio_clip, int add_ctr_clamp, float ctr_clamp, float* out, void* stream);
+/* replaces RRetinaRefineHead.refine_bboxes   r3det/models/dense_heads/rotate_retina_refine_head.py:56-97   for one
+ * level: bbox_pred (B, 5, H, W), rois (B, H*W, 5) -> out (B, H*W, 5) — the (N*H*W, 5) layout r3g_frm_* consume. */
+int r3g_refine_bboxes_f32(const float* bbox_pred, const float* rois, int64_t B, int64_t H, int64_t W, const float* means,
+                          const float* stds, int variant, double wh_ratio_clip, int add_ctr_clamp, float ctr_clamp,
+                          float* out, void* stream);
+/* replaces RAnchorHead._get_bboxes_single up to the NMS call, for a whole batch
+ *   r3det/models/dense_heads/rotate_anchor_head.py:626-664 (use_sigmoid_cls=True):
+ * per level l < L: cls_scores[l] (B, A*C, H_l, W_l), bbox_preds[l] (B, A*5, H_l, W_l), anchors[l] (H_l*W_l*A, 5) shared
+ * by the batch (anchor_batch_strides[l] == 0 or NULL array) or per image (stride in floats).  The pointer arrays,
+ * level_hw {H_0, W_0, H_1, ...}, max_shapes_hw {H, W} per image (or NULL; v1 only) and scale_factors (4 per image, or
+ * NULL = no rescale) are HOST arrays.  Levels with more than nms_pre rows keep their nms_pre best rows by
+ * max-class sigmoid score in descending order (ties: lower row index); smaller levels are kept whole in row order.
+ * boxes_out (B, rows_per_image, 5), scores_out (B, rows_per_image, C + 1) with a zero last column.
+ * At most 8 levels and 64 images per call. */
+int r3g_select_decode_sizes(int64_t L, int64_t B, int64_t A, const int64_t* level_hw, int64_t nms_pre,
+                            int64_t* rows_per_image, size_t* workspace_bytes);
+int r3g_select_decode_f32(int64_t L, const float* const* cls_scores, const float* const* bbox_preds,
+                          const float* const* anchors, const int64_t* anchor_batch_strides, const int64_t* level_hw,
+                          int64_t B, int64_t A, int64_t C, int64_t nms_pre,
+                          const float* means, const float* stds, int variant, double wh_ratio_clip, int add_ctr_clamp,
+                          float ctr_clamp, const int* max_shapes_hw, const float* scale_factors,
+                          float* boxes_out, float* scores_out, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

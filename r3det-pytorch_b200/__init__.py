@@ -12,12 +12,17 @@ Module map (reference module -> here):
   r3det/core/post_processing     -> bbox_nms_rotated  multiclass_nms_rotated
   r3det/ops/fr                   -> fr                FeatureRefineFunction, feature_refine, FR, FeatureRefineModule
   (mmdet MaxIoUAssigner + calculator, fused; §8f) -> assign   max_iou_assign, FusedMaxIoUAssigner
+  r3det/core/bbox/coder          -> coder             DeltaXYWHAOBBoxCoder, bbox2delta_v1/2/3, delta2bbox_v1/2/3
+  r3det/models/dense_heads (get_bboxes tail, filter_bboxes, refine_bboxes; §8f) -> dense_tail
   r3det/core/bbox/rtransforms    -> rtransforms       poly2obb, obb2poly, obb2hbb, hbb2obb, obb2xyxy, norm_angle, ...
 """
 from . import _lib  # noqa: F401
 from .assign import FusedMaxIoUAssigner, max_iou_assign  # noqa: F401
 from .bbox_nms_rotated import multiclass_nms_rotated  # noqa: F401
 from .box_iou_rotated import obb_overlaps  # noqa: F401
+from .coder import (DeltaXYWHAOBBoxCoder, bbox2delta_v1, bbox2delta_v2, bbox2delta_v3, delta2bbox_v1,  # noqa: F401
+                    delta2bbox_v2, delta2bbox_v3)
+from .dense_tail import filter_bboxes, get_bboxes, refine_bboxes, select_decode  # noqa: F401
 from .fr import FR, FeatureRefineFunction, FeatureRefineModule, feature_refine  # noqa: F401
 from .iou_calculators import (IOU_CALCULATORS, RBboxOverlaps2D_v1, RBboxOverlaps2D_v2,  # noqa: F401
                               RBboxOverlaps2D_v3, rbbox_overlaps_v1, rbbox_overlaps_v2, rbbox_overlaps_v3)

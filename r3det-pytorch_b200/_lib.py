@@ -23,7 +23,7 @@ NMS_STRICT = 8
 
 _lib = None
 
-_vp, _i64, _i32, _f32, _sz = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_size_t
+_vp, _i64, _i32, _f32, _sz, _f64 = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_size_t, C.c_double
 
 _SIGNATURES = {
     "r3g_last_error": (C.c_char_p, []),
@@ -49,6 +49,13 @@ _SIGNATURES = {
     "r3g_obb2hbb_f32": (_i32, [_vp, _i64, _i32, _vp, _vp]),
     "r3g_hbb2obb_f32": (_i32, [_vp, _i64, _i32, _vp, _vp]),
     "r3g_obb2xyxy_f32": (_i32, [_vp, _i64, _i32, _vp, _vp]),
+    "r3g_delta2bbox_f32": (_i32, [_vp, _i64, _i64, _vp, _i64, _vp, _vp, _i32, _vp, _f64, _i32, _f32, _vp, _vp]),
+    "r3g_bbox2delta_f32": (_i32, [_vp, _i64, _vp, _i64, _i64, _vp, _vp, _i32, _vp, _vp]),
+    "r3g_filter_bboxes_f32": (_i32, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _i32, _f64, _i32, _f32, _vp, _vp]),
+    "r3g_refine_bboxes_f32": (_i32, [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _i32, _f64, _i32, _f32, _vp, _vp]),
+    "r3g_select_decode_sizes": (_i32, [_i64, _i64, _i64, _vp, _i64, C.POINTER(_i64), C.POINTER(_sz)]),
+    "r3g_select_decode_f32": (_i32, [_i64, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _i32, _f64, _i32, _f32,
+                                     _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
 }
 
 

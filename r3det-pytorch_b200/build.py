@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libr3geo.so")
-SOURCES = ["api.cu", "iou.cu", "nms.cu", "frm.cu", "transforms.cu"]
+SOURCES = ["api.cu", "iou.cu", "nms.cu", "frm.cu", "transforms.cu", "coder.cu"]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC,-fvisibility=hidden,-O3", "--expt-relaxed-constexpr",
               "-Xptxas", "-v", "-rdc=false"]

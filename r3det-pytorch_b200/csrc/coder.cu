@@ -1,0 +1,443 @@
+// coder.cu — the rotated box coder and the steps on either side of multiclass NMS / FRM that use it, on sm_100a.
+//
+// Replaces (reference, relative to /root/reference):
+//   DeltaXYWHAOBBoxCoder.encode / .decode               r3det/core/bbox/coder/delta_xywha_rbbox_coder.py:46-101
+//     bbox2delta_v1 :104-139  delta2bbox_v1 :142-211  bbox2delta_v2 :214-252  delta2bbox_v2 :255-311
+//     bbox2delta_v3 :314-360  delta2bbox_v3 :363-423
+//   RAnchorHead._get_bboxes_single up to the NMS call    r3det/models/dense_heads/rotate_anchor_head.py:626-662
+//     (permute/reshape, sigmoid, max over classes, per-level top-k(nms_pre), three gathers, decode, rescale, zero
+//      background column: ~15 torch launches per level per image -> 3 launches + one radix sort per BATCH)
+//   RRetinaHead.filter_bboxes                            r3det/models/dense_heads/rotate_retina_head.py:117-179
+//   RRetinaRefineHead.refine_bboxes                      r3det/models/dense_heads/rotate_retina_refine_head.py:56-97
+//
+// Arithmetic follows the torch expressions operation by operation in FP32 with explicitly rounded intrinsics (no FMA
+// contraction), so results equal eager torch on the same device up to libm differences in exp/log/sin/cos.
+// All network outputs are read in their native NCHW layout (no permute/reshape copies).  HBM-bound gather work.
+#include <cub/device/device_radix_sort.cuh>
+#include <math.h>
+#include "common.cuh"
+
+namespace r3g {
+
+constexpr float PI_F = 3.14159265358979323846f;
+constexpr float HALF_PI_F = 1.57079632679489661923f;
+constexpr float QUARTER_PI_F = 0.78539816339744830962f;
+constexpr int SEL_MAX_LEVELS = 8;
+constexpr int SEL_MAX_IMAGES = 64;
+
+struct CoderP { float mean[5], stdv[5]; float max_ratio, ctr_clamp; int add_ctr_clamp, variant; };
+
+__device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float dvd(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+
+// torch.remainder: result takes the sign of the divisor
+__device__ __forceinline__ float py_rem(float a, float b) {
+    float m = fmodf(a, b);
+    if (m != 0.0f && ((b < 0.0f) != (m < 0.0f))) m += b;
+    return m;
+}
+__device__ __forceinline__ float wrap(float a, float off) { return sub(py_rem(add(a, off), PI_F), off); }   // (a + off) % pi - off
+
+// delta2bbox_v1/v2/v3 for one (roi, delta) pair
+__device__ __forceinline__ void decode_one(const CoderP& P, const float* roi, const float* d, bool clamp, float max_x, float max_y,
+                                           float* o) {
+    float dn[5];
+#pragma unroll
+    for (int k = 0; k < 5; k++) dn[k] = add(mul(d[k], P.stdv[k]), P.mean[k]);
+    const float px = roi[0], py = roi[1], pw = roi[2], ph = roi[3], pa = roi[4];
+    float dw = dn[2], dh = dn[3];
+    if (P.variant == 1) {                                                          // :171-211
+        float dxw = mul(pw, dn[0]), dyh = mul(ph, dn[1]);
+        if (P.add_ctr_clamp) {
+            dxw = clampf(dxw, -P.ctr_clamp, P.ctr_clamp); dyh = clampf(dyh, -P.ctr_clamp, P.ctr_clamp);
+            dw = fminf(dw, P.max_ratio); dh = fminf(dh, P.max_ratio);
+        } else {
+            dw = clampf(dw, -P.max_ratio, P.max_ratio); dh = clampf(dh, -P.max_ratio, P.max_ratio);
+        }
+        float gx = add(px, dxw), gy = add(py, dyh);
+        if (clamp) { gx = clampf(gx, 0.0f, max_x); gy = clampf(gy, 0.0f, max_y); }
+        o[0] = gx; o[1] = gy; o[2] = mul(pw, expf(dw)); o[3] = mul(ph, expf(dh)); o[4] = add(pa, dn[4]);
+        return;
+    }
+    dw = clampf(dw, -P.max_ratio, P.max_ratio); dh = clampf(dh, -P.max_ratio, P.max_ratio);
+    const float ang = (P.variant == 2) ? pa : -pa;                                 // v2 :298-299, v3 :407-408
+    const float c = cosf(ang), s = sinf(ang);
+    const float ax = mul(dn[0], pw), ay = mul(dn[1], ph);
+    o[0] = add(sub(mul(ax, c), mul(ay, s)), px);
+    o[1] = add(add(mul(ax, s), mul(ay, c)), py);
+    const float gw = mul(pw, expf(dw)), gh = mul(ph, expf(dh));
+    if (P.variant == 2) {
+        o[2] = gw; o[3] = gh;
+        o[4] = wrap(add(mul(dn[4], PI_F), pa), QUARTER_PI_F);                      // :289, :302-303
+    } else {
+        const float gt = add(dn[4], pa);
+        const bool big = gw > gh;                                                  // :413-417
+        o[2] = big ? gw : gh; o[3] = big ? gh : gw;
+        o[4] = wrap(big ? gt : add(gt, HALF_PI_F), HALF_PI_F);
+    }
+}
+
+// bbox2delta_v1/v2/v3 for one (proposal, gt) pair
+__device__ __forceinline__ void encode_one(const CoderP& P, const float* p, const float* g, float* o) {
+    const float px = p[0], py = p[1], pw = p[2], ph = p[3], pa = p[4];
+    const float gx = g[0], gy = g[1], gw = g[2], gh = g[3], ga = g[4];
+    float d[5];
+    if (P.variant == 1) {                                                          // :127-133
+        d[0] = dvd(sub(gx, px), pw); d[1] = dvd(sub(gy, py), ph);
+        d[2] = logf(dvd(gw, pw)); d[3] = logf(dvd(gh, ph)); d[4] = sub(ga, pa);
+    } else {
+        const float ang = (P.variant == 2) ? pa : -pa;
+        const float c = cosf(ang), s = sinf(ang);
+        const float ex = sub(gx, px), ey = sub(gy, py);
+        d[0] = dvd(add(mul(c, ex), mul(s, ey)), pw);
+        d[1] = dvd(add(mul(-s, ex), mul(c, ey)), ph);
+        if (P.variant == 2) {                                                      // :237-243
+            d[2] = logf(dvd(gw, pw)); d[3] = logf(dvd(gh, ph));
+            d[4] = dvd(wrap(sub(ga, pa), QUARTER_PI_F), PI_F);
+        } else {                                                                   // :338-352
+            const float d1 = wrap(sub(ga, pa), HALF_PI_F);
+            const float d2 = wrap(add(sub(ga, pa), HALF_PI_F), HALF_PI_F);
+            const bool first = fabsf(d1) < fabsf(d2);
+            d[2] = logf(dvd(first ? gw : gh, pw)); d[3] = logf(dvd(first ? gh : gw, ph));
+            d[4] = first ? d1 : d2;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 5; k++) o[k] = dvd(sub(d[k], P.mean[k]), P.stdv[k]);
+}
+
+__device__ __forceinline__ float sigmoidf(float x) { return dvd(1.0f, add(1.0f, expf(-x))); }
+
+// ------------------------------------------------------------------------------------------------ plain coder calls
+__global__ void delta2bbox_kernel(const float* __restrict__ rois, int64_t roi_stride, const float* __restrict__ deltas,
+                                  int64_t n, int groups, CoderP P, int clamp, float max_x, float max_y, float* __restrict__ out) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * groups) return;
+    const int64_t i = t / groups;
+    float roi[5], d[5], o[5];
+#pragma unroll
+    for (int k = 0; k < 5; k++) { roi[k] = rois[i * roi_stride + k]; d[k] = deltas[t * 5 + k]; }
+    decode_one(P, roi, d, clamp != 0, max_x, max_y, o);
+#pragma unroll
+    for (int k = 0; k < 5; k++) out[t * 5 + k] = o[k];
+}
+
+__global__ void bbox2delta_kernel(const float* __restrict__ prop, int64_t ps, const float* __restrict__ gt, int64_t gs, int64_t n,
+                                  CoderP P, float* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float p[5], g[5], o[5];
+#pragma unroll
+    for (int k = 0; k < 5; k++) { p[k] = prop[i * ps + k]; g[k] = gt[i * gs + k]; }
+    encode_one(P, p, g, o);
+#pragma unroll
+    for (int k = 0; k < 5; k++) out[i * 5 + k] = o[k];
+}
+
+// ------------------------------------------------------------------------------------------------ FRM prologue
+// filter_bboxes: per location keep the anchor whose best class logit is largest (first maximum), decode it.
+// Threads run along H*W: every class-plane read is coalesced.
+__global__ void filter_bboxes_kernel(const float* __restrict__ cls, const float* __restrict__ reg, const float* __restrict__ anchors,
+                                     int B, int A, int C, int HW, CoderP P, float* __restrict__ out) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)B * HW) return;
+    const int b = (int)(t / HW), hw = (int)(t - (int64_t)b * HW);
+    const float* cb = cls + (int64_t)b * A * C * HW + hw;
+    int best = 0; float bestv = 0.0f;
+    for (int a = 0; a < A; a++) {
+        float m = __ldg(cb + (int64_t)(a * C) * HW);
+        for (int c = 1; c < C; c++) {
+            const float v = __ldg(cb + (int64_t)(a * C + c) * HW);
+            m = (v > m || v != v) ? v : m;                                  // torch.max propagates NaN
+        }
+        if (a == 0 || (m > bestv && bestv == bestv) || (m != m && bestv == bestv)) { best = a; bestv = m; }
+    }
+    float roi[5], d[5], o[5];
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        roi[k] = __ldg(anchors + ((int64_t)hw * A + best) * 5 + k);
+        d[k] = __ldg(reg + ((int64_t)b * A * 5 + best * 5 + k) * HW + hw);
+    }
+    decode_one(P, roi, d, false, 0.0f, 0.0f, o);
+#pragma unroll
+    for (int k = 0; k < 5; k++) out[t * 5 + k] = o[k];
+}
+
+// refine_bboxes: decode the (B,5,H,W) deltas against per-image rois (B, H*W, 5)
+__global__ void refine_bboxes_kernel(const float* __restrict__ reg, const float* __restrict__ rois, int B, int HW, CoderP P,
+                                     float* __restrict__ out) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)B * HW) return;
+    const int b = (int)(t / HW), hw = (int)(t - (int64_t)b * HW);
+    float roi[5], d[5], o[5];
+#pragma unroll
+    for (int k = 0; k < 5; k++) { roi[k] = __ldg(rois + t * 5 + k); d[k] = __ldg(reg + ((int64_t)b * 5 + k) * HW + hw); }
+    decode_one(P, roi, d, false, 0.0f, 0.0f, o);
+#pragma unroll
+    for (int k = 0; k < 5; k++) out[t * 5 + k] = o[k];
+}
+
+// ------------------------------------------------------------------------------------------------ get_bboxes tail
+struct LevelDesc {
+    const float* cls;            // (B, A*C, H, W)
+    const float* reg;            // (B, A*5, H, W)
+    const float* anchors;        // (n, 5) shared by the batch, or (B, n, 5) when anchor_batch_stride != 0
+    int64_t anchor_batch_stride; // in floats
+    int HW, n, k;                // locations, rows (= HW * A), rows kept (= min(nms_pre, n) or n)
+    int row0, out0;              // prefix sums of n and k over the levels
+};
+struct SelectArgs {
+    LevelDesc lv[SEL_MAX_LEVELS];
+    int L, B, A, C, n_total, k_total, topk_on;
+    int clamp, rescale;
+    float max_x[SEL_MAX_IMAGES], max_y[SEL_MAX_IMAGES];
+    float sf[SEL_MAX_IMAGES][4];
+    CoderP P;
+};
+
+__device__ __forceinline__ int level_of(const SelectArgs& S, int r, bool by_out) {
+    int l = 0;
+#pragma unroll
+    for (int i = 1; i < SEL_MAX_LEVELS; i++)
+        if (i < S.L && r >= (by_out ? S.lv[i].out0 : S.lv[i].row0)) l = i;
+    return l;
+}
+
+// One 64-bit key per (image, level, row): segment id on top; below it the complemented bits of sigmoid(max logit) for
+// levels that need a top-k (descending score), or the row index for levels kept whole (original order, as the
+// reference leaves them).  Written at the row's own slot so that the stable sort breaks score ties by row index.
+__global__ void select_keys_kernel(const __grid_constant__ SelectArgs S, unsigned long long* __restrict__ keys, int* __restrict__ vals) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)S.B * S.n_total) return;
+    const int b = (int)(t / S.n_total), r = (int)(t - (int64_t)b * S.n_total);
+    const int l = level_of(S, r, false);
+    const LevelDesc& lv = S.lv[l];
+    const int local = r - lv.row0;                       // thread order: anchor-major, location-minor (coalesced planes)
+    const int a = local / lv.HW, hw = local - a * lv.HW;
+    const int n = hw * S.A + a;                          // row index of permute(1,2,0).reshape(-1, C)
+    unsigned low = (unsigned)n;
+    if (lv.k < lv.n) {
+        const float* cb = lv.cls + ((int64_t)b * S.A * S.C + (int64_t)a * S.C) * lv.HW + hw;
+        float m = __ldg(cb);
+        for (int c = 1; c < S.C; c++) m = fmaxf(m, __ldg(cb + (int64_t)c * lv.HW));
+        low = ~__float_as_uint(sigmoidf(m));             // sigmoid is monotone: max of sigmoids = sigmoid of the max
+    }
+    const int64_t slot = (int64_t)b * S.n_total + lv.row0 + n;
+    keys[slot] = ((unsigned long long)(b * S.L + l) << 32) | low;
+    vals[slot] = n;
+}
+
+// One thread per kept row: gather anchor + deltas, decode, clamp / rescale; then the C scores and the zero column.
+__global__ void select_decode_kernel(const __grid_constant__ SelectArgs S, const int* __restrict__ sorted_rows,
+                                     float* __restrict__ boxes, float* __restrict__ scores) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)S.B * S.k_total) return;
+    const int b = (int)(t / S.k_total), r = (int)(t - (int64_t)b * S.k_total);
+    const int l = level_of(S, r, true);
+    const LevelDesc& lv = S.lv[l];
+    const int n = sorted_rows[(int64_t)b * S.n_total + lv.row0 + (r - lv.out0)];
+    const int hw = n / S.A, a = n - hw * S.A;
+    float roi[5], d[5], o[5];
+    const float* an = lv.anchors + (int64_t)b * lv.anchor_batch_stride + (int64_t)n * 5;
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        roi[k] = __ldg(an + k);
+        d[k] = __ldg(lv.reg + ((int64_t)b * S.A * 5 + a * 5 + k) * lv.HW + hw);
+    }
+    decode_one(S.P, roi, d, S.clamp != 0, S.max_x[b], S.max_y[b], o);
+    if (S.rescale) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) o[k] = dvd(o[k], S.sf[b][k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 5; k++) boxes[t * 5 + k] = o[k];
+    const float* cb = lv.cls + ((int64_t)b * S.A * S.C + (int64_t)a * S.C) * lv.HW + hw;
+    float* so = scores + t * (S.C + 1);
+    for (int c = 0; c < S.C; c++) so[c] = sigmoidf(__ldg(cb + (int64_t)c * lv.HW));
+    so[S.C] = 0.0f;                                      // the dummy background column (rotate_anchor_head.py:659-664)
+}
+
+static int make_coder(const char* who, const float* means, const float* stds, int variant, double wh_ratio_clip, int add_ctr_clamp,
+                      float ctr_clamp, CoderP* P) {
+    R3G_REQUIRE(variant >= 1 && variant <= 3, "%s: variant must be 1, 2 or 3", who);
+    R3G_REQUIRE(means != nullptr && stds != nullptr, "%s: null means / stds", who);
+    R3G_REQUIRE(wh_ratio_clip > 0.0, "%s: wh_ratio_clip must be positive", who);
+    for (int k = 0; k < 5; k++) { P->mean[k] = means[k]; P->stdv[k] = stds[k]; }
+    P->max_ratio = (float)fabs(log(wh_ratio_clip));
+    P->ctr_clamp = ctr_clamp; P->add_ctr_clamp = add_ctr_clamp; P->variant = variant;
+    return R3G_OK;
+}
+
+struct SelectWs { unsigned long long *keys_in, *keys_out; int *vals_in, *vals_out; void* cub; size_t cub_bytes, bytes; };
+
+static int carve_select(void* ws, int64_t items, SelectWs* w) {
+    char* p = (char*)ws;
+    size_t off = 0;
+    const size_t n = (size_t)(items > 0 ? items : 1);
+    w->keys_in = (unsigned long long*)(p + off); off += align_up(8 * n, 256);
+    w->keys_out = (unsigned long long*)(p + off); off += align_up(8 * n, 256);
+    w->vals_in = (int*)(p + off); off += align_up(4 * n, 256);
+    w->vals_out = (int*)(p + off); off += align_up(4 * n, 256);
+    size_t tb = 0;
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, tb, (const unsigned long long*)nullptr, (unsigned long long*)nullptr,
+                                                    (const int*)nullptr, (int*)nullptr, (int64_t)n, 0, 64, (cudaStream_t)0);
+    if (e != cudaSuccess) { set_error("cub temp-size query failed: %s", cudaGetErrorString(e)); return R3G_ERR_CUDA; }
+    w->cub = p + off; w->cub_bytes = tb; off += align_up(tb, 256);
+    w->bytes = off;
+    return R3G_OK;
+}
+
+}  // namespace r3g
+
+using namespace r3g;
+
+R3G_API int r3g_delta2bbox_f32(const float* rois, int64_t n, int64_t roi_stride, const float* deltas, int64_t groups,
+                               const float* means, const float* stds, int variant, const int* max_shape_hw,
+                               double wh_ratio_clip, int add_ctr_clamp, float ctr_clamp, float* out, void* stream) {
+    CoderP P;
+    int rc = make_coder("r3g_delta2bbox_f32", means, stds, variant, wh_ratio_clip, add_ctr_clamp, ctr_clamp, &P);
+    if (rc != R3G_OK) return rc;
+    R3G_REQUIRE(n >= 0 && groups >= 1 && roi_stride >= 5, "r3g_delta2bbox_f32: bad sizes");
+    if (n == 0) return R3G_OK;
+    R3G_REQUIRE(rois && deltas && out, "r3g_delta2bbox_f32: null pointer");
+    const bool clamp = (variant == 1) && max_shape_hw != nullptr;      // only delta2bbox_v1 takes max_shape (:97-99)
+    const float mx = clamp ? (float)(max_shape_hw[1] - 1) : 0.0f, my = clamp ? (float)(max_shape_hw[0] - 1) : 0.0f;
+    const int64_t total = n * groups;
+    delta2bbox_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rois, roi_stride, deltas, n, (int)groups, P,
+                                                                                      clamp ? 1 : 0, mx, my, out);
+    R3G_LAUNCH_OK("delta2bbox_kernel");
+    return R3G_OK;
+}
+
+R3G_API int r3g_bbox2delta_f32(const float* proposals, int64_t proposal_stride, const float* gt, int64_t gt_stride, int64_t n,
+                               const float* means, const float* stds, int variant, float* out, void* stream) {
+    CoderP P;
+    int rc = make_coder("r3g_bbox2delta_f32", means, stds, variant, 16.0 / 1000.0, 0, 0.0f, &P);
+    if (rc != R3G_OK) return rc;
+    R3G_REQUIRE(n >= 0 && proposal_stride >= 5 && gt_stride >= 5, "r3g_bbox2delta_f32: bad sizes");
+    if (n == 0) return R3G_OK;
+    R3G_REQUIRE(proposals && gt && out, "r3g_bbox2delta_f32: null pointer");
+    bbox2delta_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(proposals, proposal_stride, gt, gt_stride, n, P, out);
+    R3G_LAUNCH_OK("bbox2delta_kernel");
+    return R3G_OK;
+}
+
+R3G_API int r3g_filter_bboxes_f32(const float* cls_score, const float* bbox_pred, const float* anchors, int64_t B, int64_t A,
+                                  int64_t C, int64_t H, int64_t W, const float* means, const float* stds, int variant,
+                                  double wh_ratio_clip, int add_ctr_clamp, float ctr_clamp, float* out, void* stream) {
+    CoderP P;
+    int rc = make_coder("r3g_filter_bboxes_f32", means, stds, variant, wh_ratio_clip, add_ctr_clamp, ctr_clamp, &P);
+    if (rc != R3G_OK) return rc;
+    R3G_REQUIRE(B >= 0 && A >= 1 && C >= 1 && H >= 0 && W >= 0 && H * W * A < (1ll << 31), "r3g_filter_bboxes_f32: bad sizes");
+    const int64_t total = B * H * W;
+    if (total == 0) return R3G_OK;
+    R3G_REQUIRE(cls_score && bbox_pred && anchors && out, "r3g_filter_bboxes_f32: null pointer");
+    filter_bboxes_kernel<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(cls_score, bbox_pred, anchors, (int)B, (int)A,
+                                                                                         (int)C, (int)(H * W), P, out);
+    R3G_LAUNCH_OK("filter_bboxes_kernel");
+    return R3G_OK;
+}
+
+R3G_API int r3g_refine_bboxes_f32(const float* bbox_pred, const float* rois, int64_t B, int64_t H, int64_t W, const float* means,
+                                  const float* stds, int variant, double wh_ratio_clip, int add_ctr_clamp, float ctr_clamp,
+                                  float* out, void* stream) {
+    CoderP P;
+    int rc = make_coder("r3g_refine_bboxes_f32", means, stds, variant, wh_ratio_clip, add_ctr_clamp, ctr_clamp, &P);
+    if (rc != R3G_OK) return rc;
+    R3G_REQUIRE(B >= 0 && H >= 0 && W >= 0 && H * W < (1ll << 31), "r3g_refine_bboxes_f32: bad sizes");
+    const int64_t total = B * H * W;
+    if (total == 0) return R3G_OK;
+    R3G_REQUIRE(bbox_pred && rois && out, "r3g_refine_bboxes_f32: null pointer");
+    refine_bboxes_kernel<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(bbox_pred, rois, (int)B, (int)(H * W), P, out);
+    R3G_LAUNCH_OK("refine_bboxes_kernel");
+    return R3G_OK;
+}
+
+static int select_sizes(const char* who, int64_t L, int64_t B, int64_t A, const int64_t* hw, int64_t nms_pre, int64_t* n_total,
+                        int64_t* k_total) {
+    R3G_REQUIRE(L >= 1 && L <= SEL_MAX_LEVELS, "%s: 1..%d levels supported", who, SEL_MAX_LEVELS);
+    R3G_REQUIRE(B >= 0 && B <= SEL_MAX_IMAGES, "%s: at most %d images per call", who, SEL_MAX_IMAGES);
+    R3G_REQUIRE(A >= 1 && hw != nullptr, "%s: bad arguments", who);
+    int64_t nt = 0, kt = 0;
+    for (int l = 0; l < L; l++) {
+        R3G_REQUIRE(hw[2 * l] >= 0 && hw[2 * l + 1] >= 0, "%s: negative feature-map size", who);
+        const int64_t n = hw[2 * l] * hw[2 * l + 1] * A;
+        nt += n; kt += (nms_pre > 0 && n > nms_pre) ? nms_pre : n;
+    }
+    R3G_REQUIRE(nt < (1ll << 31) && B * nt < (1ll << 40), "%s: too many rows", who);
+    *n_total = nt; *k_total = kt;
+    return R3G_OK;
+}
+
+R3G_API int r3g_select_decode_sizes(int64_t L, int64_t B, int64_t A, const int64_t* level_hw, int64_t nms_pre,
+                                    int64_t* rows_per_image, size_t* workspace_bytes) {
+    int64_t nt = 0, kt = 0;
+    int rc = select_sizes("r3g_select_decode_sizes", L, B, A, level_hw, nms_pre, &nt, &kt);
+    if (rc != R3G_OK) return rc;
+    R3G_REQUIRE(rows_per_image && workspace_bytes, "r3g_select_decode_sizes: null output");
+    SelectWs w;
+    rc = carve_select(nullptr, B * nt, &w);
+    if (rc != R3G_OK) return rc;
+    *rows_per_image = kt; *workspace_bytes = w.bytes;
+    return R3G_OK;
+}
+
+R3G_API int r3g_select_decode_f32(int64_t L, const float* const* cls_scores, const float* const* bbox_preds,
+                                  const float* const* anchors, const int64_t* anchor_batch_strides, const int64_t* level_hw,
+                                  int64_t B, int64_t A, int64_t C, int64_t nms_pre,
+                                  const float* means, const float* stds, int variant, double wh_ratio_clip, int add_ctr_clamp,
+                                  float ctr_clamp, const int* max_shapes_hw, const float* scale_factors,
+                                  float* boxes_out, float* scores_out, void* workspace, size_t workspace_bytes, void* stream) {
+    int64_t nt = 0, kt = 0;
+    int rc = select_sizes("r3g_select_decode_f32", L, B, A, level_hw, nms_pre, &nt, &kt);
+    if (rc != R3G_OK) return rc;
+    SelectArgs S;
+    rc = make_coder("r3g_select_decode_f32", means, stds, variant, wh_ratio_clip, add_ctr_clamp, ctr_clamp, &S.P);
+    if (rc != R3G_OK) return rc;
+    R3G_REQUIRE(C >= 1, "r3g_select_decode_f32: need at least one class");
+    if (B == 0 || kt == 0) return R3G_OK;
+    R3G_REQUIRE(cls_scores && bbox_preds && anchors && boxes_out && scores_out && workspace, "r3g_select_decode_f32: null pointer");
+    SelectWs w;
+    rc = carve_select(workspace, B * nt, &w);
+    if (rc != R3G_OK) return rc;
+    if (workspace_bytes < w.bytes) {
+        set_error("r3g_select_decode_f32: workspace too small (%zu < %zu)", workspace_bytes, w.bytes);
+        return R3G_ERR_WORKSPACE;
+    }
+    S.L = (int)L; S.B = (int)B; S.A = (int)A; S.C = (int)C; S.n_total = (int)nt; S.k_total = (int)kt;
+    int row0 = 0, out0 = 0;
+    for (int l = 0; l < SEL_MAX_LEVELS; l++) {
+        LevelDesc& lv = S.lv[l];
+        if (l >= L) { lv = S.lv[0]; lv.n = lv.k = 0; lv.row0 = row0; lv.out0 = out0; continue; }
+        const int64_t HW = level_hw[2 * l] * level_hw[2 * l + 1];
+        R3G_REQUIRE(HW == 0 || (cls_scores[l] && bbox_preds[l] && anchors[l]), "r3g_select_decode_f32: null level pointer");
+        lv.cls = cls_scores[l]; lv.reg = bbox_preds[l]; lv.anchors = anchors[l];
+        lv.anchor_batch_stride = anchor_batch_strides ? anchor_batch_strides[l] : 0;
+        lv.HW = (int)HW; lv.n = (int)(HW * A); lv.k = (nms_pre > 0 && lv.n > nms_pre) ? (int)nms_pre : lv.n;
+        lv.row0 = row0; lv.out0 = out0;
+        row0 += lv.n; out0 += lv.k;
+    }
+    S.clamp = (variant == 1 && max_shapes_hw != nullptr) ? 1 : 0;
+    S.rescale = scale_factors != nullptr ? 1 : 0;
+    for (int b = 0; b < B; b++) {
+        S.max_x[b] = S.clamp ? (float)(max_shapes_hw[2 * b + 1] - 1) : 0.0f;
+        S.max_y[b] = S.clamp ? (float)(max_shapes_hw[2 * b] - 1) : 0.0f;
+        for (int k = 0; k < 4; k++) S.sf[b][k] = S.rescale ? scale_factors[4 * b + k] : 1.0f;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t items = B * nt;
+    select_keys_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(S, w.keys_in, w.vals_in);
+    R3G_LAUNCH_OK("select_keys_kernel");
+    int seg_bits = 1;
+    while ((1ll << seg_bits) < B * L) seg_bits++;
+    size_t tb = w.cub_bytes;
+    R3G_CUDA_OK(cub::DeviceRadixSort::SortPairs(w.cub, tb, (const unsigned long long*)w.keys_in, w.keys_out, (const int*)w.vals_in,
+                                                w.vals_out, items, 0, 32 + seg_bits, st));
+    const int64_t rows = B * kt;
+    select_decode_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(S, w.vals_out, boxes_out, scores_out);
+    R3G_LAUNCH_OK("select_decode_kernel");
+    return R3G_OK;
+}
