@@ -12,7 +12,7 @@ import ctypes as C
 import torch
 
 from . import _lib as L
-from .bbox_nms_rotated import multiclass_nms_rotated
+from .bbox_nms_rotated import multiclass_nms_rotated_batch
 
 MAX_IMAGES = 64     # per r3g_select_decode_f32 call
 
@@ -94,13 +94,9 @@ def get_bboxes(cls_scores, bbox_preds, mlvl_anchors, img_metas, cfg, coder, resc
     shapes = [m['img_shape'] for m in img_metas]
     sfs = [m['scale_factor'] for m in img_metas] if rescale else None
     boxes, scores = select_decode(cls_scores, bbox_preds, mlvl_anchors, coder, get('nms_pre', -1), shapes, sfs)
-    out = []
-    for i in range(boxes.size(0)):
-        if with_nms:
-            out.append(multiclass_nms_rotated(boxes[i], scores[i], get('score_thr'), get('nms'), get('max_per_img')))
-        else:
-            out.append((boxes[i], scores[i]))
-    return out
+    if with_nms:
+        return multiclass_nms_rotated_batch(boxes, scores, get('score_thr'), get('nms'), get('max_per_img'))
+    return [(boxes[i], scores[i]) for i in range(boxes.size(0))]
 
 
 def filter_bboxes(cls_scores, bbox_preds, mlvl_anchors, coder, as_batch=False):

@@ -154,3 +154,23 @@ def test_full_size_properties(cuda_dev):
         cover = R.pairwise_iou(dc, kc, "v3")
         cover[sc[:, None] >= ks[kl == c][None, :]] = 0                       # only higher-scored kept boxes may suppress
         assert (cover.max(dim=1)[0] > thr - 1e-5).all()
+
+
+@pytest.mark.parametrize("kind", ["v1", "v2", "v3", "mmcv"])
+def test_multiclass_batch_equals_per_image(cuda_dev, kind):
+    """multiclass_nms_rotated_batch == the per-image wrapper, image by image (including an image with no candidate)."""
+    import r3det_b200 as R
+    v = "v2" if kind == "mmcv" else kind
+    rng = np.random.default_rng(4)
+    B, n, ncls = 4, 600, 15
+    boxes = np.stack([clustered(n, 30 + b, v)[0] * np.float32(1.0 + 0.3 * b) for b in range(B)])
+    sc = (rng.uniform(0, 1, (B, n, ncls + 1)) ** 8).astype(np.float32)
+    sc[2] = 0.0                                                            # image without candidates
+    mb, ms = torch.from_numpy(boxes).to(cuda_dev), torch.from_numpy(sc).to(cuda_dev)
+    for max_num in (40, 2000):
+        got = R.multiclass_nms_rotated_batch(mb, ms, 0.05, dict(type=kind, iou_thr=0.1), max_num)
+        assert len(got) == B
+        for b in range(B):
+            d, l = R.multiclass_nms_rotated(mb[b], ms[b], 0.05, dict(type=kind, iou_thr=0.1), max_num)
+            assert got[b][0].shape == d.shape and torch.equal(got[b][0], d) and torch.equal(got[b][1], l), (kind, b, max_num)
+    assert got[2][0].shape == (0, 6) and got[2][1].dtype == torch.long
