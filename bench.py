@@ -291,6 +291,7 @@ def run_gpu(args):
         line["nms"] = bench_nms(torch, R, dev, hbm)
         line["frm"] = bench_frm(torch, R, dev, hbm)
         line["fused_assign"] = bench_assign(torch, R, dev, gt_h, an_h)
+        line["dense_tail"] = bench_dense_tail(torch, R, dev)
         cores = os.cpu_count() or 1
         apt = 4000
         rate, dt, kind = cpu_pairs_per_s(apt, cores)
@@ -372,7 +373,7 @@ def bench_assign(torch, R, dev, gt_h, an_h):
     ms_e2e = _time(torch, e2e, 20)
     pairs = GT * ANCHORS
     return {"ms": ms, "gpairs_per_s": pairs / ms / 1e6, "e2e_ms": ms_e2e, "e2e_gpairs_per_s": pairs / ms_e2e / 1e6,
-            "d2h_bytes_per_step": int(res_i.numel() * 8 + res_f.numel() * 4), "passes": 2,
+            "d2h_bytes_per_step": int(res_i.numel() * 8 + res_f.numel() * 4), "pair_sweeps": 1,
             "num_pos": int((res_i > 0).sum())}
 
 
@@ -404,28 +405,72 @@ def bench_nms(torch, R, dev, hbm):
     return out
 
 
+def bench_dense_tail(torch, R, dev):
+    """SURVEY §8f ranks 2-3 on configs[1] shapes: batch 8, 1024^2 patch, 5 FPN levels, 15 classes.
+    get_bboxes: 9 anchors/location (196,416 rows/image), nms_pre 2000, score_thr 0.05, nms v1 thr 0.1, max 2000/img
+    (select + decode + multiclass NMS, the whole batch in one launch sequence).  filter / refine: the FRM prologue."""
+    rng = np.random.default_rng(9)
+    Bn, A, Cn = 8, 9, 15
+    cls, reg, anc, reg1 = [], [], [], []
+    for H, stride in ((128, 8), (64, 16), (32, 32), (16, 64), (8, 128)):
+        # focal-loss style logits: background prior 0.01 with a sparse set of confident locations
+        c = rng.normal(-4.6, 1.0, (Bn, A * Cn, H, H)).astype(np.float32)
+        hot = rng.random((Bn, A * Cn, H, H)) < 2e-4
+        c[hot] = rng.normal(1.0, 1.0, int(hot.sum())).astype(np.float32)
+        cls.append(torch.from_numpy(c).to(dev))
+        reg.append(torch.from_numpy(rng.normal(0, 0.2, (Bn, A * 5, H, H)).astype(np.float32)).to(dev))
+        reg1.append(torch.from_numpy(rng.normal(0, 0.2, (Bn, 5, H, H)).astype(np.float32)).to(dev))
+        ys, xs = np.meshgrid(np.arange(H), np.arange(H), indexing="ij")
+        ctr = (np.stack([xs, ys], -1).reshape(-1, 1, 2) * stride + stride / 2).astype(np.float32)
+        wh = (stride * 4 * np.array([[1, 1], [1.4, 0.7], [0.7, 1.4]], np.float32)[None].repeat(3, 1)
+              * np.array([1, 1, 1, 1.26, 1.26, 1.26, 1.59, 1.59, 1.59], np.float32)[None, :, None])
+        a = np.concatenate([np.broadcast_to(ctr, (H * H, A, 2)), np.broadcast_to(wh, (H * H, A, 2)), np.zeros((H * H, A, 1), np.float32)], -1)
+        anc.append(torch.from_numpy(np.ascontiguousarray(a.reshape(-1, 5))).to(dev))
+    coder = R.DeltaXYWHAOBBoxCoder((0.,) * 5, (1.,) * 5, angle_range="v1")
+    metas = [dict(img_shape=(1024, 1024, 3), scale_factor=np.ones(4, np.float32))] * Bn
+    cfg = dict(nms_pre=2000, min_bbox_size=0, score_thr=0.05, nms=dict(type="v1", iou_thr=0.1), max_per_img=2000)
+    sel = lambda: R.select_decode(cls, reg, anc, coder, 2000, [m["img_shape"] for m in metas], None)
+    full = lambda: R.get_bboxes(cls, reg, anc, metas, cfg, coder)
+    dets = full()
+    ms_sel, ms_full = _time(torch, sel, 20), _time(torch, full, 20)
+    flt = lambda: R.filter_bboxes(cls, reg, anc, coder, as_batch=True)
+    rois = flt()
+    ms_flt = _time(torch, flt, 20)
+    ms_ref = _time(torch, lambda: R.refine_bboxes(cls, reg1, rois, coder, as_batch=True), 20)
+    rows = sum(int(c.size(1) // Cn * c.size(2) * c.size(3)) for c in cls)
+    logits_bytes = sum(c.numel() * 4 for c in cls)
+    return {"images": Bn, "rows_per_image": rows, "select_decode_ms": ms_sel, "get_bboxes_ms": ms_full,
+            "images_per_s": Bn / ms_full * 1e3, "detections": int(sum(d[0].size(0) for d in dets)),
+            "select_decode_gbs": logits_bytes / ms_sel / 1e6, "filter_bboxes_ms": ms_flt, "refine_bboxes_ms": ms_ref,
+            "filter_bboxes_gbs": logits_bytes / ms_flt / 1e6}
+
+
 def bench_frm(torch, R, dev, hbm):
-    """configs[1] FRM shapes: batch 8, 256 channels, 5 FPN levels of a 1024^2 patch; 8 B per element roofline."""
-    from r3det_b200.fr import frm_backward, frm_forward
+    """configs[1] FRM shapes: batch 8, 256 channels, 5 FPN levels of a 1024^2 patch; 8 B per element roofline.
+    All five levels go through ONE launch sequence (r3g_frm_*_multi_f32), as FeatureRefineModule runs them;
+    `per_level_*` is the same work as five separate calls (the reference module's loop)."""
+    from r3det_b200.fr import frm_backward, frm_backward_multi, frm_forward, frm_forward_multi
     rng = np.random.default_rng(4)
     res = {}
+    xs, bts, scales = [], [], []
+    for H, stride in ((128, 8), (64, 16), (32, 32), (16, 64), (8, 128)):
+        xs.append(torch.randn((8, 256, H, H), device=dev))
+        ys_, xs_ = np.meshgrid(np.arange(H) * stride, np.arange(H) * stride, indexing="ij")
+        ctr = np.stack([xs_, ys_], -1).reshape(-1, 2).astype(np.float32)
+        bx = np.zeros((8, H * H, 5), np.float32)
+        bx[:, :, :2] = ctr[None] + rng.normal(0, stride, (8, H * H, 2))
+        bx[:, :, 2:4] = np.exp(rng.uniform(np.log(stride), np.log(8 * stride), (8, H * H, 2)))
+        bx[:, :, 4] = rng.uniform(-np.pi / 2, 0, (8, H * H))
+        bts.append(torch.from_numpy(bx.reshape(-1, 5)).to(dev)); scales.append(1.0 / stride)
+    elems = sum(x.numel() for x in xs)
     for P in (1, 5):
-        tf = tb = 0.0
-        elems = 0
-        for H, stride in ((128, 8), (64, 16), (32, 32), (16, 64), (8, 128)):
-            x = torch.randn((8, 256, H, H), device=dev)
-            ys, xs = np.meshgrid(np.arange(H) * stride, np.arange(H) * stride, indexing="ij")
-            ctr = np.stack([xs, ys], -1).reshape(-1, 2).astype(np.float32)
-            bx = np.zeros((8, H * H, 5), np.float32)
-            bx[:, :, :2] = ctr[None] + rng.normal(0, stride, (8, H * H, 2))
-            bx[:, :, 2:4] = np.exp(rng.uniform(np.log(stride), np.log(8 * stride), (8, H * H, 2)))
-            bx[:, :, 4] = rng.uniform(-np.pi / 2, 0, (8, H * H))
-            bt = torch.from_numpy(bx.reshape(-1, 5)).to(dev)
-            tf += _time(torch, lambda: frm_forward(x, bt, 1.0 / stride, P), 10)
-            tb += _time(torch, lambda: frm_backward(x, bt, 1.0 / stride, P), 10)
-            elems += x.numel()
+        tf = _time(torch, lambda: frm_forward_multi(xs, bts, scales, P), 10)
+        tb = _time(torch, lambda: frm_backward_multi(xs, bts, scales, P), 10)
+        tfl = sum(_time(torch, lambda: frm_forward(x, b, s, P), 10) for x, b, s in zip(xs, bts, scales))
+        tbl = sum(_time(torch, lambda: frm_backward(x, b, s, P), 10) for x, b, s in zip(xs, bts, scales))
         res[f"points{P}"] = {"fwd_ms": tf, "bwd_ms": tb, "fwd_gbs": elems * 8 / tf / 1e6, "bwd_gbs": elems * 8 / tb / 1e6,
-                             "fwd_frac_of_hbm": elems * 8 / tf / 1e6 / hbm, "bwd_frac_of_hbm": elems * 8 / tb / 1e6 / hbm}
+                             "fwd_frac_of_hbm": elems * 8 / tf / 1e6 / hbm, "bwd_frac_of_hbm": elems * 8 / tb / 1e6 / hbm,
+                             "per_level_fwd_ms": tfl, "per_level_bwd_ms": tbl}
     res["elements"] = elems
     res["bytes_per_element"] = 8
     return res

@@ -147,6 +147,19 @@ int r3g_frm_backward_f32(const float* grad_out, const float* boxes, int N, int C
                          float spatial_scale, int points, float* grad_in,
                          void* workspace, size_t workspace_bytes, void* stream);
 
+/* All FPN levels of a batch in ONE launch sequence (FeatureRefineModule.forward loops over the levels,
+ * r3det/ops/fr/feature_refine_module.py:112-127).  Pointer arrays, level_hw {H_0, W_0, H_1, ...} and spatial_scales
+ * are HOST arrays of L <= 8 entries; level l holds (N, C, H_l, W_l) features and (N*H_l*W_l, 5) boxes.
+ * residuals (array or NULL; entries may be NULL): out_l = residuals_l + FRM(feats_l) — the module's final
+ * `x_scale + feat_refined_scale` (:126) folded into the epilogue.  The backward shares one tap sort / CSR build. */
+int r3g_frm_forward_multi_f32(int L, const float* const* feats, const float* const* boxes, const float* const* residuals,
+                              int N, int C, const int* level_hw, const float* spatial_scales, int points,
+                              float* const* outs, void* stream);
+int r3g_frm_backward_multi_workspace_bytes(int L, int N, const int* level_hw, int points, size_t* bytes);
+int r3g_frm_backward_multi_f32(int L, const float* const* grad_outs, const float* const* boxes, int N, int C,
+                               const int* level_hw, const float* spatial_scales, int points, float* const* grad_ins,
+                               void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- box transforms (r3det/core/bbox/rtransforms.py) ---------------------------------------------------
  * obb2poly :367-440, poly2obb :190-277, obb2hbb :443-537, hbb2obb :540-592, obb2xyxy :595-651.
  * n boxes; version 1/2/3. */

@@ -23,7 +23,8 @@ from .box_iou_rotated import obb_overlaps  # noqa: F401
 from .coder import (DeltaXYWHAOBBoxCoder, bbox2delta_v1, bbox2delta_v2, bbox2delta_v3, delta2bbox_v1,  # noqa: F401
                     delta2bbox_v2, delta2bbox_v3)
 from .dense_tail import filter_bboxes, get_bboxes, refine_bboxes, select_decode  # noqa: F401
-from .fr import FR, FeatureRefineFunction, FeatureRefineModule, feature_refine  # noqa: F401
+from .fr import (FR, FeatureRefineFunction, FeatureRefineModule, FeatureRefineMultiFunction, feature_refine,  # noqa: F401
+                 feature_refine_multi)
 from .iou_calculators import (IOU_CALCULATORS, RBboxOverlaps2D_v1, RBboxOverlaps2D_v2,  # noqa: F401
                               RBboxOverlaps2D_v3, rbbox_overlaps_v1, rbbox_overlaps_v2, rbbox_overlaps_v3)
 from .ml_nms_rotated import ml_nms_rotated  # noqa: F401

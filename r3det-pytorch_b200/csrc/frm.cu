@@ -17,6 +17,9 @@
 //             target index ("sorted scatter"); a thread owns one target pixel and GATHERS
 //             grad_in[t] = grad_out[t] + sum_e w_e * grad_out[src_e] for 16 channels per pass.  No atomics,
 //             no pre-zeroed output, bit-reproducible (stable sort => fixed summation order).
+//   All FPN levels of a batch go through ONE launch sequence (r3g_frm_*_multi_f32): the three small levels are pure
+//   launch latency when run alone (a few hundred CTAs each), and the backward's sort / CSR build is shared.
+//   The module's residual add  x + FR(...)  (feature_refine_module.py:126) can ride along in the forward epilogue.
 // Sample-point math follows feature_refine_kernel.cu:16-65 (interpolation) and :127-151 (points), including
 // the reference's swap of box x -> row and box y -> column.
 #include <cub/cub.cuh>
@@ -88,17 +91,51 @@ static TileGeom tile_geom(int H, int W) {
     return g;
 }
 
+constexpr int FRM_MAX_LEVELS = 8;
+struct FrmLevel {
+    const float* feat;       // forward: features; backward: grad_out        (N, C, H, W)
+    const float* boxes;      // (N*H*W, 5)
+    const float* residual;   // forward only, optional: added to the output   (N, C, H, W)
+    float* out;              // forward: out; backward: grad_in
+    int H, W;
+    float scale;
+    TileGeom g;
+    int cchunks;
+    unsigned block0;         // first CTA of this level
+    unsigned loc0;           // first global location (n, h, w) of this level (backward CSR indexing)
+};
+struct FrmLevels { FrmLevel lv[FRM_MAX_LEVELS]; int L, N, C; unsigned nl; };
+
+__device__ __forceinline__ int frm_level_of_block(const FrmLevels& S, unsigned b) {
+    int l = 0;
+#pragma unroll
+    for (int i = 1; i < FRM_MAX_LEVELS; i++) if (i < S.L && b >= S.lv[i].block0) l = i;
+    return l;
+}
+__device__ __forceinline__ int frm_level_of_loc(const FrmLevels& S, unsigned i) {
+    int l = 0;
+#pragma unroll
+    for (int k = 1; k < FRM_MAX_LEVELS; k++) if (k < S.L && i >= S.lv[k].loc0) l = k;
+    return l;
+}
+
 constexpr int FRM_TILE_PITCH = 296;      // >= tile_h * (tile_w + 1) for every geometry (32x9, 16x17, 8x33, 4x65)
 constexpr int FRM_CH_FWD = 8;            // channels per shared-memory round (forward)
 
 template <int P>
-__global__ void __launch_bounds__(FRM_THREADS, (P == 1) ? 4 : 2) frm_forward_kernel(
-    const float* __restrict__ feat, const float* __restrict__ boxes, int N, int C, int H, int W,
-    float scale, TileGeom g, int cchunks, float* __restrict__ out) {
+__global__ void __launch_bounds__(FRM_THREADS, (P == 1) ? 4 : 2) frm_forward_kernel(const __grid_constant__ FrmLevels S) {
     __shared__ float tile[FRM_CH_FWD][FRM_TILE_PITCH];
-    // blockIdx.x = tile + tiles * (chunk + cchunks * n): tiles fastest so that co-resident CTAs share planes
+    const FrmLevel& lv = S.lv[frm_level_of_block(S, blockIdx.x)];
+    const float* __restrict__ feat = lv.feat;
+    const float* __restrict__ boxes = lv.boxes;
+    const float* __restrict__ resid = lv.residual;
+    float* __restrict__ out = lv.out;
+    const int C = S.C, H = lv.H, W = lv.W, cchunks = lv.cchunks;
+    const float scale = lv.scale;
+    const TileGeom g = lv.g;
+    // block = tile + tiles * (chunk + cchunks * n): tiles fastest so that co-resident CTAs share planes
     const int tiles = g.tiles_x * g.tiles_y;
-    int bid = blockIdx.x;
+    int bid = blockIdx.x - lv.block0;
     const int tl = bid % tiles; bid /= tiles;
     const int chunk = bid % cchunks;
     const int n = bid / cchunks;
@@ -172,9 +209,19 @@ __global__ void __launch_bounds__(FRM_THREADS, (P == 1) ? 4 : 2) frm_forward_ker
         // each thread re-reads only its own row-oriented slot here and overwrites only that slot at the top of the
         // next round, and every compute-mapped read of this round happened before the barrier above: no third barrier
         if (rvalid) {
+            if (resid != nullptr) {
+                const float* rp = resid + ((size_t)n * C + cb) * HW + rloc;
+                float rv[FRM_CH_FWD];
 #pragma unroll
-            for (int cc = 0; cc < FRM_CH_FWD; cc++)
-                if (cb + cc < c1) __stcs(oplane + (size_t)cc * HW, tile[cc][rslot]);
+                for (int cc = 0; cc < FRM_CH_FWD; cc++) rv[cc] = (cb + cc < c1) ? __ldg(rp + (size_t)cc * HW) : 0.0f;
+#pragma unroll
+                for (int cc = 0; cc < FRM_CH_FWD; cc++)
+                    if (cb + cc < c1) __stcs(oplane + (size_t)cc * HW, rv[cc] + tile[cc][rslot]);
+            } else {
+#pragma unroll
+                for (int cc = 0; cc < FRM_CH_FWD; cc++)
+                    if (cb + cc < c1) __stcs(oplane + (size_t)cc * HW, tile[cc][rslot]);
+            }
         }
     }
 }
@@ -182,14 +229,17 @@ __global__ void __launch_bounds__(FRM_THREADS, (P == 1) ? 4 : 2) frm_forward_ker
 // ---- backward: tap generation -> sort by target -> CSR -> gather ------------------------------------------
 
 template <int P>
-__global__ void frm_bwd_taps_kernel(const float* __restrict__ boxes, int N, int H, int W, float scale,
-                                    unsigned* __restrict__ keys, unsigned* __restrict__ ids, float* __restrict__ wts) {
-    const int HW = H * W;
-    const size_t nl = (size_t)N * HW;
+__global__ void frm_bwd_taps_kernel(const __grid_constant__ FrmLevels S, unsigned* __restrict__ keys, unsigned* __restrict__ ids,
+                                    float* __restrict__ wts) {
+    const size_t nl = S.nl;
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nl) return;
-    const int n = (int)(i / HW);
-    const float* bb = boxes + i * 5;
+    const FrmLevel& lv = S.lv[frm_level_of_loc(S, (unsigned)i)];
+    const int H = lv.H, W = lv.W, HW = H * W;
+    const float scale = lv.scale;
+    const unsigned li = (unsigned)i - lv.loc0;               // location inside the level
+    const int n = (int)(li / HW);
+    const float* bb = lv.boxes + (size_t)li * 5;
     float b5[5] = { __ldg(bb), __ldg(bb + 1), __ldg(bb + 2), __ldg(bb + 3), __ldg(bb + 4) };
     float px[5], py[5];
     frm_points<P>(b5, scale, px, py);
@@ -201,7 +251,7 @@ __global__ void frm_bwd_taps_kernel(const float* __restrict__ boxes, int N, int 
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             const size_t e = (i * P + p) * 4 + k;
-            keys[e] = ok ? (unsigned)((size_t)n * HW + t.o[k]) : sentinel;
+            keys[e] = ok ? (lv.loc0 + (unsigned)((size_t)n * HW + t.o[k])) : sentinel;
             ids[e] = (unsigned)e;
             wts[e] = t.w[k];
         }
@@ -219,21 +269,29 @@ __global__ void frm_bwd_rows_kernel(const unsigned* __restrict__ skeys, size_t E
     row_start[t] = (unsigned)lo;
 }
 
-__global__ void frm_bwd_materialize_kernel(const unsigned* __restrict__ sids, const float* __restrict__ wts,
-                                           size_t E, int HW, int P, unsigned* __restrict__ src, float* __restrict__ wsorted) {
+__global__ void frm_bwd_materialize_kernel(const __grid_constant__ FrmLevels S, const unsigned* __restrict__ sids,
+                                           const float* __restrict__ wts, size_t E, int P, unsigned* __restrict__ src,
+                                           float* __restrict__ wsorted) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= E) return;
     const unsigned e = sids[i];
-    src[i] = (unsigned)((e / (unsigned)(4 * P)) % (unsigned)HW);     // source location inside its image
+    const unsigned loc = e / (unsigned)(4 * P);
+    const FrmLevel& lv = S.lv[frm_level_of_loc(S, loc)];
+    src[i] = (loc - lv.loc0) % (unsigned)(lv.H * lv.W);              // source location inside its image
     wsorted[i] = wts[e];
 }
 
 __global__ void __launch_bounds__(FRM_THREADS) frm_backward_kernel(
-    const float* __restrict__ gout, const unsigned* __restrict__ row_start, const unsigned* __restrict__ src,
-    const float* __restrict__ wsorted, int N, int C, int H, int W, TileGeom g, int cchunks, float* __restrict__ gin) {
+    const __grid_constant__ FrmLevels S, const unsigned* __restrict__ row_start, const unsigned* __restrict__ src,
+    const float* __restrict__ wsorted) {
     __shared__ float tile[FRM_CC_BWD][FRM_TILE_PITCH];
+    const FrmLevel& lv = S.lv[frm_level_of_block(S, blockIdx.x)];
+    const float* __restrict__ gout = lv.feat;
+    float* __restrict__ gin = lv.out;
+    const int C = S.C, H = lv.H, W = lv.W, cchunks = lv.cchunks;
+    const TileGeom g = lv.g;
     const int tiles = g.tiles_x * g.tiles_y;
-    int bid = blockIdx.x;
+    int bid = blockIdx.x - lv.block0;
     const int tl = bid % tiles; bid /= tiles;
     const int chunk = bid % cchunks;
     const int n = bid / cchunks;
@@ -256,7 +314,7 @@ __global__ void __launch_bounds__(FRM_THREADS) frm_backward_kernel(
         if (rvalid && c0 + k < C) tile[k][rslot] = __ldg(base + (size_t)k * HW + rloc);
     __syncthreads();
     if (cvalid) {
-        const size_t t = (size_t)n * HW + (size_t)h * W + w;
+        const size_t t = (size_t)lv.loc0 + (size_t)n * HW + (size_t)h * W + w;
         const unsigned e0 = __ldg(row_start + t), e1 = __ldg(row_start + t + 1);
         float acc[FRM_CC_BWD];
 #pragma unroll
@@ -293,9 +351,9 @@ struct FrmBwdWs {
     size_t bytes;
 };
 
-static FrmBwdWs carve_frm(void* ws, int N, int H, int W, int P) {
+static FrmBwdWs carve_frm(void* ws, size_t nl, int P) {
     FrmBwdWs w;
-    const size_t nl = (size_t)N * H * W, E = nl * P * 4;
+    const size_t E = nl * P * 4;
     char* p = (char*)ws;
     size_t off = 0;
     auto take = [&](size_t bytes) { char* r = p + off; off += align_up(bytes, 256); return (void*)r; };
@@ -312,71 +370,115 @@ static FrmBwdWs carve_frm(void* ws, int N, int H, int W, int P) {
     return w;
 }
 
-static int check_frm_args(const char* who, const void* a, const void* b, const void* c, int N, int C, int H, int W, int points) {
-    R3G_REQUIRE(N >= 0 && C >= 0 && H >= 0 && W >= 0, "%s: negative dimension", who);
+// Validate a level list and lay the levels out (CTA ranges, location ranges).  Returns 1 when there is nothing to do.
+static int frm_plan(const char* who, int L, const float* const* in, const float* const* boxes, const float* const* residuals,
+                    float* const* out, int N, int C, const int* hw, const float* scales, int points, int cc, FrmLevels* S,
+                    size_t* blocks_out) {
+    R3G_REQUIRE(L >= 1 && L <= FRM_MAX_LEVELS, "%s: 1..%d levels per call", who, FRM_MAX_LEVELS);
+    R3G_REQUIRE(N >= 0 && C >= 0 && hw != nullptr, "%s: bad arguments", who);
     R3G_REQUIRE(points == 1 || points == 5, "%s: points must be 1 or 5 (got %d)", who, points);   // feature_refine_module.py:19
-    if ((size_t)N * C * H * W == 0) return 1;
-    R3G_REQUIRE(a && b && c, "%s: null pointer", who);
-    R3G_REQUIRE((size_t)N * H * W * (size_t)points * 4 < (1ull << 31), "%s: too many sample taps for 32-bit indexing", who);
-    R3G_REQUIRE((size_t)H * W < (1ull << 24), "%s: feature map too large", who);
-    return 0;
+    size_t blocks = 0, nl = 0;
+    S->L = 0; S->N = N; S->C = C;
+    for (int l = 0; l < L; l++) {
+        const int H = hw[2 * l], W = hw[2 * l + 1];
+        R3G_REQUIRE(H >= 0 && W >= 0, "%s: negative dimension", who);
+        if ((size_t)N * C * H * W == 0) continue;                      // empty level: nothing to compute
+        R3G_REQUIRE((size_t)H * W < (1ull << 24), "%s: feature map too large", who);
+        R3G_REQUIRE(in && boxes && out && in[l] && boxes[l] && out[l] && scales, "%s: null pointer", who);
+        FrmLevel& lv = S->lv[S->L++];
+        lv.feat = in[l]; lv.boxes = boxes[l]; lv.residual = residuals ? residuals[l] : nullptr; lv.out = out[l];
+        lv.H = H; lv.W = W; lv.scale = scales[l];
+        lv.g = tile_geom(H, W);
+        lv.cchunks = (C + cc - 1) / cc;
+        lv.block0 = (unsigned)blocks; lv.loc0 = (unsigned)nl;
+        blocks += (size_t)lv.g.tiles_x * lv.g.tiles_y * lv.cchunks * N;
+        nl += (size_t)N * H * W;
+    }
+    R3G_REQUIRE(blocks < (1ull << 31), "%s: grid too large", who);
+    R3G_REQUIRE(nl * (size_t)points * 4 < (1ull << 31), "%s: too many sample taps for 32-bit indexing", who);
+    S->nl = (unsigned)nl;
+    *blocks_out = blocks;
+    return S->L == 0 ? 1 : 0;
 }
 
 }  // namespace r3g
 
 using namespace r3g;
 
-R3G_API int r3g_frm_forward_f32(const float* feat, const float* boxes, int N, int C, int H, int W,
-                                float spatial_scale, int points, float* out, void* stream) {
-    int rc = check_frm_args("r3g_frm_forward_f32", feat, boxes, out, N, C, H, W, points);
+R3G_API int r3g_frm_forward_multi_f32(int L, const float* const* feats, const float* const* boxes, const float* const* residuals,
+                                      int N, int C, const int* level_hw, const float* spatial_scales, int points,
+                                      float* const* outs, void* stream) {
+    FrmLevels S;
+    size_t blocks = 0;
+    int rc = frm_plan("r3g_frm_forward_multi_f32", L, feats, boxes, residuals, outs, N, C, level_hw, spatial_scales, points,
+                      FRM_CCHUNK_FWD, &S, &blocks);
     if (rc < 0) return rc;
     if (rc == 1) return R3G_OK;
-    const TileGeom g = tile_geom(H, W);
-    const int cchunks = (C + FRM_CCHUNK_FWD - 1) / FRM_CCHUNK_FWD;
-    const size_t blocks = (size_t)g.tiles_x * g.tiles_y * cchunks * N;
-    R3G_REQUIRE(blocks < (1ull << 31), "r3g_frm_forward_f32: grid too large");
     cudaStream_t st = (cudaStream_t)stream;
-    if (points == 1) frm_forward_kernel<1><<<(unsigned)blocks, FRM_THREADS, 0, st>>>(feat, boxes, N, C, H, W, spatial_scale, g, cchunks, out);
-    else frm_forward_kernel<5><<<(unsigned)blocks, FRM_THREADS, 0, st>>>(feat, boxes, N, C, H, W, spatial_scale, g, cchunks, out);
+    if (points == 1) frm_forward_kernel<1><<<(unsigned)blocks, FRM_THREADS, 0, st>>>(S);
+    else frm_forward_kernel<5><<<(unsigned)blocks, FRM_THREADS, 0, st>>>(S);
     R3G_LAUNCH_OK("frm_forward_kernel");
     return R3G_OK;
 }
 
+R3G_API int r3g_frm_forward_f32(const float* feat, const float* boxes, int N, int C, int H, int W,
+                                float spatial_scale, int points, float* out, void* stream) {
+    const int hw[2] = { H, W };
+    return r3g_frm_forward_multi_f32(1, &feat, &boxes, nullptr, N, C, hw, &spatial_scale, points, &out, stream);
+}
+
+R3G_API int r3g_frm_backward_multi_workspace_bytes(int L, int N, const int* level_hw, int points, size_t* bytes) {
+    R3G_REQUIRE(bytes != nullptr && L >= 1 && L <= FRM_MAX_LEVELS && N >= 0 && level_hw != nullptr && (points == 1 || points == 5),
+                "r3g_frm_backward_multi_workspace_bytes: bad arguments");
+    size_t nl = 0;
+    for (int l = 0; l < L; l++) {
+        R3G_REQUIRE(level_hw[2 * l] >= 0 && level_hw[2 * l + 1] >= 0, "r3g_frm_backward_multi_workspace_bytes: negative dimension");
+        nl += (size_t)N * level_hw[2 * l] * level_hw[2 * l + 1];
+    }
+    R3G_REQUIRE(nl * (size_t)points * 4 < (1ull << 31), "r3g_frm_backward_multi_workspace_bytes: too many sample taps");
+    *bytes = carve_frm(nullptr, nl > 0 ? nl : 1, points).bytes;
+    return R3G_OK;
+}
+
 R3G_API int r3g_frm_backward_workspace_bytes(int N, int H, int W, int points, size_t* bytes) {
-    R3G_REQUIRE(bytes != nullptr && N >= 0 && H >= 0 && W >= 0 && (points == 1 || points == 5),
-                "r3g_frm_backward_workspace_bytes: bad arguments");
-    *bytes = carve_frm(nullptr, N > 0 ? N : 1, H > 0 ? H : 1, W > 0 ? W : 1, points).bytes;
+    const int hw[2] = { H, W };
+    return r3g_frm_backward_multi_workspace_bytes(1, N, hw, points, bytes);
+}
+
+R3G_API int r3g_frm_backward_multi_f32(int L, const float* const* grad_outs, const float* const* boxes, int N, int C,
+                                       const int* level_hw, const float* spatial_scales, int points, float* const* grad_ins,
+                                       void* workspace, size_t workspace_bytes, void* stream) {
+    FrmLevels S;
+    size_t blocks = 0;
+    int rc = frm_plan("r3g_frm_backward_multi_f32", L, grad_outs, boxes, nullptr, grad_ins, N, C, level_hw, spatial_scales, points,
+                      FRM_CC_BWD, &S, &blocks);
+    if (rc < 0) return rc;
+    if (rc == 1) return R3G_OK;
+    R3G_REQUIRE(workspace != nullptr, "r3g_frm_backward_multi_f32: null workspace");
+    const size_t nl = S.nl, E = nl * points * 4;
+    FrmBwdWs w = carve_frm(workspace, nl, points);
+    if (workspace_bytes < w.bytes) {
+        set_error("r3g_frm_backward_multi_f32: workspace too small (%zu < %zu)", workspace_bytes, w.bytes);
+        return R3G_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int tpb = 256;
+    if (points == 1) frm_bwd_taps_kernel<1><<<(unsigned)((nl + tpb - 1) / tpb), tpb, 0, st>>>(S, w.keys, w.ids, w.wts);
+    else frm_bwd_taps_kernel<5><<<(unsigned)((nl + tpb - 1) / tpb), tpb, 0, st>>>(S, w.keys, w.ids, w.wts);
+    int end_bit = 1;
+    while (((size_t)1 << end_bit) <= nl) end_bit++;            // keys are in [0, nl]
+    size_t tb = w.cub_bytes;
+    R3G_CUDA_OK(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, w.keys, w.keys2, w.ids, w.ids2, (int)E, 0, end_bit, st));
+    frm_bwd_rows_kernel<<<(unsigned)((nl + 1 + tpb - 1) / tpb), tpb, 0, st>>>(w.keys2, E, nl, w.row_start);
+    frm_bwd_materialize_kernel<<<(unsigned)((E + tpb - 1) / tpb), tpb, 0, st>>>(S, w.ids2, w.wts, E, points, w.src, w.wsorted);
+    frm_backward_kernel<<<(unsigned)blocks, FRM_THREADS, 0, st>>>(S, w.row_start, w.src, w.wsorted);
+    R3G_LAUNCH_OK("frm_backward kernels");
     return R3G_OK;
 }
 
 R3G_API int r3g_frm_backward_f32(const float* grad_out, const float* boxes, int N, int C, int H, int W,
                                  float spatial_scale, int points, float* grad_in,
                                  void* workspace, size_t workspace_bytes, void* stream) {
-    int rc = check_frm_args("r3g_frm_backward_f32", grad_out, boxes, grad_in, N, C, H, W, points);
-    if (rc < 0) return rc;
-    if (rc == 1) return R3G_OK;
-    R3G_REQUIRE(workspace != nullptr, "r3g_frm_backward_f32: null workspace");
-    FrmBwdWs w = carve_frm(workspace, N, H, W, points);
-    if (workspace_bytes < w.bytes) {
-        set_error("r3g_frm_backward_f32: workspace too small (%zu < %zu)", workspace_bytes, w.bytes);
-        return R3G_ERR_WORKSPACE;
-    }
-    cudaStream_t st = (cudaStream_t)stream;
-    const size_t nl = (size_t)N * H * W, E = nl * points * 4;
-    const int tpb = 256;
-    if (points == 1) frm_bwd_taps_kernel<1><<<(unsigned)((nl + tpb - 1) / tpb), tpb, 0, st>>>(boxes, N, H, W, spatial_scale, w.keys, w.ids, w.wts);
-    else frm_bwd_taps_kernel<5><<<(unsigned)((nl + tpb - 1) / tpb), tpb, 0, st>>>(boxes, N, H, W, spatial_scale, w.keys, w.ids, w.wts);
-    int end_bit = 1;
-    while (((size_t)1 << end_bit) <= nl) end_bit++;            // keys are in [0, nl]
-    size_t tb = w.cub_bytes;
-    R3G_CUDA_OK(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, w.keys, w.keys2, w.ids, w.ids2, (int)E, 0, end_bit, st));
-    frm_bwd_rows_kernel<<<(unsigned)((nl + 1 + tpb - 1) / tpb), tpb, 0, st>>>(w.keys2, E, nl, w.row_start);
-    frm_bwd_materialize_kernel<<<(unsigned)((E + tpb - 1) / tpb), tpb, 0, st>>>(w.ids2, w.wts, E, H * W, points, w.src, w.wsorted);
-    const TileGeom g = tile_geom(H, W);
-    const int cchunks = (C + FRM_CC_BWD - 1) / FRM_CC_BWD;
-    const size_t blocks = (size_t)g.tiles_x * g.tiles_y * cchunks * N;
-    R3G_REQUIRE(blocks < (1ull << 31), "r3g_frm_backward_f32: grid too large");
-    frm_backward_kernel<<<(unsigned)blocks, FRM_THREADS, 0, st>>>(grad_out, w.row_start, w.src, w.wsorted, N, C, H, W, g, cchunks, grad_in);
-    R3G_LAUNCH_OK("frm_backward kernels");
-    return R3G_OK;
+    const int hw[2] = { H, W };
+    return r3g_frm_backward_multi_f32(1, &grad_out, &boxes, N, C, hw, &spatial_scale, points, &grad_in, workspace, workspace_bytes, stream);
 }

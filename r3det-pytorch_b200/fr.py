@@ -1,6 +1,7 @@
 """FRM on B200 — drop-in for r3det/ops/fr/feature_refine_module.py (names, signatures, state_dict keys).
 
     feature_refine(features, best_rbboxes, spatial_scale, points=1)       autograd op (:10-43)
+    feature_refine_multi(features[], best_rbboxes[], scales[], points, residuals[])   every FPN level in one launch
     FR(spatial_scale, points=1)                                           nn.Module around it (:46-63)
     FeatureRefineModule(in_channels, featmap_strides, conv_cfg, norm_cfg) x + FR(conv_5_1(conv_1_5(x)) + conv_1_1(x)) (:66-127)
 
@@ -50,6 +51,100 @@ def frm_backward(grad_output, best_rbboxes, spatial_scale, points=1):
         L.check(lib.r3g_frm_backward_f32(L.ptr(gf), L.ptr(bf), n, c, h, w, float(spatial_scale), int(points),
                                          L.ptr(gin), L.ptr(ws), ws.numel(), L.stream_ptr(gf.device)))
     return gin if grad_output.dtype == torch.float32 else gin.to(grad_output.dtype)
+
+
+def _prep_levels(xs, boxes):
+    if len(xs) != len(boxes) or not xs:
+        raise ValueError('need one box tensor per level')
+    if len(xs) > 8:
+        raise ValueError('at most 8 levels per call')
+    prepped = [_prep(x, b) for x, b in zip(xs, boxes)]
+    n, c = prepped[0][2][0], prepped[0][2][1]
+    for _, _, (n_, c_, _, _) in prepped:
+        if (n_, c_) != (n, c):
+            raise ValueError('all levels must share batch size and channel count')
+    return prepped, n, c
+
+
+def _ptr_array(tensors):
+    return (C.c_void_p * len(tensors))(*[t.data_ptr() if t is not None and t.numel() else 0 for t in tensors])
+
+
+def frm_forward_multi(features, best_rbboxes, spatial_scales, points=1, residuals=None):
+    """All levels in one launch: out_l = [residuals_l +] features_l + sum_p bilinear(features_l, y_p, x_p)."""
+    prepped, n, c = _prep_levels(features, best_rbboxes)
+    xs = [p[0] for p in prepped]; bs = [p[1] for p in prepped]
+    outs = [torch.empty_like(x) for x in xs]
+    rs = None
+    if residuals is not None:
+        rs = [r.contiguous() if r.dtype == torch.float32 else r.float().contiguous() for r in residuals]
+        assert all(r.shape == x.shape and r.is_cuda for r, x in zip(rs, xs))
+    nl = len(xs)
+    hw = (C.c_int * (2 * nl))(*[v for x in xs for v in (x.size(2), x.size(3))])
+    sc = (C.c_float * nl)(*[float(s) for s in spatial_scales])
+    dev = xs[0].device
+    with L.device_guard(dev):
+        L.check(L.lib().r3g_frm_forward_multi_f32(nl, _ptr_array(xs), _ptr_array(bs), None if rs is None else _ptr_array(rs), n, c, hw,
+                                                  sc, int(points), _ptr_array(outs), L.stream_ptr(dev)))
+    return [o if f.dtype == torch.float32 else o.to(f.dtype) for o, f in zip(outs, features)]
+
+
+def frm_backward_multi(grad_outputs, best_rbboxes, spatial_scales, points=1):
+    """grad wrt the features of frm_forward_multi: one tap sort / CSR build and one gather launch for all levels."""
+    prepped, n, c = _prep_levels(grad_outputs, best_rbboxes)
+    gs = [p[0] for p in prepped]; bs = [p[1] for p in prepped]
+    gins = [torch.empty_like(g) for g in gs]
+    nl = len(gs)
+    hw = (C.c_int * (2 * nl))(*[v for g in gs for v in (g.size(2), g.size(3))])
+    sc = (C.c_float * nl)(*[float(s) for s in spatial_scales])
+    lib = L.lib()
+    need = C.c_size_t(0)
+    L.check(lib.r3g_frm_backward_multi_workspace_bytes(nl, n, hw, int(points), C.byref(need)))
+    dev = gs[0].device
+    ws = L.workspace(need.value, dev)
+    with L.device_guard(dev):
+        L.check(lib.r3g_frm_backward_multi_f32(nl, _ptr_array(gs), _ptr_array(bs), n, c, hw, sc, int(points), _ptr_array(gins),
+                                               L.ptr(ws), ws.numel(), L.stream_ptr(dev)))
+    return [g if go.dtype == torch.float32 else g.to(go.dtype) for g, go in zip(gins, grad_outputs)]
+
+
+class FeatureRefineMultiFunction(Function):
+    """feature_refine over every FPN level at once: apply(points, scales, with_residual, *features, *boxes[, *residuals])
+    -> tuple of refined maps.  Gradients: features get the FRM transpose, residuals the identity, boxes none
+    (as in the reference, feature_refine_module.py:27-43)."""
+
+    @staticmethod
+    def forward(ctx, points, scales, with_residual, *tensors):
+        assert points in [1, 5]
+        nl = len(scales)
+        feats, boxes = tensors[:nl], tensors[nl:2 * nl]
+        resid = tensors[2 * nl:3 * nl] if with_residual else None
+        assert all(f.is_cuda for f in feats)
+        ctx.frm = (points, tuple(scales), nl, with_residual)
+        ctx.save_for_backward(*boxes)
+        return tuple(frm_forward_multi(feats, boxes, scales, points, resid))
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, *grads):
+        points, scales, nl, with_residual = ctx.frm
+        boxes = ctx.saved_tensors
+        grads = [g.contiguous() for g in grads]
+        need = [ctx.needs_input_grad[3 + l] for l in range(nl)]
+        gin = [None] * nl
+        if any(need):
+            idx = [l for l in range(nl) if need[l]]
+            res = frm_backward_multi([grads[l] for l in idx], [boxes[l] for l in idx], [scales[l] for l in idx], points)
+            for l, g in zip(idx, res):
+                gin[l] = g
+        gres = [grads[l] if ctx.needs_input_grad[3 + 2 * nl + l] else None for l in range(nl)] if with_residual else []
+        return (None, None, None, *gin, *([None] * nl), *gres)
+
+
+def feature_refine_multi(features, best_rbboxes, spatial_scales, points=1, residuals=None):
+    """List-in / list-out wrapper of FeatureRefineMultiFunction."""
+    args = list(features) + list(best_rbboxes) + (list(residuals) if residuals is not None else [])
+    return list(FeatureRefineMultiFunction.apply(points, tuple(float(s) for s in spatial_scales), residuals is not None, *args))
 
 
 class FeatureRefineFunction(Function):
@@ -113,8 +208,7 @@ class FeatureRefineModule(nn.Module):
     def forward(self, x, best_rbboxes):
         """x: per-level feature maps; best_rbboxes[img][lvl]: (H*W, 5) refined boxes of one image and level."""
         per_level_boxes = [torch.cat(level) for level in zip(*best_rbboxes)]
-        refined = []
-        for feat, boxes, fr in zip(x, per_level_boxes, self.fr):
-            mixed = self.conv_5_1(self.conv_1_5(feat)) + self.conv_1_1(feat)
-            refined.append(feat + fr(mixed, boxes))
-        return refined
+        mixed = [self.conv_5_1(self.conv_1_5(feat)) + self.conv_1_1(feat) for feat in x]
+        # every level through one FRM launch, with the `x_scale + feat_refined_scale` add (:126) in its epilogue
+        return feature_refine_multi(mixed, per_level_boxes, [fr.spatial_scale for fr in self.fr],
+                                    self.fr[0].points if len(self.fr) else 1, residuals=list(x))

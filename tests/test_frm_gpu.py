@@ -87,3 +87,58 @@ def test_full_size_adjoint_identity(cuda_dev):
         rhs = (x.double() * frm_backward(g, b, 1.0 / stride, P).double()).sum().item()
         scale = (x.double().norm() * g.double().norm()).item()
         assert abs(lhs - rhs) / scale < 1e-6
+
+
+@pytest.mark.parametrize("P", [1, 5])
+def test_multi_level_equals_per_level(cuda_dev, P):
+    """All FPN levels in one launch sequence == the per-level calls, bit for bit (same kernels, same summation order);
+    the fused residual equals an explicit add; an empty level is skipped."""
+    from r3det_b200.fr import frm_backward, frm_backward_multi, frm_forward, frm_forward_multi
+    rng = np.random.default_rng(21)
+    N, Cc = 3, 40
+    shapes = [(40, 36, 8), (20, 18, 16), (10, 9, 32), (5, 5, 64), (3, 2, 128)]
+    feats, gouts, boxes, scales = [], [], [], []
+    for H, W, s in shapes:
+        f, g, b = _case(rng, N, Cc, H, W, s)
+        feats.append(torch.from_numpy(f).to(cuda_dev)); gouts.append(torch.from_numpy(g).to(cuda_dev))
+        boxes.append(torch.from_numpy(b).to(cuda_dev)); scales.append(1.0 / s)
+    outs = frm_forward_multi(feats, boxes, scales, P)
+    gins = frm_backward_multi(gouts, boxes, scales, P)
+    for l in range(len(shapes)):
+        assert torch.equal(outs[l], frm_forward(feats[l], boxes[l], scales[l], P)), l
+        assert torch.equal(gins[l], frm_backward(gouts[l], boxes[l], scales[l], P)), l
+        assert _rel(outs[l].cpu().numpy(), port.frm_forward(feats[l].cpu().numpy(), boxes[l].cpu().numpy(), scales[l], P)) <= RTOL
+    res = [torch.randn_like(f) for f in feats]
+    outs_r = frm_forward_multi(feats, boxes, scales, P, residuals=res)
+    for l in range(len(shapes)):
+        assert torch.allclose(outs_r[l], res[l] + outs[l], rtol=0, atol=1e-6 * float(outs[l].abs().max()))
+    # an empty level in the middle
+    e = torch.empty((N, Cc, 0, 7), device=cuda_dev)
+    o2 = frm_forward_multi([feats[0], e, feats[2]], [boxes[0], torch.empty((0, 5), device=cuda_dev), boxes[2]], [scales[0], 1.0, scales[2]], P)
+    assert torch.equal(o2[0], outs[0]) and o2[1].shape == e.shape and torch.equal(o2[2], outs[2])
+
+
+def test_multi_level_autograd(cuda_dev):
+    import r3det_b200 as R
+    rng = np.random.default_rng(8)
+    fs, bs, gs = [], [], []
+    for H, s in ((16, 8), (8, 16)):
+        f, g, b = _case(rng, 2, 12, H, H, s)
+        fs.append(torch.from_numpy(f).to(cuda_dev).requires_grad_(True)); bs.append(torch.from_numpy(b).to(cuda_dev))
+        gs.append(torch.from_numpy(g).to(cuda_dev))
+    rs = [torch.randn_like(f).requires_grad_(True) for f in fs]
+    outs = R.feature_refine_multi(fs, bs, [1 / 8, 1 / 16], 5, residuals=rs)
+    torch.autograd.backward(outs, gs)
+    for l, s in enumerate((1 / 8, 1 / 16)):
+        want = port.frm_backward(gs[l].cpu().numpy(), bs[l].cpu().numpy(), s, 5, acc64=True)
+        assert _rel(fs[l].grad.cpu().numpy(), want) <= RTOL
+        assert torch.equal(rs[l].grad, gs[l])
+    # the module (which now runs every level through one launch) against the per-level composition
+    m = R.FeatureRefineModule(12, [8, 16]).to(cuda_dev); m.init_weights()
+    xs = [f.detach() for f in fs]
+    rois = [[bs[0][:256], bs[1][:64]], [bs[0][256:], bs[1][64:]]]
+    ys = m(xs, rois)
+    for l in range(2):
+        mixed = m.conv_5_1(m.conv_1_5(xs[l])) + m.conv_1_1(xs[l])
+        want = xs[l] + R.feature_refine(mixed, bs[l], m.fr[l].spatial_scale, 1)
+        assert torch.allclose(ys[l], want, rtol=0, atol=1e-5)
