@@ -15,7 +15,7 @@
 //             pass (the reference's Python zero-fills `output` first).
 //   backward: the taps of an image are inverted once per call into a per-target CSR by a radix sort on the
 //             target index ("sorted scatter"); a thread owns one target pixel and GATHERS
-//             grad_in[t] = grad_out[t] + sum_e w_e * grad_out[src_e] for 16 channels per pass.  No atomics,
+//             grad_in[t] = grad_out[t] + sum_e w_e * grad_out[src_e] for 32 channels per pass.  No atomics,
 //             no pre-zeroed output, bit-reproducible (stable sort => fixed summation order).
 //   All FPN levels of a batch go through ONE launch sequence (r3g_frm_*_multi_f32): the three small levels are pure
 //   launch latency when run alone (a few hundred CTAs each), and the backward's sort / CSR build is shared.
@@ -29,7 +29,13 @@ namespace r3g {
 
 constexpr int FRM_THREADS = 256;
 constexpr int FRM_CCHUNK_FWD = 32;   // channels per forward CTA
-constexpr int FRM_CC_BWD = 16;       // channels accumulated together per backward thread
+#ifndef R3G_FRM_BWD_CC
+#define R3G_FRM_BWD_CC 32
+#endif
+#ifndef R3G_FRM_BWD_MINB
+#define R3G_FRM_BWD_MINB 2
+#endif
+constexpr int FRM_CC_BWD = R3G_FRM_BWD_CC;       // channels accumulated together per backward thread
 
 struct Taps4 { float w[4]; int o[4]; };
 
@@ -281,7 +287,7 @@ __global__ void frm_bwd_materialize_kernel(const __grid_constant__ FrmLevels S, 
     wsorted[i] = wts[e];
 }
 
-__global__ void __launch_bounds__(FRM_THREADS) frm_backward_kernel(
+__global__ void __launch_bounds__(FRM_THREADS, R3G_FRM_BWD_MINB) frm_backward_kernel(
     const __grid_constant__ FrmLevels S, const unsigned* __restrict__ row_start, const unsigned* __restrict__ src,
     const float* __restrict__ wsorted) {
     __shared__ float tile[FRM_CC_BWD][FRM_TILE_PITCH];
