@@ -123,6 +123,15 @@ int r3g_nms_batched_f32(const float* boxes, int64_t stride, const float* scores,
                         int64_t* keep_out, int64_t* num_keep_out,
                         void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- polygon NMS ----------------------------------------------------------------------
+ * replaces nms_rotated_ext.nms_poly   r3det/ops/nms_rotated/src/poly_nms_cuda.cu:122-262 (mask kernel + host scan)
+ * polys: K rows of `stride` >= 8 floats [x0, y0, ..., x3, y3] (arbitrary quadrilaterals), scores (K).  Greedy in
+ * descending score (ties: lower index first), suppress when IoU > thr; keep_out[0 .. *num_keep_out) = kept original
+ * indices in descending-score order (device memory, like r3g_nms_f32). */
+int r3g_poly_nms_workspace_bytes(int64_t K, size_t* bytes);
+int r3g_poly_nms_f32(const float* polys, int64_t stride, const float* scores, int64_t K, float thr,
+                     int64_t* keep_out, int64_t* num_keep_out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- multiclass candidate extraction -----------------------------------------------------------------------
  * replaces the torch prologue of multiclass_nms_rotated (r3det/core/post_processing/bbox_nms_rotated.py:34-41,
  * 98-103): candidates = (box, class) pairs with multi_scores[i, c] > score_thr for c < C (the last, background,

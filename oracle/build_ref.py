@@ -80,6 +80,10 @@ CUDA_TARGETS = {
                              f"{OPS}/box_iou_rotated/src/box_iou_rotated_cuda.cu"),
     "libref_cuda_v3nms.so": ("refcuda_v3nms.cu", "R3REF_NMS_ROTATED_CUDA",
                              f"{OPS}/nms_rotated/src/nms_rotated_cuda.cu"),
+    # these two include <THC/THC.h>, gone from torch since 1.11: refshim/thc/ holds a stand-in (allocation / ceil-div
+    # helpers only), the kernels and host loops are the reference's own
+    "libref_cuda_polynms.so": ("refcuda_polynms.cu", "R3REF_POLY_NMS_CUDA", f"{OPS}/nms_rotated/src/poly_nms_cuda.cu"),
+    "libref_cuda_v1nms.so": ("refcuda_v1nms.cu", "R3REF_RNMS_KERNEL", f"{OPS}/rnms/src/rcuda/rnms_kernel.cu"),
 }
 
 
@@ -98,7 +102,8 @@ def build_cuda_one(name, force=False):
     cmd = ["nvcc", "-std=c++17", "-O2", "-shared", "-Xcompiler", "-fPIC,-fvisibility=hidden", "-w",
            "-gencode", "arch=compute_100,code=sm_100",
            "-D__CUDA_NO_HALF_OPERATORS__", "-D__CUDA_NO_HALF_CONVERSIONS__", "-D__CUDA_NO_HALF2_OPERATORS__",
-           f"-D{macro}=\"{ref_file}\"", f"-I{os.path.dirname(ref_file)}", f"-I{os.path.join(HERE, 'refshim')}"]
+           f"-D{macro}=\"{ref_file}\"", f"-I{os.path.dirname(ref_file)}", f"-I{os.path.join(HERE, 'refshim')}",
+           f"-I{os.path.join(HERE, 'refshim', 'thc')}"]
     cmd += c + [src, "-o", out] + [x.replace("-Wl,-rpath,", "-Xlinker=-rpath=") for x in l]
     cmd += ["-ltorch_cuda", "-lc10_cuda", "-lcudart"]
     r = subprocess.run(cmd, capture_output=True, text=True)

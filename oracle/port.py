@@ -37,6 +37,10 @@ def lib():
         _lib.orc_iou_exact_f64.restype = None
         _lib.orc_nms_f32.argtypes = [_f32p, C.c_int64, _f32p, C.c_void_p, C.c_int64, C.c_float, C.c_int, C.c_int, C.c_int, _i64p]
         _lib.orc_nms_f32.restype = C.c_int64
+        _lib.orc_poly_iou_aligned_f32.argtypes = [_f32p, C.c_int64, _f32p, C.c_int64, C.c_int64, _f32p]
+        _lib.orc_poly_iou_aligned_f32.restype = None
+        _lib.orc_poly_nms_f32.argtypes = [_f32p, C.c_int64, _f32p, C.c_int64, C.c_float, _i64p]
+        _lib.orc_poly_nms_f32.restype = C.c_int64
         _lib.orc_frm_forward_f32.argtypes = [_f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _f32p]
         _lib.orc_frm_forward_f32.restype = None
         _lib.orc_frm_backward_f32.argtypes = [_f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, _f32p]
@@ -114,3 +118,23 @@ def frm_backward(gout, boxes, scale, points=1, acc64=False):
     gin = np.empty_like(gout)
     lib().orc_frm_backward_f32(gout, boxes.reshape(-1), N, Cc, H, W, float(scale), int(points), int(acc64), gin)
     return gin
+
+
+def poly_iou_aligned(p, q):
+    """IoU of 4-point polygons, row by row (poly_nms_cuda.cu:122-143): p, q (n, >=8) -> (n,)."""
+    p = np.ascontiguousarray(np.asarray(p, np.float32)); q = np.ascontiguousarray(np.asarray(q, np.float32))
+    out = np.empty((p.shape[0],), np.float32)
+    if out.size:
+        lib().orc_poly_iou_aligned_f32(p, p.shape[1], q, q.shape[1], p.shape[0], out)
+    return out
+
+
+def poly_nms(dets, thr):
+    """Greedy polygon NMS on (K, 9) rows [x0, y0, ..., x3, y3, score] (rule IoU > thr): kept indices, score order."""
+    dets = np.ascontiguousarray(np.asarray(dets, np.float32))
+    K = dets.shape[0]
+    keep = np.empty((K,), np.int64)
+    if K == 0:
+        return keep
+    n = lib().orc_poly_nms_f32(dets, dets.shape[1], np.ascontiguousarray(dets[:, 8]), K, float(thr), keep)
+    return keep[:n].copy()

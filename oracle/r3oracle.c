@@ -557,3 +557,124 @@ ORC_API void orc_frm_backward_f32(const float *gout, const float *boxes, int N, 
         free(acc);
     }
 }
+
+/* ================================================================================================
+ * polygon IoU / polygon NMS  (r3det/ops/nms_rotated/src/poly_nms_cuda.cu:22-194; the reference has no CPU
+ * implementation of this op — nms_rotated_wrapper.py:70-71 raises for CPU tensors — so this restates the CUDA
+ * device code; pinned against that code compiled unmodified in oracle/_ref/libref_cuda_polynms.so through
+ * tests/golden/poly_refcuda.npz.  The reference's build contracts a*b-c*d into FMAs and this host build does not:
+ * agreement is to FP32 cancellation noise of the origin-anchored triangle fans, not bit-for-bit.)
+ * ================================================================================================ */
+#define POLY_EPS 1E-8
+static inline int poly_sig(float d) { return ((double)d > POLY_EPS) - ((double)d < -POLY_EPS); }          /* :25-27 */
+static inline int poly_pt_eq(pt a, pt b) { return poly_sig(a.x - b.x) == 0 && poly_sig(a.y - b.y) == 0; } /* :29-31 */
+static inline float poly_cross(pt o, pt a, pt b) { return (a.x - o.x) * (b.y - o.y) - (b.x - o.x) * (a.y - o.y); } /* :47-49 */
+
+static float poly_area(pt *ps, int n)                                                                     /* :50-57 */
+{
+    ps[n] = ps[0];
+    float res = 0;
+    for (int i = 0; i < n; i++) res += ps[i].x * ps[i + 1].y - ps[i].y * ps[i + 1].x;
+    return (float)(res / 2.0);
+}
+
+static int poly_line_cross(pt a, pt b, pt c, pt d, pt *p)                                                 /* :58-67 */
+{
+    float s1 = poly_cross(a, b, c), s2 = poly_cross(a, b, d);
+    if (poly_sig(s1) == 0 && poly_sig(s2) == 0) return 2;
+    if (poly_sig(s2 - s1) == 0) return 0;
+    p->x = (c.x * s2 - d.x * s1) / (s2 - s1);
+    p->y = (c.y * s2 - d.y * s1) / (s2 - s1);
+    return 1;
+}
+
+static void poly_cut(pt *p, int *n_io, pt a, pt b, pt *pp)                                                /* :69-83 */
+{
+    int n = *n_io, m = 0;
+    p[n] = p[0];
+    for (int i = 0; i < n; i++) {
+        if (poly_sig(poly_cross(a, b, p[i])) > 0) pp[m++] = p[i];
+        if (poly_sig(poly_cross(a, b, p[i])) != poly_sig(poly_cross(a, b, p[i + 1])))
+            poly_line_cross(a, b, p[i], p[i + 1], &pp[m++]);
+    }
+    n = 0;
+    for (int i = 0; i < m; i++)
+        if (!i || !poly_pt_eq(pp[i], pp[i - 1])) p[n++] = pp[i];
+    while (n > 1 && poly_pt_eq(p[n - 1], p[0])) n--;
+    *n_io = n;
+}
+
+/* signed intersection area of the triangles (o,a,b) and (o,c,d), o = origin                                 :87-105 */
+static float poly_tri_intersect(pt a, pt b, pt c, pt d)
+{
+    pt o = { 0.0f, 0.0f };
+    int s1 = poly_sig(poly_cross(o, a, b)), s2 = poly_sig(poly_cross(o, c, d));
+    if (s1 == 0 || s2 == 0) return 0.0f;
+    if (s1 == -1) { pt t = a; a = b; b = t; }
+    if (s2 == -1) { pt t = c; c = d; d = t; }
+    pt p[10] = { o, a, b }, pp[10];
+    memset(pp, 0, sizeof pp);              /* the reference leaves pp uninitialised (read only if a crossing degenerates) */
+    int n = 3;
+    poly_cut(p, &n, o, c, pp);
+    poly_cut(p, &n, c, d, pp);
+    poly_cut(p, &n, d, o, pp);
+    float res = fabsf(poly_area(p, n));
+    if (s1 * s2 == -1) res = -res;
+    return res;
+}
+
+static void poly_reverse(pt *first, pt *last)                                                             /* :39-45 */
+{
+    while ((first != last) && (first != --last)) { pt t = *first; *first = *last; *last = t; ++first; }
+}
+
+static float poly_intersect_area(pt *ps1, int n1, pt *ps2, int n2)                                       /* :107-119 */
+{
+    if (poly_area(ps1, n1) < 0) poly_reverse(ps1, ps1 + n1);
+    if (poly_area(ps2, n2) < 0) poly_reverse(ps2, ps2 + n2);
+    ps1[n1] = ps1[0];
+    ps2[n2] = ps2[0];
+    float res = 0;
+    for (int i = 0; i < n1; i++)
+        for (int j = 0; j < n2; j++) res += poly_tri_intersect(ps1[i], ps1[i + 1], ps2[j], ps2[j + 1]);
+    return res;
+}
+
+static float poly_iou(const float *p, const float *q)                                                     /* :122-143 */
+{
+    pt ps1[10], ps2[10];
+    for (int i = 0; i < 4; i++) {
+        ps1[i].x = p[i * 2]; ps1[i].y = p[i * 2 + 1];
+        ps2[i].x = q[i * 2]; ps2[i].y = q[i * 2 + 1];
+    }
+    float inter = poly_intersect_area(ps1, 4, ps2, 4);
+    float uni = fabsf(poly_area(ps1, 4)) + fabsf(poly_area(ps2, 4)) - inter;
+    return (uni == 0) ? (inter + 1) / (uni + 1) : inter / uni;
+}
+
+/* aligned polygon IoU: out[i] = IoU(p[i], q[i]); rows of 8 floats with the given strides */
+ORC_API void orc_poly_iou_aligned_f32(const float *p, int64_t ps, const float *q, int64_t qs, int64_t n, float *out)
+{
+    for (int64_t i = 0; i < n; i++) out[i] = poly_iou(p + i * ps, q + i * qs);
+}
+
+/* greedy polygon NMS (poly_nms_cuda.cu:145-193 mask + :196-262 host scan): order by descending score (stable),
+ * suppress j when IoU(kept i, j) > thr; keep holds original indices in descending-score order */
+ORC_API int64_t orc_poly_nms_f32(const float *polys, int64_t stride, const float *scores, int64_t K, float thr, int64_t *keep)
+{
+    if (K <= 0) return 0;
+    sidx *ord = (sidx *)malloc(sizeof(sidx) * (size_t)K);
+    unsigned char *dead = (unsigned char *)calloc((size_t)K, 1);
+    for (int64_t i = 0; i < K; i++) { ord[i].s = scores[i]; ord[i].i = i; }
+    qsort(ord, (size_t)K, sizeof(sidx), cmp_desc);
+    int64_t n = 0;
+    for (int64_t a = 0; a < K; a++) {
+        if (dead[a]) continue;
+        const int64_t i = ord[a].i;
+        keep[n++] = i;
+        for (int64_t b = a + 1; b < K; b++)
+            if (!dead[b] && poly_iou(polys + i * stride, polys + ord[b].i * stride) > thr) dead[b] = 1;
+    }
+    free(ord); free(dead);
+    return n;
+}

@@ -14,7 +14,8 @@ Module map (reference module -> here):
   (mmdet MaxIoUAssigner + calculator, fused; §8f) -> assign   max_iou_assign, FusedMaxIoUAssigner
   r3det/core/bbox/coder          -> coder             DeltaXYWHAOBBoxCoder, bbox2delta_v1/2/3, delta2bbox_v1/2/3
   r3det/models/dense_heads (get_bboxes tail, filter_bboxes, refine_bboxes; §8f) -> dense_tail
-  r3det/core/bbox/rtransforms    -> rtransforms       poly2obb, obb2poly, obb2hbb, hbb2obb, obb2xyxy, norm_angle, ...
+  r3det/core/bbox/rtransforms    -> rtransforms       poly2obb, obb2poly, obb2hbb, hbb2obb, obb2xyxy, norm_angle, *_np, ...
+  r3det/datasets/dota1.py (merge_det, _merge_func, _results2submission; §8f) -> dota_submission
 """
 from . import _lib  # noqa: F401
 from .assign import FusedMaxIoUAssigner, max_iou_assign  # noqa: F401
@@ -31,5 +32,6 @@ from .ml_nms_rotated import ml_nms_rotated  # noqa: F401
 from .nms_rotated import obb_batched_nms, obb_nms, poly_nms  # noqa: F401
 from .rbbox_geo import aligned_iou, pairwise_iou, rbbox_iou  # noqa: F401
 from .rnms import batched_rnms, rnms  # noqa: F401
-from .rtransforms import (hbb2obb, norm_angle, obb2hbb, obb2poly, obb2xyxy, poly2obb, rbbox2result,  # noqa: F401
-                          rbbox2roi)
+from .rtransforms import (hbb2obb, norm_angle, obb2hbb, obb2poly, obb2poly_np, obb2xyxy, poly2obb, poly2obb_np,  # noqa: F401
+                          rbbox2result, rbbox2roi)
+from . import dota_submission  # noqa: F401

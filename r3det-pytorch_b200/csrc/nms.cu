@@ -24,6 +24,7 @@
 #include "common.cuh"
 #include "emu.cuh"
 #include "geom.cuh"
+#include "poly.cuh"
 
 namespace r3g {
 
@@ -581,6 +582,83 @@ __global__ void nms_emit_kernel(const int* __restrict__ flag, const int* __restr
 
 using namespace r3g;
 
+// ---- host stages shared by the rotated-box and the polygon entry points ------------------------------------------
+static int nms_order_stage(NmsWs& w, const float* scores, const int64_t* labels, const int64_t* batch_ids, int Ki, cudaStream_t st) {
+    const int tpb = 256, gK = (Ki + tpb - 1) / tpb;
+    // 1. rank order by descending score (stable: ties keep ascending index)
+    nms_keys_kernel<<<gK, tpb, 0, st>>>(scores, Ki, w.keyA, w.ord_tmp);
+    size_t tb = w.cub_bytes;
+    R3G_CUDA_OK(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, w.keyA, w.keyA2, w.ord_tmp, w.ord_rank, Ki, 0, 32, st));
+    if (batch_ids) {
+        // multi-image batch: rank order becomes (image asc, score desc) by a stable 16-bit pass over the image id
+        nms_batch_keys_kernel<<<gK, tpb, 0, st>>>(batch_ids, w.ord_rank, Ki, w.keyA);
+        R3G_CUDA_OK(cudaMemcpyAsync(w.ord_tmp, w.ord_rank, 4 * (size_t)Ki, cudaMemcpyDeviceToDevice, st));
+        tb = w.cub_bytes;
+        R3G_CUDA_OK(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, w.keyA, w.keyA2, w.ord_tmp, w.ord_rank, Ki, 0, 16, st));
+    }
+    // 2. position order: stable by segment key (label, or label and image) on top of the rank order
+    nms_label_keys_kernel<<<gK, tpb, 0, st>>>(labels, batch_ids, w.ord_rank, Ki, w.keyB, w.pos_tmp);
+    if (labels || batch_ids) {
+        tb = w.cub_bytes;
+        R3G_CUDA_OK(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, w.keyB, w.pos_label, w.pos_tmp, w.pos_rank, Ki, 0, 32, st));
+    } else {
+        R3G_CUDA_OK(cudaMemcpyAsync(w.pos_label, w.keyB, 4 * (size_t)Ki, cudaMemcpyDeviceToDevice, st));
+        R3G_CUDA_OK(cudaMemcpyAsync(w.pos_rank, w.pos_tmp, 4 * (size_t)Ki, cudaMemcpyDeviceToDevice, st));
+    }
+    return R3G_OK;
+}
+
+static int nms_structure_stage(NmsWs& w, int Ki, int nblk, cudaStream_t st) {
+    const int tpb = 256, gK = (Ki + tpb - 1) / tpb;
+    size_t tb = 0;
+    // 4. block / segment structure
+    nms_blocks_kernel<<<(nblk + 1 + tpb - 1) / tpb, tpb, 0, st>>>(w.pos_label, Ki, nblk, w.blk_end, w.nw, w.ng);
+    tb = w.cub_bytes;
+    R3G_CUDA_OK(cub::DeviceScan::ExclusiveSum(w.cub_tmp, tb, w.nw, w.row_base, nblk + 1, st));
+    tb = w.cub_bytes;
+    R3G_CUDA_OK(cub::DeviceScan::ExclusiveSum(w.cub_tmp, tb, w.ng, w.item_base, nblk + 1, st));
+    nms_segments_kernel<<<gK, tpb, 0, st>>>(w.pos_label, Ki, w.seg_list, w.counters);
+    R3G_LAUNCH_OK("nms structure kernels");
+
+    return R3G_OK;
+}
+
+static int nms_finish_stage(NmsWs& w, int Ki, int nblk, const int64_t* labels, const int64_t* batch_ids, int flags, int64_t K,
+                            int64_t* keep_out, int64_t* num_keep_out, cudaStream_t st) {
+    const int tpb = 256, gK = (Ki + tpb - 1) / tpb;
+    size_t tb = 0;
+    // 6. greedy scan per class segment
+    ScanArgs sa;
+    sa.mask = w.mask; sa.valid = w.valid; sa.label = w.pos_label; sa.blk_end = w.blk_end; sa.row_base = w.row_base;
+    sa.seg_list = w.seg_list; sa.counters = w.counters; sa.pos_rank = w.pos_rank; sa.ord_rank = w.ord_rank;
+    sa.keep_p = w.keep_p; sa.K = Ki;
+    const int order_index = (flags & R3G_NMS_ORDER_INDEX) ? 1 : 0;
+    sa.remv_cap = nblk;
+    size_t smem = (size_t)nblk * 8;
+    if (smem > 190 * 1024) {
+        set_error("r3g_nms_f32: K=%lld exceeds the single-image limit of this build (%d boxes)", (long long)K, 190 * 1024 / 8 * 64);
+        return R3G_ERR_ARG;
+    }
+    static bool smem_set = false;
+    if (!smem_set) {      // static (window buffers) + dynamic (removed[]) shared memory may exceed the 48 KB default
+        R3G_CUDA_OK(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 190 * 1024));
+        smem_set = true;
+    }
+    int sgrid = device_sm_count() * 2;
+    if (!labels && !batch_ids) sgrid = 1;
+    nms_scan_kernel<<<sgrid, SCAN_THREADS, smem, st>>>(sa);
+    R3G_LAUNCH_OK("nms_scan_kernel");
+    nms_flags_kernel<<<gK, tpb, 0, st>>>(w.keep_p, w.pos_rank, w.ord_rank, Ki, order_index, w.flag);
+
+    // 7. compaction in the requested order
+    tb = w.cub_bytes;
+    R3G_CUDA_OK(cub::DeviceScan::ExclusiveSum(w.cub_tmp, tb, w.flag, w.pref, Ki, st));
+    nms_emit_kernel<<<gK, tpb, 0, st>>>(w.flag, w.pref, w.ord_rank, batch_ids, Ki, order_index, keep_out,
+                                        (unsigned long long*)num_keep_out);
+    R3G_LAUNCH_OK("nms_emit_kernel");
+    return R3G_OK;
+}
+
 R3G_API int r3g_nms_workspace_bytes(int64_t K, size_t* bytes) {
     R3G_REQUIRE(bytes != nullptr && K >= 0, "r3g_nms_workspace_bytes: bad arguments");
     R3G_REQUIRE(K < (1ll << 30), "r3g_nms_workspace_bytes: K too large");
@@ -621,38 +699,14 @@ R3G_API int r3g_nms_batched_f32(const float* boxes, int64_t stride, const float*
     const int tpb = 256, gK = (Ki + tpb - 1) / tpb;
     R3G_CUDA_OK(cudaMemsetAsync(w.counters, 0, 256, st));
 
-    // 1. rank order by descending score (stable: ties keep ascending index)
-    nms_keys_kernel<<<gK, tpb, 0, st>>>(scores, Ki, w.keyA, w.ord_tmp);
-    size_t tb = w.cub_bytes;
-    R3G_CUDA_OK(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, w.keyA, w.keyA2, w.ord_tmp, w.ord_rank, Ki, 0, 32, st));
-    if (batch_ids) {
-        // multi-image batch: rank order becomes (image asc, score desc) by a stable 16-bit pass over the image id
-        nms_batch_keys_kernel<<<gK, tpb, 0, st>>>(batch_ids, w.ord_rank, Ki, w.keyA);
-        R3G_CUDA_OK(cudaMemcpyAsync(w.ord_tmp, w.ord_rank, 4 * (size_t)Ki, cudaMemcpyDeviceToDevice, st));
-        tb = w.cub_bytes;
-        R3G_CUDA_OK(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, w.keyA, w.keyA2, w.ord_tmp, w.ord_rank, Ki, 0, 16, st));
-    }
-    // 2. position order: stable by segment key (label, or label and image) on top of the rank order
-    nms_label_keys_kernel<<<gK, tpb, 0, st>>>(labels, batch_ids, w.ord_rank, Ki, w.keyB, w.pos_tmp);
-    if (labels || batch_ids) {
-        tb = w.cub_bytes;
-        R3G_CUDA_OK(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, w.keyB, w.pos_label, w.pos_tmp, w.pos_rank, Ki, 0, 32, st));
-    } else {
-        R3G_CUDA_OK(cudaMemcpyAsync(w.pos_label, w.keyB, 4 * (size_t)Ki, cudaMemcpyDeviceToDevice, st));
-        R3G_CUDA_OK(cudaMemcpyAsync(w.pos_rank, w.pos_tmp, 4 * (size_t)Ki, cudaMemcpyDeviceToDevice, st));
-    }
+    int rc = nms_order_stage(w, scores, labels, batch_ids, Ki, st);
+    if (rc != R3G_OK) return rc;
     // 3. gather + prepare
     nms_gather_kernel<<<gK, tpb, 0, st>>>(boxes, stride, w.ord_rank, w.pos_rank, w.pos_label, Ki, variant,
                                           (flags & R3G_NMS_DROP_SMALL) ? 1 : 0, class_offset, labels ? 1 : 0,
                                           batch_ids ? 1 : 0, w.p0, w.p1, w.p2r, w.p2c, w.raw, w.valid);
-    // 4. block / segment structure
-    nms_blocks_kernel<<<(nblk + 1 + tpb - 1) / tpb, tpb, 0, st>>>(w.pos_label, Ki, nblk, w.blk_end, w.nw, w.ng);
-    tb = w.cub_bytes;
-    R3G_CUDA_OK(cub::DeviceScan::ExclusiveSum(w.cub_tmp, tb, w.nw, w.row_base, nblk + 1, st));
-    tb = w.cub_bytes;
-    R3G_CUDA_OK(cub::DeviceScan::ExclusiveSum(w.cub_tmp, tb, w.ng, w.item_base, nblk + 1, st));
-    nms_segments_kernel<<<gK, tpb, 0, st>>>(w.pos_label, Ki, w.seg_list, w.counters);
-    R3G_LAUNCH_OK("nms structure kernels");
+    rc = nms_structure_stage(w, Ki, nblk, st);
+    if (rc != R3G_OK) return rc;
 
     // 5. suppression bitmask
     MaskArgs ma;
@@ -677,36 +731,63 @@ R3G_API int r3g_nms_batched_f32(const float* boxes, int64_t stride, const float*
     nms_mask_kernel<<<(unsigned)grid, NMS_THREADS, 0, st>>>(ma);
     R3G_LAUNCH_OK("nms_mask_kernel");
 
-    // 6. greedy scan per class segment
-    ScanArgs sa;
-    sa.mask = w.mask; sa.valid = w.valid; sa.label = w.pos_label; sa.blk_end = w.blk_end; sa.row_base = w.row_base;
-    sa.seg_list = w.seg_list; sa.counters = w.counters; sa.pos_rank = w.pos_rank; sa.ord_rank = w.ord_rank;
-    sa.keep_p = w.keep_p; sa.K = Ki;
-    const int order_index = (flags & R3G_NMS_ORDER_INDEX) ? 1 : 0;
-    sa.remv_cap = nblk;
-    size_t smem = (size_t)nblk * 8;
-    if (smem > 190 * 1024) {
-        set_error("r3g_nms_f32: K=%lld exceeds the single-image limit of this build (%d boxes)", (long long)K, 190 * 1024 / 8 * 64);
-        return R3G_ERR_ARG;
-    }
-    static bool smem_set = false;
-    if (!smem_set) {      // static (window buffers) + dynamic (removed[]) shared memory may exceed the 48 KB default
-        R3G_CUDA_OK(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 190 * 1024));
-        smem_set = true;
-    }
-    int sgrid = device_sm_count() * 2;
-    if (!labels && !batch_ids) sgrid = 1;
-    nms_scan_kernel<<<sgrid, SCAN_THREADS, smem, st>>>(sa);
-    R3G_LAUNCH_OK("nms_scan_kernel");
-    nms_flags_kernel<<<gK, tpb, 0, st>>>(w.keep_p, w.pos_rank, w.ord_rank, Ki, order_index, w.flag);
+    return nms_finish_stage(w, Ki, nblk, labels, batch_ids, flags, K, keep_out, num_keep_out, st);
+}
 
-    // 7. compaction in the requested order
-    tb = w.cub_bytes;
-    R3G_CUDA_OK(cub::DeviceScan::ExclusiveSum(w.cub_tmp, tb, w.flag, w.pref, Ki, st));
-    nms_emit_kernel<<<gK, tpb, 0, st>>>(w.flag, w.pref, w.ord_rank, batch_ids, Ki, order_index, keep_out,
-                                        (unsigned long long*)num_keep_out);
-    R3G_LAUNCH_OK("nms_emit_kernel");
+// ---- polygon NMS ------------------------------------------------------------------------------------------------------
+struct PolyWs { float* quad; float4* aabb; size_t bytes; };
+static PolyWs carve_poly(void* ws, size_t nms_bytes, int64_t K) {
+    PolyWs w;
+    char* p = (char*)ws;
+    size_t off = align_up(nms_bytes, 256);
+    w.quad = (float*)(p + off); off += align_up(32 * (size_t)K, 256);
+    w.aabb = (float4*)(p + off); off += align_up(16 * (size_t)K, 256);
+    w.bytes = off;
+    return w;
+}
+
+R3G_API int r3g_poly_nms_workspace_bytes(int64_t K, size_t* bytes) {
+    R3G_REQUIRE(bytes != nullptr && K >= 0 && K < (1ll << 30), "r3g_poly_nms_workspace_bytes: bad arguments");
+    const int64_t k = K > 0 ? K : 1;
+    *bytes = carve_poly(nullptr, carve_nms(nullptr, k).bytes, k).bytes;
     return R3G_OK;
+}
+
+R3G_API int r3g_poly_nms_f32(const float* polys, int64_t stride, const float* scores, int64_t K, float thr,
+                             int64_t* keep_out, int64_t* num_keep_out, void* workspace, size_t workspace_bytes, void* stream) {
+    R3G_REQUIRE(K >= 0 && K < (1ll << 30), "r3g_poly_nms_f32: bad K");
+    R3G_REQUIRE(num_keep_out != nullptr, "r3g_poly_nms_f32: null num_keep_out");
+    cudaStream_t st = (cudaStream_t)stream;
+    R3G_CUDA_OK(cudaMemsetAsync(num_keep_out, 0, sizeof(int64_t), st));
+    if (K == 0) return R3G_OK;
+    R3G_REQUIRE(polys && scores && keep_out && workspace, "r3g_poly_nms_f32: null pointer");
+    R3G_REQUIRE(stride >= 8, "r3g_poly_nms_f32: polygon stride must be >= 8 floats");
+    NmsWs w = carve_nms(workspace, K);
+    PolyWs pw = carve_poly(workspace, w.bytes, K);
+    if (workspace_bytes < pw.bytes) {
+        set_error("r3g_poly_nms_f32: workspace too small (%zu < %zu)", workspace_bytes, pw.bytes);
+        return R3G_ERR_WORKSPACE;
+    }
+    const int Ki = (int)K, nblk = (Ki + 63) / 64, tpb = 256, gK = (Ki + tpb - 1) / tpb;
+    R3G_REQUIRE((size_t)nblk * 8 <= 190 * 1024, "r3g_poly_nms_f32: K exceeds the single-call limit of this build");
+    R3G_CUDA_OK(cudaMemsetAsync(w.counters, 0, 256, st));
+    int rc = nms_order_stage(w, scores, nullptr, nullptr, Ki, st);
+    if (rc != R3G_OK) return rc;
+    poly::gather_kernel<<<gK, tpb, 0, st>>>(polys, stride, w.ord_rank, w.pos_rank, Ki, pw.quad, pw.aabb, w.valid);
+    rc = nms_structure_stage(w, Ki, nblk, st);
+    if (rc != R3G_OK) return rc;
+    poly::PolyMaskArgs ma;
+    ma.quad = pw.quad; ma.aabb = pw.aabb; ma.blk_end = w.blk_end; ma.row_base = w.row_base; ma.mask = w.mask;
+    ma.ticket = (unsigned long long*)(w.counters + 8);
+    ma.K = Ki; ma.nblk = nblk; ma.thr = thr;
+    ma.prefilter = thr >= 1e-3f ? 1 : 0;      // below that, FP32 noise of disjoint pairs could exceed the threshold: test every pair
+    const long long tiles = (long long)nblk * (nblk + 1) / 2;
+    long long grid = (tiles + 7) / 8;
+    const long long cap = (long long)device_sm_count() * 4;
+    if (grid > cap) grid = cap;
+    poly::mask_kernel<<<(unsigned)grid, 256, 0, st>>>(ma);
+    R3G_LAUNCH_OK("poly mask kernel");
+    return nms_finish_stage(w, Ki, nblk, nullptr, nullptr, 0, K, keep_out, num_keep_out, st);
 }
 
 // ---- multiclass candidate extraction --------------------------------------------------------------------------------

@@ -34,9 +34,51 @@ def obb_nms(dets, iou_thr, device_id=None):
     return dets[inds, :], inds
 
 
+def poly_nms_device(polys, scores, iou_thr):
+    """Polygon NMS on CUDA tensors: polys (K, >=8), scores (K,) -> (keep (K,) int64, num_keep 0-dim int64), both on the
+    device; no host synchronisation."""
+    import ctypes as C
+    from . import _lib as L
+    L.require_cuda(polys, scores)
+    p, stride = L.as_f32_rows(polys, 8)
+    s = scores.float().contiguous()
+    K = p.size(0)
+    keep = torch.empty((K,), dtype=torch.int64, device=p.device)
+    num = torch.zeros((), dtype=torch.int64, device=p.device)
+    if K == 0:
+        return keep, num
+    lib = L.lib()
+    nbytes = C.c_size_t(0)
+    L.check(lib.r3g_poly_nms_workspace_bytes(K, C.byref(nbytes)))
+    ws = L.workspace(nbytes.value, p.device)
+    with L.device_guard(p.device):
+        L.check(lib.r3g_poly_nms_f32(L.ptr(p), stride, L.ptr(s), K, float(iou_thr), L.ptr(keep), C.c_void_p(num.data_ptr()),
+                                     L.ptr(ws), ws.numel(), L.stream_ptr(p.device)))
+    return keep, num
+
+
 def poly_nms(dets, iou_thr, device_id=None):
-    """NMS of 8-point polygons (nms_rotated_wrapper.py:57-76) — a 'next' row of SURVEY.md §8f, not built yet."""
-    raise NotImplementedError("poly_nms is outside the round-1 hot path (SURVEY.md §8f rank 4)")
+    """Compute the NMS of polygons (nms_rotated_wrapper.py:57-76).  dets: (K, 9) [x0, y0, ..., x3, y3, score], a CUDA
+    tensor or a numpy array with `device_id`; as in the reference there is no CPU implementation."""
+    import numpy as np
+    if isinstance(dets, torch.Tensor):
+        is_numpy = False
+        dets_th = dets
+    elif isinstance(dets, np.ndarray):
+        is_numpy = True
+        device = 'cpu' if device_id is None else f'cuda:{device_id}'
+        dets_th = torch.from_numpy(dets).to(device)
+    else:
+        raise TypeError('dets must be eithr a Tensor or numpy array, '
+                        f'but got {type(dets)}')
+    if dets_th.device == torch.device('cpu'):
+        raise NotImplementedError
+    d = dets_th.float()
+    keep, num = poly_nms_device(d[:, :8], d[:, 8], iou_thr)
+    inds = keep[:int(num.item())]
+    if is_numpy:
+        inds = inds.cpu().numpy()
+    return dets[inds, :], inds
 
 
 def obb_batched_nms(bboxes, scores, inds, nms_thr, class_agnostic=False):

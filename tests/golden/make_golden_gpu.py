@@ -70,7 +70,51 @@ def main():
         f[f"{tag}_feat"], f[f"{tag}_gout"], f[f"{tag}_boxes"] = feat, gout, boxes
         f[f"{tag}_scale"] = np.float32(1.0 / stride)
     np.savez_compressed(os.path.join(out_dir, "frm_refcuda.npz"), **f)
+    poly_and_v1nms()
     print("wrote", os.listdir(out_dir))
+
+
+def quads(K, seed, jitter=0.0):
+    """polygons of clustered v1 boxes (obb2poly_v1 corner order), optionally perturbed into general quadrilaterals"""
+    from oracle import transforms_np as T
+    b, s, _ = clustered(K, seed, "v1")
+    p = T.obb2poly(b, "v1")
+    if jitter:
+        p = p + np.random.default_rng(seed).normal(0, jitter, p.shape).astype(np.float32)
+    return np.ascontiguousarray(np.concatenate([p, s[:, None]], 1), np.float32)
+
+
+def poly_and_v1nms():
+    """poly_nms_cuda.cu and rnms_kernel.cu, compiled unmodified (THC stand-in: oracle/refshim/thc)."""
+    lp = C.CDLL(os.path.join(REFDIR, "libref_cuda_polynms.so"))
+    lp.refcuda_poly_nms.restype = f32
+    lp.refcuda_poly_nms.argtypes = [vp, i64, f32, vp, vp, i32]
+    lp.refcuda_poly_iou.restype = None
+    lp.refcuda_poly_iou.argtypes = [vp, vp, i64, vp]
+    g = {}
+    for tag, (K, seed, jit, thr) in {"rect": (1500, 3, 0.0, 0.1), "quad": (900, 4, 3.0, 0.3)}.items():
+        d = quads(K, seed, jit)
+        t = torch.from_numpy(d).to(dev)
+        keep = np.empty((K,), np.int64); n = np.zeros((1,), np.int64)
+        lp.refcuda_poly_nms(t.data_ptr(), K, thr, keep.ctypes.data, n.ctypes.data, 1)
+        g[f"{tag}_dets"], g[f"{tag}_thr"], g[f"{tag}_keep"] = d, np.float32(thr), keep[:int(n[0])].copy()
+        # pairwise values for spatial neighbours (sorted by the first vertex: most of these pairs overlap)
+        order = np.lexsort((d[:, 1], np.round(d[:, 0] / 8)))
+        pairs = np.stack([order[:-1], order[1:]], 1)
+        p_, q_ = t[torch.from_numpy(pairs[:, 0]).to(dev), :8].contiguous(), t[torch.from_numpy(pairs[:, 1]).to(dev), :8].contiguous()
+        o = torch.empty((K - 1,), device=dev)
+        lp.refcuda_poly_iou(p_.data_ptr(), q_.data_ptr(), K - 1, o.data_ptr())
+        g[f"{tag}_pairs"], g[f"{tag}_iou_pairs"] = pairs, o.cpu().numpy()
+    lv = C.CDLL(os.path.join(REFDIR, "libref_cuda_v1nms.so"))
+    lv.refcuda_v1_nms.restype = f32
+    lv.refcuda_v1_nms.argtypes = [vp, i64, f32, vp, vp, i32]
+    b, s_, _ = clustered(1500, 6, "v1")
+    d = np.ascontiguousarray(np.concatenate([b, s_[:, None]], 1), np.float32)
+    t = torch.from_numpy(d).to(dev)
+    keep = np.empty((1500,), np.int64); n = np.zeros((1,), np.int64)
+    lv.refcuda_v1_nms(t.data_ptr(), 1500, 0.1, keep.ctypes.data, n.ctypes.data, 1)
+    g["v1nms_dets"], g["v1nms_keep"] = d, keep[:int(n[0])].copy()
+    np.savez_compressed(os.path.join(out_dir, "poly_refcuda.npz"), **g)
 
 
 if __name__ == "__main__":

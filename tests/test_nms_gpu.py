@@ -174,3 +174,72 @@ def test_multiclass_batch_equals_per_image(cuda_dev, kind):
             d, l = R.multiclass_nms_rotated(mb[b], ms[b], 0.05, dict(type=kind, iou_thr=0.1), max_num)
             assert got[b][0].shape == d.shape and torch.equal(got[b][0], d) and torch.equal(got[b][1], l), (kind, b, max_num)
     assert got[2][0].shape == (0, 6) and got[2][1].dtype == torch.long
+
+
+def test_polygon_nms_vs_reference_cuda_golden(cuda_dev):
+    """poly_nms against keep lists produced by the reference's own poly_nms_cuda.cu on a B200 (bit-exact indices), the
+    oracle at a second size, and the wrapper's reference behaviour (numpy + device_id, no CPU implementation)."""
+    import r3det_b200 as R
+    from oracle import transforms_np as T
+    g = golden("poly_refcuda.npz")
+    for tag in ("rect", "quad"):
+        d = g[f"{tag}_dets"]
+        dets, keep = R.poly_nms(_t(d, cuda_dev), float(g[f"{tag}_thr"]))
+        assert np.array_equal(keep.cpu().numpy(), g[f"{tag}_keep"])
+        assert torch.equal(dets, _t(d, cuda_dev)[keep])
+    d = g["rect_dets"]
+    dn, kn = R.poly_nms(d, 0.1, device_id=cuda_dev.index or 0)
+    assert isinstance(kn, np.ndarray) and np.array_equal(kn, g["rect_keep"]) and np.array_equal(dn, d[kn])
+    with pytest.raises(NotImplementedError):
+        R.poly_nms(torch.from_numpy(d), 0.1)
+    with pytest.raises(NotImplementedError):
+        R.poly_nms(d, 0.1)
+    with pytest.raises(TypeError):
+        R.poly_nms([1, 2, 3], 0.1)
+    b, s, _ = clustered(700, 77, "v1")
+    q = np.concatenate([T.obb2poly(b, "v1") + np.random.default_rng(2).normal(0, 2, (700, 8)).astype(np.float32), s[:, None]], 1).astype(np.float32)
+    for thr in (0.05, 0.5, 5e-4):                      # thr < 1e-3 disables the bounding-box prefilter
+        _, k = R.poly_nms(_t(q, cuda_dev), thr)
+        assert np.array_equal(k.cpu().numpy(), port.poly_nms(q, thr)), thr
+    e = R.poly_nms(_t(q[:0], cuda_dev), 0.1)
+    assert e[0].shape == (0, 9) and e[1].numel() == 0
+    _, k1 = R.poly_nms(_t(q[:1], cuda_dev), 0.1)
+    assert k1.tolist() == [0]
+
+
+def test_v1_nms_vs_reference_cuda_golden(cuda_dev):
+    """rnms (GPU rule IoU > thr, ascending-index keep list) against the reference's own rnms_kernel.cu run on a B200."""
+    import r3det_b200 as R
+    g = golden("poly_refcuda.npz")
+    d = g["v1nms_dets"]
+    _, keep = R.rnms(_t(d, cuda_dev), 0.1)
+    assert np.array_equal(keep.cpu().numpy(), g["v1nms_keep"])
+
+
+@pytest.mark.parametrize("version,merge_nms", [("v1", "obb"), ("v3", "obb"), ("v1", "poly")])
+def test_dota_patch_merge(cuda_dev, version, merge_nms):
+    """merge_image (all classes of an image in one launch) == the reference's per-class loop over rnms / obb_nms /
+    poly_nms (r3det/datasets/dota1.py:632-667) built from the already-pinned per-class ops."""
+    import r3det_b200 as R
+    ncls = 5
+    b, s, l = clustered(900, 12, version, ncls=ncls)
+    l[l == 3] = 2                                                            # class 3 stays empty
+    rows = np.concatenate([l[:, None].astype(np.float64), b, s[:, None]], 1)
+    got = R.dota_submission.merge_image(rows, ncls, 0.1, version, merge_nms, cuda_dev)
+    assert len(got) == ncls and got[3].shape[0] == 0
+    dets = rows[:, 1:]
+    for c in range(ncls):
+        cls = dets[l == c]
+        if len(cls) == 0:
+            continue
+        if merge_nms == "poly":
+            _, keep = R.poly_nms(R.obb2poly_np(cls, version).astype(np.float32), 0.1, device_id=cuda_dev.index or 0)
+            want = cls[keep]
+        elif version == "v1":
+            want, _ = R.rnms(cls.astype(np.float32), 0.1)
+        else:
+            want, _ = R.obb_nms(cls.astype(np.float32), 0.1)
+        assert got[c].shape == want.shape and np.allclose(got[c], want), (c, got[c].shape, want.shape)
+    ids, merged = R.dota_submission.merge_det([[rows[l == c][:, 1:].astype(np.float32) for c in range(ncls)]], ["P1__1__100___200"],
+                                              ["a", "b", "c", "d", "e"], 0.1, version, merge_nms, cuda_dev)
+    assert ids == ["P1"] and [m.shape for m in merged[0]] == [g.shape for g in got]
