@@ -181,13 +181,13 @@ R3G_HD float pair_intersection(const BoxP0& A0, const BoxP1& A1, const BoxP0& B0
 // configurations in which the reference's 1e-2 vertex de-dup / strict tests (rbbox_geo_kernel.cu:169-170,
 // 195-213) can change the polygon, i.e. where v1 departs from the geometric area.  Conservative.
 R3G_HD bool corner_near_boundary(const float* qx, const float* qy, float a, float b, float tau) {
-    bool near = false;
+    // "(|ex| < tau and ey < tau) or (|ey| < tau and ex < tau)" with ex = |x| - a, ey = |y| - b is the same set as
+    // | max(ex, ey) | < tau (the signed Chebyshev distance to the rectangle's boundary): 3 instructions per corner,
+    // and the four corners share one comparison through a running minimum.
+    float d = 3.0e38f;
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        float ex = fabsf(qx[k]) - a, ey = fabsf(qy[k]) - b;
-        near |= (fabsf(ex) < tau & ey < tau) | (fabsf(ey) < tau & ex < tau);
-    }
-    return near;
+    for (int k = 0; k < 4; k++) d = fminf(d, fabsf(fmaxf(fabsf(qx[k]) - a, fabsf(qy[k]) - b)));
+    return d < tau;
 }
 
 R3G_HD bool v1_dedup_risk(const BoxP0& A0, const BoxP1& A1, const BoxP0& B0, const BoxP1& B1,
