@@ -24,9 +24,9 @@ def nms_device(boxes, scores, thr, variant, labels=None, class_offset=None, incl
     K = boxes.size(0)
     dev = boxes.device
     keep = torch.empty((K,), dtype=torch.int64, device=dev)
-    num = torch.zeros((n_batches,) if batch_ids is not None else (), dtype=torch.int64, device=dev)
     if K == 0:
-        return keep, num
+        return keep, torch.zeros((n_batches,) if batch_ids is not None else (), dtype=torch.int64, device=dev)
+    num = torch.empty((n_batches,) if batch_ids is not None else (), dtype=torch.int64, device=dev)   # zeroed by the library
     if batch_ids is not None:
         L.require_cuda(batch_ids)
         batch_ids = batch_ids.to(torch.int64).contiguous()

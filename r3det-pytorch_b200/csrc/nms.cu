@@ -578,6 +578,128 @@ __global__ void nms_emit_kernel(const int* __restrict__ flag, const int* __restr
     if (!batch_ids && s == K - 1) *num_keep = (unsigned long long)(pref[s] + flag[s]);
 }
 
+// ---- small-K path (K <= NMS_SMALL_K): the sorts, the structure scans and the compaction are launch latency there ----
+// (two cub radix sorts = 12-18 launches of ~10 us each for a few thousand keys).  Ranks are COUNTED instead:
+//   rank(i) = #{ j : (image_j, score_key_j, j) < (image_i, score_key_i, i) }           (the stable score order)
+//   pos(i)  = #{ j : (segment_j, score_key_j, j) < (segment_i, score_key_i, i) }       (segment-major position order)
+// O(K^2) compares spread over (K/256) x slices CTAs — a few microseconds — and exactly the permutations the stable
+// radix sorts produce.  The block structure and the final compaction each become one single-CTA kernel.
+constexpr int NMS_SMALL_K = 16384;
+
+__device__ __forceinline__ unsigned seg_key_of(const int64_t* labels, const int64_t* batch_ids, int i) {
+    unsigned key = labels ? (unsigned)labels[i] : 0u;
+    if (batch_ids) key = (key << 16) | ((unsigned)batch_ids[i] & 0xffffu);
+    return key;
+}
+
+__global__ void __launch_bounds__(256) nms_rank_count_kernel(const float* __restrict__ scores, const int64_t* __restrict__ labels,
+                                                             const int64_t* __restrict__ batch_ids, int K, int slice_len,
+                                                             int* __restrict__ rcnt, int* __restrict__ pcnt) {
+    __shared__ unsigned long long ta[256];
+    __shared__ unsigned tseg[256];
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    const bool iv = i < K;
+    const unsigned long long ai = iv ? (((unsigned long long)score_key_desc(scores[i]) << 32) | (unsigned)i) : 0ull;
+    const unsigned si = iv ? seg_key_of(labels, batch_ids, i) : 0u;
+    const unsigned mi = batch_ids ? (si & 0xffffu) : 0u;
+    const unsigned img_mask = batch_ids ? 0xffffu : 0u;
+    const int j_begin = blockIdx.y * slice_len, j_end = min(K, j_begin + slice_len);
+    int r = 0, p = 0;
+    for (int j0 = j_begin; j0 < j_end; j0 += 256) {
+        const int j = j0 + threadIdx.x;
+        __syncthreads();
+        if (j < j_end) {
+            ta[threadIdx.x] = ((unsigned long long)score_key_desc(scores[j]) << 32) | (unsigned)j;
+            tseg[threadIdx.x] = seg_key_of(labels, batch_ids, j);
+        }
+        __syncthreads();
+        const int n = min(256, j_end - j0);
+#pragma unroll 4
+        for (int t = 0; t < n; t++) {
+            const unsigned long long aj = ta[t];
+            const unsigned sj = tseg[t], mj = sj & img_mask;
+            const bool lt = aj < ai;
+            r += (mj < mi) | ((mj == mi) & lt);
+            p += (sj < si) | ((sj == si) & lt);
+        }
+    }
+    if (iv) { atomicAdd(rcnt + i, r); atomicAdd(pcnt + i, p); }
+}
+
+__global__ void nms_rank_scatter_kernel(const int64_t* __restrict__ labels, const int64_t* __restrict__ batch_ids, int K,
+                                        const int* __restrict__ rcnt, const int* __restrict__ pcnt,
+                                        int* __restrict__ ord_rank, int* __restrict__ pos_rank, unsigned* __restrict__ pos_label) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= K) return;
+    const int r = rcnt[i], p = pcnt[i];
+    ord_rank[r] = i;
+    pos_rank[p] = r;
+    pos_label[p] = seg_key_of(labels, batch_ids, i);
+}
+
+// nms_blocks_kernel + the two exclusive sums + nms_segments_kernel in one CTA (nblk + 1 <= 1024)
+__global__ void __launch_bounds__(1024) nms_structure_small_kernel(const unsigned* __restrict__ pos_label, int K, int nblk,
+                                                                   int* blk_end, long long* row_base, long long* item_base,
+                                                                   int* seg_list, int* counters) {
+    typedef cub::BlockScan<long long, 1024> Scan;
+    __shared__ typename Scan::TempStorage tmp;
+    const int rb = threadIdx.x;
+    long long nw = 0, ng = 0;
+    if (rb < nblk) {
+        const int last = min(K, rb * 64 + 64) - 1;
+        const unsigned L = pos_label[last];
+        int lo = last, hi = K;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (pos_label[mid] == L) lo = mid; else hi = mid;
+        }
+        const int be = lo >> 6;
+        blk_end[rb] = be;
+        const long long w = be - rb + 1;
+        nw = w * 64;
+        ng = (w + NMS_G - 1) / NMS_G;
+    }
+    long long a, b;
+    Scan(tmp).ExclusiveSum(nw, a);
+    __syncthreads();
+    Scan(tmp).ExclusiveSum(ng, b);
+    if (rb <= nblk) { row_base[rb] = a; item_base[rb] = b; }
+    for (int p = threadIdx.x; p < K; p += 1024)
+        if (p == 0 || pos_label[p] != pos_label[p - 1]) seg_list[atomicAdd(&counters[0], 1)] = p;
+}
+
+// nms_flags_kernel + exclusive sum + nms_emit_kernel in one CTA
+__global__ void __launch_bounds__(1024) nms_finish_small_kernel(const int* __restrict__ keep_p, const int* __restrict__ pos_rank,
+                                                                const int* __restrict__ ord_rank, const int64_t* __restrict__ batch_ids,
+                                                                int K, int order_index, int* __restrict__ flag,
+                                                                int64_t* __restrict__ keep_out, unsigned long long* num_keep) {
+    typedef cub::BlockScan<int, 1024> Scan;
+    __shared__ typename Scan::TempStorage tmp;
+    __shared__ int carry;
+    for (int p = threadIdx.x; p < K; p += 1024) {
+        const int rank = pos_rank[p];
+        flag[order_index ? ord_rank[rank] : rank] = keep_p[p];
+    }
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int s0 = 0; s0 < K; s0 += 1024) {
+        const int s = s0 + threadIdx.x;
+        const int f = (s < K) ? flag[s] : 0;
+        int pre, total;
+        Scan(tmp).ExclusiveSum(f, pre, total);
+        const int base = carry;
+        if (f) {
+            const int idx = order_index ? s : ord_rank[s];
+            keep_out[base + pre] = (int64_t)idx;
+            if (batch_ids) atomicAdd(num_keep + batch_ids[idx], 1ull);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) carry = base + total;
+        __syncthreads();
+    }
+    if (!batch_ids && threadIdx.x == 0) *num_keep = (unsigned long long)carry;
+}
+
 }  // namespace r3g
 
 using namespace r3g;
@@ -585,6 +707,22 @@ using namespace r3g;
 // ---- host stages shared by the rotated-box and the polygon entry points ------------------------------------------
 static int nms_order_stage(NmsWs& w, const float* scores, const int64_t* labels, const int64_t* batch_ids, int Ki, cudaStream_t st) {
     const int tpb = 256, gK = (Ki + tpb - 1) / tpb;
+    if (Ki <= NMS_SMALL_K) {
+        // counted ranks: keyA / keyA2 double as the two count arrays
+        int* rcnt = (int*)w.keyA; int* pcnt = (int*)w.keyA2;
+        R3G_CUDA_OK(cudaMemsetAsync(rcnt, 0, 4 * (size_t)Ki, st));
+        R3G_CUDA_OK(cudaMemsetAsync(pcnt, 0, 4 * (size_t)Ki, st));
+        int slices = (device_sm_count() * 4 + gK - 1) / gK;              // ~4 CTAs per SM in total
+        const int max_slices = (Ki + 255) / 256;
+        if (slices > max_slices) slices = max_slices;
+        if (slices < 1) slices = 1;
+        const int slice_len = ((Ki + slices - 1) / slices + 255) / 256 * 256;
+        slices = (Ki + slice_len - 1) / slice_len;
+        nms_rank_count_kernel<<<dim3(gK, slices), 256, 0, st>>>(scores, labels, batch_ids, Ki, slice_len, rcnt, pcnt);
+        nms_rank_scatter_kernel<<<gK, tpb, 0, st>>>(labels, batch_ids, Ki, rcnt, pcnt, w.ord_rank, w.pos_rank, w.pos_label);
+        R3G_LAUNCH_OK("nms rank kernels");
+        return R3G_OK;
+    }
     // 1. rank order by descending score (stable: ties keep ascending index)
     nms_keys_kernel<<<gK, tpb, 0, st>>>(scores, Ki, w.keyA, w.ord_tmp);
     size_t tb = w.cub_bytes;
@@ -611,6 +749,11 @@ static int nms_order_stage(NmsWs& w, const float* scores, const int64_t* labels,
 static int nms_structure_stage(NmsWs& w, int Ki, int nblk, cudaStream_t st) {
     const int tpb = 256, gK = (Ki + tpb - 1) / tpb;
     size_t tb = 0;
+    if (Ki <= NMS_SMALL_K) {
+        nms_structure_small_kernel<<<1, 1024, 0, st>>>(w.pos_label, Ki, nblk, w.blk_end, w.row_base, w.item_base, w.seg_list, w.counters);
+        R3G_LAUNCH_OK("nms_structure_small_kernel");
+        return R3G_OK;
+    }
     // 4. block / segment structure
     nms_blocks_kernel<<<(nblk + 1 + tpb - 1) / tpb, tpb, 0, st>>>(w.pos_label, Ki, nblk, w.blk_end, w.nw, w.ng);
     tb = w.cub_bytes;
@@ -648,6 +791,12 @@ static int nms_finish_stage(NmsWs& w, int Ki, int nblk, const int64_t* labels, c
     if (!labels && !batch_ids) sgrid = 1;
     nms_scan_kernel<<<sgrid, SCAN_THREADS, smem, st>>>(sa);
     R3G_LAUNCH_OK("nms_scan_kernel");
+    if (Ki <= NMS_SMALL_K) {
+        nms_finish_small_kernel<<<1, 1024, 0, st>>>(w.keep_p, w.pos_rank, w.ord_rank, batch_ids, Ki, order_index, w.flag, keep_out,
+                                                    (unsigned long long*)num_keep_out);
+        R3G_LAUNCH_OK("nms_finish_small_kernel");
+        return R3G_OK;
+    }
     nms_flags_kernel<<<gK, tpb, 0, st>>>(w.keep_p, w.pos_rank, w.ord_rank, Ki, order_index, w.flag);
 
     // 7. compaction in the requested order
