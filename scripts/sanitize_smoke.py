@@ -29,5 +29,41 @@ for (N, Cc, H, W, stride) in ((1, 3, 1, 1, 128), (2, 5, 9, 13, 16), (1, 33, 40, 
         frm_forward(feat, t(boxes), 1.0 / stride, P); frm_backward(feat, t(boxes), 1.0 / stride, P)
 for v in ('v1', 'v2', 'v3'):
     o = t(rand_obb(1001, 4, v)); p = R.obb2poly(o, v); R.poly2obb(p, v); R.obb2hbb(o, v); R.obb2xyxy(o, v); R.hbb2obb(R.obb2xyxy(o, 'v3'), v)
+# round-1 additions: fused assigner (incl. tie-list overflow), batched NMS / multiclass batch, large-K NMS path, multi-level
+# FRM with residual, coder + dense-head tail, polygon NMS
+from r3det_b200.fr import frm_forward_multi, frm_backward_multi
+gt, an = t(rand_obb(37, 5, 'v1')), t(rand_obb(2051, 6, 'v1'))
+for aa in (True, False):
+    R.max_iou_assign(gt, an, 0.5, 0.4, 0.0, True, aa, 'v1')
+R.max_iou_assign(gt[:2], t(np.repeat(rand_obb(2, 5, 'v1'), 40000, axis=0)), 0.5, 0.4, 0.0, True, True, 'v1')
+c, s, l = clustered(1500, 9, 'v1')
+bid = torch.arange(3, device=dev).repeat_interleave(500)
+nms_device(t(c), t(s), 0.1, 'v1', labels=t(l), class_offset=torch.tensor([1025.0, 900.0, 1100.0], device=dev), order_index=True,
+           batch_ids=bid, n_batches=3)
+cb, sb, lb = clustered(17000, 10, 'v3')                      # above the small-K path
+nms_device(t(cb), t(sb), 0.1, 'v3', labels=t(lb), drop_small=True)
+R.multiclass_nms_rotated_batch(t(c[:900]).reshape(3, 300, 5), torch.rand(3, 300, 16, device=dev) ** 4, 0.05, dict(type='v1', iou_thr=0.1), 50)
+fs = [t(rng.standard_normal((2, 7, H, W)).astype(np.float32)) for H, W in ((9, 13), (5, 6), (1, 1))]
+bs = [t(np.concatenate([rng.uniform(-20, 120, (2 * f.size(2) * f.size(3), 2)), rng.uniform(1, 60, (2 * f.size(2) * f.size(3), 2)),
+                        rng.uniform(-1.6, 0, (2 * f.size(2) * f.size(3), 1))], 1).astype(np.float32)) for f in fs]
+for P in (1, 5):
+    frm_forward_multi(fs, bs, [1 / 8, 1 / 16, 1 / 64], P, residuals=fs); frm_backward_multi(fs, bs, [1 / 8, 1 / 16, 1 / 64], P)
+for v in ('v1', 'v2', 'v3'):
+    coder = R.DeltaXYWHAOBBoxCoder((0.,) * 5, (0.5,) * 5, angle_range=v)
+    rois = t(rand_obb(777, 11, v)); d = torch.randn(777, 15, device=dev) * 0.3
+    coder.decode(rois, d, max_shape=(500, 600)); coder.encode(rois, t(rand_obb(777, 12, v)))
+    A, Cn = 3, 5
+    cls = [torch.randn(2, A * Cn, H, W, device=dev) for H, W in ((9, 11), (4, 5), (2, 3))]
+    reg = [torch.randn(2, A * 5, H, W, device=dev) * 0.2 for H, W in ((9, 11), (4, 5), (2, 3))]
+    anc = [t(rand_obb(H * W * A, 13, v)) for H, W in ((9, 11), (4, 5), (2, 3))]
+    metas = [dict(img_shape=(100, 120, 3), scale_factor=np.ones(4, np.float32))] * 2
+    R.get_bboxes(cls, reg, anc, metas, dict(nms_pre=50, score_thr=0.05, nms=dict(type=v, iou_thr=0.1), max_per_img=20), coder, rescale=True)
+    fl = R.filter_bboxes(cls, reg, anc, coder, as_batch=True)
+    R.refine_bboxes(cls, [r[:, :5].contiguous() for r in reg], fl, coder)
+from oracle import transforms_np as T
+q = np.concatenate([T.obb2poly(c, 'v1') + rng.normal(0, 2, (1500, 8)).astype(np.float32), s[:, None]], 1).astype(np.float32)
+for K in (1, 64, 65, 1500):
+    R.poly_nms(t(q[:K]), 0.1)
+R.poly_nms(t(q[:300]), 0.0)
 torch.cuda.synchronize()
 print('sanitize smoke ok')
