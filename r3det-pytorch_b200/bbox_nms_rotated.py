@@ -125,33 +125,37 @@ def multiclass_nms_rotated_batch(multi_bboxes, multi_scores, score_thr, nms, max
     bid = torch.div(src, n * nc, rounding_mode='floor')
     scale = None
     if offset_rule is not None:
+        # per-image offset scale over the image's CANDIDATE boxes = rows with at least one class above the threshold;
+        # dense masked reductions over (B, n) instead of a scatter with B hot addresses
+        rowmask = (multi_scores[..., :nc] > score_thr).any(-1)
+        mb = multi_bboxes.float()
         if offset_rule == 'max':
-            hi = boxes.max(dim=1).values
-            lo = None
-        else:
-            hb = _obb2xyxy_v3(boxes)
-            hi, lo = hb.max(dim=1).values, hb.min(dim=1).values
-        top = torch.full((B,), float('-inf'), device=boxes.device).scatter_reduce_(0, bid, hi, 'amax', include_self=True)
-        if lo is None:
+            top = mb.max(-1).values.masked_fill(~rowmask, float('-inf')).max(-1).values
             scale = top + 1
         else:
-            bot = torch.full((B,), float('inf'), device=boxes.device).scatter_reduce_(0, bid, lo, 'amin', include_self=True)
+            hb = _obb2xyxy_v3(mb.reshape(B * n, 5)).reshape(B, n, 4)
+            top = hb.max(-1).values.masked_fill(~rowmask, float('-inf')).max(-1).values
+            bot = hb.min(-1).values.masked_fill(~rowmask, float('inf')).min(-1).values
             scale = (top - bot) + 1
         scale = torch.where(torch.isfinite(scale), scale, torch.ones_like(scale))      # images without candidates
     keep, num = nms_device(boxes, scores, _cfg(nms, 'iou_thr'), geometry, labels=labels, class_offset=scale,
                            order_index=by_index, drop_small=drop_small, batch_ids=bid, n_batches=B)
     counts = num.tolist()
-    dets_all = torch.cat([boxes, scores[:, None]], 1)
+    total = sum(counts)
+    keep = keep[:total]
+    dets_kept = torch.cat([boxes[keep], scores[keep][:, None]], 1)          # one gather for the whole batch, views per image
+    labels_kept = labels[keep]
     out, start = [], 0
     for b in range(B):
-        k = keep[start:start + counts[b]]
-        start += counts[b]
-        if counts[b] == 0:
+        c = counts[b]
+        if c == 0:
             out.append(empty)
             continue
-        if kind == 'v2' and k.size(0) > max_num:
-            k = k[:max_num]
+        m = c
+        if kind == 'v2' and c > max_num:
+            m = len(range(c)[:max_num])                                     # the reference's keep[:max_num], also for max_num = -1
         elif kind != 'v2' and max_num > 0:
-            k = k[:max_num]
-        out.append((dets_all[k], labels[k]))
+            m = min(c, max_num)
+        out.append((dets_kept[start:start + m], labels_kept[start:start + m]))
+        start += c
     return out

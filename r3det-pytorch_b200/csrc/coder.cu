@@ -13,7 +13,8 @@
 // Arithmetic follows the torch expressions operation by operation in FP32 with explicitly rounded intrinsics (no FMA
 // contraction), so results equal eager torch on the same device up to libm differences in exp/log/sin/cos.
 // All network outputs are read in their native NCHW layout (no permute/reshape copies).  HBM-bound gather work.
-#include <cub/device/device_radix_sort.cuh>
+#include <cub/block/block_scan.cuh>
+#include <cub/device/device_segmented_radix_sort.cuh>
 #include <math.h>
 #include "common.cuh"
 
@@ -188,57 +189,133 @@ struct LevelDesc {
     int64_t anchor_batch_stride; // in floats
     int HW, n, k;                // locations, rows (= HW * A), rows kept (= min(nms_pre, n) or n)
     int row0, out0;              // prefix sums of n and k over the levels
+    int blk0;                    // first CTA (of 256 rows) of this level inside an image's grid row
 };
 struct SelectArgs {
     LevelDesc lv[SEL_MAX_LEVELS];
-    int L, B, A, C, n_total, k_total, topk_on;
+    int L, B, A, C, n_total, k_total, blocks_per_image;
+    int row_bits;                // bits of a row index inside its level; sort key = (u - 0xC0000000) << row_bits | row
     int clamp, rescale;
     float max_x[SEL_MAX_IMAGES], max_y[SEL_MAX_IMAGES];
     float sf[SEL_MAX_IMAGES][4];
     CoderP P;
 };
 
-__device__ __forceinline__ int level_of(const SelectArgs& S, int r, bool by_out) {
+constexpr int SEL_BIN_BITS = 12;                 // histogram resolution of the top-k threshold search
+constexpr int SEL_BINS = 1 << SEL_BIN_BITS;
+
+__device__ __forceinline__ int level_of_out(const SelectArgs& S, int r) {
     int l = 0;
 #pragma unroll
-    for (int i = 1; i < SEL_MAX_LEVELS; i++)
-        if (i < S.L && r >= (by_out ? S.lv[i].out0 : S.lv[i].row0)) l = i;
+    for (int i = 1; i < SEL_MAX_LEVELS; i++) if (i < S.L && r >= S.lv[i].out0) l = i;
+    return l;
+}
+__device__ __forceinline__ int level_of_block(const SelectArgs& S, int b) {
+    int l = 0;
+#pragma unroll
+    for (int i = 1; i < SEL_MAX_LEVELS; i++) if (i < S.L && b >= S.lv[i].blk0) l = i;
     return l;
 }
 
-// One 64-bit key per (image, level, row): segment id on top; below it the complemented bits of sigmoid(max logit) for
-// levels that need a top-k (descending score), or the row index for levels kept whole (original order, as the
-// reference leaves them).  Written at the row's own slot so that the stable sort breaks score ties by row index.
-__global__ void select_keys_kernel(const __grid_constant__ SelectArgs S, unsigned long long* __restrict__ keys, int* __restrict__ vals) {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (int64_t)S.B * S.n_total) return;
-    const int b = (int)(t / S.n_total), r = (int)(t - (int64_t)b * S.n_total);
-    const int l = level_of(S, r, false);
+// Per-level top-k(nms_pre) by max-class sigmoid score, in three steps that never sort the ~200k rows of an image:
+//   1. one key per row, u = ~bits(sigmoid(max logit)) (ascending u = descending score; sigmoid is monotone, so this is
+//      the reference's `scores.max(1)`), plus a per-(image, level) histogram of the top 12 bits of u;
+//   2. per segment the smallest bin T whose cumulative count reaches k;
+//   3. rows with bin <= T (k plus the tail of one bin) are compacted as 64-bit keys (u << row_bits | row) and ONLY those are
+//      sorted (segmented radix sort): ties resolve to the lower row index, deterministically.
+// Levels with n <= nms_pre are kept whole in row order (as the reference leaves them) and skip all of this.
+// grid = (blocks_per_image, B); a CTA works inside one (image, level) segment, threads run along H*W (coalesced planes).
+__global__ void __launch_bounds__(256) select_hist_kernel(const __grid_constant__ SelectArgs S, unsigned* __restrict__ ukey,
+                                                          int* __restrict__ hist) {
+    __shared__ int h[SEL_BINS];
+    const int l = level_of_block(S, blockIdx.x);
     const LevelDesc& lv = S.lv[l];
-    const int local = r - lv.row0;                       // thread order: anchor-major, location-minor (coalesced planes)
-    const int a = local / lv.HW, hw = local - a * lv.HW;
-    const int n = hw * S.A + a;                          // row index of permute(1,2,0).reshape(-1, C)
-    unsigned low = (unsigned)n;
-    if (lv.k < lv.n) {
+    if (lv.k >= lv.n) return;                               // level kept whole
+    const int b = blockIdx.y;
+    for (int t = threadIdx.x; t < SEL_BINS; t += 256) h[t] = 0;
+    __syncthreads();
+    const int local = (blockIdx.x - lv.blk0) * 256 + threadIdx.x;        // anchor-major, location-minor
+    if (local < lv.n) {
+        const int a = local / lv.HW, hw = local - a * lv.HW;
         const float* cb = lv.cls + ((int64_t)b * S.A * S.C + (int64_t)a * S.C) * lv.HW + hw;
         float m = __ldg(cb);
         for (int c = 1; c < S.C; c++) m = fmaxf(m, __ldg(cb + (int64_t)c * lv.HW));
-        low = ~__float_as_uint(sigmoidf(m));             // sigmoid is monotone: max of sigmoids = sigmoid of the max
+        unsigned u = ~__float_as_uint(sigmoidf(m));
+        u = u < 0xC0000000u ? 0xC0000000u : u;             // NaN scores rank first, as torch.topk ranks them
+        ukey[(int64_t)b * S.n_total + lv.row0 + hw * S.A + a] = u;       // at the row's own slot
+        atomicAdd(&h[u >> (32 - SEL_BIN_BITS)], 1);
     }
-    const int64_t slot = (int64_t)b * S.n_total + lv.row0 + n;
-    keys[slot] = ((unsigned long long)(b * S.L + l) << 32) | low;
-    vals[slot] = n;
+    __syncthreads();
+    int* g = hist + (int64_t)(b * S.L + l) * SEL_BINS;
+    for (int t = threadIdx.x; t < SEL_BINS; t += 256)
+        if (h[t]) atomicAdd(g + t, h[t]);
+}
+
+// one CTA per (image, level): threshold bin + the segment's compaction cursor
+__global__ void __launch_bounds__(256) select_threshold_kernel(const __grid_constant__ SelectArgs S, const int* __restrict__ hist,
+                                                               int* __restrict__ thr, int* __restrict__ seg_begin,
+                                                               int* __restrict__ seg_end) {
+    typedef cub::BlockScan<int, 256> Scan;
+    __shared__ typename Scan::TempStorage tmp;
+    __shared__ int best;
+    const int seg = blockIdx.x, b = seg / S.L, l = seg - b * S.L;
+    const LevelDesc& lv = S.lv[l];
+    const int base = b * S.n_total + lv.row0;
+    if (threadIdx.x == 0) { seg_begin[seg] = base; seg_end[seg] = base; best = SEL_BINS - 1; }
+    if (lv.k >= lv.n) { if (threadIdx.x == 0) thr[seg] = -1; return; }
+    __syncthreads();
+    constexpr int PER = SEL_BINS / 256;
+    const int* g = hist + (int64_t)seg * SEL_BINS + threadIdx.x * PER;
+    int c[PER], sum = 0;
+#pragma unroll
+    for (int t = 0; t < PER; t++) { c[t] = g[t]; sum += c[t]; }
+    int before;
+    Scan(tmp).ExclusiveSum(sum, before);
+    if (before < lv.k && before + sum >= lv.k) {            // the k-th best row lies in one of this thread's bins
+        int run = before, t = 0;
+        for (; t < PER; t++) { run += c[t]; if (run >= lv.k) break; }
+        best = threadIdx.x * PER + t;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) thr[seg] = best;
+}
+
+__global__ void __launch_bounds__(256) select_compact_kernel(const __grid_constant__ SelectArgs S, const unsigned* __restrict__ ukey,
+                                                             const int* __restrict__ thr, int* __restrict__ seg_end,
+                                                             unsigned long long* __restrict__ keys) {
+    const int l = level_of_block(S, blockIdx.x);
+    const LevelDesc& lv = S.lv[l];
+    if (lv.k >= lv.n) return;
+    const int b = blockIdx.y, seg = b * S.L + l;
+    const int n = (blockIdx.x - lv.blk0) * 256 + threadIdx.x;            // row order here: plain coalesced key reads
+    bool take = false;
+    unsigned u = 0;
+    if (n < lv.n) {
+        u = ukey[(int64_t)b * S.n_total + lv.row0 + n];
+        take = (int)(u >> (32 - SEL_BIN_BITS)) <= thr[seg];
+    }
+    // warp-aggregated append to the segment's candidate list
+    const unsigned bal = __ballot_sync(0xffffffffu, take);
+    if (bal) {
+        const unsigned lane = threadIdx.x & 31u;
+        int base = 0;
+        if (lane == (unsigned)(__ffs(bal) - 1)) base = atomicAdd(seg_end + seg, __popc(bal));
+        base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
+        // sigmoid lies in [0, 1], so u >= 0xC07FFFFF: the two top bits carry nothing and are dropped from the sort key
+        if (take) keys[base + __popc(bal & ((1u << lane) - 1u))] = ((unsigned long long)(u - 0xC0000000u) << S.row_bits) | (unsigned)n;
+    }
 }
 
 // One thread per kept row: gather anchor + deltas, decode, clamp / rescale; then the C scores and the zero column.
-__global__ void select_decode_kernel(const __grid_constant__ SelectArgs S, const int* __restrict__ sorted_rows,
+__global__ void select_decode_kernel(const __grid_constant__ SelectArgs S, const unsigned long long* __restrict__ sorted,
                                      float* __restrict__ boxes, float* __restrict__ scores) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (int64_t)S.B * S.k_total) return;
     const int b = (int)(t / S.k_total), r = (int)(t - (int64_t)b * S.k_total);
-    const int l = level_of(S, r, true);
+    const int l = level_of_out(S, r);
     const LevelDesc& lv = S.lv[l];
-    const int n = sorted_rows[(int64_t)b * S.n_total + lv.row0 + (r - lv.out0)];
+    const int rr = r - lv.out0;
+    const int n = (lv.k < lv.n) ? (int)(sorted[(int64_t)b * S.n_total + lv.row0 + rr] & ((1ull << S.row_bits) - 1ull)) : rr;
     const int hw = n / S.A, a = n - hw * S.A;
     float roi[5], d[5], o[5];
     const float* an = lv.anchors + (int64_t)b * lv.anchor_batch_stride + (int64_t)n * 5;
@@ -271,21 +348,30 @@ static int make_coder(const char* who, const float* means, const float* stds, in
     return R3G_OK;
 }
 
-struct SelectWs { unsigned long long *keys_in, *keys_out; int *vals_in, *vals_out; void* cub; size_t cub_bytes, bytes; };
+struct SelectWs {
+    unsigned long long *keys_in, *keys_out;
+    unsigned* ukey;
+    int *hist, *thr, *seg_begin, *seg_end;
+    void* cub; size_t cub_bytes, bytes;
+};
 
-static int carve_select(void* ws, int64_t items, SelectWs* w) {
+static int carve_select(void* ws, int64_t items, int64_t segments, SelectWs* w) {
     char* p = (char*)ws;
     size_t off = 0;
-    const size_t n = (size_t)(items > 0 ? items : 1);
+    const size_t n = (size_t)(items > 0 ? items : 1), sg = (size_t)(segments > 0 ? segments : 1);
     w->keys_in = (unsigned long long*)(p + off); off += align_up(8 * n, 256);
     w->keys_out = (unsigned long long*)(p + off); off += align_up(8 * n, 256);
-    w->vals_in = (int*)(p + off); off += align_up(4 * n, 256);
-    w->vals_out = (int*)(p + off); off += align_up(4 * n, 256);
+    w->ukey = (unsigned*)(p + off); off += align_up(4 * n, 256);
+    w->hist = (int*)(p + off); off += align_up(4 * sg * SEL_BINS, 256);
+    w->thr = (int*)(p + off); off += align_up(4 * sg, 256);
+    w->seg_begin = (int*)(p + off); off += align_up(4 * sg, 256);
+    w->seg_end = (int*)(p + off); off += align_up(4 * sg, 256);
     size_t tb = 0;
-    cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, tb, (const unsigned long long*)nullptr, (unsigned long long*)nullptr,
-                                                    (const int*)nullptr, (int*)nullptr, (int64_t)n, 0, 64, (cudaStream_t)0);
+    cudaError_t e = cub::DeviceSegmentedRadixSort::SortKeys(nullptr, tb, (const unsigned long long*)nullptr,
+                                                            (unsigned long long*)nullptr, (int64_t)n, (int)sg, (const int*)nullptr,
+                                                            (const int*)nullptr, 0, 64, (cudaStream_t)0);
     if (e != cudaSuccess) { set_error("cub temp-size query failed: %s", cudaGetErrorString(e)); return R3G_ERR_CUDA; }
-    w->cub = p + off; w->cub_bytes = tb; off += align_up(tb, 256);
+    w->cub = p + off; w->cub_bytes = tb; off += align_up(tb > 0 ? tb : 1, 256);
     w->bytes = off;
     return R3G_OK;
 }
@@ -367,7 +453,7 @@ static int select_sizes(const char* who, int64_t L, int64_t B, int64_t A, const 
         const int64_t n = hw[2 * l] * hw[2 * l + 1] * A;
         nt += n; kt += (nms_pre > 0 && n > nms_pre) ? nms_pre : n;
     }
-    R3G_REQUIRE(nt < (1ll << 31) && B * nt < (1ll << 40), "%s: too many rows", who);
+    R3G_REQUIRE(nt < (1ll << 31) && B * nt < (1ll << 31), "%s: too many rows", who);
     *n_total = nt; *k_total = kt;
     return R3G_OK;
 }
@@ -379,7 +465,7 @@ R3G_API int r3g_select_decode_sizes(int64_t L, int64_t B, int64_t A, const int64
     if (rc != R3G_OK) return rc;
     R3G_REQUIRE(rows_per_image && workspace_bytes, "r3g_select_decode_sizes: null output");
     SelectWs w;
-    rc = carve_select(nullptr, B * nt, &w);
+    rc = carve_select(nullptr, B * nt, B * L, &w);
     if (rc != R3G_OK) return rc;
     *rows_per_image = kt; *workspace_bytes = w.bytes;
     return R3G_OK;
@@ -401,25 +487,32 @@ R3G_API int r3g_select_decode_f32(int64_t L, const float* const* cls_scores, con
     if (B == 0 || kt == 0) return R3G_OK;
     R3G_REQUIRE(cls_scores && bbox_preds && anchors && boxes_out && scores_out && workspace, "r3g_select_decode_f32: null pointer");
     SelectWs w;
-    rc = carve_select(workspace, B * nt, &w);
+    rc = carve_select(workspace, B * nt, B * L, &w);
     if (rc != R3G_OK) return rc;
     if (workspace_bytes < w.bytes) {
         set_error("r3g_select_decode_f32: workspace too small (%zu < %zu)", workspace_bytes, w.bytes);
         return R3G_ERR_WORKSPACE;
     }
     S.L = (int)L; S.B = (int)B; S.A = (int)A; S.C = (int)C; S.n_total = (int)nt; S.k_total = (int)kt;
-    int row0 = 0, out0 = 0;
+    int row0 = 0, out0 = 0, blk0 = 0;
+    bool any_topk = false;
     for (int l = 0; l < SEL_MAX_LEVELS; l++) {
         LevelDesc& lv = S.lv[l];
-        if (l >= L) { lv = S.lv[0]; lv.n = lv.k = 0; lv.row0 = row0; lv.out0 = out0; continue; }
+        if (l >= L) { lv = S.lv[0]; lv.n = lv.k = 0; lv.row0 = row0; lv.out0 = out0; lv.blk0 = blk0; continue; }
         const int64_t HW = level_hw[2 * l] * level_hw[2 * l + 1];
         R3G_REQUIRE(HW == 0 || (cls_scores[l] && bbox_preds[l] && anchors[l]), "r3g_select_decode_f32: null level pointer");
         lv.cls = cls_scores[l]; lv.reg = bbox_preds[l]; lv.anchors = anchors[l];
         lv.anchor_batch_stride = anchor_batch_strides ? anchor_batch_strides[l] : 0;
         lv.HW = (int)HW; lv.n = (int)(HW * A); lv.k = (nms_pre > 0 && lv.n > nms_pre) ? (int)nms_pre : lv.n;
-        lv.row0 = row0; lv.out0 = out0;
-        row0 += lv.n; out0 += lv.k;
+        lv.row0 = row0; lv.out0 = out0; lv.blk0 = blk0;
+        row0 += lv.n; out0 += lv.k; blk0 += (lv.n + 255) / 256;
+        any_topk |= lv.k < lv.n;
     }
+    S.blocks_per_image = blk0;
+    int max_n = 1;
+    for (int l = 0; l < L; l++) max_n = S.lv[l].n > max_n ? S.lv[l].n : max_n;
+    S.row_bits = 1;
+    while ((1ll << S.row_bits) < max_n) S.row_bits++;
     S.clamp = (variant == 1 && max_shapes_hw != nullptr) ? 1 : 0;
     S.rescale = scale_factors != nullptr ? 1 : 0;
     for (int b = 0; b < B; b++) {
@@ -428,16 +521,20 @@ R3G_API int r3g_select_decode_f32(int64_t L, const float* const* cls_scores, con
         for (int k = 0; k < 4; k++) S.sf[b][k] = S.rescale ? scale_factors[4 * b + k] : 1.0f;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    const int64_t items = B * nt;
-    select_keys_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(S, w.keys_in, w.vals_in);
-    R3G_LAUNCH_OK("select_keys_kernel");
-    int seg_bits = 1;
-    while ((1ll << seg_bits) < B * L) seg_bits++;
-    size_t tb = w.cub_bytes;
-    R3G_CUDA_OK(cub::DeviceRadixSort::SortPairs(w.cub, tb, (const unsigned long long*)w.keys_in, w.keys_out, (const int*)w.vals_in,
-                                                w.vals_out, items, 0, 32 + seg_bits, st));
+    if (any_topk) {
+        const int segs = (int)(B * L);
+        R3G_CUDA_OK(cudaMemsetAsync(w.hist, 0, sizeof(int) * (size_t)segs * SEL_BINS, st));
+        const dim3 grid((unsigned)S.blocks_per_image, (unsigned)B);
+        select_hist_kernel<<<grid, 256, 0, st>>>(S, w.ukey, w.hist);
+        select_threshold_kernel<<<segs, 256, 0, st>>>(S, w.hist, w.thr, w.seg_begin, w.seg_end);
+        select_compact_kernel<<<grid, 256, 0, st>>>(S, w.ukey, w.thr, w.seg_end, w.keys_in);
+        R3G_LAUNCH_OK("select kernels");
+        size_t tb = w.cub_bytes;
+        R3G_CUDA_OK(cub::DeviceSegmentedRadixSort::SortKeys(w.cub, tb, (const unsigned long long*)w.keys_in, w.keys_out, B * nt, segs,
+                                                            (const int*)w.seg_begin, (const int*)w.seg_end, 0, 30 + S.row_bits, st));
+    }
     const int64_t rows = B * kt;
-    select_decode_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(S, w.vals_out, boxes_out, scores_out);
+    select_decode_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(S, w.keys_out, boxes_out, scores_out);
     R3G_LAUNCH_OK("select_decode_kernel");
     return R3G_OK;
 }
