@@ -35,6 +35,10 @@ METRIC, UNIT = "rotated_iou_pairs_per_s", "Gpairs/s"
 AR = {'v1': (-np.pi / 2, 0), 'v2': (-np.pi / 4, 3 * np.pi / 4), 'v3': (-np.pi / 2, np.pi / 2)}
 
 
+# DRAM traffic of one iou_matrix_kernel launch on this workload, from the committed ncu capture (bytes)
+NCU_DRAM_BYTES_PER_LAUNCH = 86795776 + 886307840
+
+
 def rand_obb(n, seed, version='v1', lo=8, hi=512, span=1024):
     rng = np.random.default_rng(seed)
     cx = rng.uniform(0, span, n); cy = rng.uniform(0, span, n)
@@ -279,7 +283,8 @@ def run_gpu(args):
                 "ms_per_step": ms_e2e, "steps": e2e_steps},
         "gpu_launches": 3 * args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                     "traffic": None, "peak_source": peak_src, "kernel": "iou_matrix_kernel<true>",
+                     "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum "
+                     "(profiles/r01_iou_matrix_kernel_ncu_full.txt; 800 MB of it is the result matrix)", "peak_source": peak_src, "kernel": "iou_matrix_kernel<true>",
                      "kernel_ms": ms_kernel, "algorithmic_bytes_per_launch": 4 * pairs,
                      "pairs_circle_pass": stats[0], "pairs_sat_pass": stats[1], "pairs_strict": stats[2]},
         "clocks": clocks.summary(),
@@ -288,12 +293,13 @@ def run_gpu(args):
     if world > 1:
         line["collectives"] = exercise_collectives(torch, dist, R, dev, rank, world)
     if rank == 0:
+        line["iou_variants"] = bench_iou_variants(torch, R, dev)
         line["nms"] = bench_nms(torch, R, dev, hbm)
         line["frm"] = bench_frm(torch, R, dev, hbm)
         line["fused_assign"] = bench_assign(torch, R, dev, gt_h, an_h)
         line["dense_tail"] = bench_dense_tail(torch, R, dev)
         cores = os.cpu_count() or 1
-        apt = 4000
+        apt = 12000
         rate, dt, kind = cpu_pairs_per_s(apt, cores)
         line["cpu_baseline"] = {"value": rate / 1e9, "unit": UNIT, "cores": cores, "kind": kind,
                                 "sample": f"{GT} GT x {apt * cores} anchors ({apt} per thread, {dt:.1f} s wall)"}
@@ -354,6 +360,18 @@ def _time(torch, fn, iters, warm=3):
     e1.record()
     e1.synchronize()
     return e0.elapsed_time(e1) / iters
+
+
+def bench_iou_variants(torch, R, dev):
+    """configs[2] names all three angle conventions: the same 1000 x 200000 matrix for v1 / v2 / v3 (device-resident inputs,
+    strict reference parity, whole op = two prepare launches + the pair kernel) and the IoF mode of v1."""
+    out = {}
+    for v, mode in (("v1", "iou"), ("v2", "iou"), ("v3", "iou"), ("v1", "iof")):
+        gt = torch.from_numpy(rand_obb(GT, 1, v)).to(dev)
+        an = torch.from_numpy(rand_obb(ANCHORS, 1000, v)).to(dev)
+        ms = _time(torch, lambda: R.pairwise_iou(gt, an, v, mode), 30)
+        out[f"{v}_{mode}"] = {"ms": ms, "gpairs_per_s": GT * ANCHORS / ms / 1e6}
+    return out
 
 
 def bench_assign(torch, R, dev, gt_h, an_h):
