@@ -163,7 +163,7 @@ def run_reference(args):
     pairs = GT * apt * cores * args.steps
     val = pairs / dt / 1e9
     sample = f"{GT} GT x {apt * cores} anchors per step ({apt} per thread), {args.steps} steps"
-    print(json.dumps({
+    _emit({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / max(args.steps, 1) * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -172,7 +172,7 @@ def run_reference(args):
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    })
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
@@ -303,7 +303,7 @@ def run_gpu(args):
         rate, dt, kind = cpu_pairs_per_s(apt, cores)
         line["cpu_baseline"] = {"value": rate / 1e9, "unit": UNIT, "cores": cores, "kind": kind,
                                 "sample": f"{GT} GT x {apt * cores} anchors ({apt} per thread, {dt:.1f} s wall)"}
-        print(json.dumps(line))
+        _emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -501,10 +501,30 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_gpu(args)
+    # stdout carries exactly ONE line (the JSON record): libraries that write there (NCCL prints its version banner on
+    # the first communicator) are diverted to stderr for the duration of the run; _emit() restores the descriptor.
+    global _STDOUT_FD
+    sys.stdout.flush()
+    _STDOUT_FD = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_gpu(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(_STDOUT_FD, 1)
+
+
+_STDOUT_FD = None
+
+
+def _emit(record):
+    """Print the one JSON line on the real stdout."""
+    sys.stdout.flush()
+    line = json.dumps(record) + "\n"
+    os.write(_STDOUT_FD if _STDOUT_FD is not None else 1, line.encode())
 
 
 if __name__ == "__main__":
