@@ -467,7 +467,7 @@ def bench_frm(torch, R, dev, hbm):
     """configs[1] FRM shapes: batch 8, 256 channels, 5 FPN levels of a 1024^2 patch; 8 B per element roofline.
     All five levels go through ONE launch sequence (r3g_frm_*_multi_f32), as FeatureRefineModule runs them;
     `per_level_*` is the same work as five separate calls (the reference module's loop)."""
-    from r3det_b200.fr import frm_backward, frm_backward_multi, frm_forward, frm_forward_multi
+    from r3det_b200.fr import FrmBackwardPlan, frm_backward, frm_backward_multi, frm_forward, frm_forward_multi
     rng = np.random.default_rng(4)
     res = {}
     xs, bts, scales = [], [], []
@@ -484,11 +484,14 @@ def bench_frm(torch, R, dev, hbm):
     for P in (1, 5):
         tf = _time(torch, lambda: frm_forward_multi(xs, bts, scales, P), 10)
         tb = _time(torch, lambda: frm_backward_multi(xs, bts, scales, P), 10)
+        plan = FrmBackwardPlan([tuple(x.shape) for x in xs], bts, scales, P)
+        torch.cuda.synchronize()
+        tba = _time(torch, lambda: plan.apply(xs), 10)      # the gather alone: what a training step pays when the plan overlapped the forward
         tfl = sum(_time(torch, lambda: frm_forward(x, b, s, P), 10) for x, b, s in zip(xs, bts, scales))
         tbl = sum(_time(torch, lambda: frm_backward(x, b, s, P), 10) for x, b, s in zip(xs, bts, scales))
         res[f"points{P}"] = {"fwd_ms": tf, "bwd_ms": tb, "fwd_gbs": elems * 8 / tf / 1e6, "bwd_gbs": elems * 8 / tb / 1e6,
                              "fwd_frac_of_hbm": elems * 8 / tf / 1e6 / hbm, "bwd_frac_of_hbm": elems * 8 / tb / 1e6 / hbm,
-                             "per_level_fwd_ms": tfl, "per_level_bwd_ms": tbl}
+                             "bwd_apply_ms": tba, "per_level_fwd_ms": tfl, "per_level_bwd_ms": tbl}
     res["elements"] = elems
     res["bytes_per_element"] = 8
     return res

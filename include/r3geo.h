@@ -169,6 +169,16 @@ int r3g_frm_backward_multi_f32(int L, const float* const* grad_outs, const float
                                const int* level_hw, const float* spatial_scales, int points, float* const* grad_ins,
                                void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same backward in two halves: PLAN depends on the boxes only (tap sort + per-target CSR into the workspace) and can
+ * run on a side stream while the forward pass executes; APPLY is the gather.  plan + apply == r3g_frm_backward_multi_f32
+ * bit for bit.  The workspace (r3g_frm_backward_multi_workspace_bytes) must stay untouched between the two calls, and the
+ * level list (empty levels included) must be the same. */
+int r3g_frm_backward_plan_multi_f32(int L, const float* const* boxes, int N, const int* level_hw, const float* spatial_scales,
+                                    int points, void* workspace, size_t workspace_bytes, void* stream);
+int r3g_frm_backward_apply_multi_f32(int L, const float* const* grad_outs, const float* const* boxes, int N, int C,
+                                     const int* level_hw, const float* spatial_scales, int points, float* const* grad_ins,
+                                     const void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- box transforms (r3det/core/bbox/rtransforms.py) ---------------------------------------------------
  * obb2poly :367-440, poly2obb :190-277, obb2hbb :443-537, hbb2obb :540-592, obb2xyxy :595-651.
  * n boxes; version 1/2/3. */

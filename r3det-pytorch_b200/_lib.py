@@ -49,6 +49,8 @@ _SIGNATURES = {
     "r3g_frm_forward_multi_f32": (_i32, [_i32, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _i32, _vp, _vp]),
     "r3g_frm_backward_multi_workspace_bytes": (_i32, [_i32, _i32, _vp, _i32, C.POINTER(_sz)]),
     "r3g_frm_backward_multi_f32": (_i32, [_i32, _vp, _vp, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _sz, _vp]),
+    "r3g_frm_backward_plan_multi_f32": (_i32, [_i32, _vp, _i32, _vp, _vp, _i32, _vp, _sz, _vp]),
+    "r3g_frm_backward_apply_multi_f32": (_i32, [_i32, _vp, _vp, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _sz, _vp]),
     "r3g_obb2poly_f32": (_i32, [_vp, _i64, _i32, _vp, _vp]),
     "r3g_poly2obb_f32": (_i32, [_vp, _i64, _i32, _vp, _vp]),
     "r3g_obb2hbb_f32": (_i32, [_vp, _i64, _i32, _vp, _vp]),

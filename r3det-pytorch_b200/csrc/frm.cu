@@ -451,23 +451,16 @@ R3G_API int r3g_frm_backward_workspace_bytes(int N, int H, int W, int points, si
     return r3g_frm_backward_multi_workspace_bytes(1, N, hw, points, bytes);
 }
 
-R3G_API int r3g_frm_backward_multi_f32(int L, const float* const* grad_outs, const float* const* boxes, int N, int C,
-                                       const int* level_hw, const float* spatial_scales, int points, float* const* grad_ins,
-                                       void* workspace, size_t workspace_bytes, void* stream) {
-    FrmLevels S;
-    size_t blocks = 0;
-    int rc = frm_plan("r3g_frm_backward_multi_f32", L, grad_outs, boxes, nullptr, grad_ins, N, C, level_hw, spatial_scales, points,
-                      FRM_CC_BWD, &S, &blocks);
-    if (rc < 0) return rc;
-    if (rc == 1) return R3G_OK;
-    R3G_REQUIRE(workspace != nullptr, "r3g_frm_backward_multi_f32: null workspace");
+// The backward in two halves: the PLAN (tap sort + CSR) depends on the boxes only, so a training step can build it on a
+// side stream while the forward pass is still running; APPLY is the gather over that CSR.
+static int frm_bwd_plan(const FrmLevels& S, int points, void* workspace, size_t workspace_bytes, cudaStream_t st, const char* who) {
+    R3G_REQUIRE(workspace != nullptr, "%s: null workspace", who);
     const size_t nl = S.nl, E = nl * points * 4;
     FrmBwdWs w = carve_frm(workspace, nl, points);
     if (workspace_bytes < w.bytes) {
-        set_error("r3g_frm_backward_multi_f32: workspace too small (%zu < %zu)", workspace_bytes, w.bytes);
+        set_error("%s: workspace too small (%zu < %zu)", who, workspace_bytes, w.bytes);
         return R3G_ERR_WORKSPACE;
     }
-    cudaStream_t st = (cudaStream_t)stream;
     const int tpb = 256;
     if (points == 1) frm_bwd_taps_kernel<1><<<(unsigned)((nl + tpb - 1) / tpb), tpb, 0, st>>>(S, w.keys, w.ids, w.wts);
     else frm_bwd_taps_kernel<5><<<(unsigned)((nl + tpb - 1) / tpb), tpb, 0, st>>>(S, w.keys, w.ids, w.wts);
@@ -477,9 +470,60 @@ R3G_API int r3g_frm_backward_multi_f32(int L, const float* const* grad_outs, con
     R3G_CUDA_OK(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, w.keys, w.keys2, w.ids, w.ids2, (int)E, 0, end_bit, st));
     frm_bwd_rows_kernel<<<(unsigned)((nl + 1 + tpb - 1) / tpb), tpb, 0, st>>>(w.keys2, E, nl, w.row_start);
     frm_bwd_materialize_kernel<<<(unsigned)((E + tpb - 1) / tpb), tpb, 0, st>>>(S, w.ids2, w.wts, E, points, w.src, w.wsorted);
-    frm_backward_kernel<<<(unsigned)blocks, FRM_THREADS, 0, st>>>(S, w.row_start, w.src, w.wsorted);
-    R3G_LAUNCH_OK("frm_backward kernels");
+    R3G_LAUNCH_OK("frm backward plan kernels");
     return R3G_OK;
+}
+
+static int frm_bwd_apply(const FrmLevels& S, size_t blocks, int points, void* workspace, size_t workspace_bytes, cudaStream_t st,
+                         const char* who) {
+    R3G_REQUIRE(workspace != nullptr, "%s: null workspace", who);
+    FrmBwdWs w = carve_frm(workspace, S.nl, points);
+    if (workspace_bytes < w.bytes) {
+        set_error("%s: workspace too small (%zu < %zu)", who, workspace_bytes, w.bytes);
+        return R3G_ERR_WORKSPACE;
+    }
+    frm_backward_kernel<<<(unsigned)blocks, FRM_THREADS, 0, st>>>(S, w.row_start, w.src, w.wsorted);
+    R3G_LAUNCH_OK("frm_backward_kernel");
+    return R3G_OK;
+}
+
+R3G_API int r3g_frm_backward_plan_multi_f32(int L, const float* const* boxes, int N, const int* level_hw, const float* spatial_scales,
+                                            int points, void* workspace, size_t workspace_bytes, void* stream) {
+    // the plan ignores the feature pointers and the channel count: a one-channel table over the boxes pointers
+    FrmLevels S;
+    size_t blocks = 0;
+    int rc = frm_plan("r3g_frm_backward_plan_multi_f32", L, boxes, boxes, nullptr, (float* const*)boxes, N, 1, level_hw, spatial_scales,
+                      points, FRM_CC_BWD, &S, &blocks);
+    if (rc < 0) return rc;
+    if (rc == 1) return R3G_OK;
+    return frm_bwd_plan(S, points, workspace, workspace_bytes, (cudaStream_t)stream, "r3g_frm_backward_plan_multi_f32");
+}
+
+R3G_API int r3g_frm_backward_apply_multi_f32(int L, const float* const* grad_outs, const float* const* boxes, int N, int C,
+                                             const int* level_hw, const float* spatial_scales, int points, float* const* grad_ins,
+                                             const void* workspace, size_t workspace_bytes, void* stream) {
+    FrmLevels S;
+    size_t blocks = 0;
+    int rc = frm_plan("r3g_frm_backward_apply_multi_f32", L, grad_outs, boxes, nullptr, grad_ins, N, C, level_hw, spatial_scales, points,
+                      FRM_CC_BWD, &S, &blocks);
+    if (rc < 0) return rc;
+    if (rc == 1) return R3G_OK;
+    return frm_bwd_apply(S, blocks, points, const_cast<void*>(workspace), workspace_bytes, (cudaStream_t)stream,
+                         "r3g_frm_backward_apply_multi_f32");
+}
+
+R3G_API int r3g_frm_backward_multi_f32(int L, const float* const* grad_outs, const float* const* boxes, int N, int C,
+                                       const int* level_hw, const float* spatial_scales, int points, float* const* grad_ins,
+                                       void* workspace, size_t workspace_bytes, void* stream) {
+    FrmLevels S;
+    size_t blocks = 0;
+    int rc = frm_plan("r3g_frm_backward_multi_f32", L, grad_outs, boxes, nullptr, grad_ins, N, C, level_hw, spatial_scales, points,
+                      FRM_CC_BWD, &S, &blocks);
+    if (rc < 0) return rc;
+    if (rc == 1) return R3G_OK;
+    rc = frm_bwd_plan(S, points, workspace, workspace_bytes, (cudaStream_t)stream, "r3g_frm_backward_multi_f32");
+    if (rc != R3G_OK) return rc;
+    return frm_bwd_apply(S, blocks, points, workspace, workspace_bytes, (cudaStream_t)stream, "r3g_frm_backward_multi_f32");
 }
 
 R3G_API int r3g_frm_backward_f32(const float* grad_out, const float* boxes, int N, int C, int H, int W,

@@ -108,6 +108,50 @@ def frm_backward_multi(grad_outputs, best_rbboxes, spatial_scales, points=1):
     return [g if go.dtype == torch.float32 else g.to(go.dtype) for g, go in zip(gins, grad_outputs)]
 
 
+class FrmBackwardPlan:
+    """The box-only half of the backward (tap sort + per-target CSR) for a list of levels, built on a SIDE stream so that it
+    overlaps the forward kernels; `apply(grads)` runs the gather on the current stream after waiting for the plan."""
+
+    _side = {}
+
+    def __init__(self, shapes, best_rbboxes, spatial_scales, points):
+        self.points = int(points)
+        self.n, self.c = shapes[0][0], shapes[0][1]
+        self.boxes = [b.float().contiguous() for b in best_rbboxes]
+        nl = len(shapes)
+        self.nl = nl
+        self.hw = (C.c_int * (2 * nl))(*[v for sh in shapes for v in (sh[2], sh[3])])
+        self.sc = (C.c_float * nl)(*[float(s) for s in spatial_scales])
+        dev = self.boxes[0].device
+        self.dev = dev
+        lib = L.lib()
+        need = C.c_size_t(0)
+        L.check(lib.r3g_frm_backward_multi_workspace_bytes(nl, self.n, self.hw, self.points, C.byref(need)))
+        self.ws = L.workspace(need.value, dev)
+        side = FrmBackwardPlan._side.get(dev.index)
+        if side is None:
+            side = FrmBackwardPlan._side[dev.index] = torch.cuda.Stream(device=dev)
+        cur = torch.cuda.current_stream(dev)
+        side.wait_stream(cur)                                  # the boxes are produced on the current stream
+        with L.device_guard(dev), torch.cuda.stream(side):
+            L.check(lib.r3g_frm_backward_plan_multi_f32(nl, _ptr_array(self.boxes), self.n, self.hw, self.sc, self.points,
+                                                        L.ptr(self.ws), self.ws.numel(), C.c_void_p(side.cuda_stream)))
+            self.ready = side.record_event()
+        for t in self.boxes + [self.ws]:
+            t.record_stream(side)
+
+    def apply(self, grad_outputs):
+        gs = [g.contiguous() if g.dtype == torch.float32 else g.float().contiguous() for g in grad_outputs]
+        gins = [torch.empty_like(g) for g in gs]
+        cur = torch.cuda.current_stream(self.dev)
+        cur.wait_event(self.ready)
+        with L.device_guard(self.dev):
+            L.check(L.lib().r3g_frm_backward_apply_multi_f32(self.nl, _ptr_array(gs), _ptr_array(self.boxes), self.n, gs[0].size(1),
+                                                             self.hw, self.sc, self.points, _ptr_array(gins), L.ptr(self.ws),
+                                                             self.ws.numel(), L.stream_ptr(self.dev)))
+        return [g if go.dtype == torch.float32 else g.to(go.dtype) for g, go in zip(gins, grad_outputs)]
+
+
 class FeatureRefineMultiFunction(Function):
     """feature_refine over every FPN level at once: apply(points, scales, with_residual, *features, *boxes[, *residuals])
     -> tuple of refined maps.  Gradients: features get the FRM transpose, residuals the identity, boxes none
@@ -122,6 +166,13 @@ class FeatureRefineMultiFunction(Function):
         assert all(f.is_cuda for f in feats)
         ctx.frm = (points, tuple(scales), nl, with_residual)
         ctx.save_for_backward(*boxes)
+        need = [ctx.needs_input_grad[3 + l] for l in range(nl)]
+        ctx.plan = None
+        if any(need) and all(f.numel() for f in feats):
+            # the backward's CSR depends on the boxes only: build it now, on a side stream, under the forward kernels
+            idx = [l for l in range(nl) if need[l]]
+            ctx.plan = (idx, FrmBackwardPlan([tuple(feats[l].shape) for l in idx], [boxes[l] for l in idx],
+                                             [scales[l] for l in idx], points))
         return tuple(frm_forward_multi(feats, boxes, scales, points, resid))
 
     @staticmethod
@@ -133,8 +184,12 @@ class FeatureRefineMultiFunction(Function):
         need = [ctx.needs_input_grad[3 + l] for l in range(nl)]
         gin = [None] * nl
         if any(need):
-            idx = [l for l in range(nl) if need[l]]
-            res = frm_backward_multi([grads[l] for l in idx], [boxes[l] for l in idx], [scales[l] for l in idx], points)
+            if ctx.plan is not None:
+                idx, plan = ctx.plan
+                res = plan.apply([grads[l] for l in idx])
+            else:
+                idx = [l for l in range(nl) if need[l]]
+                res = frm_backward_multi([grads[l] for l in idx], [boxes[l] for l in idx], [scales[l] for l in idx], points)
             for l, g in zip(idx, res):
                 gin[l] = g
         gres = [grads[l] if ctx.needs_input_grad[3 + 2 * nl + l] else None for l in range(nl)] if with_residual else []

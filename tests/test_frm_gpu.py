@@ -142,3 +142,27 @@ def test_multi_level_autograd(cuda_dev):
         mixed = m.conv_5_1(m.conv_1_5(xs[l])) + m.conv_1_1(xs[l])
         want = xs[l] + R.feature_refine(mixed, bs[l], m.fr[l].spatial_scale, 1)
         assert torch.allclose(ys[l], want, rtol=0, atol=1e-5)
+
+
+def test_backward_plan_apply_split(cuda_dev):
+    """plan (side stream, boxes only) + apply == the one-call backward bit for bit; the autograd path uses the split."""
+    from r3det_b200.fr import FrmBackwardPlan, frm_backward_multi
+    import r3det_b200 as R
+    rng = np.random.default_rng(31)
+    fs, bs, gs, sc = [], [], [], []
+    for H, W, s in ((24, 20, 8), (12, 10, 16), (3, 5, 64)):
+        f, g, b = _case(rng, 2, 20, H, W, s)
+        fs.append(torch.from_numpy(f).to(cuda_dev)); gs.append(torch.from_numpy(g).to(cuda_dev)); bs.append(torch.from_numpy(b).to(cuda_dev))
+        sc.append(1.0 / s)
+    for P in (1, 5):
+        plan = FrmBackwardPlan([tuple(f.shape) for f in fs], bs, sc, P)
+        got = plan.apply(gs)
+        want = frm_backward_multi(gs, bs, sc, P)
+        assert all(torch.equal(a, b) for a, b in zip(got, want))
+        got2 = plan.apply([g * 2 for g in gs])                       # a plan can be applied more than once
+        assert all(torch.allclose(a, 2 * b, rtol=1e-6, atol=1e-6) for a, b in zip(got2, want))
+    xs = [f.clone().requires_grad_(True) for f in fs]
+    outs = R.feature_refine_multi(xs, bs, sc, 5)
+    torch.autograd.backward(outs, gs)
+    want = frm_backward_multi(gs, bs, sc, 5)
+    assert all(torch.equal(x.grad, w) for x, w in zip(xs, want))
