@@ -207,11 +207,18 @@ __global__ void __launch_bounds__(NMS_THREADS, 3) nms_mask_kernel(const MaskArgs
     unsigned short* q2 = q2_all[warp];
     uint2* q3 = q3_all[warp];
     unsigned long long* sm = sm_all[warp];
-    const long long total = A.item_base[A.nblk];
+    // When there are fewer items than warps in the grid (small K: a detection head's per-image call), an item's 64 rows
+    // are split over up to 8 warps: the kernel is then bound by ONE warp's serial work (its SAT / area / restatement
+    // batches), not by throughput.
+    const long long base_items = A.item_base[A.nblk];
+    int split = 1;
+    while (split < 8 && base_items * (split * 2) <= (long long)gridDim.x * NMS_WARPS) split *= 2;
+    const long long total = base_items * split;
+    const int rows_per_sub = 64 / split;
     int c1 = 0, c2 = 0, c3 = 0;
     int i0 = 0, j0 = 0;
 
-    int rb = -1, cb0 = 0, ncb = 0;
+    int rb = -1, cb0 = 0, ncb = 0, r_lo = 0, r_hi = 64;      // r_lo .. r_hi: this warp's rows of the item in flight
     auto decide = [&](int il, int jl, float r) {
         const bool sup = A.inclusive ? (r >= A.thr) : (r > A.thr);
         if (sup) atomicOr(&sm[il * NMS_G + (jl >> 6)], 1ull << (jl & 63));
@@ -227,7 +234,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 3) nms_mask_kernel(const MaskArgs
             const bool sup = A.inclusive ? (r >= A.thr) : (r > A.thr);
             if (sup) {
                 const int rbi = i >> 6, cbj = j >> 6;
-                if (rbi == rb && cbj >= cb0 && cbj < cb0 + ncb) {
+                if (rbi == rb && cbj >= cb0 && cbj < cb0 + ncb && (i & 63) >= r_lo && (i & 63) < r_hi) {
                     atomicOr(&sm[(i & 63) * NMS_G + (cbj - cb0)], 1ull << (j & 63));
                 } else {
                     const long long base = A.row_base[rbi];
@@ -289,6 +296,8 @@ __global__ void __launch_bounds__(NMS_THREADS, 3) nms_mask_kernel(const MaskArgs
         if (lane == 0) item = (long long)atomicAdd(A.ticket, 1ull);
         item = __shfl_sync(0xffffffffu, item, 0);
         if (item >= total) break;
+        const int sub = (int)(item % split);
+        item /= split;
         // row block of this item: last rb with item_base[rb] <= item
         int lo = 0, hi = A.nblk;
         while (hi - lo > 1) {
@@ -296,13 +305,14 @@ __global__ void __launch_bounds__(NMS_THREADS, 3) nms_mask_kernel(const MaskArgs
             if (A.item_base[mid] <= item) lo = mid; else hi = mid;
         }
         rb = lo;
+        r_lo = sub * rows_per_sub; r_hi = r_lo + rows_per_sub;
         const int g = (int)(item - A.item_base[rb]);
         const int be = A.blk_end[rb];
         cb0 = rb + g * NMS_G;                                 // first column block of the item
         ncb = min(NMS_G, be - cb0 + 1);                       // valid column blocks
         i0 = rb * 64;
         j0 = cb0 * 64;
-        const int i1 = min(A.K, i0 + 64);
+        const int i1 = min(A.K, i0 + r_hi);
         const int j1 = min(A.K, j0 + ncb * 64);
         const int jb = j0 + (int)lane * NMS_CPL;
 
@@ -323,7 +333,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 3) nms_mask_kernel(const MaskArgs
         const bool interior = (cb0 > rb) && (A.label[i0] == A.label[j1 - 1]);
         __syncwarp();
 
-        for (int ig = i0; ig < i1; ig += NMS_RG) {
+        for (int ig = i0 + r_lo; ig < i1; ig += NMS_RG) {
             const int nr = min(NMS_RG, i1 - ig);
             unsigned m = 0;
 #pragma unroll
@@ -377,7 +387,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 3) nms_mask_kernel(const MaskArgs
         // write the item's words: row r of block rb holds (be - rb + 1) words, word index = cb - rb
         const long long base = A.row_base[rb];
         const int nwr = be - rb + 1;
-        for (int k = lane; k < 64 * NMS_G; k += 32) {
+        for (int k = r_lo * NMS_G + lane; k < r_hi * NMS_G; k += 32) {
             const int il = k / NMS_G, c = k % NMS_G;
             if (c < ncb) A.mask[base + (long long)il * nwr + (cb0 - rb + c)] = sm[k];
         }
