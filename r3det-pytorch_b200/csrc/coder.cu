@@ -366,12 +366,9 @@ static int carve_select(void* ws, int64_t items, int64_t segments, SelectWs* w) 
     w->thr = (int*)(p + off); off += align_up(4 * sg, 256);
     w->seg_begin = (int*)(p + off); off += align_up(4 * sg, 256);
     w->seg_end = (int*)(p + off); off += align_up(4 * sg, 256);
-    size_t tb = 0;
-    cudaError_t e = cub::DeviceSegmentedRadixSort::SortKeys(nullptr, tb, (const unsigned long long*)nullptr,
-                                                            (unsigned long long*)nullptr, (int64_t)n, (int)sg, (const int*)nullptr,
-                                                            (const int*)nullptr, 0, 64, (cudaStream_t)0);
-    if (e != cudaSuccess) { set_error("cub temp-size query failed: %s", cudaGetErrorString(e)); return R3G_ERR_CUDA; }
-    w->cub = p + off; w->cub_bytes = tb; off += align_up(tb > 0 ? tb : 1, 256);
+    // the sort ping-pongs between keys_in and keys_out (cub::DoubleBuffer), so cub itself needs no scratch worth
+    // mentioning; a fixed kilobyte is handed over (and no device query is needed to size the workspace)
+    w->cub = p + off; w->cub_bytes = 1024; off += 1024;
     w->bytes = off;
     return R3G_OK;
 }
@@ -521,6 +518,7 @@ R3G_API int r3g_select_decode_f32(int64_t L, const float* const* cls_scores, con
         for (int k = 0; k < 4; k++) S.sf[b][k] = S.rescale ? scale_factors[4 * b + k] : 1.0f;
     }
     cudaStream_t st = (cudaStream_t)stream;
+    const unsigned long long* sorted_keys = w.keys_out;
     if (any_topk) {
         const int segs = (int)(B * L);
         R3G_CUDA_OK(cudaMemsetAsync(w.hist, 0, sizeof(int) * (size_t)segs * SEL_BINS, st));
@@ -530,11 +528,13 @@ R3G_API int r3g_select_decode_f32(int64_t L, const float* const* cls_scores, con
         select_compact_kernel<<<grid, 256, 0, st>>>(S, w.ukey, w.thr, w.seg_end, w.keys_in);
         R3G_LAUNCH_OK("select kernels");
         size_t tb = w.cub_bytes;
-        R3G_CUDA_OK(cub::DeviceSegmentedRadixSort::SortKeys(w.cub, tb, (const unsigned long long*)w.keys_in, w.keys_out, B * nt, segs,
-                                                            (const int*)w.seg_begin, (const int*)w.seg_end, 0, 30 + S.row_bits, st));
+        cub::DoubleBuffer<unsigned long long> db(w.keys_in, w.keys_out);
+        R3G_CUDA_OK(cub::DeviceSegmentedRadixSort::SortKeys(w.cub, tb, db, B * nt, segs, (const int*)w.seg_begin,
+                                                            (const int*)w.seg_end, 0, 30 + S.row_bits, st));
+        sorted_keys = db.Current();
     }
     const int64_t rows = B * kt;
-    select_decode_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(S, w.keys_out, boxes_out, scores_out);
+    select_decode_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(S, sorted_keys, boxes_out, scores_out);
     R3G_LAUNCH_OK("select_decode_kernel");
     return R3G_OK;
 }

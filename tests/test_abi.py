@@ -82,3 +82,43 @@ def test_registry_names():
     for name in ("RBboxOverlaps2D_v1", "RBboxOverlaps2D_v2", "RBboxOverlaps2D_v3"):
         calc = r3det_b200.IOU_CALCULATORS.build(dict(type=name))
         assert repr(calc) == name + "()"
+
+
+def test_next_row_entry_points_validate_arguments(lib):
+    """coder / dense-head tail / multi-level FRM / polygon NMS / assigner: size queries and argument errors (host only)."""
+    f5 = (C.c_float * 5)(0, 0, 0, 0, 0); one5 = (C.c_float * 5)(1, 1, 1, 1, 1)
+    # coder
+    assert lib.r3g_delta2bbox_f32(None, 4, 5, None, 1, f5, one5, 4, None, 0.016, 0, 32.0, None, None) < 0
+    assert b"variant" in lib.r3g_last_error()
+    assert lib.r3g_delta2bbox_f32(None, 4, 5, None, 1, None, one5, 1, None, 0.016, 0, 32.0, None, None) < 0
+    assert lib.r3g_delta2bbox_f32(None, 4, 5, None, 1, f5, one5, 1, None, -1.0, 0, 32.0, None, None) < 0
+    assert b"wh_ratio_clip" in lib.r3g_last_error()
+    assert lib.r3g_delta2bbox_f32(None, 0, 5, None, 1, f5, one5, 1, None, 0.016, 0, 32.0, None, None) == 0
+    assert lib.r3g_bbox2delta_f32(None, 5, None, 5, 0, f5, one5, 3, None, None) == 0
+    assert lib.r3g_bbox2delta_f32(None, 4, None, 5, 3, f5, one5, 3, None, None) < 0
+    # get_bboxes tail: rows per image = sum over levels of min(nms_pre, H*W*A)
+    hw = (C.c_int64 * 10)(128, 128, 64, 64, 32, 32, 16, 16, 8, 8)
+    rows, nbytes = C.c_int64(0), C.c_size_t(0)
+    assert lib.r3g_select_decode_sizes(5, 8, 9, hw, 2000, C.byref(rows), C.byref(nbytes)) == 0
+    assert rows.value == 2000 * 4 + 8 * 8 * 9 == 8576 and nbytes.value > 8 * 196416 * 20
+    assert lib.r3g_select_decode_sizes(5, 8, 9, hw, -1, C.byref(rows), C.byref(nbytes)) == 0 and rows.value == 196416
+    assert lib.r3g_select_decode_sizes(9, 8, 9, hw, 2000, C.byref(rows), C.byref(nbytes)) < 0
+    assert b"levels" in lib.r3g_last_error()
+    assert lib.r3g_select_decode_sizes(5, 65, 9, hw, 2000, C.byref(rows), C.byref(nbytes)) < 0
+    assert b"images" in lib.r3g_last_error()
+    # FRM over several levels
+    ihw = (C.c_int * 4)(16, 16, 8, 8)
+    assert lib.r3g_frm_backward_multi_workspace_bytes(2, 2, ihw, 5, C.byref(nbytes)) == 0 and nbytes.value > 2 * 320 * 20 * 4
+    assert lib.r3g_frm_backward_multi_workspace_bytes(9, 2, ihw, 5, C.byref(nbytes)) < 0
+    sc = (C.c_float * 2)(0.125, 0.0625)
+    assert lib.r3g_frm_forward_multi_f32(2, None, None, None, 2, 4, ihw, sc, 1, None, None) < 0      # null level pointers
+    assert lib.r3g_frm_forward_multi_f32(2, None, None, None, 0, 4, ihw, sc, 1, None, None) == 0     # empty batch
+    assert lib.r3g_frm_forward_multi_f32(2, None, None, None, 2, 4, ihw, sc, 2, None, None) < 0
+    assert b"points" in lib.r3g_last_error()
+    # polygon NMS
+    assert lib.r3g_poly_nms_workspace_bytes(5000, C.byref(nbytes)) == 0 and nbytes.value > 5000 * 48
+    keep = C.c_int64(0)
+    assert lib.r3g_poly_nms_f32(None, 9, None, 5, 0.1, None, None, None, 0, None) < 0               # null num_keep_out
+    # assigner
+    assert lib.r3g_assign_workspace_bytes(1000, 200000, C.byref(nbytes)) == 0 and nbytes.value > 200000 * 12
+    assert lib.r3g_max_iou_assign_f32(None, 3, 5, None, 4, 5, 9, 0, 0.5, 0.4, 0.0, 1, 1, None, None, None, None, None, None, 0, None) < 0
