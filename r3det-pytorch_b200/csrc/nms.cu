@@ -602,37 +602,43 @@ __device__ __forceinline__ unsigned seg_key_of(const int64_t* labels, const int6
     return key;
 }
 
+template <bool BATCHED>
 __global__ void __launch_bounds__(256) nms_rank_count_kernel(const float* __restrict__ scores, const int64_t* __restrict__ labels,
                                                              const int64_t* __restrict__ batch_ids, int K, int slice_len,
                                                              int* __restrict__ rcnt, int* __restrict__ pcnt) {
-    __shared__ unsigned long long ta[256];
-    __shared__ unsigned tseg[256];
+    __shared__ uint4 tile[256];                              // {key low (index), key high (score key), segment key, -}
     const int i = blockIdx.x * 256 + threadIdx.x;
     const bool iv = i < K;
     const unsigned long long ai = iv ? (((unsigned long long)score_key_desc(scores[i]) << 32) | (unsigned)i) : 0ull;
     const unsigned si = iv ? seg_key_of(labels, batch_ids, i) : 0u;
-    const unsigned mi = batch_ids ? (si & 0xffffu) : 0u;
-    const unsigned img_mask = batch_ids ? 0xffffu : 0u;
+    const unsigned mi = si & 0xffffu;
     const int j_begin = blockIdx.y * slice_len, j_end = min(K, j_begin + slice_len);
-    int r = 0, p = 0;
+    int r = 0, p = 0, r1 = 0, p1 = 0, r2 = 0, p2 = 0, r3 = 0, p3 = 0;
     for (int j0 = j_begin; j0 < j_end; j0 += 256) {
         const int j = j0 + threadIdx.x;
         __syncthreads();
-        if (j < j_end) {
-            ta[threadIdx.x] = ((unsigned long long)score_key_desc(scores[j]) << 32) | (unsigned)j;
-            tseg[threadIdx.x] = seg_key_of(labels, batch_ids, j);
-        }
+        if (j < j_end) tile[threadIdx.x] = make_uint4((unsigned)j, score_key_desc(scores[j]), seg_key_of(labels, batch_ids, j), 0u);
         __syncthreads();
         const int n = min(256, j_end - j0);
-#pragma unroll 4
-        for (int t = 0; t < n; t++) {
-            const unsigned long long aj = ta[t];
-            const unsigned sj = tseg[t], mj = sj & img_mask;
-            const bool lt = aj < ai;
-            r += (mj < mi) | ((mj == mi) & lt);
-            p += (sj < si) | ((sj == si) & lt);
+        auto one = [&](int t, int& rr, int& pp) {
+            const uint4 e = tile[t];                         // one broadcast read per candidate
+            const bool lt = (((unsigned long long)e.y << 32) | e.x) < ai;
+            if (BATCHED) {
+                const unsigned mj = e.z & 0xffffu;
+                rr += (mj < mi) | ((mj == mi) & lt);
+            } else {
+                rr += lt;
+            }
+            pp += (e.z < si) | ((e.z == si) & lt);
+        };
+        int t = 0;
+#pragma unroll 2
+        for (; t + 4 <= n; t += 4) {                         // four independent counter chains
+            one(t, r, p); one(t + 1, r1, p1); one(t + 2, r2, p2); one(t + 3, r3, p3);
         }
+        for (; t < n; t++) one(t, r, p);
     }
+    r += r1 + r2 + r3; p += p1 + p2 + p3;
     if (iv) { atomicAdd(rcnt + i, r); atomicAdd(pcnt + i, p); }
 }
 
@@ -728,7 +734,8 @@ static int nms_order_stage(NmsWs& w, const float* scores, const int64_t* labels,
         if (slices < 1) slices = 1;
         const int slice_len = ((Ki + slices - 1) / slices + 255) / 256 * 256;
         slices = (Ki + slice_len - 1) / slice_len;
-        nms_rank_count_kernel<<<dim3(gK, slices), 256, 0, st>>>(scores, labels, batch_ids, Ki, slice_len, rcnt, pcnt);
+        if (batch_ids) nms_rank_count_kernel<true><<<dim3(gK, slices), 256, 0, st>>>(scores, labels, batch_ids, Ki, slice_len, rcnt, pcnt);
+        else nms_rank_count_kernel<false><<<dim3(gK, slices), 256, 0, st>>>(scores, labels, batch_ids, Ki, slice_len, rcnt, pcnt);
         nms_rank_scatter_kernel<<<gK, tpb, 0, st>>>(labels, batch_ids, Ki, rcnt, pcnt, w.ord_rank, w.pos_rank, w.pos_label);
         R3G_LAUNCH_OK("nms rank kernels");
         return R3G_OK;
