@@ -6,7 +6,7 @@
 //     bbox2delta_v3 :314-360  delta2bbox_v3 :363-423
 //   RAnchorHead._get_bboxes_single up to the NMS call    r3det/models/dense_heads/rotate_anchor_head.py:626-662
 //     (permute/reshape, sigmoid, max over classes, per-level top-k(nms_pre), three gathers, decode, rescale, zero
-//      background column: ~15 torch launches per level per image -> 3 launches + one radix sort per BATCH)
+//      background column: ~15 torch launches per level per image -> 5 launches + one segmented sort per BATCH)
 //   RRetinaHead.filter_bboxes                            r3det/models/dense_heads/rotate_retina_head.py:117-179
 //   RRetinaRefineHead.refine_bboxes                      r3det/models/dense_heads/rotate_retina_refine_head.py:56-97
 //

@@ -6,18 +6,19 @@
 //   ml_nms_rotated                               r3det/ops/ml_nms_rotated/src/nms_rotated_cuda.cu:13-137 (v2)
 // The reference computes the FULL K x K bitmask (cross-class pairs included, via a coordinate offset
 // trick), copies it to the host and scans it serially on the CPU.  Here:
-//   1. radix sort by score (and a stable second pass by label) -> position space p = (label asc, score desc);
+//   1. position space p = (segment asc, score desc), segment = label or (label, image): two stable radix sorts, or —
+//      for K <= 16384, where the sorts are pure launch latency — ranks COUNTED in one O(K^2) kernel;
 //   2. boxes are gathered/prepared once in p-order (class offsets applied in FP32 exactly as the
 //      reference's batched wrappers do, so the geometry sees the same rounded coordinates);
-//   3. mask kernel: only upper-triangular 64x64 tiles INSIDE a class segment are visited; a warp owns a
-//      64-row x 256-column item, rejects pairs with the circumradius test at one lane per column,
-//      compacts the survivors with ballot/popc into a shared-memory queue and evaluates them 32 at a
-//      time with the clamped-boundary integral (geom.cuh); suppression bits are OR-ed into shared-memory
-//      64-bit words and written once;
-//   4. scan kernel: one CTA per class; per 64-row block the intra-block chain is resolved from the 64
-//      diagonal words with ffs-jumps over already-suppressed rows, then the kept rows' mask words are
-//      OR-ed into the shared-memory `removed` bit-vector by all threads (no host round trip);
-//   5. flags -> exclusive scan -> keep list in score order or index order.
+//   3. mask kernel: only upper-triangular 64x64 tiles INSIDE a segment are visited; persistent warps pull
+//      (64 rows x 128 columns) items from a ticket (rows split over up to 8 warps when the grid has spare warps);
+//      a lane owns 4 adjacent columns, the circumradius test shifts its sign bit into a 32-bit mask per 8 rows,
+//      survivors are compacted into shared-memory queues and evaluated 32 at a time (separating axes, then the
+//      clamped-boundary integral of geom.cuh); suppression bits are OR-ed into shared-memory words, written once;
+//   4. scan kernel: one 512-thread CTA per segment, superblocks of 4 x 64 rows: warp 0 resolves the chains from a
+//      shared-memory window with ffs-jumps, the other warps prefetch the next window and OR the kept rows' words
+//      into the shared-memory `removed` bit-vector (no host round trip);
+//   5. keep bits -> flags -> exclusive scan -> keep list in score order or index order.
 // Pairs whose IoU lies within `margin` of the threshold (or that trip the degeneracy test) are decided
 // by the reference's own algorithm (emu.cuh), which makes the keep set the reference's.
 #include <cub/cub.cuh>
