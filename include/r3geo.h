@@ -44,6 +44,7 @@ extern "C" {
 #define R3G_NMS_ORDER_INDEX 2   /* keep list in ascending original index (rnms_kernel.cu:331-334); default descending score */
 #define R3G_NMS_DROP_SMALL 4    /* boxes with min(w,h) < 1e-3 take no part (nms_rotated_wrapper.py:40-46) */
 #define R3G_NMS_STRICT 8        /* decide near-threshold / degenerate pairs with the reference's own algorithm */
+#define R3G_NMS_SORT_PATH 16    /* diagnostic: take the radix-sort path that serves K > 16384 whatever K is */
 
 const char* r3g_last_error(void);
 int r3g_version(void);

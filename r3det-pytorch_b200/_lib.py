@@ -20,6 +20,7 @@ NMS_INCLUSIVE = 1
 NMS_ORDER_INDEX = 2
 NMS_DROP_SMALL = 4
 NMS_STRICT = 8
+NMS_SORT_PATH = 16
 
 _lib = None
 

@@ -7,7 +7,7 @@ from . import _lib as L
 
 
 def nms_device(boxes, scores, thr, variant, labels=None, class_offset=None, inclusive=False,
-               order_index=False, drop_small=False, strict=True, batch_ids=None, n_batches=1):
+               order_index=False, drop_small=False, strict=True, batch_ids=None, n_batches=1, sort_path=False):
     """Rotated NMS on CUDA tensors.
 
     boxes (K, >=5) f32, scores (K,) f32, labels (K,) int64 or None, class_offset: 0-dim CUDA f32 tensor or None.
@@ -38,7 +38,7 @@ def nms_device(boxes, scores, thr, variant, labels=None, class_offset=None, incl
         if class_offset.numel() != (n_batches if batch_ids is not None else 1):
             raise ValueError('class_offset must hold one scale per image')
     flags = (L.NMS_INCLUSIVE if inclusive else 0) | (L.NMS_ORDER_INDEX if order_index else 0) | \
-            (L.NMS_DROP_SMALL if drop_small else 0) | (L.NMS_STRICT if strict else 0)
+            (L.NMS_DROP_SMALL if drop_small else 0) | (L.NMS_STRICT if strict else 0) | (L.NMS_SORT_PATH if sort_path else 0)
     lib = L.lib()
     nbytes = C.c_size_t(0)
     L.check(lib.r3g_nms_workspace_bytes(K, C.byref(nbytes)))

@@ -722,9 +722,10 @@ __global__ void __launch_bounds__(1024) nms_finish_small_kernel(const int* __res
 using namespace r3g;
 
 // ---- host stages shared by the rotated-box and the polygon entry points ------------------------------------------
-static int nms_order_stage(NmsWs& w, const float* scores, const int64_t* labels, const int64_t* batch_ids, int Ki, cudaStream_t st) {
+static int nms_order_stage(NmsWs& w, const float* scores, const int64_t* labels, const int64_t* batch_ids, int Ki, cudaStream_t st,
+                           bool small) {
     const int tpb = 256, gK = (Ki + tpb - 1) / tpb;
-    if (Ki <= NMS_SMALL_K) {
+    if (small) {
         // counted ranks: keyA / keyA2 double as the two count arrays
         int* rcnt = (int*)w.keyA; int* pcnt = (int*)w.keyA2;
         R3G_CUDA_OK(cudaMemsetAsync(rcnt, 0, 4 * (size_t)Ki, st));
@@ -764,10 +765,10 @@ static int nms_order_stage(NmsWs& w, const float* scores, const int64_t* labels,
     return R3G_OK;
 }
 
-static int nms_structure_stage(NmsWs& w, int Ki, int nblk, cudaStream_t st) {
+static int nms_structure_stage(NmsWs& w, int Ki, int nblk, cudaStream_t st, bool small) {
     const int tpb = 256, gK = (Ki + tpb - 1) / tpb;
     size_t tb = 0;
-    if (Ki <= NMS_SMALL_K) {
+    if (small) {
         nms_structure_small_kernel<<<1, 1024, 0, st>>>(w.pos_label, Ki, nblk, w.blk_end, w.row_base, w.item_base, w.seg_list, w.counters);
         R3G_LAUNCH_OK("nms_structure_small_kernel");
         return R3G_OK;
@@ -784,7 +785,7 @@ static int nms_structure_stage(NmsWs& w, int Ki, int nblk, cudaStream_t st) {
     return R3G_OK;
 }
 
-static int nms_finish_stage(NmsWs& w, int Ki, int nblk, const int64_t* labels, const int64_t* batch_ids, int flags, int64_t K,
+static int nms_finish_stage(NmsWs& w, int Ki, int nblk, const int64_t* labels, const int64_t* batch_ids, int flags, int64_t K, bool small,
                             int64_t* keep_out, int64_t* num_keep_out, cudaStream_t st) {
     const int tpb = 256, gK = (Ki + tpb - 1) / tpb;
     size_t tb = 0;
@@ -809,7 +810,7 @@ static int nms_finish_stage(NmsWs& w, int Ki, int nblk, const int64_t* labels, c
     if (!labels && !batch_ids) sgrid = 1;
     nms_scan_kernel<<<sgrid, SCAN_THREADS, smem, st>>>(sa);
     R3G_LAUNCH_OK("nms_scan_kernel");
-    if (Ki <= NMS_SMALL_K) {
+    if (small) {
         nms_finish_small_kernel<<<1, 1024, 0, st>>>(w.keep_p, w.pos_rank, w.ord_rank, batch_ids, Ki, order_index, w.flag, keep_out,
                                                     (unsigned long long*)num_keep_out);
         R3G_LAUNCH_OK("nms_finish_small_kernel");
@@ -866,13 +867,14 @@ R3G_API int r3g_nms_batched_f32(const float* boxes, int64_t stride, const float*
     const int tpb = 256, gK = (Ki + tpb - 1) / tpb;
     R3G_CUDA_OK(cudaMemsetAsync(w.counters, 0, 256, st));
 
-    int rc = nms_order_stage(w, scores, labels, batch_ids, Ki, st);
+    const bool small = Ki <= NMS_SMALL_K && !(flags & R3G_NMS_SORT_PATH);
+    int rc = nms_order_stage(w, scores, labels, batch_ids, Ki, st, small);
     if (rc != R3G_OK) return rc;
     // 3. gather + prepare
     nms_gather_kernel<<<gK, tpb, 0, st>>>(boxes, stride, w.ord_rank, w.pos_rank, w.pos_label, Ki, variant,
                                           (flags & R3G_NMS_DROP_SMALL) ? 1 : 0, class_offset, labels ? 1 : 0,
                                           batch_ids ? 1 : 0, w.p0, w.p1, w.p2r, w.p2c, w.raw, w.valid);
-    rc = nms_structure_stage(w, Ki, nblk, st);
+    rc = nms_structure_stage(w, Ki, nblk, st, small);
     if (rc != R3G_OK) return rc;
 
     // 5. suppression bitmask
@@ -898,7 +900,7 @@ R3G_API int r3g_nms_batched_f32(const float* boxes, int64_t stride, const float*
     nms_mask_kernel<<<(unsigned)grid, NMS_THREADS, 0, st>>>(ma);
     R3G_LAUNCH_OK("nms_mask_kernel");
 
-    return nms_finish_stage(w, Ki, nblk, labels, batch_ids, flags, K, keep_out, num_keep_out, st);
+    return nms_finish_stage(w, Ki, nblk, labels, batch_ids, flags, K, small, keep_out, num_keep_out, st);
 }
 
 // ---- polygon NMS ------------------------------------------------------------------------------------------------------
@@ -938,10 +940,11 @@ R3G_API int r3g_poly_nms_f32(const float* polys, int64_t stride, const float* sc
     const int Ki = (int)K, nblk = (Ki + 63) / 64, tpb = 256, gK = (Ki + tpb - 1) / tpb;
     R3G_REQUIRE((size_t)nblk * 8 <= 190 * 1024, "r3g_poly_nms_f32: K exceeds the single-call limit of this build");
     R3G_CUDA_OK(cudaMemsetAsync(w.counters, 0, 256, st));
-    int rc = nms_order_stage(w, scores, nullptr, nullptr, Ki, st);
+    const bool small = Ki <= NMS_SMALL_K;
+    int rc = nms_order_stage(w, scores, nullptr, nullptr, Ki, st, small);
     if (rc != R3G_OK) return rc;
     poly::gather_kernel<<<gK, tpb, 0, st>>>(polys, stride, w.ord_rank, w.pos_rank, Ki, pw.quad, pw.aabb, w.valid);
-    rc = nms_structure_stage(w, Ki, nblk, st);
+    rc = nms_structure_stage(w, Ki, nblk, st, small);
     if (rc != R3G_OK) return rc;
     poly::PolyMaskArgs ma;
     ma.quad = pw.quad; ma.aabb = pw.aabb; ma.blk_end = w.blk_end; ma.row_base = w.row_base; ma.mask = w.mask;
@@ -954,7 +957,7 @@ R3G_API int r3g_poly_nms_f32(const float* polys, int64_t stride, const float* sc
     if (grid > cap) grid = cap;
     poly::mask_kernel<<<(unsigned)grid, 256, 0, st>>>(ma);
     R3G_LAUNCH_OK("poly mask kernel");
-    return nms_finish_stage(w, Ki, nblk, nullptr, nullptr, 0, K, keep_out, num_keep_out, st);
+    return nms_finish_stage(w, Ki, nblk, nullptr, nullptr, 0, K, small, keep_out, num_keep_out, st);
 }
 
 // ---- multiclass candidate extraction --------------------------------------------------------------------------------

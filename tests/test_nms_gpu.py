@@ -243,3 +243,32 @@ def test_dota_patch_merge(cuda_dev, version, merge_nms):
     ids, merged = R.dota_submission.merge_det([[rows[l == c][:, 1:].astype(np.float32) for c in range(ncls)]], ["P1__1__100___200"],
                                               ["a", "b", "c", "d", "e"], 0.1, version, merge_nms, cuda_dev)
     assert ids == ["P1"] and [m.shape for m in merged[0]] == [g.shape for g in got]
+
+
+@pytest.mark.parametrize("v", ["v1", "v3"])
+def test_sort_path_equals_counted_rank_path(cuda_dev, v):
+    """K <= 16384 takes the counted-rank path, larger K the radix-sort path: forcing the latter (R3G_NMS_SORT_PATH) must
+    give the identical keep list — single class, per-class, multi-image, with score ties — and both equal the oracle."""
+    from r3det_b200._nms_core import nms_device
+    b, s, l = clustered(3000, 61, v)
+    s[::7] = s[3]                                                          # many exact score ties
+    bid = np.repeat(np.arange(3), 1000).astype(np.int64)
+    B, S, Lb, Bi = _t(b, cuda_dev), _t(s, cuda_dev), _t(l, cuda_dev), _t(bid, cuda_dev)
+    scales = torch.tensor([1100.0, 1200.0, 1300.0], device=cuda_dev)
+    for kw in (dict(), dict(labels=Lb), dict(labels=Lb, order_index=True, class_offset=scales[:1]),
+               dict(labels=Lb, batch_ids=Bi, n_batches=3, class_offset=scales, order_index=(v == "v1"))):
+        k1, n1 = nms_device(B, S, 0.1, v, **kw)
+        k2, n2 = nms_device(B, S, 0.1, v, sort_path=True, **kw)
+        assert torch.equal(n1, n2) and torch.equal(k1[:int(n1.sum())], k2[:int(n2.sum())]), list(kw)
+    k, n = nms_device(B, S, 0.1, v, labels=Lb)
+    want = port.nms(b, s, 0.1, v, labels=l.astype(np.float32), inclusive=False)
+    assert np.array_equal(k[:int(n)].cpu().numpy(), want)
+
+
+def test_radix_path_large_k_vs_oracle(cuda_dev):
+    """K = 20000 (above the counted-rank limit), 40 classes: keep list equal to the oracle's."""
+    from r3det_b200._nms_core import nms_device
+    b, s, l = clustered(20000, 71, "v1", ncls=40)
+    k, n = nms_device(_t(b, cuda_dev), _t(s, cuda_dev), 0.1, "v1", labels=_t(l, cuda_dev))
+    want = port.nms(b, s, 0.1, "v1", labels=l.astype(np.float32), inclusive=False)
+    assert np.array_equal(k[:int(n)].cpu().numpy(), want)
