@@ -167,3 +167,30 @@ def test_filter_refine_vs_oracle(cuda_dev):
         rf = R.refine_bboxes([t(cls)], [t(np.ascontiguousarray(reg1))], [fl], coder, as_batch=True)[0]
         for b in range(B):
             close(rf[b], cn.refine_bboxes(reg1[b], fl[b].cpu().numpy(), cd))
+
+
+def test_select_decode_many_images_and_ties(cuda_dev):
+    """More images than one C call takes (64): the wrapper chunks; identical scores everywhere (a freshly initialised
+    head): the top-k falls back to the lowest row indices, as a stable sort of the reference's keys would."""
+    import r3det_b200 as R
+    rng = np.random.default_rng(5)
+    B, A, C = 70, 2, 4
+    cls, reg, anc = _level_inputs(rng, B, A, C, 6, 5, 8, "v1")
+    coder = R.DeltaXYWHAOBBoxCoder(ZERO, ONE, angle_range="v1")
+    t = lambda x: torch.from_numpy(x).to(cuda_dev)
+    boxes, scores = R.select_decode([t(cls)], [t(reg)], [t(anc)], coder, 20, None, None)
+    assert boxes.shape == (B, 20, 5) and scores.shape == (B, 20, C + 1)
+    cd = dict(means=ZERO, stds=ONE, variant="v1")
+    for b in (0, 63, 64, 69):
+        wb, ws = cn.select_decode([cls[b]], [reg[b]], [anc], None, None, 20, C, cd)
+        close(scores[b], ws, 1e-6); close(boxes[b], wb)
+    flat = np.zeros_like(cls)                                              # all logits equal -> all scores tie
+    bt, st = R.select_decode([t(flat[:2])], [t(reg[:2])], [t(anc)], coder, 20, None, None)
+    wb, _ = cn.select_decode([flat[0]], [reg[0]], [anc], None, None, 20, C, cd)      # stable argsort: rows 0..19
+    close(bt[0], wb)
+    assert torch.all(st[..., :C] == 0.5) and torch.all(st[..., C] == 0)
+    # a batch whose scores never pass score_thr: every image comes back empty
+    metas = [dict(img_shape=(48, 40, 3), scale_factor=np.ones(4, np.float32))] * 2
+    out = R.get_bboxes([t(flat[:2] - 20)], [t(reg[:2])], [t(anc)], metas, dict(nms_pre=20, score_thr=0.05, nms=dict(type="v1", iou_thr=0.1),
+                                                                                  max_per_img=10), coder)
+    assert len(out) == 2 and all(d.shape == (0, 6) and l.shape == (0,) for d, l in out)
