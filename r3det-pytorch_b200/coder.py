@@ -115,3 +115,12 @@ class DeltaXYWHAOBBoxCoder:
             raise NotImplementedError
         return (_f5(self.means), _f5(self.stds), _VER[self.angle_range], float(wh_ratio_clip), int(bool(self.add_ctr_clamp)),
                 float(self.ctr_clamp))
+
+
+try:  # pragma: no cover - mmdet is not installed in the build image
+    from mmdet.core.bbox.builder import BBOX_CODERS
+    # same registry name as the reference class, so `bbox_coder=dict(type='DeltaXYWHAOBBoxCoder', ...)` in every config under
+    # configs/** resolves to this implementation once r3det_b200 is imported after (or instead of) r3det.core.bbox.coder
+    BBOX_CODERS.register_module(name='DeltaXYWHAOBBoxCoder', force=True)(DeltaXYWHAOBBoxCoder)
+except Exception:  # noqa: BLE001
+    pass
