@@ -232,8 +232,9 @@ R3G_HD float pair_overlap(const BoxP0& A0, const BoxP1& A1, const BoxP0& B0, con
         // 4 px carries a relative area noise above the 1e-5 gate that only the same arithmetic reproduces.
         // (IoF divides by the first box alone: there the reference's own FP32 noise passes 1e-5 below 16 px, all variants.)
         const float thin = (mode == MODE_IOF) ? 8.0f : ((variant == V1) ? 2.0f : tau);
-        risk = (fminf(fminf(fabsf(A1.hw), fabsf(A1.hh)), fminf(fabsf(B1.hw), fabsf(B1.hh))) < thin) ||
-               v1_dedup_risk(A0, A1, B0, B1, f, tau);
+        const float mina = fminf(fabsf(A1.hw), fabsf(A1.hh)), minb = fminf(fabsf(B1.hw), fabsf(B1.hh));
+        const float thin_b = (mode == MODE_IOF) ? ((variant == V1) ? 2.0f : tau) : thin;   // IoF divides by box A alone
+        risk = (mina < thin) || (minb < thin_b) || v1_dedup_risk(A0, A1, B0, B1, f, tau);
     }
     return overlap_ratio(inter, A0.area, B0.area, variant, mode);
 }
