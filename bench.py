@@ -407,6 +407,17 @@ def bench_nms(torch, R, dev, hbm):
         keep, num = fn()
         ms = _time(torch, fn, 5 if K >= 80000 else 20)
         out["sweep"][str(K)] = {"ms": ms, "mcands_per_s": K / ms / 1e3, "kept": int(num)}
+        if K <= 20000:
+            # the same call captured in a CUDA graph (the library never syncs or allocates): device time without the
+            # Python wrapper's host overhead, which dominates below ~10k candidates
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    fn()
+                gms = _time(torch, g.replay, 20)
+                out["sweep"][str(K)].update({"graph_ms": gms, "graph_mcands_per_s": K / gms / 1e3})
+            except Exception as e:  # noqa: BLE001
+                out["sweep"][str(K)]["graph_ms"] = f"capture failed: {e}"
     # configs[3] per-GPU batch: 8 images x K candidates in ONE launch sequence ((image, class) pairs are segments)
     out["batch8"] = {}
     for K in (2000, 8000, 20000):
