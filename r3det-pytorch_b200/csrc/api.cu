@@ -14,6 +14,12 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+int current_device_slot() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) dev = 0;
+    return dev & 63;
+}
+
 int device_sm_count() {
     static int cached[64] = {0};
     int dev = 0;

@@ -250,7 +250,10 @@ __global__ void __launch_bounds__(256) select_hist_kernel(const __grid_constant_
         const int a = local / lv.HW, hw = local - a * lv.HW;
         const float* cb = lv.cls + ((int64_t)b * S.A * S.C + (int64_t)a * S.C) * lv.HW + hw;
         float m = __ldg(cb);
-        for (int c = 1; c < S.C; c++) m = fmaxf(m, __ldg(cb + (int64_t)c * lv.HW));
+        for (int c = 1; c < S.C; c++) {
+            const float v = __ldg(cb + (int64_t)c * lv.HW);
+            m = (v > m || v != v) ? v : m;                  // torch.max propagates NaN
+        }
         unsigned u = ~__float_as_uint(sigmoidf(m));
         u = u < 0xC0000000u ? 0xC0000000u : u;             // NaN scores rank first, as torch.topk ranks them
         ukey[(int64_t)b * S.n_total + lv.row0 + hw * S.A + a] = u;       // at the row's own slot

@@ -11,6 +11,7 @@ namespace r3g {
 
 void set_error(const char* fmt, ...);      // api.cu; thread-local message for r3g_last_error()
 int device_sm_count();                     // cached per device
+int current_device_slot();                 // current device index clamped to [0, 64): index for per-device one-time setup
 
 #define R3G_REQUIRE(cond, ...)                         \
     do {                                               \

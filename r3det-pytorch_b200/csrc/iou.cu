@@ -442,7 +442,8 @@ R3G_API int r3g_iou_workspace_bytes(int64_t m, int64_t n, size_t* bytes) {
 template <bool VEC, int OUT>
 static int launch_sweep(const IouArgs& a, cudaStream_t st) {
     const size_t smem = sizeof(WarpSmem) * IOU_WARPS;
-    static int occ = 0;
+    static int occ_of[64] = {0};          // per device: function attributes live in the device's context
+    int& occ = occ_of[current_device_slot()];
     if (occ == 0) {
         R3G_CUDA_OK(cudaFuncSetAttribute(iou_matrix_kernel<VEC, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         R3G_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, iou_matrix_kernel<VEC, OUT>, IOU_THREADS, smem));

@@ -801,7 +801,8 @@ static int nms_finish_stage(NmsWs& w, int Ki, int nblk, const int64_t* labels, c
         set_error("r3g_nms_f32: K=%lld exceeds the single-image limit of this build (%d boxes)", (long long)K, 190 * 1024 / 8 * 64);
         return R3G_ERR_ARG;
     }
-    static bool smem_set = false;
+    static bool smem_set_of[64] = {false};                  // per device
+    bool& smem_set = smem_set_of[current_device_slot()];
     if (!smem_set) {      // static (window buffers) + dynamic (removed[]) shared memory may exceed the 48 KB default
         R3G_CUDA_OK(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 190 * 1024));
         smem_set = true;
@@ -886,7 +887,8 @@ R3G_API int r3g_nms_batched_f32(const float* boxes, int64_t stride, const float*
     ma.thr = thr;
     ma.tau = (flags & R3G_NMS_STRICT) ? 2e-2f : 0.0f;
     ma.margin = (variant == R3G_V1) ? 1e-3f : 5e-5f;
-    static int occ = 0;
+    static int occ_of[64] = {0};
+    int& occ = occ_of[current_device_slot()];
     if (occ == 0) {
         R3G_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, nms_mask_kernel, NMS_THREADS, 0));
         if (occ < 1) occ = 1;

@@ -55,3 +55,27 @@ def test_repeated_calls_are_deterministic(cuda_dev):
         assert np.array_equal(R.obb_batched_nms(C, S, Lb, 0.1)[1].cpu().numpy(), first)
     o1 = R.pairwise_iou(C[:500], C, "v3")
     assert torch.equal(o1, R.pairwise_iou(C[:500], C, "v3"))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_second_device_in_the_same_process():
+    """One process driving two GPUs: per-device kernel attributes / occupancy caches, device guards, streams."""
+    import r3det_b200 as R
+    from r3det_b200._nms_core import nms_device
+    from tests.util import clustered, rand_obb
+    outs = []
+    for idx in (0, 1, 0):
+        dev = torch.device("cuda", idx)
+        t = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+        iou = R.pairwise_iou(t(rand_obb(70, 1)), t(rand_obb(5000, 2)), "v1")
+        b, s, l = clustered(20000, 3, "v1")
+        keep, num = nms_device(t(b), t(s), 0.1, "v1", labels=t(l))
+        f = torch.from_numpy(np.random.default_rng(0).standard_normal((2, 8, 16, 16)).astype(np.float32)).to(dev)
+        y = R.feature_refine(f, t(np.concatenate([np.random.default_rng(1).uniform(0, 128, (512, 2)), np.full((512, 2), 20.0),
+                                                   np.zeros((512, 1))], 1).astype(np.float32)), 0.125, 5)
+        assert iou.device == dev and keep.device == dev and y.device == dev
+        outs.append((iou.cpu(), keep[:int(num)].cpu(), y.cpu()))
+    for a, b_ in zip(outs[0], outs[1]):
+        assert torch.equal(a, b_)
+    for a, b_ in zip(outs[0], outs[2]):
+        assert torch.equal(a, b_)
