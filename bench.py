@@ -298,6 +298,7 @@ def run_gpu(args):
         line["frm"] = bench_frm(torch, R, dev, hbm)
         line["fused_assign"] = bench_assign(torch, R, dev, gt_h, an_h)
         line["dense_tail"] = bench_dense_tail(torch, R, dev)
+        line["train_step_hot_path"] = bench_train_step(torch, R, dev)
         cores = os.cpu_count() or 1
         apt = 12000
         rate, dt, kind = cpu_pairs_per_s(apt, cores)
@@ -431,6 +432,46 @@ def bench_nms(torch, R, dev, hbm):
         keep, num = fn()
         ms = _time(torch, fn, 10)
         out["batch8"][str(K)] = {"ms": ms, "mcands_per_s": 8 * K / ms / 1e3, "kept": int(num.sum())}
+    return out
+
+
+def bench_train_step(torch, R, dev):
+    """configs[4] / configs[1]: the hot-path part of one R3Det training step on one GPU — 8 patches, per patch the
+    assignment of 128 GT against the 196,416 RRetinaNet anchors and against the 21,824 refine-stage boxes (fused
+    MaxIoUAssigner, v1), plus FRM forward + backward over the five FPN levels for the batch.  Eager launches and the same
+    sequence replayed from a CUDA graph."""
+    from r3det_b200.fr import frm_backward_multi, frm_forward_multi
+    rng = np.random.default_rng(12)
+    gts = [torch.from_numpy(rand_obb(128, 300 + i, "v1", 10, 300)).to(dev) for i in range(8)]
+    anc = torch.from_numpy(rand_obb(196416, 400, "v1", 16, 512)).to(dev)
+    refs = [torch.from_numpy(rand_obb(21824, 500 + i, "v1", 10, 400)).to(dev) for i in range(8)]
+    xs, bts, scales = [], [], []
+    for H, stride in ((128, 8), (64, 16), (32, 32), (16, 64), (8, 128)):
+        xs.append(torch.randn((8, 256, H, H), device=dev))
+        ys_, xs_ = np.meshgrid(np.arange(H) * stride, np.arange(H) * stride, indexing="ij")
+        ctr = np.stack([xs_, ys_], -1).reshape(-1, 2).astype(np.float32)
+        bx = np.zeros((8, H * H, 5), np.float32)
+        bx[:, :, :2] = ctr[None] + rng.normal(0, stride, (8, H * H, 2))
+        bx[:, :, 2:4] = np.exp(rng.uniform(np.log(stride), np.log(8 * stride), (8, H * H, 2)))
+        bx[:, :, 4] = rng.uniform(-np.pi / 2, 0, (8, H * H))
+        bts.append(torch.from_numpy(bx.reshape(-1, 5)).to(dev)); scales.append(1.0 / stride)
+
+    def step():
+        for i in range(8):
+            R.max_iou_assign(gts[i], anc, 0.5, 0.4, 0.0, True, True, "v1")
+            R.max_iou_assign(gts[i], refs[i], 0.5, 0.4, 0.0, True, True, "v1")
+        frm_forward_multi(xs, bts, scales, 1)
+        frm_backward_multi(xs, bts, scales, 1)
+
+    ms = _time(torch, step, 10)
+    out = {"images": 8, "gt_per_image": 128, "ms": ms, "pairs": 8 * 128 * (196416 + 21824)}
+    try:
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            step()
+        out["graph_ms"] = _time(torch, g.replay, 10)
+    except Exception as e:  # noqa: BLE001
+        out["graph_ms"] = f"capture failed: {e}"
     return out
 
 
