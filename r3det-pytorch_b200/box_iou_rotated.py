@@ -38,6 +38,8 @@ def obb_overlaps(bboxes1, bboxes2, mode='iou', is_aligned=False, device_id=None)
         outputs = aligned_iou(b1, b2, 'v3', mode, L.FLAG_STRICT | L.FLAG_SMALL_MASK)[:, None]
     else:
         outputs = pairwise_iou(b1, b2, 'v3', mode, L.FLAG_STRICT | L.FLAG_SMALL_MASK)
+    if isinstance(bboxes1, torch.Tensor) and bboxes1.is_floating_point() and outputs.dtype != bboxes1.dtype:
+        outputs = outputs.to(bboxes1.dtype)                    # same dtype out as in, like the reference op; FP32 arithmetic
     if is_numpy:
         outputs = outputs.cpu().numpy()
     elif isinstance(bboxes1, torch.Tensor) and not bboxes1.is_cuda:

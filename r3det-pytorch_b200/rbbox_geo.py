@@ -50,6 +50,6 @@ def aligned_iou(b1, b2, variant, mode="iou", flags=L.FLAG_STRICT):
 def rbbox_iou(rb1, rb2, vec=False, iof=False):
     """Compute the IoU of oriented bboxes (reference: r3det/ops/rbbox_geo/rbbox_geo.py:4-9)."""
     mode = "iof" if iof else "iou"
-    if vec:
-        return aligned_iou(rb1, rb2, "v1", mode)
-    return pairwise_iou(rb1, rb2, "v1", mode)
+    out = aligned_iou(rb1, rb2, "v1", mode) if vec else pairwise_iou(rb1, rb2, "v1", mode)
+    # the reference dispatches on the input dtype (rbbox_geo_kernel.cu:318) and returns it; arithmetic here is FP32
+    return out if rb1.dtype == torch.float32 or not rb1.is_floating_point() else out.to(rb1.dtype)

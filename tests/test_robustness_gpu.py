@@ -79,3 +79,17 @@ def test_second_device_in_the_same_process():
         assert torch.equal(a, b_)
     for a, b_ in zip(outs[0], outs[2]):
         assert torch.equal(a, b_)
+
+
+def test_half_and_double_inputs_keep_their_dtype(cuda_dev):
+    """The reference ops dispatch on the input dtype and return it; here the arithmetic is FP32 and the result is cast."""
+    import r3det_b200 as R
+    a = torch.from_numpy(rand_obb(20, 1)).to(cuda_dev); b = torch.from_numpy(rand_obb(300, 2)).to(cuda_dev)
+    for dt, tol in ((torch.float64, 1e-6), (torch.float16, 1e-3)):
+        ref = R.rbbox_iou(a.to(dt).float(), b.to(dt).float())             # the same (dtype-rounded) boxes in FP32
+        got = R.rbbox_iou(a.to(dt), b.to(dt))
+        assert got.dtype == dt and (got.float() - ref).abs().max().item() <= tol
+        got3 = R.obb_overlaps(a.to(dt), b.to(dt))
+        assert got3.dtype == dt and got3.shape == (20, 300)
+    calc = R.RBboxOverlaps2D_v1()
+    assert calc(a.double(), b.double()).shape == (20, 300)
