@@ -456,15 +456,24 @@ def bench_train_step(torch, R, dev):
         bx[:, :, 4] = rng.uniform(-np.pi / 2, 0, (8, H * H))
         bts.append(torch.from_numpy(bx.reshape(-1, 5)).to(dev)); scales.append(1.0 / stride)
 
-    def step():
+    refs_b = torch.stack(refs)
+
+    def step_per_image():
         for i in range(8):
             R.max_iou_assign(gts[i], anc, 0.5, 0.4, 0.0, True, True, "v1")
             R.max_iou_assign(gts[i], refs[i], 0.5, 0.4, 0.0, True, True, "v1")
         frm_forward_multi(xs, bts, scales, 1)
         frm_backward_multi(xs, bts, scales, 1)
 
+    def step():
+        R.max_iou_assign_batched(gts, anc, 0.5, 0.4, 0.0, True, True, "v1")          # the 8 patches in one launch sequence
+        R.max_iou_assign_batched(gts, refs_b, 0.5, 0.4, 0.0, True, True, "v1")
+        frm_forward_multi(xs, bts, scales, 1)
+        frm_backward_multi(xs, bts, scales, 1)
+
     ms = _time(torch, step, 10)
-    out = {"images": 8, "gt_per_image": 128, "ms": ms, "pairs": 8 * 128 * (196416 + 21824)}
+    out = {"images": 8, "gt_per_image": 128, "ms": ms, "per_image_assign_calls_ms": _time(torch, step_per_image, 10),
+           "pairs": 8 * 128 * (196416 + 21824)}
     try:
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):

@@ -95,6 +95,18 @@ int r3g_max_iou_assign_f32(const float* gt, int64_t G, int64_t gt_stride,
 /* counters of the last r3g_iou_matrix_f32 launch on this workspace (device-side, 4 x uint64 at the
  * start of the workspace): pairs passing the circumradius test, passing the separating-axis test,
  * re-evaluated by the strict path, total pairs.  For roofline accounting (bench.py). */
+/* A batch of images in ONE launch sequence (B <= 64): gt = the images' GT boxes concatenated (gt_counts[b] rows each,
+ * HOST array), anchors = (A, stride) shared by the batch (anchors_shared = 1, the anchor-head stage) or (B, A, stride)
+ * contiguous (anchors_shared = 0, the refine stage's per-image boxes).  Per-anchor outputs are (B, A); per-GT outputs are
+ * concatenated like gt, with indices relative to the image. */
+int r3g_assign_batched_workspace_bytes(int64_t B, const int64_t* gt_counts, int64_t A, int anchors_shared, size_t* bytes);
+int r3g_max_iou_assign_batched_f32(int64_t B, const float* gt, const int64_t* gt_counts, int64_t gt_stride,
+                                   const float* anchors, int64_t A, int64_t anchor_stride, int anchors_shared,
+                                   int variant, int flags, float pos_iou_thr, float neg_iou_thr, float min_pos_iou,
+                                   int match_low_quality, int gt_max_assign_all,
+                                   int64_t* assigned_gt_inds, float* max_overlaps, int64_t* argmax_overlaps,
+                                   float* gt_max_overlaps, int64_t* gt_argmax_overlaps,
+                                   void* workspace, size_t workspace_bytes, void* stream);
 #define R3G_IOU_STATS_U64 4
 
 /* ---- rotated NMS ------------------------------------------------------------------------------------

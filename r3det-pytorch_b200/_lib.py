@@ -37,6 +37,9 @@ _SIGNATURES = {
     "r3g_assign_workspace_bytes": (_i32, [_i64, _i64, C.POINTER(_sz)]),
     "r3g_max_iou_assign_f32": (_i32, [_vp, _i64, _i64, _vp, _i64, _i64, _i32, _i32, _f32, _f32, _f32, _i32, _i32,
                                       _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "r3g_assign_batched_workspace_bytes": (_i32, [_i64, _vp, _i64, _i32, C.POINTER(_sz)]),
+    "r3g_max_iou_assign_batched_f32": (_i32, [_i64, _vp, _vp, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _f32, _f32, _f32, _i32, _i32,
+                                              _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "r3g_nms_workspace_bytes": (_i32, [_i64, C.POINTER(_sz)]),
     "r3g_nms_f32": (_i32, [_vp, _i64, _vp, _vp, _i64, _f32, _i32, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
     "r3g_nms_batched_f32": (_i32, [_vp, _i64, _vp, _vp, _vp, _i32, _i64, _f32, _i32, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),

@@ -58,6 +58,60 @@ def max_iou_assign(gt_bboxes, bboxes, pos_iou_thr, neg_iou_thr, min_pos_iou=0.0,
     return AssignOutput(G, assigned, max_ov, labels, argmax, gt_max, gt_arg)
 
 
+def max_iou_assign_batched(gt_bboxes_list, bboxes, pos_iou_thr, neg_iou_thr, min_pos_iou=0.0, match_low_quality=True,
+                           gt_max_assign_all=True, variant='v1', flags=L.FLAG_STRICT):
+    """`max_iou_assign` for a batch of images in one launch sequence (what the anchor heads do per image in a Python loop,
+    rotate_anchor_head.py:316-333 via multi_apply).  gt_bboxes_list: B tensors (G_b, >=5), empty ones allowed;
+    bboxes: (A, >=5) anchors shared by the batch, or (B, A, >=5) per-image boxes (refine stage).
+    Returns a list of B AssignOutput (labels None); the per-anchor tensors are rows of one (B, A) allocation."""
+    B = len(gt_bboxes_list)
+    L.require_cuda(bboxes)
+    shared = bboxes.dim() == 2
+    if not shared:
+        assert bboxes.dim() == 3 and bboxes.size(0) == B
+    if B > 64:
+        out = []
+        for s in range(0, B, 64):
+            out += max_iou_assign_batched(gt_bboxes_list[s:s + 64], bboxes if shared else bboxes[s:s + 64], pos_iou_thr, neg_iou_thr,
+                                          min_pos_iou, match_low_quality, gt_max_assign_all, variant, flags)
+        return out
+    anchors = bboxes.float().contiguous()
+    A, sa = anchors.size(-2), anchors.size(-1)
+    assert sa >= 5
+    dev = anchors.device
+    counts = [0 if g is None else int(g.size(0)) for g in gt_bboxes_list]
+    NR = sum(counts)
+    if NR:
+        parts = [g.float()[:, :5] for g, c in zip(gt_bboxes_list, counts) if c]
+        for g in parts:
+            L.require_cuda(g)
+        gt = torch.cat(parts).contiguous()
+    else:
+        gt = None
+    assigned = torch.empty((B, A), dtype=torch.int64, device=dev)
+    max_ov = torch.empty((B, A), dtype=torch.float32, device=dev)
+    argmax = torch.empty((B, A), dtype=torch.int64, device=dev)
+    gt_max = torch.empty((NR,), dtype=torch.float32, device=dev)
+    gt_arg = torch.empty((NR,), dtype=torch.int64, device=dev)
+    if A and B:
+        lib = L.lib()
+        cnt = (C.c_int64 * B)(*counts)
+        need = C.c_size_t(0)
+        L.check(lib.r3g_assign_batched_workspace_bytes(B, cnt, A, int(shared), C.byref(need)))
+        ws = L.workspace(need.value, dev)
+        with L.device_guard(dev):
+            L.check(lib.r3g_max_iou_assign_batched_f32(B, L.ptr(gt), cnt, 5, L.ptr(anchors), A, sa, int(shared), L.V[variant], flags,
+                                                       float(pos_iou_thr), float(neg_iou_thr), float(min_pos_iou),
+                                                       int(bool(match_low_quality)), int(bool(gt_max_assign_all)),
+                                                       L.ptr(assigned), L.ptr(max_ov), L.ptr(argmax), L.ptr(gt_max), L.ptr(gt_arg),
+                                                       L.ptr(ws), ws.numel(), L.stream_ptr(dev)))
+    out, r0 = [], 0
+    for b in range(B):
+        out.append(AssignOutput(counts[b], assigned[b], max_ov[b], None, argmax[b], gt_max[r0:r0 + counts[b]], gt_arg[r0:r0 + counts[b]]))
+        r0 += counts[b]
+    return out
+
+
 class FusedMaxIoUAssigner(object):
     """MaxIoUAssigner with the IoU calculator fused in (same constructor arguments; `iou_calculator` selects the variant)."""
 

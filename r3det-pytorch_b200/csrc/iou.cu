@@ -78,7 +78,13 @@ __device__ __noinline__ float emu_pair_call(const float* b1, const float* b2, in
     return emu::pair(x, y, variant, mode);
 }
 
-struct __attribute__((aligned(16))) TieRec { int row, col; float iou; int pad; };
+struct __attribute__((aligned(16))) TieRec { int row, slot; float iou; int val; };   // global row, lowq slot, overlap, row-in-image + 1
+
+// Batched assignment: image p owns rows [row0, row0 + m) of the row planes and columns [col0, col0 + n) of the column
+// planes (col0 = 0 for every image when the anchors are shared); its per-anchor results live at slot = column + cb_shift.
+constexpr int ASSIGN_MAX_IMAGES = 64;
+struct AssignProb { int row0, m, col0, n, cb_shift, pad; long long item0; };
+struct AssignTable { AssignProb p[ASSIGN_MAX_IMAGES]; int nprob, pad; long long total_items; };
 
 struct IouArgs {
     const BoxP0* r0; const BoxP1* r1; const RowP2* r2; int m;
@@ -98,7 +104,10 @@ struct IouArgs {
     // tie candidates of pass 1 (gt_max_assign_all): pairs whose overlap reached their row's running maximum when they
     // were evaluated.  The running maximum only grows, so every pair that equals the FINAL maximum is in the list.
     TieRec* ties; unsigned tie_cap;  // stats[5] counts the records (may exceed tie_cap: then pass 2 sweeps instead)
+    const AssignTable* table;        // OUT = 1, 2: the images of the batch (device memory)
 };
+
+struct ItemCtx { int row0, col0, cb_shift, prob; };      // the image an item (or a queued pair) belongs to
 
 // OUT selects what the kernel does with the overlaps it computes:
 //   0  store the (M, N) matrix                                         (RBboxOverlaps2D_v*)
@@ -115,22 +124,22 @@ __device__ __forceinline__ void update_best(unsigned long long* slot, unsigned l
 }
 
 template <int OUT>
-__device__ __forceinline__ void emit_overlap(const IouArgs& A, int i, int j, float r) {
+__device__ __forceinline__ void emit_overlap(const IouArgs& A, int i, int j, float r, const ItemCtx& c) {
     if (OUT == OUT_MATRIX) {
         A.out[(int64_t)i * A.n + j] = r;
     } else if (OUT == OUT_ASSIGN_MAX) {
         if (r > 0.0f) {
-            update_best(A.col_best + j, pack_best(r, i));
-            const unsigned long long cand = pack_best(r, j), cur = __ldcg(A.row_best + i);
+            update_best(A.col_best + j + c.cb_shift, pack_best(r, i - c.row0));
+            const unsigned long long cand = pack_best(r, j - c.col0), cur = __ldcg(A.row_best + i);
             if (cand > cur) atomicMax(A.row_best + i, cand);
             if (A.ties != nullptr && r >= __uint_as_float((unsigned)(cur >> 32)) && r >= A.min_pos_iou) {
                 const unsigned long long t = atomicAdd(A.stats + 5, 1ull);
-                if (t < A.tie_cap) { TieRec e = { i, j, r, 0 }; A.ties[t] = e; }
+                if (t < A.tie_cap) { TieRec e = { i, j + c.cb_shift, r, i - c.row0 + 1 }; A.ties[t] = e; }
             }
         }
     } else {
         const float gm = __uint_as_float((unsigned)(__ldcg(A.row_best + i) >> 32));
-        if (r == gm && gm >= A.min_pos_iou) atomicMax(A.lowq + j, i + 1);
+        if (r == gm && gm >= A.min_pos_iou) atomicMax(A.lowq + j + c.cb_shift, i - c.row0 + 1);
     }
 }
 
@@ -152,6 +161,7 @@ struct __attribute__((aligned(16))) WarpSmem {
     uint2 q3[64];                                  // flagged pairs (absolute row, col); persists across items
     unsigned short q1[IOU_Q1CAP];                  // circumradius survivors, item-relative (row << 7 | col)
     unsigned short q2[64];                         // separating-axis survivors
+    int ctx[4];                                    // assigner modes: row0, col0, cb_shift, image of the item in flight
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -163,23 +173,24 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 __device__ __forceinline__ BoxP0 as_p0(float4 v) { BoxP0 b = { v.x, v.y, v.z, v.w }; return b; }
 __device__ __forceinline__ BoxP1 as_p1(float4 v) { BoxP1 b = { v.x, v.y, v.z, v.w }; return b; }
 
-template <bool VEC, int OUT>
+template <bool VEC, int OUT, bool BATCH>
 __global__ void __launch_bounds__(IOU_THREADS, R3G_IOU_MINB) iou_matrix_kernel(const IouArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const unsigned warp = threadIdx.x >> 5, lane = lane_id();
     WarpSmem& W = reinterpret_cast<WarpSmem*>(smem_raw)[warp];
     int c1 = 0, c2 = 0, c3 = 0;
     const unsigned lt = lanemask_lt();
-    const int tiles_n = (A.n + IOU_TN - 1) / IOU_TN;
+    // matrix mode: one (m, n) problem.  Assigner modes: the images of the batch, items enumerated image by image.
+    const int tiles_n_all = (A.n + IOU_TN - 1) / IOU_TN;
     const int tiles_m = (A.m + IOU_TM - 1) / IOU_TM;
-    const long long total = (long long)tiles_m * tiles_n;
+    const long long total = BATCH ? A.table->total_items : (long long)tiles_m * tiles_n_all;
     unsigned n_circle = 0, n_sat = 0, n_emu = 0;
     if (OUT == OUT_ASSIGN_TIES && A.ties != nullptr && __ldcg(A.stats + 5) <= A.tie_cap) return;   // the list was complete
     float ox = __ldg(A.origin_box), oy = __ldg(A.origin_box + 1);     // common origin of the expanded circle test
     if (!isfinite(ox)) ox = 0.0f;
     if (!isfinite(oy)) oy = 0.0f;
 
-    int i0 = 0, j0 = 0, i1 = 0, ig = 0, jb = 0;
+    int i0 = 0, j0 = 0, i1 = 0, ig = 0, jb = 0, cshift = 0;
     float cx[IOU_CPL], cy[IOU_CPL], cr[IOU_CPL], ck[IOU_CPL];
     float cm[IOU_CPL] = { 0.f, 0.f, 0.f, 0.f };     // OUT_ASSIGN_TIES: the columns' best overlap (from pass 1)
     float gm_lo = 0.f, gm_hi = 0.f, cmax_item = 0.f;  // OUT_ASSIGN_TIES: row maxima of the item, best column maximum
@@ -194,13 +205,19 @@ __global__ void __launch_bounds__(IOU_THREADS, R3G_IOU_MINB) iou_matrix_kernel(c
             const int nb = min(32, c3);
             __syncwarp();
             if ((int)lane < nb) {
-                const uint2 e = W.q3[c3 - nb + lane];
+                uint2 e = W.q3[c3 - nb + lane];
+                ItemCtx ec = { 0, 0, 0, 0 };
+                if (BATCH) {                              // the pair may belong to an earlier image: its id rides in the top bits
+                    const AssignProb& pr = A.table->p[e.x >> 26];
+                    ec.row0 = pr.row0; ec.col0 = pr.col0; ec.cb_shift = pr.cb_shift;
+                    e.x &= 0x3ffffffu;
+                }
                 float r = emu_pair_call(A.raw1 + (int64_t)e.x * A.s1, A.raw2 + (int64_t)e.y * A.s2, A.variant, A.mode);
                 if (A.small_mask) {
                     const float4 a1 = ldg4(A.r1 + e.x), b1 = ldg4(A.c1 + e.y);
                     if (fminf(a1.z, a1.w) * 2.0f < 0.001f || fminf(b1.z, b1.w) * 2.0f < 0.001f) r = 0.0f;
                 }
-                emit_overlap<OUT>(A, (int)e.x, (int)e.y, r);
+                emit_overlap<OUT>(A, (int)e.x, (int)e.y, r, ec);
             }
             __syncwarp();
             c3 -= nb;
@@ -222,13 +239,17 @@ __global__ void __launch_bounds__(IOU_THREADS, R3G_IOU_MINB) iou_matrix_kernel(c
                 const BoxP1 A1 = as_p1(W.r1[il]), B1 = as_p1(W.c1[jl]);
                 float r = pair_overlap(A0, A1, B0, B1, A.variant, A.mode, A.tau, risk);
                 if (A.small_mask && (fminf(A1.hw, A1.hh) * 2.0f < 0.001f || fminf(B1.hw, B1.hh) * 2.0f < 0.001f)) r = 0.0f;
-                if (!risk && r != 0.0f) emit_overlap<OUT>(A, i, j, r);
+                if (!risk && r != 0.0f) {
+                    ItemCtx ctx = { 0, 0, 0, 0 };
+                    if (BATCH) { ctx.row0 = W.ctx[0]; ctx.col0 = W.ctx[1]; ctx.cb_shift = W.ctx[2]; }
+                    emit_overlap<OUT>(A, i, j, r, ctx);
+                }
             }
             __syncwarp();
             c2 -= nb;
             n_sat += nb;
             const unsigned bal = __ballot_sync(0xffffffffu, risk);
-            if (risk) W.q3[c3 + __popc(bal & lt)] = make_uint2((unsigned)i, (unsigned)j);
+            if (risk) W.q3[c3 + __popc(bal & lt)] = make_uint2((unsigned)i | (BATCH ? ((unsigned)W.ctx[3] << 26) : 0u), (unsigned)j);
             c3 += __popc(bal);
             continue;
         }
@@ -257,19 +278,38 @@ __global__ void __launch_bounds__(IOU_THREADS, R3G_IOU_MINB) iou_matrix_kernel(c
             if (lane == 0) item = (long long)atomicAdd(A.stats + 4, 1ull);
             item = __shfl_sync(0xffffffffu, item, 0);
             if (item >= total) { done = true; continue; }
+            int tiles_n = tiles_n_all, i_end = A.m, j_end = A.n;      // row / column limits of the item's problem
+            if (BATCH) {
+                // image of this item: last p with item0[p] <= item
+                int lo = 0, hi = A.table->nprob;
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (A.table->p[mid].item0 <= item) lo = mid; else hi = mid;
+                }
+                const AssignProb pr = A.table->p[lo];
+                item -= pr.item0;
+                tiles_n = (pr.n + IOU_TN - 1) / IOU_TN;
+                __syncwarp();
+                if (lane == 0) { W.ctx[0] = pr.row0; W.ctx[1] = pr.col0; W.ctx[2] = pr.cb_shift; W.ctx[3] = lo; }
+                i_end = pr.row0 + pr.m; j_end = pr.col0 + pr.n;
+                cshift = pr.cb_shift;
+                i0 = pr.row0; j0 = pr.col0;
+            } else {
+                i0 = 0; j0 = 0;
+            }
             const int tm = (int)(item / tiles_n), tn = (int)(item - (long long)tm * tiles_n);
-            i0 = tm * IOU_TM; j0 = tn * IOU_TN;
-            i1 = min(A.m, i0 + IOU_TM);
+            i0 += tm * IOU_TM; j0 += tn * IOU_TN;
+            i1 = min(i_end, i0 + IOU_TM);
             ig = i0;
             jb = j0 + (int)lane * IOU_CPL;
             __syncwarp();
             // stage the item's prepared boxes: 2 x 64 row records + 2 x 128 column records, 16 bytes each
             for (int t = lane; t < IOU_TM; t += 32) {
-                const int i = min(i0 + t, A.m - 1);
+                const int i = min(i0 + t, i_end - 1);
                 cp_async16(&W.r0[t], A.r0 + i); cp_async16(&W.r1[t], A.r1 + i);
             }
             for (int t = lane; t < IOU_TN; t += 32) {
-                const int j = min(j0 + t, A.n - 1);
+                const int j = min(j0 + t, j_end - 1);
                 cp_async16(&W.c0[t], A.c0 + j); cp_async16(&W.c1[t], A.c1 + j);
             }
             cp_async_wait_all();
@@ -277,7 +317,7 @@ __global__ void __launch_bounds__(IOU_THREADS, R3G_IOU_MINB) iou_matrix_kernel(c
             // this lane's 4 columns relative to the origin; invalid columns are pushed to +inf (always rejected)
 #pragma unroll
             for (int k = 0; k < IOU_CPL; k++) {
-                if (jb + k < A.n) {
+                if (jb + k < j_end) {
                     const float4 b = W.c0[lane * IOU_CPL + k];
                     cx[k] = b.x - ox; cy[k] = b.y - oy; cr[k] = b.z;
                     const float q = cx[k] * cx[k] + cy[k] * cy[k], rr = b.z * b.z;
@@ -286,12 +326,12 @@ __global__ void __launch_bounds__(IOU_THREADS, R3G_IOU_MINB) iou_matrix_kernel(c
                     cx[k] = 0.0f; cy[k] = 0.0f; cr[k] = 0.0f; ck[k] = 3.0e38f;
                 }
             }
-            full4 = VEC && (jb + IOU_CPL <= A.n);
+            full4 = VEC && (jb + IOU_CPL <= j_end);
             if (OUT == OUT_MATRIX) orow = A.out + (int64_t)i0 * A.n + jb;
             if (OUT == OUT_ASSIGN_TIES) {
 #pragma unroll
                 for (int k = 0; k < IOU_CPL; k++)
-                    cm[k] = (jb + k < A.n) ? __uint_as_float((unsigned)(__ldcg(A.col_best + jb + k) >> 32)) : -1.0f;
+                    cm[k] = (jb + k < j_end) ? __uint_as_float((unsigned)(__ldcg(A.col_best + jb + k + cshift) >> 32)) : -1.0f;
                 // row maxima of the item (lane t holds rows t and t+32) and the best column maximum of the item:
                 // a row whose maximum exceeds every column maximum of the item cannot tie here and is skipped whole
                 gm_lo = (i0 + (int)lane < i1) ? __uint_as_float((unsigned)(__ldcg(A.row_best + i0 + lane) >> 32)) : 0.0f;
@@ -342,7 +382,7 @@ __global__ void __launch_bounds__(IOU_THREADS, R3G_IOU_MINB) iou_matrix_kernel(c
                         } else {
 #pragma unroll
                             for (int k = 0; k < IOU_CPL; k++)
-                                if (jb + k < A.n) st_cs_f1(orow + k, 0.f);
+                                if (jb + k < A.n) st_cs_f1(orow + k, 0.f);      // matrix mode only: one problem
                         }
                         orow += A.n;
                     }
@@ -439,21 +479,23 @@ R3G_API int r3g_iou_workspace_bytes(int64_t m, int64_t n, size_t* bytes) {
 }
 
 // Launch the pair sweep in one of its output modes (persistent grid = SMs x occupancy, dynamic item tickets).
-template <bool VEC, int OUT>
-static int launch_sweep(const IouArgs& a, cudaStream_t st) {
+template <bool VEC, int OUT, bool BATCH = false>
+static int launch_sweep(const IouArgs& a, cudaStream_t st, int64_t item_count = -1) {
     const size_t smem = sizeof(WarpSmem) * IOU_WARPS;
     static int occ_of[64] = {0};          // per device: function attributes live in the device's context
     int& occ = occ_of[current_device_slot()];
     if (occ == 0) {
-        R3G_CUDA_OK(cudaFuncSetAttribute(iou_matrix_kernel<VEC, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        R3G_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, iou_matrix_kernel<VEC, OUT>, IOU_THREADS, smem));
+        R3G_CUDA_OK(cudaFuncSetAttribute(iou_matrix_kernel<VEC, OUT, BATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        R3G_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, iou_matrix_kernel<VEC, OUT, BATCH>, IOU_THREADS, smem));
         if (occ < 1) occ = 1;
     }
-    const int64_t items = (((int64_t)a.m + IOU_TM - 1) / IOU_TM) * (((int64_t)a.n + IOU_TN - 1) / IOU_TN);
+    const int64_t items = item_count >= 0 ? item_count
+                                           : (((int64_t)a.m + IOU_TM - 1) / IOU_TM) * (((int64_t)a.n + IOU_TN - 1) / IOU_TN);
     int64_t grid = (items + IOU_WARPS - 1) / IOU_WARPS;
+    if (grid < 1) grid = 1;
     const int64_t cap = (int64_t)device_sm_count() * occ;
     if (grid > cap) grid = cap;
-    iou_matrix_kernel<VEC, OUT><<<(unsigned)grid, IOU_THREADS, smem, st>>>(a);
+    iou_matrix_kernel<VEC, OUT, BATCH><<<(unsigned)grid, IOU_THREADS, smem, st>>>(a);
     R3G_LAUNCH_OK("iou_matrix_kernel");
     return R3G_OK;
 }
@@ -556,28 +598,48 @@ R3G_API int r3g_iou_aligned_f32(const float* boxes1, int64_t n1, int64_t stride1
 // finalize kernel applies the thresholds.  The IoU values are the matrix kernel's, bit for bit (same code path).
 namespace r3g {
 
-__global__ void assign_init_kernel(unsigned long long* col_best, int64_t A, unsigned long long* row_best, int64_t G, int* lowq) {
+// the image table travels in kernel-parameter space (graph-capturable: no host buffer outlives the call)
+__global__ void assign_table_kernel(const __grid_constant__ AssignTable T, AssignTable* out) {
+    if (threadIdx.x < ASSIGN_MAX_IMAGES) out->p[threadIdx.x] = T.p[threadIdx.x];
+    if (threadIdx.x == 0) { out->nprob = T.nprob; out->pad = 0; out->total_items = T.total_items; }
+}
+
+__global__ void assign_init_kernel(unsigned long long* col_best, int64_t NC, unsigned long long* row_best, int64_t NR, int* lowq,
+                                   int* zero_gt) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned long long zero_first = 0xFFFFFFFFull;            // overlap 0, index 0 (torch.max returns the first maximum)
-    if (t < A) { col_best[t] = zero_first; lowq[t] = 0; }
-    if (t < G) row_best[t] = zero_first;
+    if (t < NC) { col_best[t] = zero_first; lowq[t] = 0; }
+    if (t < NR) row_best[t] = zero_first;
+    if (t < ASSIGN_MAX_IMAGES) zero_gt[t] = 0;
+}
+
+__device__ __forceinline__ int image_of_row(const AssignTable* T, int i) {
+    int lo = 0, hi = T->nprob;                                       // last p with row0[p] <= i and m[p] > 0 covering i
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (T->p[mid].row0 <= i) lo = mid; else hi = mid;
+    }
+    return lo;
 }
 
 // per GT: low-quality matching that does not need the tie pass
 //   gt_max_assign_all == 0: assigned[gt_argmax[i]] = i + 1 for gt_max[i] >= min_pos_iou        (later GTs win)
 //   gt_max[i] == 0 with min_pos_iou <= 0: `overlaps[i, :] == gt_max[i]` holds for EVERY anchor (mmdet quirk)
-__global__ void assign_gt_kernel(const unsigned long long* __restrict__ row_best, int64_t G, float min_pos_iou,
-                                 int assign_all, int* lowq, int* zero_gt, float* gt_max, int64_t* gt_argmax) {
+__global__ void assign_gt_kernel(const unsigned long long* __restrict__ row_best, int64_t NR, const AssignTable* __restrict__ T,
+                                 float min_pos_iou, int assign_all, int* lowq, int* zero_gt, float* gt_max, int64_t* gt_argmax) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= G) return;
+    if (i >= NR) return;
     const unsigned long long b = row_best[i];
     const float v = __uint_as_float((unsigned)(b >> 32));
     const int arg = (int)(0xFFFFFFFFu - (unsigned)(b & 0xFFFFFFFFull));
     if (gt_max) gt_max[i] = v;
     if (gt_argmax) gt_argmax[i] = arg;
     if (v >= min_pos_iou) {
-        if (!assign_all) atomicMax(lowq + arg, (int)i + 1);
-        else if (v == 0.0f) atomicMax(zero_gt, (int)i + 1);
+        const int p = image_of_row(T, (int)i);
+        const AssignProb& pr = T->p[p];
+        const int rel = (int)i - pr.row0 + 1;
+        if (!assign_all) atomicMax(lowq + pr.col0 + arg + pr.cb_shift, rel);
+        else if (v == 0.0f) atomicMax(zero_gt + p, rel);
     }
 }
 
@@ -589,47 +651,58 @@ __global__ void assign_ties_kernel(const TieRec* __restrict__ ties, const unsign
     for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (unsigned long long)gridDim.x * blockDim.x) {
         const TieRec e = ties[t];
         const float gm = __uint_as_float((unsigned)(row_best[e.row] >> 32));
-        if (e.iou == gm && gm >= min_pos_iou) atomicMax(lowq + e.col, e.row + 1);
+        if (e.iou == gm && gm >= min_pos_iou) atomicMax(lowq + e.slot, e.val);
     }
 }
 
+// one thread per (image, anchor) slot
 __global__ void assign_finalize_kernel(const unsigned long long* __restrict__ col_best, const int* __restrict__ lowq,
-                                       const int* __restrict__ zero_gt, int64_t A, int64_t G, float pos_thr, float neg_thr,
-                                       int match_low_quality, int64_t* assigned, float* max_overlaps, int64_t* argmax) {
+                                       const int* __restrict__ zero_gt, const AssignTable* __restrict__ T, int64_t A,
+                                       float pos_thr, float neg_thr, int match_low_quality, int64_t* assigned,
+                                       float* max_overlaps, int64_t* argmax) {
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int p = blockIdx.y;
     if (j >= A) return;
-    if (G == 0) {                                                    // no GT: everything is background
-        assigned[j] = 0; if (max_overlaps) max_overlaps[j] = 0.0f; if (argmax) argmax[j] = 0;
+    const AssignProb& pr = T->p[p];
+    const int64_t o = (int64_t)p * A + j;                            // output slot; results live at column + cb_shift
+    const int64_t slot = pr.col0 + j + pr.cb_shift;
+    if (pr.m == 0) {                                                 // no GT in this image: everything is background
+        assigned[o] = 0; if (max_overlaps) max_overlaps[o] = 0.0f; if (argmax) argmax[o] = 0;
         return;
     }
-    const unsigned long long b = col_best[j];
+    const unsigned long long b = col_best[slot];
     const float v = __uint_as_float((unsigned)(b >> 32));
     const int arg = (int)(0xFFFFFFFFu - (unsigned)(b & 0xFFFFFFFFull));
     int64_t a = -1;
     if (v >= 0.0f && v < neg_thr) a = 0;
     if (v >= pos_thr) a = arg + 1;
     if (match_low_quality) {
-        const int lq = max(lowq[j], zero_gt[0]);
+        const int lq = max(lowq[slot], zero_gt[p]);
         if (lq > 0) a = lq;
     }
-    assigned[j] = a;
-    if (max_overlaps) max_overlaps[j] = v;
-    if (argmax) argmax[j] = arg;
+    assigned[o] = a;
+    if (max_overlaps) max_overlaps[o] = v;
+    if (argmax) argmax[o] = arg;
 }
 
-struct AssignWs { IouWorkspace iou; unsigned long long *col_best, *row_best; int *lowq, *zero_gt; TieRec* ties; unsigned tie_cap; size_t bytes; };
+struct AssignWs {
+    IouWorkspace iou; unsigned long long *col_best, *row_best; int *lowq, *zero_gt; TieRec* ties; unsigned tie_cap;
+    AssignTable* table; size_t bytes;
+};
 
-static AssignWs carve_assign(void* ws, int64_t G, int64_t A) {
+// NR rows (all GT of the batch), NCP column records (anchors: A shared, or B * A), NC result slots (B * A)
+static AssignWs carve_assign(void* ws, int64_t NR, int64_t NCP, int64_t NC) {
     AssignWs w;
-    w.iou = carve(ws, G, A);
+    w.iou = carve(ws, NR, NCP);
     char* p = (char*)ws;
     size_t off = w.iou.bytes;
-    w.col_best = (unsigned long long*)(p + off); off += align_up(8 * (size_t)(A > 0 ? A : 1), 256);
-    w.row_best = (unsigned long long*)(p + off); off += align_up(8 * (size_t)(G > 0 ? G : 1), 256);
-    w.lowq = (int*)(p + off); off += align_up(4 * (size_t)(A > 0 ? A : 1), 256);
+    w.col_best = (unsigned long long*)(p + off); off += align_up(8 * (size_t)(NC > 0 ? NC : 1), 256);
+    w.row_best = (unsigned long long*)(p + off); off += align_up(8 * (size_t)(NR > 0 ? NR : 1), 256);
+    w.lowq = (int*)(p + off); off += align_up(4 * (size_t)(NC > 0 ? NC : 1), 256);
     w.zero_gt = (int*)(p + off); off += 256;
+    w.table = (AssignTable*)(p + off); off += align_up(sizeof(AssignTable), 256);
     // expected records: a few (~ln of the overlapping columns) per row; far above that the list gives way to the sweep
-    w.tie_cap = (unsigned)(65536 + 64 * (size_t)(G > 0 ? G : 0));
+    w.tie_cap = (unsigned)(65536 + 64 * (size_t)(NR > 0 ? NR : 0));
     w.ties = (TieRec*)(p + off); off += align_up(sizeof(TieRec) * (size_t)w.tie_cap, 256);
     w.bytes = off;
     return w;
@@ -637,9 +710,106 @@ static AssignWs carve_assign(void* ws, int64_t G, int64_t A) {
 
 }  // namespace r3g
 
+using namespace r3g;
+
+static int assign_sizes(const char* who, int64_t B, const int64_t* gt_counts, int64_t A, int shared, int64_t* NR, int64_t* NCP) {
+    R3G_REQUIRE(B >= 1 && B <= ASSIGN_MAX_IMAGES, "%s: 1..%d images per call", who, ASSIGN_MAX_IMAGES);
+    R3G_REQUIRE(gt_counts != nullptr && A >= 0, "%s: bad arguments", who);
+    int64_t nr = 0;
+    for (int64_t b = 0; b < B; b++) { R3G_REQUIRE(gt_counts[b] >= 0, "%s: negative GT count", who); nr += gt_counts[b]; }
+    R3G_REQUIRE(nr < (1ll << 26) && B * A < (1ll << 31), "%s: problem too large", who);
+    *NR = nr; *NCP = shared ? A : B * A;
+    return R3G_OK;
+}
+
+R3G_API int r3g_assign_batched_workspace_bytes(int64_t B, const int64_t* gt_counts, int64_t A, int anchors_shared, size_t* bytes) {
+    int64_t NR = 0, NCP = 0;
+    int rc = assign_sizes("r3g_assign_batched_workspace_bytes", B, gt_counts, A, anchors_shared, &NR, &NCP);
+    if (rc != R3G_OK) return rc;
+    R3G_REQUIRE(bytes != nullptr, "r3g_assign_batched_workspace_bytes: null output");
+    *bytes = carve_assign(nullptr, NR, NCP, B * A).bytes;
+    return R3G_OK;
+}
+
 R3G_API int r3g_assign_workspace_bytes(int64_t G, int64_t A, size_t* bytes) {
     R3G_REQUIRE(bytes != nullptr && G >= 0 && A >= 0, "r3g_assign_workspace_bytes: bad arguments");
-    *bytes = carve_assign(nullptr, G, A).bytes;
+    return r3g_assign_batched_workspace_bytes(1, &G, A, 1, bytes);
+}
+
+R3G_API int r3g_max_iou_assign_batched_f32(int64_t B, const float* gt, const int64_t* gt_counts, int64_t gt_stride,
+                                           const float* anchors, int64_t A, int64_t anchor_stride, int anchors_shared,
+                                           int variant, int flags, float pos_iou_thr, float neg_iou_thr, float min_pos_iou,
+                                           int match_low_quality, int gt_max_assign_all,
+                                           int64_t* assigned_gt_inds, float* max_overlaps, int64_t* argmax_overlaps,
+                                           float* gt_max_overlaps, int64_t* gt_argmax_overlaps,
+                                           void* workspace, size_t workspace_bytes, void* stream) {
+    const char* who = "r3g_max_iou_assign_batched_f32";
+    int64_t NR = 0, NCP = 0;
+    int rc = assign_sizes(who, B, gt_counts, A, anchors_shared, &NR, &NCP);
+    if (rc != R3G_OK) return rc;
+    rc = iou_check_common(who, NR, NCP, variant, R3G_MODE_IOU);
+    if (rc != R3G_OK) return rc;
+    if (A == 0) return R3G_OK;
+    R3G_REQUIRE(anchors && assigned_gt_inds && workspace, "%s: null pointer", who);
+    R3G_REQUIRE(NR == 0 || gt != nullptr, "%s: null gt", who);
+    const int64_t NC = B * A;
+    AssignWs w = carve_assign(workspace, NR, NCP, NC);
+    if (workspace_bytes < w.bytes) {
+        set_error("%s: workspace too small (%zu < %zu)", who, workspace_bytes, w.bytes);
+        return R3G_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int tpb = 256;
+    AssignTable T;
+    int64_t row0 = 0, item0 = 0;
+    for (int b = 0; b < ASSIGN_MAX_IMAGES; b++) {
+        AssignProb& pr = T.p[b];
+        const int64_t m = b < B ? gt_counts[b] : 0;
+        pr.row0 = (int)row0; pr.m = (int)m;
+        pr.col0 = (b < B && !anchors_shared) ? (int)(b * A) : 0;
+        pr.n = b < B ? (int)A : 0;
+        pr.cb_shift = (b < B && anchors_shared) ? (int)(b * A) : 0;        // slot = column + cb_shift = b * A + anchor
+        pr.pad = 0; pr.item0 = item0;
+        if (b < B) { row0 += m; item0 += ((m + IOU_TM - 1) / IOU_TM) * ((A + IOU_TN - 1) / IOU_TN); }
+    }
+    T.nprob = (int)B; T.pad = 0; T.total_items = item0;
+    assign_table_kernel<<<1, ASSIGN_MAX_IMAGES, 0, st>>>(T, w.table);
+    const int64_t mx = NC > NR ? NC : NR;
+    assign_init_kernel<<<(unsigned)((mx + tpb - 1) / tpb), tpb, 0, st>>>(w.col_best, NC, w.row_best, NR, w.lowq, w.zero_gt);
+    if (NR > 0) {
+        rc = r3g_iou_prepare_f32(gt, NR, gt_stride, anchors, NCP, anchor_stride, variant, workspace, w.iou.bytes, stream);
+        if (rc != R3G_OK) return rc;
+        IouArgs a = {};
+        a.r0 = w.iou.r0; a.r1 = w.iou.r1; a.r2 = w.iou.r2; a.m = (int)NR; a.c0 = w.iou.c0; a.c1 = w.iou.c1; a.n = (int)NCP;
+        a.raw1 = gt; a.s1 = gt_stride; a.raw2 = anchors; a.s2 = anchor_stride; a.origin_box = gt;
+        a.variant = variant; a.mode = R3G_MODE_IOU;
+        a.small_mask = (variant == R3G_V3 && (flags & R3G_FLAG_SMALL_MASK)) ? 1 : 0;
+        a.tau = (flags & R3G_FLAG_EMULATE_ALL) ? 1e30f : ((flags & R3G_FLAG_STRICT) ? 2e-2f : 0.0f);
+        a.out = nullptr; a.stats = w.iou.stats;
+        a.col_best = w.col_best; a.row_best = w.row_best; a.lowq = w.lowq; a.min_pos_iou = min_pos_iou;
+        a.table = w.table;
+        const bool want_ties = match_low_quality && gt_max_assign_all;
+        a.ties = want_ties ? w.ties : nullptr; a.tie_cap = w.tie_cap;
+        R3G_CUDA_OK(cudaMemsetAsync(w.iou.stats, 0, 256, st));
+        const bool batch = !(B == 1 && anchors_shared);      // one image over shared anchors: the plain single-problem kernels
+        rc = batch ? launch_sweep<false, OUT_ASSIGN_MAX, true>(a, st, item0) : launch_sweep<false, OUT_ASSIGN_MAX, false>(a, st);
+        if (rc != R3G_OK) return rc;
+        assign_gt_kernel<<<(unsigned)((NR + tpb - 1) / tpb), tpb, 0, st>>>(w.row_best, NR, w.table, min_pos_iou, gt_max_assign_all,
+                                                                         w.lowq, w.zero_gt, gt_max_overlaps, gt_argmax_overlaps);
+        if (want_ties) {
+            assign_ties_kernel<<<(unsigned)((w.tie_cap + 4 * tpb - 1) / (4 * tpb)), tpb, 0, st>>>(w.ties, w.iou.stats + 5, w.tie_cap,
+                                                                                            w.row_best, min_pos_iou, w.lowq);
+            // list overflow (massive ties, e.g. many identical anchors): exact sweep; its warps return at once otherwise.
+            // stats[5] must survive the reset of the item ticket, so only the ticket is cleared.
+            R3G_CUDA_OK(cudaMemsetAsync(w.iou.stats + 4, 0, 8, st));
+            rc = batch ? launch_sweep<false, OUT_ASSIGN_TIES, true>(a, st, item0) : launch_sweep<false, OUT_ASSIGN_TIES, false>(a, st);
+            if (rc != R3G_OK) return rc;
+        }
+    }
+    const dim3 fgrid((unsigned)((A + tpb - 1) / tpb), (unsigned)B);
+    assign_finalize_kernel<<<fgrid, tpb, 0, st>>>(w.col_best, w.lowq, w.zero_gt, w.table, A, pos_iou_thr, neg_iou_thr,
+                                                  match_low_quality, assigned_gt_inds, max_overlaps, argmax_overlaps);
+    R3G_LAUNCH_OK("assign kernels");
     return R3G_OK;
 }
 
@@ -650,52 +820,8 @@ R3G_API int r3g_max_iou_assign_f32(const float* gt, int64_t G, int64_t gt_stride
                                    int64_t* assigned_gt_inds, float* max_overlaps, int64_t* argmax_overlaps,
                                    float* gt_max_overlaps, int64_t* gt_argmax_overlaps,
                                    void* workspace, size_t workspace_bytes, void* stream) {
-    int rc = iou_check_common("r3g_max_iou_assign_f32", G, A, variant, R3G_MODE_IOU);
-    if (rc != R3G_OK) return rc;
-    if (A == 0) return R3G_OK;
-    R3G_REQUIRE(anchors && assigned_gt_inds && workspace, "r3g_max_iou_assign_f32: null pointer");
-    R3G_REQUIRE(G == 0 || gt != nullptr, "r3g_max_iou_assign_f32: null gt");
-    AssignWs w = carve_assign(workspace, G, A);
-    if (workspace_bytes < w.bytes) {
-        set_error("r3g_max_iou_assign_f32: workspace too small (%zu < %zu)", workspace_bytes, w.bytes);
-        return R3G_ERR_WORKSPACE;
-    }
-    cudaStream_t st = (cudaStream_t)stream;
-    const int tpb = 256;
-    const int64_t mx = A > G ? A : G;
-    assign_init_kernel<<<(unsigned)((mx + tpb - 1) / tpb), tpb, 0, st>>>(w.col_best, A, w.row_best, G, w.lowq);
-    R3G_CUDA_OK(cudaMemsetAsync(w.zero_gt, 0, 256, st));
-    if (G > 0) {
-        rc = r3g_iou_prepare_f32(gt, G, gt_stride, anchors, A, anchor_stride, variant, workspace, w.iou.bytes, stream);
-        if (rc != R3G_OK) return rc;
-        IouArgs a = {};
-        a.r0 = w.iou.r0; a.r1 = w.iou.r1; a.r2 = w.iou.r2; a.m = (int)G; a.c0 = w.iou.c0; a.c1 = w.iou.c1; a.n = (int)A;
-        a.raw1 = gt; a.s1 = gt_stride; a.raw2 = anchors; a.s2 = anchor_stride; a.origin_box = gt;
-        a.variant = variant; a.mode = R3G_MODE_IOU;
-        a.small_mask = (variant == R3G_V3 && (flags & R3G_FLAG_SMALL_MASK)) ? 1 : 0;
-        a.tau = (flags & R3G_FLAG_EMULATE_ALL) ? 1e30f : ((flags & R3G_FLAG_STRICT) ? 2e-2f : 0.0f);
-        a.out = nullptr; a.stats = w.iou.stats;
-        a.col_best = w.col_best; a.row_best = w.row_best; a.lowq = w.lowq; a.min_pos_iou = min_pos_iou;
-        const bool want_ties = match_low_quality && gt_max_assign_all;
-        a.ties = want_ties ? w.ties : nullptr; a.tie_cap = w.tie_cap;
-        R3G_CUDA_OK(cudaMemsetAsync(w.iou.stats, 0, 256, st));
-        rc = launch_sweep<false, OUT_ASSIGN_MAX>(a, st);
-        if (rc != R3G_OK) return rc;
-        assign_gt_kernel<<<(unsigned)((G + tpb - 1) / tpb), tpb, 0, st>>>(w.row_best, G, min_pos_iou, gt_max_assign_all,
-                                                                        w.lowq, w.zero_gt, gt_max_overlaps, gt_argmax_overlaps);
-        if (want_ties) {
-            assign_ties_kernel<<<(unsigned)((w.tie_cap + 4 * tpb - 1) / (4 * tpb)), tpb, 0, st>>>(w.ties, w.iou.stats + 5, w.tie_cap,
-                                                                                            w.row_best, min_pos_iou, w.lowq);
-            // list overflow (massive ties, e.g. many identical anchors): exact sweep; its warps return at once otherwise.
-            // stats[5] must survive the reset of the item ticket, so only the ticket is cleared.
-            R3G_CUDA_OK(cudaMemsetAsync(w.iou.stats + 4, 0, 8, st));
-            rc = launch_sweep<false, OUT_ASSIGN_TIES>(a, st);
-            if (rc != R3G_OK) return rc;
-        }
-    }
-    assign_finalize_kernel<<<(unsigned)((A + tpb - 1) / tpb), tpb, 0, st>>>(w.col_best, w.lowq, w.zero_gt, A, G, pos_iou_thr,
-                                                                         neg_iou_thr, match_low_quality, assigned_gt_inds,
-                                                                         max_overlaps, argmax_overlaps);
-    R3G_LAUNCH_OK("assign kernels");
-    return R3G_OK;
+    R3G_REQUIRE(G >= 0, "r3g_max_iou_assign_f32: negative size");
+    return r3g_max_iou_assign_batched_f32(1, gt, &G, gt_stride, anchors, A, anchor_stride, 1, variant, flags, pos_iou_thr, neg_iou_thr,
+                                          min_pos_iou, match_low_quality, gt_max_assign_all, assigned_gt_inds, max_overlaps,
+                                          argmax_overlaps, gt_max_overlaps, gt_argmax_overlaps, workspace, workspace_bytes, stream);
 }

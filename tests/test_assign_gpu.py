@@ -87,3 +87,38 @@ def test_massive_ties_take_the_sweep(cuda_dev):
         want, _ = assign_wrt_overlaps(ov, pos, 0.4, minpos, True, True)
         out = R.max_iou_assign(G_, A_, pos, 0.4, minpos, True, True, "v1")
         assert torch.equal(out.gt_inds, want), int((out.gt_inds != want).sum())
+
+
+@pytest.mark.parametrize("v", ["v1", "v3"])
+@pytest.mark.parametrize("shared", [True, False])
+def test_batched_equals_per_image(cuda_dev, v, shared):
+    """One launch sequence for a batch of images == the per-image calls, bit for bit (shared anchors: the anchor-head stage;
+    per-image boxes: the refine stage); images without GT and GT counts that are not multiples of the row tile included."""
+    import r3det_b200 as R
+    t = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(cuda_dev)
+    counts = [37, 0, 130, 1, 64]
+    gts = [t(rand_obb(c, 50 + i, v, 10, 300)) for i, c in enumerate(counts)]
+    A = 5003
+    if shared:
+        anchors = t(rand_obb(A, 9, v))
+    else:
+        anchors = t(np.stack([rand_obb(A, 20 + i, v) for i in range(len(counts))]))
+    for lq, aa in ((True, True), (True, False), (False, True)):
+        got = R.max_iou_assign_batched(gts, anchors, 0.5, 0.4, 0.0, lq, aa, v)
+        assert len(got) == len(counts)
+        for b, c in enumerate(counts):
+            want = R.max_iou_assign(gts[b], anchors if shared else anchors[b], 0.5, 0.4, 0.0, lq, aa, v)
+            assert got[b].num_gts == c
+            for k in ("gt_inds", "max_overlaps", "argmax_overlaps", "gt_max_overlaps", "gt_argmax_overlaps"):
+                assert torch.equal(getattr(got[b], k), getattr(want, k)), (v, shared, lq, aa, b, k)
+    # exact ties across a batch (the symmetric set of test_against_matrix_reduction) + the tie-list overflow in one image
+    g = t(np.array([[100, 100, 40, 40, 0.0]], np.float32))
+    an = t(np.array([[90, 100, 40, 40, 0.0], [110, 100, 40, 40, 0.0], [100, 90, 40, 40, 0.0], [300, 300, 10, 10, 0.0]], np.float32))
+    got = R.max_iou_assign_batched([g, g[:0], g], an, 0.9, 0.4, 0.0, True, True, "v1")
+    want = R.max_iou_assign(g, an, 0.9, 0.4, 0.0, True, True, "v1")
+    assert torch.equal(got[0].gt_inds, want.gt_inds) and torch.equal(got[2].gt_inds, want.gt_inds) and (got[1].gt_inds == 0).all()
+    big = rand_obb(3, 11, "v1", 30, 200)
+    many = t(np.concatenate([np.repeat(big, 30000, axis=0), rand_obb(2000, 12, "v1")]).astype(np.float32))
+    got = R.max_iou_assign_batched([t(big), t(big[:1])], many, 1.5, 0.4, 0.3, True, True, "v1")
+    for b, gb in enumerate((t(big), t(big[:1]))):
+        assert torch.equal(got[b].gt_inds, R.max_iou_assign(gb, many, 1.5, 0.4, 0.3, True, True, "v1").gt_inds)
