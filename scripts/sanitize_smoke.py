@@ -36,6 +36,8 @@ gt, an = t(rand_obb(37, 5, 'v1')), t(rand_obb(2051, 6, 'v1'))
 for aa in (True, False):
     R.max_iou_assign(gt, an, 0.5, 0.4, 0.0, True, aa, 'v1')
 R.max_iou_assign(gt[:2], t(np.repeat(rand_obb(2, 5, 'v1'), 40000, axis=0)), 0.5, 0.4, 0.0, True, True, 'v1')
+R.max_iou_assign_batched([gt, gt[:0], gt[:5]], an, 0.5, 0.4, 0.0, True, True, 'v1')
+R.max_iou_assign_batched([gt[:3], gt[:65]], torch.stack([an[:1001], an[1001:2002]]), 0.5, 0.4, 0.0, True, True, 'v3')
 c, s, l = clustered(1500, 9, 'v1')
 bid = torch.arange(3, device=dev).repeat_interleave(500)
 nms_device(t(c), t(s), 0.1, 'v1', labels=t(l), class_offset=torch.tensor([1025.0, 900.0, 1100.0], device=dev), order_index=True,
