@@ -11,7 +11,7 @@ Module map (reference module -> here):
   r3det/core/bbox/iou_calculators-> iou_calculators   RBboxOverlaps2D_v1/v2/v3, rbbox_overlaps_v1/v2/v3
   r3det/core/post_processing     -> bbox_nms_rotated  multiclass_nms_rotated
   r3det/ops/fr                   -> fr                FeatureRefineFunction, feature_refine, FR, FeatureRefineModule
-  (mmdet MaxIoUAssigner + calculator, fused; §8f) -> assign   max_iou_assign, FusedMaxIoUAssigner
+  (mmdet MaxIoUAssigner + calculator, fused; §8f) -> assign   max_iou_assign, max_iou_assign_batched, FusedMaxIoUAssigner
   r3det/core/bbox/coder          -> coder             DeltaXYWHAOBBoxCoder, bbox2delta_v1/2/3, delta2bbox_v1/2/3
   r3det/models/dense_heads (get_bboxes tail, filter_bboxes, refine_bboxes; §8f) -> dense_tail
   r3det/core/bbox/rtransforms    -> rtransforms       poly2obb, obb2poly, obb2hbb, hbb2obb, obb2xyxy, norm_angle, *_np, ...
