@@ -924,7 +924,7 @@ R3G_API int r3g_poly_nms_workspace_bytes(int64_t K, size_t* bytes) {
     return R3G_OK;
 }
 
-R3G_API int r3g_poly_nms_f32(const float* polys, int64_t stride, const float* scores, int64_t K, float thr,
+R3G_API int r3g_poly_nms_f32(const float* polys, int64_t stride, const float* scores, const int64_t* labels, int64_t K, float thr,
                              int64_t* keep_out, int64_t* num_keep_out, void* workspace, size_t workspace_bytes, void* stream) {
     R3G_REQUIRE(K >= 0 && K < (1ll << 30), "r3g_poly_nms_f32: bad K");
     R3G_REQUIRE(num_keep_out != nullptr, "r3g_poly_nms_f32: null num_keep_out");
@@ -943,13 +943,13 @@ R3G_API int r3g_poly_nms_f32(const float* polys, int64_t stride, const float* sc
     R3G_REQUIRE((size_t)nblk * 8 <= 190 * 1024, "r3g_poly_nms_f32: K exceeds the single-call limit of this build");
     R3G_CUDA_OK(cudaMemsetAsync(w.counters, 0, 256, st));
     const bool small = Ki <= NMS_SMALL_K;
-    int rc = nms_order_stage(w, scores, nullptr, nullptr, Ki, st, small);
+    int rc = nms_order_stage(w, scores, labels, nullptr, Ki, st, small);
     if (rc != R3G_OK) return rc;
     poly::gather_kernel<<<gK, tpb, 0, st>>>(polys, stride, w.ord_rank, w.pos_rank, Ki, pw.quad, pw.aabb, w.valid);
     rc = nms_structure_stage(w, Ki, nblk, st, small);
     if (rc != R3G_OK) return rc;
     poly::PolyMaskArgs ma;
-    ma.quad = pw.quad; ma.aabb = pw.aabb; ma.blk_end = w.blk_end; ma.row_base = w.row_base; ma.mask = w.mask;
+    ma.quad = pw.quad; ma.aabb = pw.aabb; ma.label = w.pos_label; ma.blk_end = w.blk_end; ma.row_base = w.row_base; ma.mask = w.mask;
     ma.ticket = (unsigned long long*)(w.counters + 8);
     ma.K = Ki; ma.nblk = nblk; ma.thr = thr;
     ma.prefilter = thr >= 1e-3f ? 1 : 0;      // below that, FP32 noise of disjoint pairs could exceed the threshold: test every pair
@@ -959,7 +959,7 @@ R3G_API int r3g_poly_nms_f32(const float* polys, int64_t stride, const float* sc
     if (grid > cap) grid = cap;
     poly::mask_kernel<<<(unsigned)grid, 256, 0, st>>>(ma);
     R3G_LAUNCH_OK("poly mask kernel");
-    return nms_finish_stage(w, Ki, nblk, nullptr, nullptr, 0, K, small, keep_out, num_keep_out, st);
+    return nms_finish_stage(w, Ki, nblk, labels, nullptr, 0, K, small, keep_out, num_keep_out, st);
 }
 
 // ---- multiclass candidate extraction --------------------------------------------------------------------------------

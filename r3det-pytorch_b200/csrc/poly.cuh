@@ -114,6 +114,7 @@ __global__ void gather_kernel(const float* __restrict__ polys, int64_t stride, c
 
 struct PolyMaskArgs {
     const float* quad; const float4* aabb;
+    const unsigned* label;                 // segment key per position (class-wise NMS: pairs across segments never interact)
     const int* blk_end; const long long* row_base;
     unsigned long long* mask; unsigned long long* ticket;
     int K, nblk, prefilter;
@@ -142,12 +143,14 @@ __global__ void __launch_bounds__(256) mask_kernel(const PolyMaskArgs A) {
         }
         const int rb = lo;
         const int cb = rb + (int)(item - ((long long)rb * A.nblk - (long long)rb * (rb - 1) / 2));
+        if (cb > A.blk_end[rb]) continue;                // beyond the segment of the block's last row: no word to write
         const int i0 = rb * 64, j0 = cb * 64;
         sm[lane] = 0ull; sm[lane + 32] = 0ull;
         // this lane's two columns
         const int ja = j0 + (int)lane, jb = ja + 32;
         const float4 ca = ja < A.K ? __ldg(A.aabb + ja) : make_float4(3e38f, 3e38f, -3e38f, -3e38f);
         const float4 cbx = jb < A.K ? __ldg(A.aabb + jb) : make_float4(3e38f, 3e38f, -3e38f, -3e38f);
+        const unsigned la = ja < A.K ? __ldg(A.label + ja) : 0xffffffffu, lb = jb < A.K ? __ldg(A.label + jb) : 0xffffffffu;
         __syncwarp();
         int cnt = 0;
         auto drain = [&](int nb) {
@@ -165,7 +168,8 @@ __global__ void __launch_bounds__(256) mask_kernel(const PolyMaskArgs A) {
         for (int il = 0; il < rows; il++) {
             const int i = i0 + il;
             const float4 r = __ldg(A.aabb + i);
-            bool oka = ja > i && ja < A.K, okb = jb > i && jb < A.K;
+            const unsigned li = __ldg(A.label + i);
+            bool oka = ja > i && ja < A.K && la == li, okb = jb > i && jb < A.K && lb == li;
             if (A.prefilter) {
                 oka = oka && !(ca.x > r.z || ca.z < r.x || ca.y > r.w || ca.w < r.y);
                 okb = okb && !(cbx.x > r.z || cbx.z < r.x || cbx.y > r.w || cbx.w < r.y);

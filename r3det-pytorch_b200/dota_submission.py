@@ -3,7 +3,7 @@ write the `Task1_<class>.txt` files — mirror of DOTADataset.merge_det / _merge
 (r3det/datasets/dota1.py:209-292, 632-667), the on-disk side of the NMS path.
 
 The reference runs one NMS call per (image, class) from a Python loop; here ALL classes of an image go through one
-launch sequence (labels are segments of the same call), and only the polygon variant still loops over classes."""
+launch sequence (labels are segments of the same call), the polygon variant included."""
 import os
 import re
 import zipfile
@@ -50,15 +50,14 @@ def merge_image(label_dets, num_classes, iou_thr=0.1, version='v1', merge_nms='o
     labels, dets = label_dets[:, 0], label_dets[:, 1:]
     out = []
     if merge_nms == 'poly':
-        for c in range(num_classes):
-            cls = dets[labels == c]
-            if len(cls) == 0:
-                out.append(cls)
-                continue
-            polys = torch.from_numpy(np.ascontiguousarray(obb2poly_np(cls, version), np.float32)).to(device)
-            keep, num = poly_nms_device(polys[:, :8], polys[:, 8], iou_thr)
-            out.append(cls[keep[:int(num.item())].cpu().numpy()])
-        return out
+        if len(dets) == 0:
+            return [dets[labels == c] for c in range(num_classes)]
+        polys = torch.from_numpy(np.ascontiguousarray(obb2poly_np(dets, version), np.float32)).to(device)
+        lab = torch.from_numpy(labels.astype(np.int64)).to(device)
+        keep, num = poly_nms_device(polys[:, :8], polys[:, 8], iou_thr, labels=lab)        # every class in one call
+        keep = keep[:int(num.item())].cpu().numpy()                                        # descending score
+        kept_labels = labels[keep]
+        return [dets[keep[kept_labels == c]] for c in range(num_classes)]
     if len(dets) == 0:
         return [dets[labels == c] for c in range(num_classes)]
     d = torch.from_numpy(np.ascontiguousarray(dets, np.float32)).to(device)

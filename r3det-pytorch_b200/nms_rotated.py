@@ -34,9 +34,9 @@ def obb_nms(dets, iou_thr, device_id=None):
     return dets[inds, :], inds
 
 
-def poly_nms_device(polys, scores, iou_thr):
+def poly_nms_device(polys, scores, iou_thr, labels=None):
     """Polygon NMS on CUDA tensors: polys (K, >=8), scores (K,) -> (keep (K,) int64, num_keep 0-dim int64), both on the
-    device; no host synchronisation."""
+    device; no host synchronisation.  labels (K,) int64: class-wise NMS in one call."""
     import ctypes as C
     from . import _lib as L
     L.require_cuda(polys, scores)
@@ -47,12 +47,15 @@ def poly_nms_device(polys, scores, iou_thr):
     num = torch.zeros((), dtype=torch.int64, device=p.device)
     if K == 0:
         return keep, num
+    if labels is not None:
+        L.require_cuda(labels)
+        labels = labels.to(torch.int64).contiguous()
     lib = L.lib()
     nbytes = C.c_size_t(0)
     L.check(lib.r3g_poly_nms_workspace_bytes(K, C.byref(nbytes)))
     ws = L.workspace(nbytes.value, p.device)
     with L.device_guard(p.device):
-        L.check(lib.r3g_poly_nms_f32(L.ptr(p), stride, L.ptr(s), K, float(iou_thr), L.ptr(keep), C.c_void_p(num.data_ptr()),
+        L.check(lib.r3g_poly_nms_f32(L.ptr(p), stride, L.ptr(s), L.ptr(labels), K, float(iou_thr), L.ptr(keep), C.c_void_p(num.data_ptr()),
                                      L.ptr(ws), ws.numel(), L.stream_ptr(p.device)))
     return keep, num
 

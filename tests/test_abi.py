@@ -118,7 +118,7 @@ def test_next_row_entry_points_validate_arguments(lib):
     # polygon NMS
     assert lib.r3g_poly_nms_workspace_bytes(5000, C.byref(nbytes)) == 0 and nbytes.value > 5000 * 48
     keep = C.c_int64(0)
-    assert lib.r3g_poly_nms_f32(None, 9, None, 5, 0.1, None, None, None, 0, None) < 0               # null num_keep_out
+    assert lib.r3g_poly_nms_f32(None, 9, None, None, 5, 0.1, None, None, None, 0, None) < 0         # null num_keep_out
     # assigner
     assert lib.r3g_assign_workspace_bytes(1000, 200000, C.byref(nbytes)) == 0 and nbytes.value > 200000 * 12
     assert lib.r3g_max_iou_assign_f32(None, 3, 5, None, 4, 5, 9, 0, 0.5, 0.4, 0.0, 1, 1, None, None, None, None, None, None, 0, None) < 0

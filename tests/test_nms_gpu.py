@@ -203,6 +203,17 @@ def test_polygon_nms_vs_reference_cuda_golden(cuda_dev):
         assert np.array_equal(k.cpu().numpy(), port.poly_nms(q, thr)), thr
     e = R.poly_nms(_t(q[:0], cuda_dev), 0.1)
     assert e[0].shape == (0, 9) and e[1].numel() == 0
+    # class-wise in one call == one call per class
+    from r3det_b200.nms_rotated import poly_nms_device
+    lab = np.random.default_rng(3).integers(0, 6, 700)
+    lab[lab == 4] = 5                                                      # an empty class
+    keep, num = poly_nms_device(_t(q[:, :8], cuda_dev), _t(q[:, 8], cuda_dev), 0.1, labels=_t(lab.astype(np.int64), cuda_dev))
+    keep = keep[:int(num)].cpu().numpy()
+    assert np.all(np.diff(q[keep, 8]) <= 0)                                # descending score overall
+    for c in range(6):
+        idx = np.nonzero(lab == c)[0]
+        want = idx[port.poly_nms(q[idx], 0.1)] if len(idx) else idx
+        assert np.array_equal(keep[lab[keep] == c], want), c
     _, k1 = R.poly_nms(_t(q[:1], cuda_dev), 0.1)
     assert k1.tolist() == [0]
 
