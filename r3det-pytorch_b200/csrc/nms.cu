@@ -98,14 +98,15 @@ __global__ void nms_keys_kernel(const float* __restrict__ scores, int K, unsigne
     if (i < K) { keyA[i] = score_key_desc(scores[i]); idx[i] = i; }
 }
 
-// segment key of rank r: the label, or (label << 16 | image) for multi-image batches
+// segment key of rank r: the label, or (image << 16 | label) for multi-image batches (image-major: an image's
+// segments are contiguous in position space)
 __global__ void nms_label_keys_kernel(const int64_t* __restrict__ labels, const int64_t* __restrict__ batch_ids,
                                       const int* __restrict__ ord_rank, int K, unsigned* keyB, int* rank_iota) {
     int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r < K) {
         const int idx = ord_rank[r];
         unsigned key = labels ? (unsigned)labels[idx] : 0u;
-        if (batch_ids) key = (key << 16) | ((unsigned)batch_ids[idx] & 0xffffu);
+        if (batch_ids) key = (((unsigned)batch_ids[idx] & 0xffffu) << 16) | (key & 0xffffu);
         keyB[r] = key;
         rank_iota[r] = r;
     }
@@ -131,8 +132,8 @@ __global__ void nms_gather_kernel(const float* __restrict__ boxes, int64_t strid
     float off = 0.0f;
     if (class_offset != nullptr && has_labels) {
         const unsigned key = pos_label[p];
-        const float scale = batched ? class_offset[key & 0xffffu] : class_offset[0];       // per-image offset scale
-        off = __fmul_rn((float)(int)(batched ? (key >> 16) : key), scale);
+        const float scale = batched ? class_offset[key >> 16] : class_offset[0];           // per-image offset scale
+        off = __fmul_rn((float)(int)(batched ? (key & 0xffffu) : key), scale);
         x[0] = __fadd_rn(x[0], off);
         x[1] = __fadd_rn(x[1], off);
     }
@@ -599,7 +600,7 @@ constexpr int NMS_SMALL_K = 16384;
 
 __device__ __forceinline__ unsigned seg_key_of(const int64_t* labels, const int64_t* batch_ids, int i) {
     unsigned key = labels ? (unsigned)labels[i] : 0u;
-    if (batch_ids) key = (key << 16) | ((unsigned)batch_ids[i] & 0xffffu);
+    if (batch_ids) key = (((unsigned)batch_ids[i] & 0xffffu) << 16) | (key & 0xffffu);
     return key;
 }
 
@@ -608,24 +609,46 @@ __global__ void __launch_bounds__(256) nms_rank_count_kernel(const float* __rest
                                                              const int64_t* __restrict__ batch_ids, int K, int slice_len,
                                                              int* __restrict__ rcnt, int* __restrict__ pcnt) {
     __shared__ uint4 tile[256];                              // {key low (index), key high (score key), segment key, -}
+    __shared__ unsigned img_lo, img_hi;                      // BATCHED: image range of the tile
     const int i = blockIdx.x * 256 + threadIdx.x;
     const bool iv = i < K;
     const unsigned long long ai = iv ? (((unsigned long long)score_key_desc(scores[i]) << 32) | (unsigned)i) : 0ull;
     const unsigned si = iv ? seg_key_of(labels, batch_ids, i) : 0u;
-    const unsigned mi = si & 0xffffu;
+    const unsigned mi = si >> 16;                            // BATCHED: the image (segment keys are image-major)
     const int j_begin = blockIdx.y * slice_len, j_end = min(K, j_begin + slice_len);
     int r = 0, p = 0, r1 = 0, p1 = 0, r2 = 0, p2 = 0, r3 = 0, p3 = 0;
     for (int j0 = j_begin; j0 < j_end; j0 += 256) {
         const int j = j0 + threadIdx.x;
         __syncthreads();
-        if (j < j_end) tile[threadIdx.x] = make_uint4((unsigned)j, score_key_desc(scores[j]), seg_key_of(labels, batch_ids, j), 0u);
+        if (BATCHED && threadIdx.x == 0) { img_lo = 0xffffffffu; img_hi = 0u; }
+        __syncthreads();
+        unsigned lo = 0xffffffffu, hi = 0u;
+        if (j < j_end) {
+            const unsigned sj = seg_key_of(labels, batch_ids, j);
+            tile[threadIdx.x] = make_uint4((unsigned)j, score_key_desc(scores[j]), sj, 0u);
+            lo = hi = sj >> 16;
+        }
+        if (BATCHED) {                                       // one shared-memory atomic pair per warp
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+                hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+            }
+            if ((threadIdx.x & 31) == 0 && lo <= hi) { atomicMin(&img_lo, lo); atomicMax(&img_hi, hi); }
+        }
         __syncthreads();
         const int n = min(256, j_end - j0);
+        if (BATCHED) {
+            // candidates usually arrive image by image: a tile wholly of earlier images counts in full, one wholly of later
+            // images not at all — both without looking at its entries
+            if (img_hi < mi) { r += n; p += n; continue; }
+            if (img_lo > mi) continue;
+        }
         auto one = [&](int t, int& rr, int& pp) {
             const uint4 e = tile[t];                         // one broadcast read per candidate
             const bool lt = (((unsigned long long)e.y << 32) | e.x) < ai;
             if (BATCHED) {
-                const unsigned mj = e.z & 0xffffu;
+                const unsigned mj = e.z >> 16;
                 rr += (mj < mi) | ((mj == mi) & lt);
             } else {
                 rr += lt;
@@ -730,7 +753,9 @@ static int nms_order_stage(NmsWs& w, const float* scores, const int64_t* labels,
         int* rcnt = (int*)w.keyA; int* pcnt = (int*)w.keyA2;
         R3G_CUDA_OK(cudaMemsetAsync(rcnt, 0, 4 * (size_t)Ki, st));
         R3G_CUDA_OK(cudaMemsetAsync(pcnt, 0, 4 * (size_t)Ki, st));
-        int slices = (device_sm_count() * 4 + gK - 1) / gK;              // ~4 CTAs per SM in total
+        // ~4 CTAs per SM in total; batches get single-tile slices: most (i-block, tile) pairs are of different images and
+        // return at once, so the remaining work needs the finer split to spread over the SMs
+        int slices = batch_ids ? (Ki + 255) / 256 : (device_sm_count() * 4 + gK - 1) / gK;
         const int max_slices = (Ki + 255) / 256;
         if (slices > max_slices) slices = max_slices;
         if (slices < 1) slices = 1;
