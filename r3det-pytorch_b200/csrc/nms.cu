@@ -836,7 +836,7 @@ static int nms_finish_stage(NmsWs& w, int Ki, int nblk, const int64_t* labels, c
     if (!labels && !batch_ids) sgrid = 1;
     nms_scan_kernel<<<sgrid, SCAN_THREADS, smem, st>>>(sa);
     R3G_LAUNCH_OK("nms_scan_kernel");
-    if (small) {
+    if (small && Ki <= 4096) {            // one CTA walks K / 1024 chunks: past a few thousand the three-kernel path is faster
         nms_finish_small_kernel<<<1, 1024, 0, st>>>(w.keep_p, w.pos_rank, w.ord_rank, batch_ids, Ki, order_index, w.flag, keep_out,
                                                     (unsigned long long*)num_keep_out);
         R3G_LAUNCH_OK("nms_finish_small_kernel");
