@@ -782,7 +782,10 @@ static int nms_order_stage(NmsWs& w, const float* scores, const int64_t* labels,
     nms_label_keys_kernel<<<gK, tpb, 0, st>>>(labels, batch_ids, w.ord_rank, Ki, w.keyB, w.pos_tmp);
     if (labels || batch_ids) {
         tb = w.cub_bytes;
-        R3G_CUDA_OK(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, w.keyB, w.pos_label, w.pos_tmp, w.pos_rank, Ki, 0, 32, st));
+        // in a batch the rank order is already image-major: sorting on the 16 label bits alone keeps every (image, label)
+        // segment contiguous (label-major), the full keys travel with the permutation
+        R3G_CUDA_OK(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, w.keyB, w.pos_label, w.pos_tmp, w.pos_rank, Ki, 0,
+                                                    batch_ids ? 16 : 32, st));
     } else {
         R3G_CUDA_OK(cudaMemcpyAsync(w.pos_label, w.keyB, 4 * (size_t)Ki, cudaMemcpyDeviceToDevice, st));
         R3G_CUDA_OK(cudaMemcpyAsync(w.pos_rank, w.pos_tmp, 4 * (size_t)Ki, cudaMemcpyDeviceToDevice, st));
