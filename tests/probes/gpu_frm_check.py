@@ -1,7 +1,7 @@
 """Development probe (GPU box): FRM + transforms parity vs oracle/reference CUDA, timing."""
 import ctypes as C, os, sys
 import numpy as np, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import r3det_b200
 from r3det_b200.fr import frm_forward, frm_backward
 from oracle import port

@@ -1,7 +1,7 @@
 """Development probe (GPU box): IoU parity vs oracle + timing vs the reference CUDA kernels."""
 import ctypes as C, os, sys, time, json
 import numpy as np, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import r3det_b200
 from r3det_b200.rbbox_geo import pairwise_iou, aligned_iou
 from oracle import port

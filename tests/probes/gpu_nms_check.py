@@ -1,7 +1,7 @@
 """Development probe (GPU box): NMS parity vs oracle + timing."""
 import os, sys, time
 import numpy as np, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import r3det_b200
 from r3det_b200._nms_core import nms_device
 from oracle import port

@@ -1,13 +1,13 @@
 """Development probe (GPU box): polygon NMS + v1 NMS vs the reference's own CUDA kernels (oracle/_ref), parity and timing."""
 import ctypes as C, os, sys
 import numpy as np, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import r3det_b200 as R
 from r3det_b200.nms_rotated import poly_nms_device
 from oracle import port, transforms_np as T
 from tests.util import clustered
 dev = torch.device('cuda:0')
-REFDIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'oracle', '_ref')
+REFDIR = os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), 'oracle', '_ref')
 vp, i64, f32, i32 = C.c_void_p, C.c_int64, C.c_float, C.c_int
 lp = C.CDLL(os.path.join(REFDIR, 'libref_cuda_polynms.so'))
 lp.refcuda_poly_nms.restype = f32; lp.refcuda_poly_nms.argtypes = [vp, i64, f32, vp, vp, i32]

@@ -1,7 +1,7 @@
 """compute-sanitizer target: small invocations of every kernel (odd sizes, tails, empty inputs)."""
 import os, sys
 import numpy as np, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import r3det_b200 as R
 from r3det_b200._nms_core import nms_device
 from r3det_b200.fr import frm_forward, frm_backward
