@@ -34,7 +34,7 @@ def timeit(fn, iters=10, warm=3):
     return float(np.median(ts))
 lf = None
 try:
-    lf = C.CDLL(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'oracle', '_ref', 'libref_cuda_frm.so'))
+    lf = C.CDLL(os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), 'oracle', '_ref', 'libref_cuda_frm.so'))
     for fn in (lf.refcuda_frm_forward, lf.refcuda_frm_backward):
         fn.restype = C.c_float; fn.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_int]
 except Exception as e:

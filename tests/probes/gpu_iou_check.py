@@ -59,7 +59,7 @@ for v in ['v1']:
     print('dense', v, 'median %.3f ms -> %.1f Gpairs/s' % (med, 2e8/med/1e6), 'stats', stats.cpu().numpy().tolist(), 'max diff %.3g n>1e-5 %d' % (d.max(), (d > 1e-5).sum()))
 
 # reference CUDA kernels
-refdir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'oracle', '_ref')
+refdir = os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), 'oracle', '_ref')
 try:
     l1 = C.CDLL(os.path.join(refdir, 'libref_cuda_v1iou.so'))
     l1.refcuda_v1_iou_matrix.restype = C.c_float
