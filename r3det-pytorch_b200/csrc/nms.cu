@@ -73,7 +73,7 @@ static NmsWs carve_nms(void* ws, int64_t K) {
     w.pos_rank = (int*)take(4 * K); w.pos_tmp = (int*)take(4 * K);
     w.pos_label = (unsigned*)take(4 * K);
     w.p0 = (BoxP0*)take(16 * K); w.p1 = (BoxP1*)take(16 * K);
-    w.p2r = (float4*)take(16 * K); w.p2c = (float4*)take(16 * K);
+    w.p2r = (float4*)take(32 * K); w.p2c = (float4*)take(16 * K);       // row plane: every constant twice (f32x2 operands)
     w.raw = (float*)take(20 * K); w.valid = (unsigned char*)take(K);
     w.blk_end = (int*)take(4 * nblk);
     w.nw = (long long*)take(8 * (nblk + 1)); w.row_base = (long long*)take(8 * (nblk + 1));
@@ -150,7 +150,9 @@ __global__ void nms_gather_kernel(const float* __restrict__ boxes, int64_t strid
     const float X = a.cx - off, Y = a.cy - off;
     const float q = X * X + Y * Y, rr = a.r * a.r;
     const float kk = ok ? (q - rr) - NMS_SLACK * (q + rr) - 1e-6f : 3.0e38f;
-    p2r[p] = make_float4(-2.0f * X, -2.0f * Y, -2.0f * a.r, kk);
+    // row constants stored twice: two 16-byte halves that load straight into aligned register pairs (packed f32x2 stage 1)
+    p2r[2 * p] = make_float4(-2.0f * X, -2.0f * X, -2.0f * Y, -2.0f * Y);
+    p2r[2 * p + 1] = make_float4(-2.0f * a.r, -2.0f * a.r, kk, kk);
     p2c[p] = make_float4(X, Y, a.r, kk);
 }
 
@@ -196,6 +198,21 @@ struct MaskArgs {
 };
 
 __device__ __forceinline__ float4 nldg4(const void* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// packed f32x2 arithmetic (FFMA2 / FADD2 on sm_100): low half = element 0
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+    return ((unsigned long long)__float_as_uint(hi) << 32) | __float_as_uint(lo);
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
 
 __global__ void __launch_bounds__(NMS_THREADS, 3) nms_mask_kernel(const MaskArgs A) {
     // per-warp: q1 circumradius survivors -> q2 separating-axis survivors -> (q3 near-threshold / degenerate pairs);
@@ -331,6 +348,12 @@ __global__ void __launch_bounds__(NMS_THREADS, 3) nms_mask_kernel(const MaskArgs
                 cx[k] = 0.0f; cy[k] = 0.0f; cr[k] = 0.0f; ck[k] = 3.0e38f; cl[k] = 0xffffffffu;
             }
         }
+        unsigned long long CX[NMS_CPL / 2], CY[NMS_CPL / 2], CR[NMS_CPL / 2], CK[NMS_CPL / 2];     // two columns per register pair
+#pragma unroll
+        for (int h = 0; h < NMS_CPL / 2; h++) {
+            CX[h] = pack2(cx[2 * h], cx[2 * h + 1]); CY[h] = pack2(cy[2 * h], cy[2 * h + 1]);
+            CR[h] = pack2(cr[2 * h], cr[2 * h + 1]); CK[h] = pack2(ck[2 * h], ck[2 * h + 1]);
+        }
         // interior items (one label throughout, all columns after all rows) need no per-pair label / order test
         const bool interior = (cb0 > rb) && (A.label[i0] == A.label[j1 - 1]);
         __syncwarp();
@@ -341,13 +364,18 @@ __global__ void __launch_bounds__(NMS_THREADS, 3) nms_mask_kernel(const MaskArgs
 #pragma unroll
             for (int r = 0; r < NMS_RG; r++) {
                 if (r < nr) {
-                    const float4 a = nldg4(A.p2r + ig + r);
+                    // two columns per instruction (FFMA2 / FADD2): the kernel is issue-bound, and the packed form does the same
+                    // operations in the same order as the scalar one
+                    const ulonglong2 ra = __ldg(reinterpret_cast<const ulonglong2*>(A.p2r + 2 * (ig + r)));       // {-2X, -2X}, {-2Y, -2Y}
+                    const ulonglong2 rb = __ldg(reinterpret_cast<const ulonglong2*>(A.p2r + 2 * (ig + r) + 1));   // {-2r, -2r}, {k, k}
 #pragma unroll
-                    for (int k = 0; k < NMS_CPL; k++) {
-                        float s = fmaf(a.x, cx[k], ck[k] + a.w);
-                        s = fmaf(a.y, cy[k], s);
-                        s = fmaf(a.z, cr[k], s);
-                        m = __funnelshift_l(__float_as_uint(s), m, 1);
+                    for (int h = 0; h < NMS_CPL / 2; h++) {
+                        unsigned long long t = add2(CK[h], rb.y);
+                        t = fma2(ra.x, CX[h], t);
+                        t = fma2(ra.y, CY[h], t);
+                        t = fma2(rb.x, CR[h], t);
+                        m = __funnelshift_l((unsigned)t, m, 1);
+                        m = __funnelshift_l((unsigned)(t >> 32), m, 1);
                     }
                 }
             }
