@@ -16,7 +16,7 @@ for name, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     print("%-72s launches %4d  total %10.1f us  share %5.1f%%" % (name, n, t / 1e3, 100 * t / tot))
 # the headline step = r3g_iou_matrix_f32 = prep_boxes_kernel x2 + iou_matrix_kernel<1,0>
 names = [re.sub(r"\(.*", "", r[4]).strip() for r in body]
-steps = [i for i, n in enumerate(names) if "iou_matrix_kernel<1, 0>" in n and i >= 2 and "prep_boxes" in names[i - 1] and "prep_boxes" in names[i - 2]]
+steps = [i for i, n in enumerate(names) if "iou_matrix_kernel<1, 0" in n and i >= 2 and "prep_boxes" in names[i - 1] and "prep_boxes" in names[i - 2]]
 if steps:
     i = steps[min(4, len(steps) - 1)]          # a timed headline step (after the warm-up launches)
     d = [float(body[j][-1]) for j in (i - 2, i - 1, i)]
