@@ -283,3 +283,12 @@ def test_radix_path_large_k_vs_oracle(cuda_dev):
     k, n = nms_device(_t(b, cuda_dev), _t(s, cuda_dev), 0.1, "v1", labels=_t(l, cuda_dev))
     want = port.nms(b, s, 0.1, "v1", labels=l.astype(np.float32), inclusive=False)
     assert np.array_equal(k[:int(n)].cpu().numpy(), want)
+
+
+def test_randomised_configurations_vs_oracle(cuda_dev):
+    """45 random (variant, images, classes, sizes incl. 0 / 1 / 63..65, threshold, ties, offsets, order, path) cases: every
+    image's keep list equals the oracle's (tests/probes/fuzz_nms.py; 300 further cases were run once during development)."""
+    import importlib.util, os
+    spec = importlib.util.spec_from_file_location("fuzz_nms", os.path.join(os.path.dirname(__file__), "probes", "fuzz_nms.py"))
+    m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
+    assert m.run(seed=5, iters=45, dev=cuda_dev, verbose=True) == 0
