@@ -122,3 +122,25 @@ def test_batched_equals_per_image(cuda_dev, v, shared):
     got = R.max_iou_assign_batched([t(big), t(big[:1])], many, 1.5, 0.4, 0.3, True, True, "v1")
     for b, gb in enumerate((t(big), t(big[:1]))):
         assert torch.equal(got[b].gt_inds, R.max_iou_assign(gb, many, 1.5, 0.4, 0.3, True, True, "v1").gt_inds)
+
+
+def test_batched_randomised(cuda_dev):
+    """Random batch shapes (1..9 images, 0..300 GT each, 1..9000 anchors, shared or per-image, every low-quality mode)."""
+    import r3det_b200 as R
+    rng = np.random.default_rng(21)
+    t = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(cuda_dev)
+    for it in range(14):
+        v = ["v1", "v2", "v3"][it % 3]
+        B = int(rng.integers(1, 10))
+        counts = [int(rng.choice([0, 1, 2, 63, 64, 65, 128, 300])) for _ in range(B)]
+        A = int(rng.choice([1, 127, 128, 129, 2000, 9000]))
+        shared = bool(rng.integers(2))
+        gts = [t(rand_obb(c, int(rng.integers(1 << 30)), v, 10, 300)) if c else torch.zeros((0, 5), device=cuda_dev) for c in counts]
+        anchors = t(rand_obb(A, int(rng.integers(1 << 30)), v)) if shared else t(np.stack([rand_obb(A, int(rng.integers(1 << 30)), v) for _ in range(B)]))
+        pos, neg, minpos = [(0.5, 0.4, 0.0), (0.6, 0.5, 0.3), (0.3, 0.3, 0.1)][it % 3]
+        lq, aa = bool(rng.integers(2)), bool(rng.integers(2))
+        got = R.max_iou_assign_batched(gts, anchors, pos, neg, minpos, lq, aa, v)
+        for b in range(B):
+            want = R.max_iou_assign(gts[b], anchors if shared else anchors[b], pos, neg, minpos, lq, aa, v)
+            for k in ("gt_inds", "max_overlaps", "argmax_overlaps", "gt_max_overlaps", "gt_argmax_overlaps"):
+                assert torch.equal(getattr(got[b], k), getattr(want, k)), (it, v, B, counts, A, shared, lq, aa, b, k)
