@@ -157,3 +157,23 @@ def test_full_size_properties(cuda_dev):
         want = port.iou_matrix(gt, an[sel], v, wrapper_mask=False)
         assert np.abs(out[:, sel].cpu().numpy() - want).max() <= TOL
         del out, tr
+
+
+def test_randomised_shapes(cuda_dev):
+    """Random (m, n) incl. tile-edge sizes, (N, 5) and (N, 6) inputs, IoU / IoF, all variants, matrix and aligned mode."""
+    import r3det_b200 as R
+    rng = np.random.default_rng(33)
+    for it in range(18):
+        v = ["v1", "v2", "v3"][it % 3]
+        mode = ["iou", "iof"][(it // 3) % 2]
+        m = int(rng.choice([1, 2, 63, 64, 65, 129, 300])); n = int(rng.choice([1, 3, 127, 128, 129, 515, 4001]))
+        lo, hi = [(8, 512), (16, 300), (30, 900)][it % 3]
+        a, b = rand_obb(m, int(rng.integers(1 << 30)), v, lo, hi), rand_obb(n, int(rng.integers(1 << 30)), v, lo, hi)
+        if rng.integers(2):                                                   # a 6th (score) column must be ignored
+            a = np.concatenate([a, rng.random((m, 1)).astype(np.float32)], 1)
+        got = R.pairwise_iou(_t(a, cuda_dev), _t(b, cuda_dev), v, mode).cpu().numpy()
+        want = port.iou_matrix(a[:, :5], b, v, mode, wrapper_mask=False)
+        assert got.shape == (m, n) and np.abs(got - want).max() <= TOL, (it, v, mode, m, n, float(np.abs(got - want).max()))
+        k = min(m, n)
+        al = R.aligned_iou(_t(a[:k], cuda_dev), _t(b[:k], cuda_dev), v, mode).cpu().numpy()
+        assert np.abs(al - np.diagonal(want[:k, :k])).max() <= TOL
