@@ -1,88 +1,88 @@
-// nms.cu — rotated NMS (single class and per-class segmented) entirely on the device, sm_100a.
+// nms.cu — rotated NMS (single class and per-class segmented) and polygon NMS entirely on the device, sm_100a.
 //
 // Replaces (reference, relative to /root/reference):
 //   nmsr_kernel + nmsr_cuda host scan            r3det/ops/rnms/src/rcuda/rnms_kernel.cu:229-335        (v1)
 //   nms_rotated_cuda_kernel + host scan          r3det/ops/nms_rotated/src/nms_rotated_cuda.cu:12-134    (v3)
 //   ml_nms_rotated                               r3det/ops/ml_nms_rotated/src/nms_rotated_cuda.cu:13-137 (v2)
+//   poly_nms_kernel + host scan                  r3det/ops/nms_rotated/src/poly_nms_cuda.cu:122-262
 // The reference computes the FULL K x K bitmask (cross-class pairs included, via a coordinate offset
 // trick), copies it to the host and scans it serially on the CPU.  Here:
-//   1. position space p = (segment asc, score desc), segment = label or (label, image): two stable radix sorts, or —
+//   1. position space p = (segment asc, score desc), segment = label or (image, label): two stable radix sorts, or —
 //      for K <= 16384, where the sorts are pure launch latency — ranks COUNTED in one O(K^2) kernel;
 //   2. boxes are gathered/prepared once in p-order (class offsets applied in FP32 exactly as the
 //      reference's batched wrappers do, so the geometry sees the same rounded coordinates);
-//   3. mask kernel: only upper-triangular 64x64 tiles INSIDE a segment are visited; persistent warps pull
-//      (64 rows x 128 columns) items from a ticket (rows split over up to 8 warps when the grid has spare warps);
-//      a lane owns 4 adjacent columns, the circumradius test shifts its sign bit into a 32-bit mask per 8 rows,
-//      survivors are compacted into shared-memory queues and evaluated 32 at a time (separating axes, then the
-//      clamped-boundary integral of geom.cuh); suppression bits are OR-ed into shared-memory words, written once;
-//   4. scan kernel: one 512-thread CTA per segment, superblocks of 4 x 64 rows: warp 0 resolves the chains from a
-//      shared-memory window with ffs-jumps, the other warps prefetch the next window and OR the kept rows' words
-//      into the shared-memory `removed` bit-vector (no host round trip);
-//   5. keep bits -> flags -> exclusive scan -> keep list in score order or index order.
+//   3. ONE persistent kernel (nms_rounds.cuh) runs the greedy selection in rounds — chunk of the next <= 2048 alive
+//      candidates per segment, chunk-local bitmask, scan, kept rows applied to the rest of the segment — so that only
+//      pairs (kept row, later column) and pairs inside a chunk are ever evaluated, the workspace is linear in K and no
+//      host round trip exists;
+//   4. keep bits -> flags -> exclusive scan -> keep list in score order or index order.
 // Pairs whose IoU lies within `margin` of the threshold (or that trip the degeneracy test) are decided
 // by the reference's own algorithm (emu.cuh), which makes the keep set the reference's.
 #include <cub/cub.cuh>
+#include <stdlib.h>
 #include "common.cuh"
 #include "emu.cuh"
 #include "geom.cuh"
+#include "nms_rounds.cuh"
 #include "poly.cuh"
 
 namespace r3g {
 
-constexpr int NMS_THREADS = 256;
-constexpr int NMS_WARPS = NMS_THREADS / 32;
-constexpr int NMS_G = 2;                       // column blocks (of 64) per item
-constexpr int NMS_TN = NMS_G * 64;             // 128 columns per item
-constexpr int NMS_CPL = NMS_TN / 32;           // 4 adjacent columns per lane
-constexpr int NMS_RG = 8;                      // rows per mask group (8 rows x 4 columns = 32 mask bits per lane)
-constexpr int NMS_Q1CAP = 32 + NMS_RG * NMS_TN;
 constexpr float NMS_SLACK = 1.0f / 262144.0f;  // 2^-18 relative slack of the expanded circumradius test
+constexpr int NMS_SMALL_K = 16384;             // up to here ranks are counted instead of sorted
+
+// rows of a mask item are split over this many warps when K is small (the kernel is then bound by one warp's serial work)
+static int nms_split_of(int64_t K) { return K <= 4096 ? 8 : (K <= 8192 ? 4 : (K <= 16384 ? 2 : 1)); }
 
 struct NmsWs {
+    unsigned char* ctrl;                            // 512 bytes: rn::Ctrl[2] at 0, barrier counter at 128
     unsigned *keyA, *keyA2, *keyB, *keyB2;
     int *ord_rank, *ord_tmp, *pos_rank, *pos_tmp;   // ord_rank[r] = original index of rank r; pos_rank[p] = rank at position p
     unsigned* pos_label;
-    BoxP0* p0; BoxP1* p1; float4* p2r; float4* p2c; float* raw; unsigned char* valid;
-    int* blk_end; long long *nw, *row_base, *ng, *item_base;
-    int* seg_list; int* counters;                   // counters[0] = nseg
+    float4 *p0, *p1, *p2r, *p2c; float* raw;
+    unsigned long long* alive; size_t alive_bytes;
+    int *seg_cur, *seg_pe, *act;
+    rn::Entry* ent;
+    int *spos, *klist, *ownerB, *ownerD;
     int *flag, *pref, *keep_p;
     void* cub_tmp; size_t cub_bytes;
     unsigned long long* mask;
     size_t bytes;
 };
 
-static size_t cub_temp_bytes(int64_t K, int64_t nblk) {
-    size_t a = 0, b = 0, c = 0;
+static size_t cub_temp_bytes(int64_t K) {
+    size_t a = 0, b = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, a, (unsigned*)nullptr, (unsigned*)nullptr, (int*)nullptr, (int*)nullptr, (int)K);
     cub::DeviceScan::ExclusiveSum(nullptr, b, (int*)nullptr, (int*)nullptr, (int)K);
-    cub::DeviceScan::ExclusiveSum(nullptr, c, (long long*)nullptr, (long long*)nullptr, (int)nblk + 1);
-    size_t m = a > b ? a : b;
-    return align_up(m > c ? m : c, 256);
+    return align_up(a > b ? a : b, 256);
 }
 
 static NmsWs carve_nms(void* ws, int64_t K) {
     NmsWs w;
-    const int64_t nblk = (K + 63) / 64;
     char* p = (char*)ws;
     size_t off = 0;
     auto take = [&](size_t bytes) { char* r = p + off; off += align_up(bytes, 256); return (void*)r; };
-    w.counters = (int*)take(256);
+    w.ctrl = (unsigned char*)take(512);
     w.keyA = (unsigned*)take(4 * K); w.keyA2 = (unsigned*)take(4 * K);
     w.keyB = (unsigned*)take(4 * K); w.keyB2 = (unsigned*)take(4 * K);
     w.ord_rank = (int*)take(4 * K); w.ord_tmp = (int*)take(4 * K);
     w.pos_rank = (int*)take(4 * K); w.pos_tmp = (int*)take(4 * K);
     w.pos_label = (unsigned*)take(4 * K);
-    w.p0 = (BoxP0*)take(16 * K); w.p1 = (BoxP1*)take(16 * K);
+    w.p0 = (float4*)take(16 * K); w.p1 = (float4*)take(16 * K);
     w.p2r = (float4*)take(32 * K); w.p2c = (float4*)take(16 * K);       // row plane: every constant twice (f32x2 operands)
-    w.raw = (float*)take(20 * K); w.valid = (unsigned char*)take(K);
-    w.blk_end = (int*)take(4 * nblk);
-    w.nw = (long long*)take(8 * (nblk + 1)); w.row_base = (long long*)take(8 * (nblk + 1));
-    w.ng = (long long*)take(8 * (nblk + 1)); w.item_base = (long long*)take(8 * (nblk + 1));
-    w.seg_list = (int*)take(4 * K);
+    w.raw = (float*)take(20 * K);
+    w.alive_bytes = 16 * (size_t)((K + 127) / 128);                     // two 64-bit words per 128-column group
+    w.alive = (unsigned long long*)take(w.alive_bytes);
+    w.seg_cur = (int*)take(4 * K); w.seg_pe = (int*)take(4 * K); w.act = (int*)take(8 * K);
+    w.ent = (rn::Entry*)take(sizeof(rn::Entry) * (size_t)(K / 2 + 2));  // chunks of >= 2 rows
+    w.spos = (int*)take(4 * K); w.klist = (int*)take(4 * K);
+    // mask items: <= K/2 single-block chunks + 17 n / 64 for the others; apply items: <= K B / 8192 + K / 32
+    w.ownerB = (int*)take(4 * (size_t)(K + 64) * (size_t)nms_split_of(K));
+    w.ownerD = (int*)take(4 * (size_t)(K / 2 + 64));
     w.flag = (int*)take(4 * K); w.pref = (int*)take(4 * K); w.keep_p = (int*)take(4 * K);
-    w.cub_bytes = cub_temp_bytes(K, nblk);
+    w.cub_bytes = cub_temp_bytes(K);
     w.cub_tmp = take(w.cub_bytes);
-    w.mask = (unsigned long long*)take((size_t)8 * 64 * (size_t)(nblk * (nblk + 1) / 2));
+    w.mask = (unsigned long long*)take((size_t)8 * (size_t)K * (rn::B_MAX / 64 + 1));   // sum over chunks of n * ceil(n / 64)
     w.bytes = off;
     return w;
 }
@@ -119,481 +119,67 @@ __global__ void nms_batch_keys_kernel(const int64_t* __restrict__ batch_ids, con
 
 // Gather + prepare boxes in position order; class offsets in FP32 as the reference wrappers compute them:
 //   offsets = label.to(float) * scale ; box[:, :2] += offsets      (rnms_wrapper.py:61-64, nms_rotated_wrapper.py:84-90)
+// Whole warps run to the ballot that builds the `alive` bit vector (blockDim is a multiple of 32).
 __global__ void nms_gather_kernel(const float* __restrict__ boxes, int64_t stride, const int* __restrict__ ord_rank,
                                   const int* __restrict__ pos_rank, const unsigned* __restrict__ pos_label, int K,
                                   int variant, int drop_small, const float* __restrict__ class_offset, int has_labels,
-                                  int batched,
-                                  BoxP0* p0, BoxP1* p1, float4* p2r, float4* p2c, float* raw, unsigned char* valid) {
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= K) return;
-    const int idx = ord_rank[pos_rank[p]];
-    const float* b = boxes + (int64_t)idx * stride;
-    float x[5] = { b[0], b[1], b[2], b[3], b[4] };
-    float off = 0.0f;
-    if (class_offset != nullptr && has_labels) {
-        const unsigned key = pos_label[p];
-        const float scale = batched ? class_offset[key >> 16] : class_offset[0];           // per-image offset scale
-        off = __fmul_rn((float)(int)(batched ? (key & 0xffffu) : key), scale);
-        x[0] = __fadd_rn(x[0], off);
-        x[1] = __fadd_rn(x[1], off);
+                                  int batched, int n_batches,
+                                  float4* p0, float4* p1, float4* p2r, float4* p2c, float* raw, unsigned* alive32) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    bool ok = false;
+    if (p < K) {
+        const int idx = ord_rank[pos_rank[p]];
+        const float* b = boxes + (int64_t)idx * stride;
+        float x[5] = { b[0], b[1], b[2], b[3], b[4] };
+        float off = 0.0f;
+        ok = true;
+        if (batched && (pos_label[p] >> 16) >= (unsigned)n_batches) ok = false;    // image id out of range: takes no part
+        if (class_offset != nullptr && has_labels) {
+            const unsigned key = pos_label[p];
+            const float scale = batched ? class_offset[min(key >> 16, (unsigned)n_batches - 1u)] : class_offset[0];   // per-image offset scale
+            off = __fmul_rn((float)(int)(batched ? (key & 0xffffu) : key), scale);
+            x[0] = __fadd_rn(x[0], off);
+            x[1] = __fadd_rn(x[1], off);
+        }
+        BoxP0 a; BoxP1 c;
+        emu::prep_box_strict(x, variant, a, c);
+        p0[p] = make_float4(a.cx, a.cy, a.r, a.area);
+        p1[p] = make_float4(c.c, c.s, c.hw, c.hh);
+#pragma unroll
+        for (int k = 0; k < 5; k++) raw[(int64_t)p * 5 + k] = x[k];
+        if (drop_small && fminf(x[2], x[3]) < 0.001f) ok = false;           // nms_rotated_wrapper.py:40-46
+        // expanded circumradius test planes, in class-local coordinates (the class offset is removed again so that the
+        // squares stay small): row form {-2X, -2Y, -2r, |X|^2 - r^2 - slack}, column form {X, Y, r, |X|^2 - r^2 - slack};
+        // boxes that take no part are pushed to +inf (never pass)
+        const float X = a.cx - off, Y = a.cy - off;
+        const float q = X * X + Y * Y, rr = a.r * a.r;
+        const float kk = ok ? (q - rr) - NMS_SLACK * (q + rr) - 1e-6f : 3.0e38f;
+        // row constants stored twice: two 16-byte halves that load straight into aligned register pairs (packed f32x2 stage 1)
+        p2r[2 * (size_t)p] = make_float4(-2.0f * X, -2.0f * X, -2.0f * Y, -2.0f * Y);
+        p2r[2 * (size_t)p + 1] = make_float4(-2.0f * a.r, -2.0f * a.r, kk, kk);
+        p2c[p] = make_float4(X, Y, a.r, kk);
     }
-    BoxP0 a; BoxP1 c;
-    emu::prep_box_strict(x, variant, a, c);
-    p0[p] = a; p1[p] = c;
-#pragma unroll
-    for (int k = 0; k < 5; k++) raw[(int64_t)p * 5 + k] = x[k];
-    const bool ok = !(drop_small && fminf(x[2], x[3]) < 0.001f);      // nms_rotated_wrapper.py:40-46
-    valid[p] = ok ? 1 : 0;
-    // expanded circumradius test planes, in class-local coordinates (the class offset is removed again so that the
-    // squares stay small): row form {-2X, -2Y, -2r, |X|^2 - r^2 - slack}, column form {X, Y, r, |X|^2 - r^2 - slack};
-    // boxes that take no part are pushed to +inf (never pass)
-    const float X = a.cx - off, Y = a.cy - off;
-    const float q = X * X + Y * Y, rr = a.r * a.r;
-    const float kk = ok ? (q - rr) - NMS_SLACK * (q + rr) - 1e-6f : 3.0e38f;
-    // row constants stored twice: two 16-byte halves that load straight into aligned register pairs (packed f32x2 stage 1)
-    p2r[2 * p] = make_float4(-2.0f * X, -2.0f * X, -2.0f * Y, -2.0f * Y);
-    p2r[2 * p + 1] = make_float4(-2.0f * a.r, -2.0f * a.r, kk, kk);
-    p2c[p] = make_float4(X, Y, a.r, kk);
+    const unsigned bal = __ballot_sync(0xffffffffu, ok);
+    if ((threadIdx.x & 31) == 0 && p < K) alive32[p >> 5] = bal;
 }
 
-// per 64-row block: last column block its rows can interact with (end of the class segment of its last row)
-__global__ void nms_blocks_kernel(const unsigned* __restrict__ pos_label, int K, int nblk,
-                                  int* blk_end, long long* nw, long long* ng) {
-    int rb = blockIdx.x * blockDim.x + threadIdx.x;
-    if (rb > nblk) return;
-    if (rb == nblk) { nw[rb] = 0; ng[rb] = 0; return; }
-    int last = min(K, rb * 64 + 64) - 1;
-    unsigned L = pos_label[last];
-    int lo = last, hi = K;                          // first p > last with label != L (labels sorted ascending)
-    while (hi - lo > 1) {
-        int mid = (lo + hi) >> 1;
-        if (pos_label[mid] == L) lo = mid; else hi = mid;
+// polygons: corners into the two 16-byte planes, bounding box into the column plane
+__global__ void poly_gather_kernel(const float* __restrict__ polys, int64_t stride, const int* __restrict__ ord_rank,
+                                   const int* __restrict__ pos_rank, int K, float4* p0, float4* p1, float4* p2c, unsigned* alive32) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < K) {
+        const float* s = polys + (int64_t)ord_rank[pos_rank[p]] * stride;
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = s[k];
+        p0[p] = make_float4(v[0], v[1], v[2], v[3]);
+        p1[p] = make_float4(v[4], v[5], v[6], v[7]);
+        const float x0 = fminf(fminf(v[0], v[2]), fminf(v[4], v[6])), x1 = fmaxf(fmaxf(v[0], v[2]), fmaxf(v[4], v[6]));
+        const float y0 = fminf(fminf(v[1], v[3]), fminf(v[5], v[7])), y1 = fmaxf(fmaxf(v[1], v[3]), fmaxf(v[5], v[7]));
+        p2c[p] = make_float4(x0, y0, x1, y1);
     }
-    int be = lo >> 6;
-    blk_end[rb] = be;
-    long long w = be - rb + 1;
-    nw[rb] = w * 64;                                // words of this row block (64 rows x w words)
-    ng[rb] = (w + NMS_G - 1) / NMS_G;               // items of this row block
-}
-
-__global__ void nms_segments_kernel(const unsigned* __restrict__ pos_label, int K, int* seg_list, int* counters) {
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= K) return;
-    if (p == 0 || pos_label[p] != pos_label[p - 1]) seg_list[atomicAdd(&counters[0], 1)] = p;
-}
-
-__device__ __noinline__ float nms_emu_call(const float* b1, const float* b2, int variant) {
-    float x[5] = { b1[0], b1[1], b1[2], b1[3], b1[4] };
-    float y[5] = { b2[0], b2[1], b2[2], b2[3], b2[4] };
-    return emu::pair(x, y, variant, MODE_IOU);
-}
-
-struct MaskArgs {
-    const BoxP0* p0; const BoxP1* p1; const float4* p2r; const float4* p2c; const float* raw; const unsigned char* valid;
-    const unsigned* label; unsigned long long* ticket;
-    const int* blk_end; const long long* row_base; const long long* item_base;
-    unsigned long long* mask;
-    int K, nblk, variant, inclusive;
-    float thr, tau, margin;
-};
-
-__device__ __forceinline__ float4 nldg4(const void* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
-
-// packed f32x2 arithmetic (FFMA2 / FADD2 on sm_100): low half = element 0
-__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
-    return ((unsigned long long)__float_as_uint(hi) << 32) | __float_as_uint(lo);
-}
-__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
-    unsigned long long r;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-    return r;
-}
-__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
-    unsigned long long r;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-
-__global__ void __launch_bounds__(NMS_THREADS, 3) nms_mask_kernel(const MaskArgs A) {
-    // per-warp: q1 circumradius survivors -> q2 separating-axis survivors -> (q3 near-threshold / degenerate pairs);
-    // q1/q2 entries are item-relative (row << 7 | col); all queues are flushed at item end (bits land in `sm`)
-    __shared__ unsigned short q1_all[NMS_WARPS][NMS_Q1CAP];
-    __shared__ unsigned short q2_all[NMS_WARPS][64];
-    __shared__ uint2 q3_all[NMS_WARPS][96];          // (row, col) positions of pairs left to the reference restatement; persists across items
-    __shared__ unsigned long long sm_all[NMS_WARPS][64 * NMS_G];
-    const unsigned warp = threadIdx.x >> 5, lane = lane_id(), lt = lanemask_lt();
-    unsigned short* q1 = q1_all[warp];
-    unsigned short* q2 = q2_all[warp];
-    uint2* q3 = q3_all[warp];
-    unsigned long long* sm = sm_all[warp];
-    // When there are fewer items than warps in the grid (small K: a detection head's per-image call), an item's 64 rows
-    // are split over up to 8 warps: the kernel is then bound by ONE warp's serial work (its SAT / area / restatement
-    // batches), not by throughput.
-    const long long base_items = A.item_base[A.nblk];
-    int split = 1;
-    while (split < 8 && base_items * (split * 2) <= (long long)gridDim.x * NMS_WARPS) split *= 2;
-    const long long total = base_items * split;
-    const int rows_per_sub = 64 / split;
-    int c1 = 0, c2 = 0, c3 = 0;
-    int i0 = 0, j0 = 0;
-
-    int rb = -1, cb0 = 0, ncb = 0, r_lo = 0, r_hi = 64;      // r_lo .. r_hi: this warp's rows of the item in flight
-    auto decide = [&](int il, int jl, float r) {
-        const bool sup = A.inclusive ? (r >= A.thr) : (r > A.thr);
-        if (sup) atomicOr(&sm[il * NMS_G + (jl >> 6)], 1ull << (jl & 63));
-    };
-    // Pairs decided by the reference's own algorithm.  Entries of the item in flight go to its shared-memory words;
-    // entries of finished items (their words are already in global memory) are OR-ed into the global mask.
-    auto drain_emu = [&](int nb) {
-        __syncwarp();
-        if ((int)lane < nb) {
-            const uint2 e = q3[c3 - nb + lane];
-            const int i = (int)e.x, j = (int)e.y;
-            const float r = nms_emu_call(A.raw + (int64_t)i * 5, A.raw + (int64_t)j * 5, A.variant);
-            const bool sup = A.inclusive ? (r >= A.thr) : (r > A.thr);
-            if (sup) {
-                const int rbi = i >> 6, cbj = j >> 6;
-                if (rbi == rb && cbj >= cb0 && cbj < cb0 + ncb && (i & 63) >= r_lo && (i & 63) < r_hi) {
-                    atomicOr(&sm[(i & 63) * NMS_G + (cbj - cb0)], 1ull << (j & 63));
-                } else {
-                    const long long base = A.row_base[rbi];
-                    const int nwr = A.blk_end[rbi] - rbi + 1;
-                    atomicOr(A.mask + base + (long long)(i & 63) * nwr + (cbj - rbi), 1ull << (j & 63));
-                }
-            }
-        }
-        __syncwarp();
-        c3 -= nb;
-    };
-    auto drain_area = [&](int nb) {
-        __syncwarp();
-        bool emu = false;
-        unsigned e = 0;
-        if ((int)lane < nb) {
-            e = q2[c2 - nb + lane];
-            const int il = (int)(e >> 7), jl = (int)(e & 127u);
-            const int i = i0 + il, j = j0 + jl;
-            float4 a0 = nldg4(A.p0 + i), a1 = nldg4(A.p1 + i), b0 = nldg4(A.p0 + j), b1 = nldg4(A.p1 + j);
-            BoxP0 A0 = { a0.x, a0.y, a0.z, a0.w }; BoxP1 A1 = { a1.x, a1.y, a1.z, a1.w };
-            BoxP0 B0 = { b0.x, b0.y, b0.z, b0.w }; BoxP1 B1 = { b1.x, b1.y, b1.z, b1.w };
-            bool risk;
-            const float r = pair_overlap(A0, A1, B0, B1, A.variant, MODE_IOU, A.tau, risk);
-            emu = A.tau > 0.0f && (risk || fabsf(r - A.thr) < A.margin);
-            if (!emu) decide(il, jl, r);
-        }
-        __syncwarp();
-        c2 -= nb;
-        const unsigned bal = __ballot_sync(0xffffffffu, emu);
-        if (bal) {
-            if (emu) q3[c3 + __popc(bal & lt)] = make_uint2((unsigned)(i0 + (int)(e >> 7)), (unsigned)(j0 + (int)(e & 127u)));
-            c3 += __popc(bal);
-            if (c3 >= 64) drain_emu(32);
-        }
-    };
-    auto drain_sat = [&](int nb) {
-        __syncwarp();
-        bool ok = false;
-        unsigned e = 0;
-        if ((int)lane < nb) {
-            e = q1[c1 - nb + lane];
-            const int i = i0 + (int)(e >> 7), j = j0 + (int)(e & 127u);
-            float4 a0 = nldg4(A.p0 + i), a1 = nldg4(A.p1 + i), b0 = nldg4(A.p0 + j), b1 = nldg4(A.p1 + j);
-            BoxP0 A0 = { a0.x, a0.y, a0.z, a0.w }; BoxP1 A1 = { a1.x, a1.y, a1.z, a1.w };
-            BoxP0 B0 = { b0.x, b0.y, b0.z, b0.w }; BoxP1 B1 = { b1.x, b1.y, b1.z, b1.w };
-            ok = pair_sat(A0, A1, B0, B1);
-        }
-        __syncwarp();
-        c1 -= nb;
-        const unsigned bal = __ballot_sync(0xffffffffu, ok);
-        if (ok) q2[c2 + __popc(bal & lt)] = (unsigned short)e;
-        c2 += __popc(bal);
-        if (c2 >= 32) drain_area(32);
-    };
-
-    while (true) {
-        long long item = 0;
-        if (lane == 0) item = (long long)atomicAdd(A.ticket, 1ull);
-        item = __shfl_sync(0xffffffffu, item, 0);
-        if (item >= total) break;
-        const int sub = (int)(item % split);
-        item /= split;
-        // row block of this item: last rb with item_base[rb] <= item
-        int lo = 0, hi = A.nblk;
-        while (hi - lo > 1) {
-            int mid = (lo + hi) >> 1;
-            if (A.item_base[mid] <= item) lo = mid; else hi = mid;
-        }
-        rb = lo;
-        r_lo = sub * rows_per_sub; r_hi = r_lo + rows_per_sub;
-        const int g = (int)(item - A.item_base[rb]);
-        const int be = A.blk_end[rb];
-        cb0 = rb + g * NMS_G;                                 // first column block of the item
-        ncb = min(NMS_G, be - cb0 + 1);                       // valid column blocks
-        i0 = rb * 64;
-        j0 = cb0 * 64;
-        const int i1 = min(A.K, i0 + r_hi);
-        const int j1 = min(A.K, j0 + ncb * 64);
-        const int jb = j0 + (int)lane * NMS_CPL;
-
-        for (int k = lane; k < 64 * NMS_G; k += 32) sm[k] = 0ull;
-        float cx[NMS_CPL], cy[NMS_CPL], cr[NMS_CPL], ck[NMS_CPL];
-        unsigned cl[NMS_CPL];
-#pragma unroll
-        for (int k = 0; k < NMS_CPL; k++) {
-            if (jb + k < j1) {
-                const float4 b = nldg4(A.p2c + jb + k);
-                cx[k] = b.x; cy[k] = b.y; cr[k] = b.z; ck[k] = b.w;
-                cl[k] = A.label[jb + k];
-            } else {
-                cx[k] = 0.0f; cy[k] = 0.0f; cr[k] = 0.0f; ck[k] = 3.0e38f; cl[k] = 0xffffffffu;
-            }
-        }
-        unsigned long long CX[NMS_CPL / 2], CY[NMS_CPL / 2], CR[NMS_CPL / 2], CK[NMS_CPL / 2];     // two columns per register pair
-#pragma unroll
-        for (int h = 0; h < NMS_CPL / 2; h++) {
-            CX[h] = pack2(cx[2 * h], cx[2 * h + 1]); CY[h] = pack2(cy[2 * h], cy[2 * h + 1]);
-            CR[h] = pack2(cr[2 * h], cr[2 * h + 1]); CK[h] = pack2(ck[2 * h], ck[2 * h + 1]);
-        }
-        // interior items (one label throughout, all columns after all rows) need no per-pair label / order test
-        const bool interior = (cb0 > rb) && (A.label[i0] == A.label[j1 - 1]);
-        __syncwarp();
-
-        for (int ig = i0 + r_lo; ig < i1; ig += NMS_RG) {
-            const int nr = min(NMS_RG, i1 - ig);
-            unsigned m = 0;
-#pragma unroll
-            for (int r = 0; r < NMS_RG; r++) {
-                if (r < nr) {
-                    // two columns per instruction (FFMA2 / FADD2): the kernel is issue-bound, and the packed form does the same
-                    // operations in the same order as the scalar one
-                    const ulonglong2 ra = __ldg(reinterpret_cast<const ulonglong2*>(A.p2r + 2 * (ig + r)));       // {-2X, -2X}, {-2Y, -2Y}
-                    const ulonglong2 rb = __ldg(reinterpret_cast<const ulonglong2*>(A.p2r + 2 * (ig + r) + 1));   // {-2r, -2r}, {k, k}
-#pragma unroll
-                    for (int h = 0; h < NMS_CPL / 2; h++) {
-                        unsigned long long t = add2(CK[h], rb.y);
-                        t = fma2(ra.x, CX[h], t);
-                        t = fma2(ra.y, CY[h], t);
-                        t = fma2(rb.x, CR[h], t);
-                        m = __funnelshift_l((unsigned)t, m, 1);
-                        m = __funnelshift_l((unsigned)(t >> 32), m, 1);
-                    }
-                }
-            }
-            if (!interior && m != 0) {      // boundary items only (diagonal block / class boundary): label and order per pair
-                unsigned allow = 0;
-                for (int r = 0; r < nr; r++) {
-                    const unsigned la = A.label[ig + r];
-#pragma unroll
-                    for (int k = 0; k < NMS_CPL; k++)
-                        allow = (allow << 1) | ((cl[k] == la && jb + k > ig + r) ? 1u : 0u);
-                }
-                m &= allow;
-            }
-            const int cnt = __popc(m);
-            int incl = cnt;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, incl, d);
-                if ((int)lane >= d) incl += t;
-            }
-            const int tot = __shfl_sync(0xffffffffu, incl, 31);
-            if (tot) {
-                int pos = c1 + incl - cnt;
-                const int nbits = nr * NMS_CPL;
-                const unsigned rowbase = (unsigned)(ig - i0);
-                while (m) {
-                    const int b = 31 - __clz(m);
-                    m ^= 1u << b;
-                    const unsigned idx = (unsigned)(nbits - 1 - b);
-                    q1[pos++] = (unsigned short)(((rowbase + (idx >> 2)) << 7) | (lane * NMS_CPL + (idx & 3u)));
-                }
-                c1 += tot;
-                while (c1 >= 32) drain_sat(32);
-            }
-        }
-        if (c1 > 0) drain_sat(c1);
-        if (c2 > 0) drain_area(c2);
-        __syncwarp();
-        // write the item's words: row r of block rb holds (be - rb + 1) words, word index = cb - rb
-        const long long base = A.row_base[rb];
-        const int nwr = be - rb + 1;
-        for (int k = r_lo * NMS_G + lane; k < r_hi * NMS_G; k += 32) {
-            const int il = k / NMS_G, c = k % NMS_G;
-            if (c < ncb) A.mask[base + (long long)il * nwr + (cb0 - rb + c)] = sm[k];
-        }
-        __syncwarp();
-        rb = -1;                               // the item's words are in global memory now
-        while (c3 >= 32) drain_emu(32);
-    }
-    rb = -1;
-    if (c3 > 0) drain_emu(c3);
-}
-
-struct ScanArgs {
-    const unsigned long long* mask; const unsigned char* valid; const unsigned* label;
-    const int* blk_end; const long long* row_base; const int* seg_list; const int* counters;
-    const int* pos_rank; const int* ord_rank;
-    int* keep_p;                                       // per position: 1 = kept
-    int K, remv_cap;
-};
-
-// Greedy scan, one CTA per class segment, software-pipelined in SUPERBLOCKS of 4 x 64 rows so that one barrier and one
-// global-memory round trip are paid per 256 rows and none of it sits on the serial chain.  For superblock S (column
-// window = its own 4 blocks + the next 4):
-//   warp 0      : for each of the 4 blocks: chain over the 64 diagonal words (shared memory) with ffs jumps -> kept;
-//                 lanes 0..7 OR the kept rows' window words into removed[] so the next block / superblock sees them;
-//   warps 1..7  : prefetch the 256 x 8 window words + valid bits of superblock S+1 into the other buffer, apply the
-//                 kept rows of superblock S-1 to removed[] beyond its window (global mask words, 4 loads in flight),
-//                 and write the keep flags of S-1.
-// removed[] lives in shared memory and is updated with atomicOr.
-constexpr int NMS_SB = 4;                       // blocks per superblock
-constexpr int NMS_WIN = 2 * NMS_SB;             // window words per row
-constexpr int SCAN_THREADS = 512;               // 1 resolver warp + 15 warps of prefetch / apply work
-
-__global__ void __launch_bounds__(SCAN_THREADS) nms_scan_kernel(const ScanArgs A) {
-    extern __shared__ unsigned long long remv[];          // remv_cap words
-    __shared__ unsigned long long Wd[2][64 * NMS_SB][NMS_WIN];
-    __shared__ unsigned long long vbits[2][NMS_SB], kept_s[2][NMS_SB];
-    __shared__ long long mbase[4][NMS_SB];                // row_base / words-per-row, ring over superblocks S-1 .. S+2
-    __shared__ int mnwr[4][NMS_SB];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int nseg = A.counters[0];
-    for (int s = blockIdx.x; s < nseg; s += gridDim.x) {
-        const int ps = A.seg_list[s];
-        const unsigned L = A.label[ps];
-        int lo = ps, hi = A.K;
-        while (hi - lo > 1) {
-            int mid = (lo + hi) >> 1;
-            if (A.label[mid] == L) lo = mid; else hi = mid;
-        }
-        const int pe = lo + 1;
-        const int bf = ps >> 6, bl = (pe - 1) >> 6;
-        const int nb = bl - bf + 1;
-        const int nsb = (nb + NMS_SB - 1) / NMS_SB;
-        __syncthreads();                                   // previous segment fully done with shared memory
-        for (int w = tid; w < nb; w += SCAN_THREADS) remv[w] = 0ull;
-        auto load_meta = [&](int S) {                      // one thread per block of superblock S
-            const int q = tid & (NMS_SB - 1), b = bf + S * NMS_SB + q;
-            if (b <= bl) { mbase[S & 3][q] = A.row_base[b]; mnwr[S & 3][q] = A.blk_end[b] - b + 1; }
-        };
-        if (tid < NMS_SB) { load_meta(0); kept_s[0][tid] = 0ull; kept_s[1][tid] = 0ull; }
-        else if (tid < 2 * NMS_SB && nsb > 1) load_meta(1);
-        __syncthreads();
-
-        // window words + valid bits of superblock S into buffer `buf`.  `nt` threads (rank `u`) share the 256 x 8 words as
-        // flattened (row, word) pairs so that every thread has ~9 independent loads in flight; the valid bits are ballots
-        // over whole warps (callers pass warp-aligned thread ranges).
-        auto prefetch = [&](int S, int buf, int u, int nt) {
-            const int b0 = bf + S * NMS_SB;
-            constexpr int PAIRS = 64 * NMS_SB * NMS_WIN;
-            constexpr int PER = (PAIRS + (SCAN_THREADS - 32) - 1) / (SCAN_THREADS - 32);
-            unsigned long long v[PER];
-#pragma unroll
-            for (int j = 0; j < PER; j++) {
-                const int idx = u + j * nt;
-                unsigned long long x = 0ull;
-                if (idx < PAIRS) {
-                    const int r = idx >> 3, k = idx & (NMS_WIN - 1), q = r >> 6, t = r & 63, b = b0 + q, col = b0 + k;
-                    const int p = b * 64 + t;
-                    if (b <= bl && col >= b && col <= bl && p >= ps && p < pe)
-                        x = A.mask[mbase[S & 3][q] + (long long)t * mnwr[S & 3][q] + (col - b)];
-                }
-                v[j] = x;
-            }
-            for (int r0 = 0; r0 < 64 * NMS_SB; r0 += nt) {             // valid bits (rows of other segments / dropped boxes = 0)
-                const int r = r0 + u;
-                bool ok = false;
-                if (r < 64 * NMS_SB) {
-                    const int p = (b0 + (r >> 6)) * 64 + (r & 63);
-                    ok = (b0 + (r >> 6) <= bl) && p >= ps && p < pe && A.valid[p];
-                }
-                const unsigned bal = __ballot_sync(0xffffffffu, ok);
-                if (r < 64 * NMS_SB && (r & 31) == 0) reinterpret_cast<unsigned*>(&vbits[buf][r >> 6])[(r >> 5) & 1] = bal;
-            }
-#pragma unroll
-            for (int j = 0; j < PER; j++) {
-                const int idx = u + j * nt;
-                if (idx < PAIRS) Wd[buf][idx >> 3][idx & (NMS_WIN - 1)] = v[j];
-            }
-        };
-        prefetch(0, 0, tid, SCAN_THREADS);
-
-        for (int S = 0; S < nsb; S++) {
-            const int buf = S & 1;
-            const int b0 = bf + S * NMS_SB;
-            __syncthreads();
-            if (warp == 0) {
-                for (int q = 0; q < NMS_SB; q++) {
-                    const int b = b0 + q;
-                    if (b > bl) break;
-                    const unsigned long long vb = vbits[buf][q];
-                    unsigned long long cur = remv[b - bf], kept = 0ull, acc = 0ull;
-                    unsigned long long avail = vb & ~cur;
-                    while (avail) {                           // warp-uniform; one kept row per trip
-                        const int t = __ffsll((long long)avail) - 1;
-                        kept |= 1ull << t;
-                        cur |= Wd[buf][q * 64 + t][q];
-                        if (lane < NMS_WIN) acc |= Wd[buf][q * 64 + t][lane];
-                        const unsigned long long above = (t == 63) ? 0ull : (~0ull << (t + 1));
-                        avail = vb & ~cur & above;
-                    }
-                    if (lane < NMS_WIN && lane > q && b0 + lane <= bl && acc) atomicOr(&remv[b0 + lane - bf], acc);
-                    if (lane == 0) kept_s[buf][q] = kept;
-                    __syncwarp();
-                }
-            } else {
-                const int u = tid - 32;                        // 0 .. SCAN_THREADS - 33
-                const int nw_threads = SCAN_THREADS - 32;
-                if (S + 1 < nsb) prefetch(S + 1, buf ^ 1, u, nw_threads);
-                if (u < NMS_SB && S + 2 < nsb) load_meta(S + 2);
-                if (S > 0) {
-                    const int pb0 = b0 - NMS_SB;                 // previous superblock
-                    for (int r = u; r < 64 * NMS_SB; r += nw_threads) {      // its keep bits, by position (store only)
-                        const int q = r >> 6, t = r & 63, p = (pb0 + q) * 64 + t;
-                        if (pb0 + q <= bl && p >= ps && p < pe) A.keep_p[p] = (int)((kept_s[buf ^ 1][q] >> t) & 1ull);
-                    }
-                    // its kept rows -> removed[] beyond its window (columns pb0 + NMS_WIN .. bl): the first four kept rows
-                    // of each of the four blocks are fetched together (16 independent loads), the rest in a tail loop
-                    const int first = pb0 + NMS_WIN;
-                    unsigned long long kq[NMS_SB];
-#pragma unroll
-                    for (int q = 0; q < NMS_SB; q++) kq[q] = (pb0 + q <= bl) ? kept_s[buf ^ 1][q] : 0ull;
-                    if (kq[0] | kq[1] | kq[2] | kq[3]) {
-                        for (int col = first + u; col <= bl; col += nw_threads) {
-                            unsigned long long kk[NMS_SB], acc = 0ull;
-#pragma unroll
-                            for (int q = 0; q < NMS_SB; q++) kk[q] = kq[q];
-                            while (kk[0] | kk[1] | kk[2] | kk[3]) {                 // 16 independent loads per trip
-                                unsigned long long v[NMS_SB * 4];
-#pragma unroll
-                                for (int q = 0; q < NMS_SB; q++) {
-                                    const unsigned long long* cp = A.mask + mbase[(S - 1) & 3][q] + (col - (pb0 + q));
-                                    const int nwr = mnwr[(S - 1) & 3][q];
-#pragma unroll
-                                    for (int j = 0; j < 4; j++) {
-                                        const int t = kk[q] ? __ffsll((long long)kk[q]) - 1 : -1;
-                                        kk[q] &= kk[q] - 1;
-                                        v[q * 4 + j] = (t >= 0) ? cp[(long long)t * nwr] : 0ull;
-                                    }
-                                }
-#pragma unroll
-                                for (int j = 0; j < NMS_SB * 4; j++) acc |= v[j];
-                            }
-                            if (acc) atomicOr(&remv[col - bf], acc);
-                        }
-                    }
-                }
-            }
-        }
-        __syncthreads();
-        {   // keep bits of the segment's last superblock
-            const int S = nsb - 1, pb0 = bf + S * NMS_SB;
-            for (int r = tid; r < 64 * NMS_SB; r += SCAN_THREADS) {
-                const int q = r >> 6, t = r & 63, p = (pb0 + q) * 64 + t;
-                if (pb0 + q <= bl && p >= ps && p < pe) A.keep_p[p] = (int)((kept_s[S & 1][q] >> t) & 1ull);
-            }
-        }
-    }
+    const unsigned bal = __ballot_sync(0xffffffffu, p < K);
+    if ((threadIdx.x & 31) == 0 && p < K) alive32[p >> 5] = bal;
 }
 
 // keep bits by position -> flags in output-slot order (rank order, or original index for R3G_NMS_ORDER_INDEX)
@@ -606,14 +192,17 @@ __global__ void nms_flags_kernel(const int* __restrict__ keep_p, const int* __re
 }
 
 __global__ void nms_emit_kernel(const int* __restrict__ flag, const int* __restrict__ pref, const int* __restrict__ ord_rank,
-                                const int64_t* __restrict__ batch_ids, int K, int order_index, int64_t* keep_out,
+                                const int64_t* __restrict__ batch_ids, int n_batches, int K, int order_index, int64_t* keep_out,
                                 unsigned long long* num_keep) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= K) return;
     if (flag[s]) {
         const int idx = order_index ? s : ord_rank[s];
         keep_out[pref[s]] = (int64_t)idx;
-        if (batch_ids) atomicAdd(num_keep + batch_ids[idx], 1ull);       // per-image counts (zeroed by the launcher)
+        if (batch_ids) {                                                  // per-image counts (zeroed by the launcher)
+            const int64_t b = batch_ids[idx];
+            if (b >= 0 && b < n_batches) atomicAdd(num_keep + b, 1ull);
+        }
     }
     if (!batch_ids && s == K - 1) *num_keep = (unsigned long long)(pref[s] + flag[s]);
 }
@@ -623,8 +212,7 @@ __global__ void nms_emit_kernel(const int* __restrict__ flag, const int* __restr
 //   rank(i) = #{ j : (image_j, score_key_j, j) < (image_i, score_key_i, i) }           (the stable score order)
 //   pos(i)  = #{ j : (segment_j, score_key_j, j) < (segment_i, score_key_i, i) }       (segment-major position order)
 // O(K^2) compares spread over (K/256) x slices CTAs — a few microseconds — and exactly the permutations the stable
-// radix sorts produce.  The block structure and the final compaction each become one single-CTA kernel.
-constexpr int NMS_SMALL_K = 16384;
+// radix sorts produce.  The final compaction becomes one single-CTA kernel.
 
 __device__ __forceinline__ unsigned seg_key_of(const int64_t* labels, const int64_t* batch_ids, int i) {
     unsigned key = labels ? (unsigned)labels[i] : 0u;
@@ -705,41 +293,10 @@ __global__ void nms_rank_scatter_kernel(const int64_t* __restrict__ labels, cons
     pos_label[p] = seg_key_of(labels, batch_ids, i);
 }
 
-// nms_blocks_kernel + the two exclusive sums + nms_segments_kernel in one CTA (nblk + 1 <= 1024)
-__global__ void __launch_bounds__(1024) nms_structure_small_kernel(const unsigned* __restrict__ pos_label, int K, int nblk,
-                                                                   int* blk_end, long long* row_base, long long* item_base,
-                                                                   int* seg_list, int* counters) {
-    typedef cub::BlockScan<long long, 1024> Scan;
-    __shared__ typename Scan::TempStorage tmp;
-    const int rb = threadIdx.x;
-    long long nw = 0, ng = 0;
-    if (rb < nblk) {
-        const int last = min(K, rb * 64 + 64) - 1;
-        const unsigned L = pos_label[last];
-        int lo = last, hi = K;
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (pos_label[mid] == L) lo = mid; else hi = mid;
-        }
-        const int be = lo >> 6;
-        blk_end[rb] = be;
-        const long long w = be - rb + 1;
-        nw = w * 64;
-        ng = (w + NMS_G - 1) / NMS_G;
-    }
-    long long a, b;
-    Scan(tmp).ExclusiveSum(nw, a);
-    __syncthreads();
-    Scan(tmp).ExclusiveSum(ng, b);
-    if (rb <= nblk) { row_base[rb] = a; item_base[rb] = b; }
-    for (int p = threadIdx.x; p < K; p += 1024)
-        if (p == 0 || pos_label[p] != pos_label[p - 1]) seg_list[atomicAdd(&counters[0], 1)] = p;
-}
-
 // nms_flags_kernel + exclusive sum + nms_emit_kernel in one CTA
 __global__ void __launch_bounds__(1024) nms_finish_small_kernel(const int* __restrict__ keep_p, const int* __restrict__ pos_rank,
                                                                 const int* __restrict__ ord_rank, const int64_t* __restrict__ batch_ids,
-                                                                int K, int order_index, int* __restrict__ flag,
+                                                                int n_batches, int K, int order_index, int* __restrict__ flag,
                                                                 int64_t* __restrict__ keep_out, unsigned long long* num_keep) {
     typedef cub::BlockScan<int, 1024> Scan;
     __shared__ typename Scan::TempStorage tmp;
@@ -759,7 +316,10 @@ __global__ void __launch_bounds__(1024) nms_finish_small_kernel(const int* __res
         if (f) {
             const int idx = order_index ? s : ord_rank[s];
             keep_out[base + pre] = (int64_t)idx;
-            if (batch_ids) atomicAdd(num_keep + batch_ids[idx], 1ull);
+            if (batch_ids) {
+                const int64_t b = batch_ids[idx];
+                if (b >= 0 && b < n_batches) atomicAdd(num_keep + b, 1ull);
+            }
         }
         __syncthreads();
         if (threadIdx.x == 0) carry = base + total;
@@ -821,64 +381,70 @@ static int nms_order_stage(NmsWs& w, const float* scores, const int64_t* labels,
     return R3G_OK;
 }
 
-static int nms_structure_stage(NmsWs& w, int Ki, int nblk, cudaStream_t st, bool small) {
-    const int tpb = 256, gK = (Ki + tpb - 1) / tpb;
-    size_t tb = 0;
-    if (small) {
-        nms_structure_small_kernel<<<1, 1024, 0, st>>>(w.pos_label, Ki, nblk, w.blk_end, w.row_base, w.item_base, w.seg_list, w.counters);
-        R3G_LAUNCH_OK("nms_structure_small_kernel");
-        return R3G_OK;
-    }
-    // 4. block / segment structure
-    nms_blocks_kernel<<<(nblk + 1 + tpb - 1) / tpb, tpb, 0, st>>>(w.pos_label, Ki, nblk, w.blk_end, w.nw, w.ng);
-    tb = w.cub_bytes;
-    R3G_CUDA_OK(cub::DeviceScan::ExclusiveSum(w.cub_tmp, tb, w.nw, w.row_base, nblk + 1, st));
-    tb = w.cub_bytes;
-    R3G_CUDA_OK(cub::DeviceScan::ExclusiveSum(w.cub_tmp, tb, w.ng, w.item_base, nblk + 1, st));
-    nms_segments_kernel<<<gK, tpb, 0, st>>>(w.pos_label, Ki, w.seg_list, w.counters);
-    R3G_LAUNCH_OK("nms structure kernels");
-
+// state the rounds kernel starts from: control block, keep flags and the tail of the alive vector zero (the gather kernels
+// write the alive words that hold candidates)
+static int nms_reset_stage(NmsWs& w, int Ki, cudaStream_t st) {
+    R3G_CUDA_OK(cudaMemsetAsync(w.ctrl, 0, 512, st));
+    R3G_CUDA_OK(cudaMemsetAsync(w.keep_p, 0, 4 * (size_t)Ki, st));
+    R3G_CUDA_OK(cudaMemsetAsync(w.alive, 0, w.alive_bytes, st));
     return R3G_OK;
 }
 
-static int nms_finish_stage(NmsWs& w, int Ki, int nblk, const int64_t* labels, const int64_t* batch_ids, int flags, int64_t K, bool small,
+static int nms_env_int(const char* name, int dflt, int lo, int hi) {
+    const char* s = getenv(name);
+    if (!s || !*s) return dflt;
+    const int v = atoi(s);
+    return v < lo ? lo : (v > hi ? hi : v);
+}
+
+// greedy selection in rounds: one cooperative launch (the grid barrier needs every CTA resident)
+template <int GEOM>
+static int nms_rounds_stage(NmsWs& w, int Ki, int variant, int inclusive, float thr, float tau, float margin, int prefilter,
+                            cudaStream_t st) {
+    static int occ_of[64] = {0};
+    int& occ = occ_of[current_device_slot()];
+    if (occ == 0) {
+        R3G_CUDA_OK(cudaFuncSetAttribute(rn::nms_rounds_kernel<GEOM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rn::SMEM_BYTES));
+        int o = 0;
+        R3G_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, rn::nms_rounds_kernel<GEOM>, rn::THREADS, rn::SMEM_BYTES));
+        if (o < 1) { set_error("nms_rounds_kernel does not fit on this device"); return R3G_ERR_CUDA; }
+        occ = o;
+    }
+    static const int chunk_env = nms_env_int("R3G_NMS_CHUNK", rn::B_MAX, 64, rn::B_MAX) / 64 * 64;     // tuning knobs
+    static const int grid_env = nms_env_int("R3G_NMS_GRID", 0, 0, 1 << 20);
+    rn::Args a;
+    a.p0 = w.p0; a.p1 = w.p1; a.p2r = w.p2r; a.p2c = w.p2c; a.raw = w.raw; a.label = w.pos_label; a.K = Ki;
+    a.alive = w.alive; a.seg_cur = w.seg_cur; a.seg_pe = w.seg_pe; a.act = w.act; a.ent = w.ent; a.spos = w.spos; a.klist = w.klist;
+    a.ownerB = w.ownerB; a.ownerD = w.ownerD; a.mask = w.mask; a.keep_p = w.keep_p;
+    a.ctrl = reinterpret_cast<rn::Ctrl*>(w.ctrl); a.bar = reinterpret_cast<unsigned*>(w.ctrl + 128);
+    a.B = chunk_env; a.split = nms_split_of(Ki);
+    a.variant = variant; a.inclusive = inclusive; a.prefilter = prefilter; a.thr = thr; a.tau = tau; a.margin = margin;
+    const long long cap = (long long)device_sm_count() * occ;
+    long long grid = Ki / 32;
+    if (grid < 64) grid = 64;
+    if (grid_env > 0) grid = grid_env;
+    if (grid > cap) grid = cap;
+    void* params[] = { (void*)&a };
+    R3G_CUDA_OK(cudaLaunchCooperativeKernel((const void*)rn::nms_rounds_kernel<GEOM>, dim3((unsigned)grid), dim3(rn::THREADS), params,
+                                            rn::SMEM_BYTES, st));
+    return R3G_OK;
+}
+
+static int nms_finish_stage(NmsWs& w, int Ki, const int64_t* batch_ids, int n_batches, int flags, bool small,
                             int64_t* keep_out, int64_t* num_keep_out, cudaStream_t st) {
     const int tpb = 256, gK = (Ki + tpb - 1) / tpb;
-    size_t tb = 0;
-    // 6. greedy scan per class segment
-    ScanArgs sa;
-    sa.mask = w.mask; sa.valid = w.valid; sa.label = w.pos_label; sa.blk_end = w.blk_end; sa.row_base = w.row_base;
-    sa.seg_list = w.seg_list; sa.counters = w.counters; sa.pos_rank = w.pos_rank; sa.ord_rank = w.ord_rank;
-    sa.keep_p = w.keep_p; sa.K = Ki;
     const int order_index = (flags & R3G_NMS_ORDER_INDEX) ? 1 : 0;
-    sa.remv_cap = nblk;
-    size_t smem = (size_t)nblk * 8;
-    if (smem > 190 * 1024) {
-        set_error("r3g_nms_f32: K=%lld exceeds the single-image limit of this build (%d boxes)", (long long)K, 190 * 1024 / 8 * 64);
-        return R3G_ERR_ARG;
-    }
-    static bool smem_set_of[64] = {false};                  // per device
-    bool& smem_set = smem_set_of[current_device_slot()];
-    if (!smem_set) {      // static (window buffers) + dynamic (removed[]) shared memory may exceed the 48 KB default
-        R3G_CUDA_OK(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 190 * 1024));
-        smem_set = true;
-    }
-    int sgrid = device_sm_count() * 2;
-    if (!labels && !batch_ids) sgrid = 1;
-    nms_scan_kernel<<<sgrid, SCAN_THREADS, smem, st>>>(sa);
-    R3G_LAUNCH_OK("nms_scan_kernel");
     if (small && Ki <= 4096) {            // one CTA walks K / 1024 chunks: past a few thousand the three-kernel path is faster
-        nms_finish_small_kernel<<<1, 1024, 0, st>>>(w.keep_p, w.pos_rank, w.ord_rank, batch_ids, Ki, order_index, w.flag, keep_out,
-                                                    (unsigned long long*)num_keep_out);
+        nms_finish_small_kernel<<<1, 1024, 0, st>>>(w.keep_p, w.pos_rank, w.ord_rank, batch_ids, n_batches, Ki, order_index, w.flag,
+                                                    keep_out, (unsigned long long*)num_keep_out);
         R3G_LAUNCH_OK("nms_finish_small_kernel");
         return R3G_OK;
     }
     nms_flags_kernel<<<gK, tpb, 0, st>>>(w.keep_p, w.pos_rank, w.ord_rank, Ki, order_index, w.flag);
-
-    // 7. compaction in the requested order
-    tb = w.cub_bytes;
+    // compaction in the requested order
+    size_t tb = w.cub_bytes;
     R3G_CUDA_OK(cub::DeviceScan::ExclusiveSum(w.cub_tmp, tb, w.flag, w.pref, Ki, st));
-    nms_emit_kernel<<<gK, tpb, 0, st>>>(w.flag, w.pref, w.ord_rank, batch_ids, Ki, order_index, keep_out,
+    nms_emit_kernel<<<gK, tpb, 0, st>>>(w.flag, w.pref, w.ord_rank, batch_ids, n_batches, Ki, order_index, keep_out,
                                         (unsigned long long*)num_keep_out);
     R3G_LAUNCH_OK("nms_emit_kernel");
     return R3G_OK;
@@ -886,7 +452,7 @@ static int nms_finish_stage(NmsWs& w, int Ki, int nblk, const int64_t* labels, c
 
 R3G_API int r3g_nms_workspace_bytes(int64_t K, size_t* bytes) {
     R3G_REQUIRE(bytes != nullptr && K >= 0, "r3g_nms_workspace_bytes: bad arguments");
-    R3G_REQUIRE(K < (1ll << 30), "r3g_nms_workspace_bytes: K too large");
+    R3G_REQUIRE(K <= (1ll << 26), "r3g_nms_workspace_bytes: K too large (limit 2^26 candidates per call)");
     *bytes = carve_nms(nullptr, K > 0 ? K : 1).bytes;
     return R3G_OK;
 }
@@ -904,7 +470,7 @@ R3G_API int r3g_nms_batched_f32(const float* boxes, int64_t stride, const float*
                                 int64_t K, float thr, int variant, int flags, const float* class_offset,
                                 int64_t* keep_out, int64_t* num_keep_out,
                                 void* workspace, size_t workspace_bytes, void* stream) {
-    R3G_REQUIRE(K >= 0 && K < (1ll << 30), "r3g_nms_f32: bad K");
+    R3G_REQUIRE(K >= 0 && K <= (1ll << 26), "r3g_nms_f32: bad K (limit 2^26 candidates per call)");
     R3G_REQUIRE(n_batches >= 1 && n_batches <= 65535, "r3g_nms_batched_f32: n_batches must be in [1, 65535]");
     R3G_REQUIRE(batch_ids != nullptr || n_batches == 1, "r3g_nms_batched_f32: n_batches > 1 needs batch_ids");
     R3G_REQUIRE(variant >= 1 && variant <= 3, "r3g_nms_f32: variant must be 1, 2 or 3 (got %d)", variant);
@@ -920,69 +486,30 @@ R3G_API int r3g_nms_batched_f32(const float* boxes, int64_t stride, const float*
         return R3G_ERR_WORKSPACE;
     }
     const int Ki = (int)K;
-    const int nblk = (Ki + 63) / 64;
     const int tpb = 256, gK = (Ki + tpb - 1) / tpb;
-    R3G_CUDA_OK(cudaMemsetAsync(w.counters, 0, 256, st));
-
-    const bool small = Ki <= NMS_SMALL_K && !(flags & R3G_NMS_SORT_PATH);
-    int rc = nms_order_stage(w, scores, labels, batch_ids, Ki, st, small);
+    int rc = nms_reset_stage(w, Ki, st);
     if (rc != R3G_OK) return rc;
-    // 3. gather + prepare
+    const bool small = Ki <= NMS_SMALL_K && !(flags & R3G_NMS_SORT_PATH);
+    rc = nms_order_stage(w, scores, labels, batch_ids, Ki, st, small);
+    if (rc != R3G_OK) return rc;
     nms_gather_kernel<<<gK, tpb, 0, st>>>(boxes, stride, w.ord_rank, w.pos_rank, w.pos_label, Ki, variant,
                                           (flags & R3G_NMS_DROP_SMALL) ? 1 : 0, class_offset, labels ? 1 : 0,
-                                          batch_ids ? 1 : 0, w.p0, w.p1, w.p2r, w.p2c, w.raw, w.valid);
-    rc = nms_structure_stage(w, Ki, nblk, st, small);
+                                          batch_ids ? 1 : 0, n_batches, w.p0, w.p1, w.p2r, w.p2c, w.raw, (unsigned*)w.alive);
+    R3G_LAUNCH_OK("nms_gather_kernel");
+    rc = nms_rounds_stage<rn::GEOM_BOX>(w, Ki, variant, (flags & R3G_NMS_INCLUSIVE) ? 1 : 0, thr,
+                                        (flags & R3G_NMS_STRICT) ? 2e-2f : 0.0f, (variant == R3G_V1) ? 1e-3f : 5e-5f, 0, st);
     if (rc != R3G_OK) return rc;
-
-    // 5. suppression bitmask
-    MaskArgs ma;
-    ma.p0 = w.p0; ma.p1 = w.p1; ma.p2r = w.p2r; ma.p2c = w.p2c; ma.raw = w.raw; ma.valid = w.valid; ma.label = w.pos_label;
-    ma.ticket = (unsigned long long*)(w.counters + 8);
-    ma.blk_end = w.blk_end; ma.row_base = w.row_base; ma.item_base = w.item_base; ma.mask = w.mask;
-    ma.K = Ki; ma.nblk = nblk; ma.variant = variant; ma.inclusive = (flags & R3G_NMS_INCLUSIVE) ? 1 : 0;
-    ma.thr = thr;
-    ma.tau = (flags & R3G_NMS_STRICT) ? 2e-2f : 0.0f;
-    ma.margin = (variant == R3G_V1) ? 1e-3f : 5e-5f;
-    static int occ_of[64] = {0};
-    int& occ = occ_of[current_device_slot()];
-    if (occ == 0) {
-        R3G_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, nms_mask_kernel, NMS_THREADS, 0));
-        if (occ < 1) occ = 1;
-    }
-    // persistent warps pulling items from a ticket counter (zeroed with the other counters above);
-    // upper bound on items: triangular number of (row block, group) pairs
-    long long max_items = (long long)nblk * ((nblk + NMS_G - 1) / NMS_G + 1);
-    long long grid = (max_items + NMS_WARPS - 1) / NMS_WARPS;
-    const long long cap = (long long)device_sm_count() * occ;
-    if (grid > cap) grid = cap;
-    nms_mask_kernel<<<(unsigned)grid, NMS_THREADS, 0, st>>>(ma);
-    R3G_LAUNCH_OK("nms_mask_kernel");
-
-    return nms_finish_stage(w, Ki, nblk, labels, batch_ids, flags, K, small, keep_out, num_keep_out, st);
+    return nms_finish_stage(w, Ki, batch_ids, n_batches, flags, small, keep_out, num_keep_out, st);
 }
 
 // ---- polygon NMS ------------------------------------------------------------------------------------------------------
-struct PolyWs { float* quad; float4* aabb; size_t bytes; };
-static PolyWs carve_poly(void* ws, size_t nms_bytes, int64_t K) {
-    PolyWs w;
-    char* p = (char*)ws;
-    size_t off = align_up(nms_bytes, 256);
-    w.quad = (float*)(p + off); off += align_up(32 * (size_t)K, 256);
-    w.aabb = (float4*)(p + off); off += align_up(16 * (size_t)K, 256);
-    w.bytes = off;
-    return w;
-}
-
 R3G_API int r3g_poly_nms_workspace_bytes(int64_t K, size_t* bytes) {
-    R3G_REQUIRE(bytes != nullptr && K >= 0 && K < (1ll << 30), "r3g_poly_nms_workspace_bytes: bad arguments");
-    const int64_t k = K > 0 ? K : 1;
-    *bytes = carve_poly(nullptr, carve_nms(nullptr, k).bytes, k).bytes;
-    return R3G_OK;
+    return r3g_nms_workspace_bytes(K, bytes);
 }
 
 R3G_API int r3g_poly_nms_f32(const float* polys, int64_t stride, const float* scores, const int64_t* labels, int64_t K, float thr,
                              int64_t* keep_out, int64_t* num_keep_out, void* workspace, size_t workspace_bytes, void* stream) {
-    R3G_REQUIRE(K >= 0 && K < (1ll << 30), "r3g_poly_nms_f32: bad K");
+    R3G_REQUIRE(K >= 0 && K <= (1ll << 26), "r3g_poly_nms_f32: bad K (limit 2^26 candidates per call)");
     R3G_REQUIRE(num_keep_out != nullptr, "r3g_poly_nms_f32: null num_keep_out");
     cudaStream_t st = (cudaStream_t)stream;
     R3G_CUDA_OK(cudaMemsetAsync(num_keep_out, 0, sizeof(int64_t), st));
@@ -990,32 +517,22 @@ R3G_API int r3g_poly_nms_f32(const float* polys, int64_t stride, const float* sc
     R3G_REQUIRE(polys && scores && keep_out && workspace, "r3g_poly_nms_f32: null pointer");
     R3G_REQUIRE(stride >= 8, "r3g_poly_nms_f32: polygon stride must be >= 8 floats");
     NmsWs w = carve_nms(workspace, K);
-    PolyWs pw = carve_poly(workspace, w.bytes, K);
-    if (workspace_bytes < pw.bytes) {
-        set_error("r3g_poly_nms_f32: workspace too small (%zu < %zu)", workspace_bytes, pw.bytes);
+    if (workspace_bytes < w.bytes) {
+        set_error("r3g_poly_nms_f32: workspace too small (%zu < %zu)", workspace_bytes, w.bytes);
         return R3G_ERR_WORKSPACE;
     }
-    const int Ki = (int)K, nblk = (Ki + 63) / 64, tpb = 256, gK = (Ki + tpb - 1) / tpb;
-    R3G_REQUIRE((size_t)nblk * 8 <= 190 * 1024, "r3g_poly_nms_f32: K exceeds the single-call limit of this build");
-    R3G_CUDA_OK(cudaMemsetAsync(w.counters, 0, 256, st));
+    const int Ki = (int)K, tpb = 256, gK = (Ki + tpb - 1) / tpb;
+    int rc = nms_reset_stage(w, Ki, st);
+    if (rc != R3G_OK) return rc;
     const bool small = Ki <= NMS_SMALL_K;
-    int rc = nms_order_stage(w, scores, labels, nullptr, Ki, st, small);
+    rc = nms_order_stage(w, scores, labels, nullptr, Ki, st, small);
     if (rc != R3G_OK) return rc;
-    poly::gather_kernel<<<gK, tpb, 0, st>>>(polys, stride, w.ord_rank, w.pos_rank, Ki, pw.quad, pw.aabb, w.valid);
-    rc = nms_structure_stage(w, Ki, nblk, st, small);
+    poly_gather_kernel<<<gK, tpb, 0, st>>>(polys, stride, w.ord_rank, w.pos_rank, Ki, w.p0, w.p1, w.p2c, (unsigned*)w.alive);
+    R3G_LAUNCH_OK("poly_gather_kernel");
+    // below 1e-3 the FP32 noise of disjoint pairs could exceed the threshold: test every pair (no bounding-box filter)
+    rc = nms_rounds_stage<rn::GEOM_QUAD>(w, Ki, 0, 0, thr, 0.0f, 0.0f, thr >= 1e-3f ? 1 : 0, st);      // poly_nms_cuda.cu:183: IoU > thr
     if (rc != R3G_OK) return rc;
-    poly::PolyMaskArgs ma;
-    ma.quad = pw.quad; ma.aabb = pw.aabb; ma.label = w.pos_label; ma.blk_end = w.blk_end; ma.row_base = w.row_base; ma.mask = w.mask;
-    ma.ticket = (unsigned long long*)(w.counters + 8);
-    ma.K = Ki; ma.nblk = nblk; ma.thr = thr;
-    ma.prefilter = thr >= 1e-3f ? 1 : 0;      // below that, FP32 noise of disjoint pairs could exceed the threshold: test every pair
-    const long long tiles = (long long)nblk * (nblk + 1) / 2;
-    long long grid = (tiles + 7) / 8;
-    const long long cap = (long long)device_sm_count() * 4;
-    if (grid > cap) grid = cap;
-    poly::mask_kernel<<<(unsigned)grid, 256, 0, st>>>(ma);
-    R3G_LAUNCH_OK("poly mask kernel");
-    return nms_finish_stage(w, Ki, nblk, labels, nullptr, 0, K, small, keep_out, num_keep_out, st);
+    return nms_finish_stage(w, Ki, nullptr, 1, 0, small, keep_out, num_keep_out, st);
 }
 
 // ---- multiclass candidate extraction --------------------------------------------------------------------------------

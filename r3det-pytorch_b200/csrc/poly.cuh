@@ -96,99 +96,5 @@ __device__ __noinline__ float quad_iou(const float* __restrict__ pa, const float
     return (uni == 0) ? (inter + 1) / (uni + 1) : inter / uni;
 }
 
-// gather the polygons into position (= score) order, with their bounding boxes
-__global__ void gather_kernel(const float* __restrict__ polys, int64_t stride, const int* __restrict__ ord_rank,
-                              const int* __restrict__ pos_rank, int K, float* __restrict__ quad, float4* __restrict__ aabb,
-                              unsigned char* __restrict__ valid) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= K) return;
-    const float* s = polys + (int64_t)ord_rank[pos_rank[p]] * stride;
-    float v[8];
-#pragma unroll
-    for (int k = 0; k < 8; k++) { v[k] = s[k]; quad[(int64_t)p * 8 + k] = v[k]; }
-    const float x0 = fminf(fminf(v[0], v[2]), fminf(v[4], v[6])), x1 = fmaxf(fmaxf(v[0], v[2]), fmaxf(v[4], v[6]));
-    const float y0 = fminf(fminf(v[1], v[3]), fminf(v[5], v[7])), y1 = fmaxf(fmaxf(v[1], v[3]), fmaxf(v[5], v[7]));
-    aabb[p] = make_float4(x0, y0, x1, y1);
-    valid[p] = 1;
-}
-
-struct PolyMaskArgs {
-    const float* quad; const float4* aabb;
-    const unsigned* label;                 // segment key per position (class-wise NMS: pairs across segments never interact)
-    const int* blk_end; const long long* row_base;
-    unsigned long long* mask; unsigned long long* ticket;
-    int K, nblk, prefilter;
-    float thr;
-};
-
-// One warp per 64 x 64 tile (row block rb, column block cb >= rb), tiles handed out by an atomic ticket.
-__global__ void __launch_bounds__(256) mask_kernel(const PolyMaskArgs A) {
-    __shared__ unsigned long long sm_all[8][64];
-    __shared__ unsigned short q_all[8][128];
-    const unsigned warp = threadIdx.x >> 5, lane = lane_id(), lt = lanemask_lt();
-    unsigned long long* sm = sm_all[warp];
-    unsigned short* q = q_all[warp];
-    const long long total = (long long)A.nblk * (A.nblk + 1) / 2;
-    while (true) {
-        long long item = 0;
-        if (lane == 0) item = (long long)atomicAdd(A.ticket, 1ull);
-        item = __shfl_sync(0xffffffffu, item, 0);
-        if (item >= total) break;
-        // item -> (rb, cb): rows of the upper triangle have nblk - rb tiles
-        int lo = 0, hi = A.nblk;                         // largest rb with first(rb) <= item, first(rb) = rb*nblk - rb(rb-1)/2
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            const long long first = (long long)mid * A.nblk - (long long)mid * (mid - 1) / 2;
-            if (first <= item) lo = mid; else hi = mid;
-        }
-        const int rb = lo;
-        const int cb = rb + (int)(item - ((long long)rb * A.nblk - (long long)rb * (rb - 1) / 2));
-        if (cb > A.blk_end[rb]) continue;                // beyond the segment of the block's last row: no word to write
-        const int i0 = rb * 64, j0 = cb * 64;
-        sm[lane] = 0ull; sm[lane + 32] = 0ull;
-        // this lane's two columns
-        const int ja = j0 + (int)lane, jb = ja + 32;
-        const float4 ca = ja < A.K ? __ldg(A.aabb + ja) : make_float4(3e38f, 3e38f, -3e38f, -3e38f);
-        const float4 cbx = jb < A.K ? __ldg(A.aabb + jb) : make_float4(3e38f, 3e38f, -3e38f, -3e38f);
-        const unsigned la = ja < A.K ? __ldg(A.label + ja) : 0xffffffffu, lb = jb < A.K ? __ldg(A.label + jb) : 0xffffffffu;
-        __syncwarp();
-        int cnt = 0;
-        auto drain = [&](int nb) {
-            __syncwarp();
-            if ((int)lane < nb) {
-                const unsigned e = q[cnt - nb + lane];
-                const int il = (int)(e >> 6), jl = (int)(e & 63u);
-                const float v = quad_iou(A.quad + (int64_t)(i0 + il) * 8, A.quad + (int64_t)(j0 + jl) * 8);
-                if (v > A.thr) atomicOr(&sm[il], 1ull << jl);                 // poly_nms_cuda.cu:183
-            }
-            __syncwarp();
-            cnt -= nb;
-        };
-        const int rows = min(64, A.K - i0);
-        for (int il = 0; il < rows; il++) {
-            const int i = i0 + il;
-            const float4 r = __ldg(A.aabb + i);
-            const unsigned li = __ldg(A.label + i);
-            bool oka = ja > i && ja < A.K && la == li, okb = jb > i && jb < A.K && lb == li;
-            if (A.prefilter) {
-                oka = oka && !(ca.x > r.z || ca.z < r.x || ca.y > r.w || ca.w < r.y);
-                okb = okb && !(cbx.x > r.z || cbx.z < r.x || cbx.y > r.w || cbx.w < r.y);
-            }
-            const unsigned ba = __ballot_sync(0xffffffffu, oka), bb = __ballot_sync(0xffffffffu, okb);
-            if (oka) q[cnt + __popc(ba & lt)] = (unsigned short)((il << 6) | lane);
-            if (okb) q[cnt + __popc(ba) + __popc(bb & lt)] = (unsigned short)((il << 6) | (lane + 32));
-            cnt += __popc(ba) + __popc(bb);
-            while (cnt >= 32) drain(32);
-        }
-        if (cnt > 0) drain(cnt);
-        __syncwarp();
-        const long long base = A.row_base[rb];
-        const int nwr = A.blk_end[rb] - rb + 1;
-        A.mask[base + (long long)lane * nwr + (cb - rb)] = sm[lane];
-        A.mask[base + (long long)(lane + 32) * nwr + (cb - rb)] = sm[lane + 32];
-        __syncwarp();
-    }
-}
-
 }  // namespace poly
 }  // namespace r3g
