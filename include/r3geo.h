@@ -45,6 +45,7 @@ extern "C" {
 #define R3G_NMS_DROP_SMALL 4    /* boxes with min(w,h) < 1e-3 take no part (nms_rotated_wrapper.py:40-46) */
 #define R3G_NMS_STRICT 8        /* decide near-threshold / degenerate pairs with the reference's own algorithm */
 #define R3G_NMS_SORT_PATH 16    /* diagnostic: take the radix-sort path that serves K > 16384 whatever K is */
+#define R3G_NMS_LABEL_BITS(n) (((n) & 63) << 8) /* optional promise: every label is < 2^n (saves radix passes); 0 = unknown */
 
 const char* r3g_last_error(void);
 int r3g_version(void);
@@ -118,7 +119,9 @@ int r3g_max_iou_assign_batched_f32(int64_t B, const float* gt, const int64_t* gt
  * keep_out: (K) int64 original indices, first *num_keep_out valid (both device memory).
  * With labels, `class_offset` != NULL points to ONE device float: the reference's per-class coordinate
  * offset scale (rnms_wrapper.py:61-64 / nms_rotated_wrapper.py:84-90); boxes are then evaluated at
- * x + label*scale, y + label*scale in FP32 exactly as the reference's batched wrappers do. */
+ * x + label*scale, y + label*scale in FP32 exactly as the reference's batched wrappers do.
+ * The greedy selection runs in rounds inside one persistent kernel (only pairs of kept rows are evaluated); the
+ * workspace is linear in K (~0.5 KB per candidate).  K <= 2^26 per call. */
 int r3g_nms_workspace_bytes(int64_t K, size_t* bytes);
 int r3g_nms_f32(const float* boxes, int64_t stride, const float* scores, const int64_t* labels,
                 int64_t K, float thr, int variant, int flags, const float* class_offset,
@@ -127,7 +130,8 @@ int r3g_nms_f32(const float* boxes, int64_t stride, const float* scores, const i
 
 /* Multi-image form of r3g_nms_f32: one launch sequence for a whole batch of images (BASELINE configs[3]: images are
  * independent, so (image, class) pairs are simply more segments).  batch_ids: (K) int64 in [0, n_batches) or NULL
- * (n_batches = 1); labels < 65536 when batch_ids is given; class_offset: n_batches device floats (per-image scale) or
+ * (n_batches = 1; candidates with an id outside the range take no part); labels < 65536 when batch_ids is given (the
+ * segment key packs image and label into 32 bits); class_offset: n_batches device floats (per-image scale) or
  * NULL.  keep_out: kept original indices grouped by image — ascending index (R3G_NMS_ORDER_INDEX; candidates are
  * expected to be concatenated image by image) or descending score within each image; num_keep_out: n_batches int64. */
 int r3g_nms_batched_f32(const float* boxes, int64_t stride, const float* scores, const int64_t* labels,

@@ -7,7 +7,7 @@ from . import _lib as L
 
 
 def nms_device(boxes, scores, thr, variant, labels=None, class_offset=None, inclusive=False,
-               order_index=False, drop_small=False, strict=True, batch_ids=None, n_batches=1, sort_path=False):
+               order_index=False, drop_small=False, strict=True, batch_ids=None, n_batches=1, sort_path=False, stats=None, label_bits=0):
     """Rotated NMS on CUDA tensors.
 
     boxes (K, >=5) f32, scores (K,) f32, labels (K,) int64 or None, class_offset: 0-dim CUDA f32 tensor or None.
@@ -17,6 +17,15 @@ def nms_device(boxes, scores, thr, variant, labels=None, class_offset=None, incl
     Multi-image batches (one launch sequence for many images): batch_ids (K,) int64 in [0, n_batches) with the
     candidates concatenated image by image, class_offset a (n_batches,) tensor of per-image scales; num_keep is then a
     (n_batches,) int64 tensor and keep is grouped by image (index order or per-image score order).
+    In a batch, labels must lie in [0, 65536) (the segment key packs image and label into 32 bits) and candidates whose
+    batch id is outside [0, n_batches) take no part.
+
+    label_bits: optional promise that every label is < 2**label_bits (a caller that knows its class count saves radix-sort
+    passes above 16384 candidates); 0 = unknown.
+
+    stats: optional dict; receives `counters` — a (64,) int64 CUDA tensor view of the library's work counters for this
+    call (read it after synchronising): [0] stage-1 pair tests, [1] separating-axis tests, [2] area evaluations,
+    [3] reference restatements, [4] rounds, [5] mask items, [6] apply items, [8] n, [9..] phase time stamps in ns.
     """
     L.require_cuda(boxes, scores)
     boxes, stride = L.as_f32_rows(boxes)
@@ -38,7 +47,8 @@ def nms_device(boxes, scores, thr, variant, labels=None, class_offset=None, incl
         if class_offset.numel() != (n_batches if batch_ids is not None else 1):
             raise ValueError('class_offset must hold one scale per image')
     flags = (L.NMS_INCLUSIVE if inclusive else 0) | (L.NMS_ORDER_INDEX if order_index else 0) | \
-            (L.NMS_DROP_SMALL if drop_small else 0) | (L.NMS_STRICT if strict else 0) | (L.NMS_SORT_PATH if sort_path else 0)
+            (L.NMS_DROP_SMALL if drop_small else 0) | (L.NMS_STRICT if strict else 0) | (L.NMS_SORT_PATH if sort_path else 0) | \
+            ((int(label_bits) & 63) << 8)
     lib = L.lib()
     nbytes = C.c_size_t(0)
     L.check(lib.r3g_nms_workspace_bytes(K, C.byref(nbytes)))
@@ -47,6 +57,8 @@ def nms_device(boxes, scores, thr, variant, labels=None, class_offset=None, incl
         L.check(lib.r3g_nms_batched_f32(L.ptr(boxes), stride, L.ptr(scores), L.ptr(labels), L.ptr(batch_ids),
                                         int(n_batches), K, float(thr), L.V[variant], flags, L.ptr(class_offset),
                                         L.ptr(keep), C.c_void_p(num.data_ptr()), L.ptr(ws), ws.numel(), L.stream_ptr(dev)))
+    if stats is not None:
+        stats['counters'] = ws[512:1024].view(torch.int64)
     return keep, num
 
 

@@ -90,7 +90,7 @@ def multiclass_nms_rotated(multi_bboxes, multi_scores, score_thr, nms, max_num=-
         hb = _obb2xyxy_v3(boxes)
         scale = (hb.max() - hb.min()) + 1
     keep, num = nms_device(boxes, scores, iou_thr, geometry, labels=labels, class_offset=scale, inclusive=host_in,
-                           order_index=by_index, drop_small=drop_small)
+                           order_index=by_index, drop_small=drop_small, label_bits=max(1, (multi_scores.size(1) - 2).bit_length()))
     keep = keep[:int(num.item())]
 
     if kind == 'v2' and keep.size(0) > max_num:          # reference :119-124 (also fires for max_num = -1)
@@ -139,7 +139,8 @@ def multiclass_nms_rotated_batch(multi_bboxes, multi_scores, score_thr, nms, max
             scale = (top - bot) + 1
         scale = torch.where(torch.isfinite(scale), scale, torch.ones_like(scale))      # images without candidates
     keep, num = nms_device(boxes, scores, _cfg(nms, 'iou_thr'), geometry, labels=labels, class_offset=scale,
-                           order_index=by_index, drop_small=drop_small, batch_ids=bid, n_batches=B)
+                           order_index=by_index, drop_small=drop_small, batch_ids=bid, n_batches=B,
+                           label_bits=max(1, (nc - 1).bit_length()))
     counts = num.tolist()
     total = sum(counts)
     keep = keep[:total]

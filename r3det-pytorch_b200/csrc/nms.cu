@@ -35,12 +35,12 @@ constexpr int NMS_SMALL_K = 16384;             // up to here ranks are counted i
 static int nms_split_of(int64_t K) { return K <= 4096 ? 8 : (K <= 8192 ? 4 : (K <= 16384 ? 2 : 1)); }
 
 struct NmsWs {
-    unsigned char* ctrl;                            // 512 bytes: rn::Ctrl[2] at 0, barrier counter at 128
+    unsigned char* ctrl;                            // 1 KB: rn::Ctrl[2] at 0, barrier counter at 128, counters / time stamps at 512
     unsigned *keyA, *keyA2, *keyB, *keyB2;
     int *ord_rank, *ord_tmp, *pos_rank, *pos_tmp;   // ord_rank[r] = original index of rank r; pos_rank[p] = rank at position p
     unsigned* pos_label;
     float4 *p0, *p1, *p2r, *p2c; float* raw;
-    unsigned long long* alive; size_t alive_bytes;
+    unsigned long long* alive; size_t alive_bytes, zero_bytes, zero_bytes_small;
     int *seg_cur, *seg_pe, *act;
     rn::Entry* ent;
     int *spos, *klist, *ownerB, *ownerD;
@@ -62,8 +62,14 @@ static NmsWs carve_nms(void* ws, int64_t K) {
     char* p = (char*)ws;
     size_t off = 0;
     auto take = [&](size_t bytes) { char* r = p + off; off += align_up(bytes, 256); return (void*)r; };
-    w.ctrl = (unsigned char*)take(512);
+    // zeroed by one memset per call: control block, alive bits, keep flags (and the two rank counters of the small-K path)
+    w.ctrl = (unsigned char*)take(1024);
+    w.alive_bytes = 16 * (size_t)((K + 127) / 128);                     // two 64-bit words per 128-column group
+    w.alive = (unsigned long long*)take(w.alive_bytes);
+    w.keep_p = (int*)take(4 * K);
+    w.zero_bytes = off;
     w.keyA = (unsigned*)take(4 * K); w.keyA2 = (unsigned*)take(4 * K);
+    w.zero_bytes_small = off;
     w.keyB = (unsigned*)take(4 * K); w.keyB2 = (unsigned*)take(4 * K);
     w.ord_rank = (int*)take(4 * K); w.ord_tmp = (int*)take(4 * K);
     w.pos_rank = (int*)take(4 * K); w.pos_tmp = (int*)take(4 * K);
@@ -71,15 +77,13 @@ static NmsWs carve_nms(void* ws, int64_t K) {
     w.p0 = (float4*)take(16 * K); w.p1 = (float4*)take(16 * K);
     w.p2r = (float4*)take(32 * K); w.p2c = (float4*)take(16 * K);       // row plane: every constant twice (f32x2 operands)
     w.raw = (float*)take(20 * K);
-    w.alive_bytes = 16 * (size_t)((K + 127) / 128);                     // two 64-bit words per 128-column group
-    w.alive = (unsigned long long*)take(w.alive_bytes);
     w.seg_cur = (int*)take(4 * K); w.seg_pe = (int*)take(4 * K); w.act = (int*)take(8 * K);
     w.ent = (rn::Entry*)take(sizeof(rn::Entry) * (size_t)(K / 2 + 2));  // chunks of >= 2 rows
     w.spos = (int*)take(4 * K); w.klist = (int*)take(4 * K);
     // mask items: <= K/2 single-block chunks + 17 n / 64 for the others; apply items: <= K B / 8192 + K / 32
     w.ownerB = (int*)take(4 * (size_t)(K + 64) * (size_t)nms_split_of(K));
     w.ownerD = (int*)take(4 * (size_t)(K / 2 + 64));
-    w.flag = (int*)take(4 * K); w.pref = (int*)take(4 * K); w.keep_p = (int*)take(4 * K);
+    w.flag = (int*)take(4 * K); w.pref = (int*)take(4 * K);
     w.cub_bytes = cub_temp_bytes(K);
     w.cub_tmp = take(w.cub_bytes);
     w.mask = (unsigned long long*)take((size_t)8 * (size_t)K * (rn::B_MAX / 64 + 1));   // sum over chunks of n * ceil(n / 64)
@@ -334,13 +338,11 @@ using namespace r3g;
 
 // ---- host stages shared by the rotated-box and the polygon entry points ------------------------------------------
 static int nms_order_stage(NmsWs& w, const float* scores, const int64_t* labels, const int64_t* batch_ids, int Ki, cudaStream_t st,
-                           bool small) {
+                           bool small, int label_bits) {
     const int tpb = 256, gK = (Ki + tpb - 1) / tpb;
     if (small) {
         // counted ranks: keyA / keyA2 double as the two count arrays
-        int* rcnt = (int*)w.keyA; int* pcnt = (int*)w.keyA2;
-        R3G_CUDA_OK(cudaMemsetAsync(rcnt, 0, 4 * (size_t)Ki, st));
-        R3G_CUDA_OK(cudaMemsetAsync(pcnt, 0, 4 * (size_t)Ki, st));
+        int* rcnt = (int*)w.keyA; int* pcnt = (int*)w.keyA2;           // zeroed by nms_reset_stage
         // ~4 CTAs per SM in total; batches get single-tile slices: most (i-block, tile) pairs are of different images and
         // return at once, so the remaining work needs the finer split to spread over the SMs
         int slices = batch_ids ? (Ki + 255) / 256 : (device_sm_count() * 4 + gK - 1) / gK;
@@ -372,8 +374,9 @@ static int nms_order_stage(NmsWs& w, const float* scores, const int64_t* labels,
         tb = w.cub_bytes;
         // in a batch the rank order is already image-major: sorting on the 16 label bits alone keeps every (image, label)
         // segment contiguous (label-major), the full keys travel with the permutation
+        // (one 8-bit digit pass per 8 label bits: a caller that knows its class count saves three of the four passes)
         R3G_CUDA_OK(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, w.keyB, w.pos_label, w.pos_tmp, w.pos_rank, Ki, 0,
-                                                    batch_ids ? 16 : 32, st));
+                                                    batch_ids ? (label_bits < 16 ? label_bits : 16) : label_bits, st));
     } else {
         R3G_CUDA_OK(cudaMemcpyAsync(w.pos_label, w.keyB, 4 * (size_t)Ki, cudaMemcpyDeviceToDevice, st));
         R3G_CUDA_OK(cudaMemcpyAsync(w.pos_rank, w.pos_tmp, 4 * (size_t)Ki, cudaMemcpyDeviceToDevice, st));
@@ -383,10 +386,8 @@ static int nms_order_stage(NmsWs& w, const float* scores, const int64_t* labels,
 
 // state the rounds kernel starts from: control block, keep flags and the tail of the alive vector zero (the gather kernels
 // write the alive words that hold candidates)
-static int nms_reset_stage(NmsWs& w, int Ki, cudaStream_t st) {
-    R3G_CUDA_OK(cudaMemsetAsync(w.ctrl, 0, 512, st));
-    R3G_CUDA_OK(cudaMemsetAsync(w.keep_p, 0, 4 * (size_t)Ki, st));
-    R3G_CUDA_OK(cudaMemsetAsync(w.alive, 0, w.alive_bytes, st));
+static int nms_reset_stage(NmsWs& w, bool small, cudaStream_t st) {
+    R3G_CUDA_OK(cudaMemsetAsync(w.ctrl, 0, small ? w.zero_bytes_small : w.zero_bytes, st));
     return R3G_OK;
 }
 
@@ -417,6 +418,7 @@ static int nms_rounds_stage(NmsWs& w, int Ki, int variant, int inclusive, float 
     a.alive = w.alive; a.seg_cur = w.seg_cur; a.seg_pe = w.seg_pe; a.act = w.act; a.ent = w.ent; a.spos = w.spos; a.klist = w.klist;
     a.ownerB = w.ownerB; a.ownerD = w.ownerD; a.mask = w.mask; a.keep_p = w.keep_p;
     a.ctrl = reinterpret_cast<rn::Ctrl*>(w.ctrl); a.bar = reinterpret_cast<unsigned*>(w.ctrl + 128);
+    a.dbg = reinterpret_cast<unsigned long long*>(w.ctrl + 512);
     a.B = chunk_env; a.split = nms_split_of(Ki);
     a.variant = variant; a.inclusive = inclusive; a.prefilter = prefilter; a.thr = thr; a.tau = tau; a.margin = margin;
     const long long cap = (long long)device_sm_count() * occ;
@@ -487,10 +489,12 @@ R3G_API int r3g_nms_batched_f32(const float* boxes, int64_t stride, const float*
     }
     const int Ki = (int)K;
     const int tpb = 256, gK = (Ki + tpb - 1) / tpb;
-    int rc = nms_reset_stage(w, Ki, st);
-    if (rc != R3G_OK) return rc;
     const bool small = Ki <= NMS_SMALL_K && !(flags & R3G_NMS_SORT_PATH);
-    rc = nms_order_stage(w, scores, labels, batch_ids, Ki, st, small);
+    int rc = nms_reset_stage(w, small, st);
+    if (rc != R3G_OK) return rc;
+    int label_bits = (flags >> 8) & 63;                 // R3G_NMS_LABEL_BITS(n): labels < 2^n; 0 = unknown
+    if (label_bits == 0 || label_bits > 32) label_bits = 32;
+    rc = nms_order_stage(w, scores, labels, batch_ids, Ki, st, small, label_bits);
     if (rc != R3G_OK) return rc;
     nms_gather_kernel<<<gK, tpb, 0, st>>>(boxes, stride, w.ord_rank, w.pos_rank, w.pos_label, Ki, variant,
                                           (flags & R3G_NMS_DROP_SMALL) ? 1 : 0, class_offset, labels ? 1 : 0,
@@ -522,10 +526,10 @@ R3G_API int r3g_poly_nms_f32(const float* polys, int64_t stride, const float* sc
         return R3G_ERR_WORKSPACE;
     }
     const int Ki = (int)K, tpb = 256, gK = (Ki + tpb - 1) / tpb;
-    int rc = nms_reset_stage(w, Ki, st);
-    if (rc != R3G_OK) return rc;
     const bool small = Ki <= NMS_SMALL_K;
-    rc = nms_order_stage(w, scores, labels, nullptr, Ki, st, small);
+    int rc = nms_reset_stage(w, small, st);
+    if (rc != R3G_OK) return rc;
+    rc = nms_order_stage(w, scores, labels, nullptr, Ki, st, small, 32);
     if (rc != R3G_OK) return rc;
     poly_gather_kernel<<<gK, tpb, 0, st>>>(polys, stride, w.ord_rank, w.pos_rank, Ki, w.p0, w.p1, w.p2c, (unsigned*)w.alive);
     R3G_LAUNCH_OK("poly_gather_kernel");

@@ -75,6 +75,8 @@ struct Args {
     int* keep_p;                                // out: 1 per kept position (zeroed by the launcher)
     Ctrl* ctrl;                                 // [2]
     unsigned* bar;                              // grid barrier counter (zero at launch)
+    unsigned long long* dbg;                    // [0] stage-1 pairs [1] separating-axis tests [2] area evaluations [3] restatements
+                                                // [4] rounds [5] mask items [6] apply items [8] n stamps [9..] phase time stamps (ns)
     int B, split;                               // chunk rows (<= B_MAX); row split of a mask item (1, 2, 4, 8)
     int variant, inclusive, prefilter;
     float thr, tau, margin;
@@ -91,7 +93,7 @@ struct __attribute__((aligned(16))) WarpSmem {
     unsigned short q2[64];          // separating-axis survivors
 };
 constexpr size_t SMEM_BYTES = sizeof(WarpSmem) * WARPS;
-static_assert(2 * 64 * 32 * 8 + 64 * 8 + 64 <= SMEM_BYTES, "scan buffers alias the per-warp working sets");
+static_assert(2 * 256 * 8 * 8 + 64 * 8 + 64 <= SMEM_BYTES, "scan buffers alias the per-warp working sets");
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
     unsigned v;
@@ -143,17 +145,36 @@ __global__ void __launch_bounds__(THREADS, 2) nms_rounds_kernel(const Args A) {
     const unsigned gwarp = blockIdx.x * WARPS + warp, nwarps = gridDim.x * WARPS;
     const unsigned FULL = 0xffffffffu;
 
-    unsigned epoch = 0;
+    unsigned long long n_s1 = 0, n_sat = 0, n_area = 0, n_emu = 0;      // work counters of this warp (lane 0 publishes them)
+    int n_stamp = 0;
+    auto stamp = [&]() {                                                // CTA 0, thread 0: a time stamp per phase boundary
+        if (blockIdx.x == 0 && tid == 0 && n_stamp < 54) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            A.dbg[9 + n_stamp++] = t;
+            A.dbg[8] = (unsigned long long)n_stamp;
+        }
+    };
+    stamp();
+    // Grid barrier (the launch is cooperative: every CTA is resident).  Arrivals count on one cache line; the last arriver
+    // publishes the generation on another line, which is the only one the waiting CTAs poll (read-shared in L2, so the
+    // pollers do not queue behind the arrival atomics).
+    unsigned gen = 0;
     auto grid_barrier = [&]() {
         __syncthreads();
-        epoch += gridDim.x;
+        gen++;
         if (tid == 0) {
             __threadfence();
-            atomicAdd(A.bar, 1u);
-            while (ld_acquire_u32(A.bar) < epoch) __nanosleep(40);
+            const unsigned old = atomicAdd(A.bar, 1u);
+            if (old + 1u == gen * gridDim.x) {
+                asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(A.bar + 32), "r"(gen) : "memory");
+            } else {
+                while (ld_acquire_u32(A.bar + 32) < gen) __nanosleep(20);
+            }
             __threadfence();
         }
         __syncthreads();
+        stamp();
     };
 
     // ---- phase 0: class segments of the position space ----
@@ -193,6 +214,7 @@ __global__ void __launch_bounds__(THREADS, 2) nms_rounds_kernel(const Args A) {
         }
         __syncwarp();
         c3 -= nb;
+        n_emu += nb;
     };
     // stage 3: the pairs queued in `q` (item-relative row << 7 | col) -> decision
     auto drain_area = [&](unsigned short* q, int& cq, int nb) {
@@ -220,6 +242,7 @@ __global__ void __launch_bounds__(THREADS, 2) nms_rounds_kernel(const Args A) {
         }
         __syncwarp();
         cq -= nb;
+        n_area += nb;
         if (GEOM == GEOM_BOX) {
             const unsigned bal = __ballot_sync(FULL, emu);
             if (bal) {
@@ -253,6 +276,7 @@ __global__ void __launch_bounds__(THREADS, 2) nms_rounds_kernel(const Args A) {
         }
         __syncwarp();
         c1 -= nb;
+        n_sat += nb;
         const unsigned bal = __ballot_sync(FULL, ok);
         if (ok) W.q2[c2 + __popc(bal & lt)] = (unsigned short)e;
         c2 += __popc(bal);
@@ -275,6 +299,7 @@ __global__ void __launch_bounds__(THREADS, 2) nms_rounds_kernel(const Args A) {
                 CR[h] = pk2(cr[2 * h], cr[2 * h + 1]); CK[h] = pk2(ck[2 * h], ck[2 * h + 1]);
             }
         }
+        n_s1 += (unsigned long long)(r_hi - r_lo) * TN;
         for (int ig = r_lo; ig < r_hi; ig += RG) {
             const int nr = min(RG, r_hi - ig);
             unsigned m = 0;
@@ -376,17 +401,34 @@ __global__ void __launch_bounds__(THREADS, 2) nms_rounds_kernel(const Args A) {
                 }
                 const int total = __shfl_sync(FULL, incl, 31);
                 const int base = n + incl - cnt;
-                int k = 0, mylast = -1;
-                while (bits && base + k < B) {
-                    const int t = __ffsll((long long)bits) - 1;
-                    bits &= bits - 1ull;
-                    mylast = w * 64 + t;
-                    if (base + k == 0) myfirst = mylast;
-                    A.spos[row_base + base + k] = mylast;
-                    k++;
+                // every set bit finds its slot by a population count: no serial chain over the word
+                const unsigned lo32 = (unsigned)bits, hi32 = (unsigned)(bits >> 32);
+                const int clo = __popc(lo32);
+                int mylast = -1;                                   // position of the row that fills slot B - 1 (if this lane holds it)
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    if ((lo32 >> j) & 1u) {
+                        const int slot = base + __popc(lo32 & ((1u << j) - 1u));
+                        if (slot < B) {
+                            A.spos[row_base + slot] = w * 64 + j;
+                            if (slot == 0) myfirst = w * 64 + j;
+                            if (slot == B - 1) mylast = w * 64 + j;
+                        }
+                    }
                 }
-                if (n + total >= B) {                          // chunk full: the cursor moves behind its last row
-                    const unsigned who = __ballot_sync(FULL, base < B && base + cnt >= B);
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    if ((hi32 >> j) & 1u) {
+                        const int slot = base + clo + __popc(hi32 & ((1u << j) - 1u));
+                        if (slot < B) {
+                            A.spos[row_base + slot] = w * 64 + 32 + j;
+                            if (slot == 0) myfirst = w * 64 + 32 + j;
+                            if (slot == B - 1) mylast = w * 64 + 32 + j;
+                        }
+                    }
+                }
+                if (n + total >= B) {                              // chunk full: the cursor moves behind its last row
+                    const unsigned who = __ballot_sync(FULL, mylast >= 0);
                     cur_new = __shfl_sync(FULL, mylast, __ffs((int)who) - 1) + 1;
                     n = B;
                     break;
@@ -399,18 +441,21 @@ __global__ void __launch_bounds__(THREADS, 2) nms_rounds_kernel(const Args A) {
             } else if (n >= 2) {
                 const int nb = (n + 63) >> 6;
                 const int items = items_of(nb) * A.split;
-                int e = 0, itemB0 = 0;
+                // the three allocations travel together: lanes 0..2 issue one atomic each
+                unsigned long long got = 0ull;
+                if (lane == 0) got = atomicAdd(&C->n_ent, 1u);
+                else if (lane == 1) got = atomicAdd(&C->words_used, (unsigned long long)n * (unsigned long long)nb);
+                else if (lane == 2) got = atomicAdd(&C->itemsB, (unsigned)items);
+                const int e = (int)__shfl_sync(FULL, got, 0);
+                const unsigned wbase = (unsigned)__shfl_sync(FULL, got, 1);
+                const int itemB0 = (int)__shfl_sync(FULL, got, 2);
                 if (lane == 0) {
-                    e = (int)atomicAdd(&C->n_ent, 1u);
-                    const unsigned long long wbase = atomicAdd(&C->words_used, (unsigned long long)n * (unsigned long long)nb);
-                    itemB0 = (int)atomicAdd(&C->itemsB, (unsigned)items);
                     int4* ep = reinterpret_cast<int4*>(A.ent + e);
                     ep[0] = make_int4(s, row_base, n, nb);
-                    ep[1] = make_int4((int)(unsigned)wbase, itemB0, cur_new, pe);
+                    ep[1] = make_int4((int)wbase, itemB0, cur_new, pe);
                     ep[2] = make_int4(0, 0, 0, 0);
                     ep[3] = make_int4(0, 0, 0, 0);
                 }
-                e = __shfl_sync(FULL, e, 0); itemB0 = __shfl_sync(FULL, itemB0, 0);
                 for (int k = lane; k < items; k += 32) A.ownerB[itemB0 + k] = e;
             }
             if (cur_new < pe && lane == 0) {
@@ -493,55 +538,107 @@ __global__ void __launch_bounds__(THREADS, 2) nms_rounds_kernel(const Args A) {
         grid_barrier();
 
         // ---- phase C: greedy scan of each chunk-local mask (one CTA per chunk) ----
+        // Software-pipelined in SUPERBLOCKS of 4 x 64 rows, so that one barrier and one global-memory round trip are paid per
+        // 256 rows and neither sits on the serial chain.  For superblock S (column window = its 4 blocks + the next 4):
+        //   warp 0     : for each of the 4 blocks, chain over the 64 diagonal words (shared memory) with ffs jumps -> kept rows;
+        //                lanes 0..7 OR the kept rows' window words into removed[] for the blocks that follow inside the window;
+        //   warps 1..7 : prefetch the 256 x 8 window words of superblock S+1 into the other buffer and OR the kept rows of
+        //                superblock S-1 into removed[] for the columns BEYOND its window (global mask words).
         {
-            typedef unsigned long long Row[32];
-            Row* buf0 = reinterpret_cast<Row*>(rn_smem);                           // [64][32]
-            Row* buf1 = buf0 + 64;
-            unsigned long long* keptw = reinterpret_cast<unsigned long long*>(rn_smem + 2 * 64 * 32 * 8);   // [32]
-            int* misc = reinterpret_cast<int*>(keptw + 64);
+            constexpr int SB = 4, WIN = 8, SBROWS = 64 * SB;
+            typedef unsigned long long WinRow[WIN];
+            WinRow* Wd = reinterpret_cast<WinRow*>(rn_smem);                                      // [2][SBROWS]
+            unsigned long long* remv = reinterpret_cast<unsigned long long*>(rn_smem + 2 * SBROWS * WIN * 8);   // [32]
+            unsigned long long* keptw = remv + 32;                                                // [32]
+            int* misc = reinterpret_cast<int*>(keptw + 32);
             const unsigned n_ent = __ldcg(&C->n_ent);
             for (unsigned e = blockIdx.x; e < n_ent; e += gridDim.x) {
                 const int4 e0 = __ldcg(reinterpret_cast<const int4*>(A.ent + e));
                 const int4 e1 = __ldcg(reinterpret_cast<const int4*>(A.ent + e) + 1);
                 const int row_base = e0.y, n = e0.z, nb = e0.w, cur_new = e1.z, pe = e1.w;
                 const unsigned wbase = (unsigned)e1.x;
-                auto prefetch = [&](int b, Row* buf, int u, int nt) {             // rows of block b, words b .. nb-1
-                    const int wn = nb - b, tot = 64 * wn;
-                    for (int idx = u; idx < tot; idx += nt) {
-                        const int t = idx / wn, c = b + idx - t * wn, lr = b * 64 + t;
-                        buf[t][c] = (lr < n) ? __ldcg(A.mask + wbase + (unsigned)(lr * nb + c)) : 0ull;
+                const int nsb = (nb + SB - 1) / SB;
+                auto prefetch = [&](int S, int bufi, int u, int nt) {             // all loads of a thread are issued before the first store
+                    constexpr int PAIRS = SBROWS * WIN;
+                    constexpr int PER = (PAIRS + (THREADS - 32) - 1) / (THREADS - 32);
+                    unsigned long long v[PER];
+#pragma unroll
+                    for (int j = 0; j < PER; j++) {
+                        const int idx = u + j * nt;
+                        unsigned long long x = 0ull;
+                        if (idx < PAIRS) {
+                            const int r = idx >> 3, k = idx & (WIN - 1), bb = S * SB + (r >> 6), col = S * SB + k, lr = bb * 64 + (r & 63);
+                            if (bb < nb && col >= bb && col < nb && lr < n) x = __ldcg(A.mask + wbase + (unsigned)(lr * nb + col));
+                        }
+                        v[j] = x;
+                    }
+#pragma unroll
+                    for (int j = 0; j < PER; j++) {
+                        const int idx = u + j * nt;
+                        if (idx < PAIRS) Wd[bufi * SBROWS + (idx >> 3)][idx & (WIN - 1)] = v[j];
                     }
                 };
                 __syncthreads();                                                   // the previous chunk is done with shared memory
-                if (tid < 32) keptw[tid] = 0ull;
-                prefetch(0, buf0, (int)tid, THREADS);
-                unsigned long long remv = 0ull;                                    // warp 0: lane c holds the removed bits of block c
-                for (int b = 0; b < nb; b++) {
-                    Row* buf = (b & 1) ? buf1 : buf0;
+                if (tid < 64) remv[tid] = 0ull;                                    // removed[] and keptw[]
+                prefetch(0, 0, (int)tid, THREADS);
+                for (int S = 0; S < nsb; S++) {
+                    const int bufi = S & 1;
                     __syncthreads();
                     if (warp == 0) {
-                        const int rows = min(64, n - b * 64);
-                        const unsigned long long vb = (rows == 64) ? ~0ull : ((1ull << rows) - 1ull);
-                        unsigned long long cur = __shfl_sync(FULL, remv, b);
-                        unsigned long long avail = vb & ~cur, kept = 0ull, acc = 0ull;
-                        while (avail) {                                            // warp-uniform; one kept row per trip
-                            const int t = __ffsll((long long)avail) - 1;
-                            kept |= 1ull << t;
-                            cur |= buf[t][b];
-                            if ((int)lane > b && (int)lane < nb) acc |= buf[t][lane];
-                            const unsigned long long above = (t == 63) ? 0ull : (~0ull << (t + 1));
-                            avail = vb & ~cur & above;
+                        for (int q = 0; q < SB; q++) {
+                            const int bb = S * SB + q;
+                            if (bb >= nb) break;
+                            const int rows = min(64, n - bb * 64);
+                            const unsigned long long vb = (rows == 64) ? ~0ull : ((1ull << rows) - 1ull);
+                            unsigned long long cur = remv[bb], kept = 0ull, acc = 0ull;
+                            unsigned long long avail = vb & ~cur;
+                            while (avail) {                                        // warp-uniform; one kept row per trip
+                                const int t = __ffsll((long long)avail) - 1;
+                                kept |= 1ull << t;
+                                cur |= Wd[bufi * SBROWS + q * 64 + t][q];
+                                if (lane < WIN) acc |= Wd[bufi * SBROWS + q * 64 + t][lane];
+                                const unsigned long long above = (t == 63) ? 0ull : (~0ull << (t + 1));
+                                avail = vb & ~cur & above;
+                            }
+                            if ((int)lane > q && lane < WIN && S * SB + (int)lane < nb && acc) atomicOr(&remv[S * SB + lane], acc);
+                            if (lane == 0) keptw[bb] = kept;
+                            __syncwarp();
                         }
-                        remv |= acc;
-                        if (lane == 0) keptw[b] = kept;
-                    } else if (b + 1 < nb) {
-                        prefetch(b + 1, (b & 1) ? buf0 : buf1, (int)tid - 32, THREADS - 32);
+                    } else {
+                        const int u = (int)tid - 32, nt = THREADS - 32;
+                        if (S + 1 < nsb) prefetch(S + 1, bufi ^ 1, u, nt);
+                        const int first = (S - 1) * SB + WIN;                     // first column beyond the window of superblock S-1
+                        const int ncb = nb - first;
+                        if (S > 0 && ncb > 0) {
+                            const int groups = nt / ncb;                           // ncb <= 24: every column gets >= 9 threads
+                            const int g = u / ncb, c = first + (u - g * ncb);
+                            if (g < groups) {
+                                unsigned long long kq[SB];
+#pragma unroll
+                                for (int q = 0; q < SB; q++) kq[q] = ((S - 1) * SB + q < nb) ? keptw[(S - 1) * SB + q] : 0ull;
+                                unsigned long long acc = 0ull;
+                                for (int r0 = g; r0 < SBROWS; r0 += 4 * groups) {  // four independent loads per trip
+                                    unsigned long long v[4];
+#pragma unroll
+                                    for (int j = 0; j < 4; j++) {
+                                        const int r = r0 + j * groups;
+                                        v[j] = 0ull;
+                                        if (r < SBROWS && ((kq[r >> 6] >> (r & 63)) & 1ull)) {
+                                            const int lr = ((S - 1) * SB + (r >> 6)) * 64 + (r & 63);
+                                            v[j] = __ldcg(A.mask + wbase + (unsigned)(lr * nb + c));
+                                        }
+                                    }
+                                    acc |= (v[0] | v[1]) | (v[2] | v[3]);
+                                }
+                                if (acc) atomicOr(&remv[c], acc);
+                            }
+                        }
                     }
                 }
                 __syncthreads();
                 if (tid == 0) {
                     int nk = 0;
-                    for (int b = 0; b < nb; b++) nk += __popcll(keptw[b]);
+                    for (int bb = 0; bb < nb; bb++) nk += __popcll(keptw[bb]);
                     const int kbase = (int)atomicAdd(&C->kept_used, (unsigned)nk);
                     int itemsD = 0, itemD0 = 0, ncg = 0, cg0 = 0;
                     if (cur_new < pe && nk > 0) {
@@ -558,11 +655,11 @@ __global__ void __launch_bounds__(THREADS, 2) nms_rounds_kernel(const Args A) {
                 __syncthreads();
                 const int kbase = misc[0], itemD0 = misc[1], itemsD = misc[2];
                 for (int lr = tid; lr < n; lr += THREADS) {
-                    const int b = lr >> 6, t = lr & 63;
-                    const unsigned long long kw = keptw[b];
+                    const int bb = lr >> 6, t = lr & 63;
+                    const unsigned long long kw = keptw[bb];
                     if ((kw >> t) & 1ull) {
                         int idx = __popcll(kw & ((1ull << t) - 1ull));
-                        for (int q = 0; q < b; q++) idx += __popcll(keptw[q]);
+                        for (int q = 0; q < bb; q++) idx += __popcll(keptw[q]);
                         const int p = __ldcg(A.spos + row_base + lr);
                         A.klist[kbase + idx] = p;
                         A.keep_p[p] = 1;
@@ -635,6 +732,13 @@ __global__ void __launch_bounds__(THREADS, 2) nms_rounds_kernel(const Args A) {
         }
         grid_barrier();
         par ^= 1;
+        if (blockIdx.x == 0 && tid == 0) { A.dbg[4] += 1ull; A.dbg[5] += __ldcg(&C->itemsB); A.dbg[6] += __ldcg(&C->itemsD); }
+    }
+    if (lane == 0) {
+        if (n_s1) atomicAdd(A.dbg + 0, n_s1);
+        if (n_sat) atomicAdd(A.dbg + 1, n_sat);
+        if (n_area) atomicAdd(A.dbg + 2, n_area);
+        if (n_emu) atomicAdd(A.dbg + 3, n_emu);
     }
 }
 

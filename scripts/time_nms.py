@@ -16,6 +16,7 @@ from r3det_b200._nms_core import nms_device  # noqa: E402
 from tests.util import clustered, rand_obb  # noqa: E402
 
 dev = torch.device("cuda:0")
+LB = int(os.environ.get("LABEL_BITS", "4"))
 
 
 def timeit(fn, iters=10, warm=3):
@@ -45,9 +46,16 @@ for K in sizes:
     b, s, l = clustered(K, 2, "v1")
     B, S, Lb = (torch.from_numpy(x).to(dev) for x in (b, s, l))
     sc = torch.tensor(float(b.max() + 1), device=dev)
-    fn = lambda: nms_device(B, S, 0.1, "v1", labels=Lb, class_offset=sc, order_index=True)
+    fn = lambda: nms_device(B, S, 0.1, "v1", labels=Lb, class_offset=sc, order_index=True, label_bits=LB)
     keep, num = fn()
-    rec = {"ms": timeit(fn, 5 if K >= 80000 else 20), "kept": int(num)}
+    st = {}
+    nms_device(B, S, 0.1, "v1", labels=Lb, class_offset=sc, order_index=True, stats=st)
+    torch.cuda.synchronize()
+    c = st["counters"].cpu().numpy()
+    ts = c[9:9 + int(c[8])]
+    rec = {"ms": timeit(fn, 5 if K >= 80000 else 20), "kept": int(num), "pairs_stage1": int(c[0]), "pairs_sat": int(c[1]),
+           "pairs_area": int(c[2]), "pairs_emu": int(c[3]), "rounds": int(c[4]), "items_mask": int(c[5]), "items_apply": int(c[6]),
+           "phase_us": [round(float(x) / 1e3, 1) for x in np.diff(ts)]}
     try:
         rec["graph_ms"] = graph_time(fn)
     except Exception as e:  # noqa: BLE001

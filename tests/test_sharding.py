@@ -21,10 +21,16 @@ def _worker(rank, world, port_no, q):
     import r3det_b200  # noqa: F401
     from r3det_b200 import sharding
     from oracle import port
-    iou_fn = lambda g, a: torch.from_numpy(port.iou_matrix(g.numpy(), a.numpy(), "v1"))
+    from collections import namedtuple
+    Out = namedtuple("Out", "max_overlaps gt_max_overlaps gt_argmax_overlaps")
+
+    def assign_fn(g, a):          # stands in for r3det_b200.max_iou_assign (the fused CUDA assigner): same three outputs
+        m = torch.from_numpy(port.iou_matrix(g.numpy(), a.numpy(), "v1"))
+        return Out(m.max(dim=0).values, m.max(dim=1).values, m.max(dim=1).indices)
+
     gt = torch.from_numpy(rand_obb(40, 1)); anchors = torch.from_numpy(rand_obb(1001, 2))
-    local, lo, hi = sharding.sharded_pairwise_iou(gt, anchors, iou_fn)
-    gmax, garg, npos, nneg = sharding.assigner_stats(local, lo, 0.5, 0.4)
+    out, lo, hi = sharding.sharded_assign(gt, anchors, assign_fn)
+    gmax, garg, npos, nneg = sharding.assigner_stats(out.gt_max_overlaps, out.gt_argmax_overlaps, out.max_overlaps, lo, 0.5, 0.4)
     # image-sharded keep lists
     num_images, max_per = 5, 30
     ilo, ihi = sharding.shard_range(num_images, rank, world)
@@ -35,6 +41,18 @@ def _worker(rank, world, port_no, q):
         dets.append(torch.from_numpy(np.concatenate([b[keep], s[keep, None]], 1)))
         labels.append(torch.from_numpy(l[keep]))
     all_dets, all_labels = sharding.gather_keep_lists(dets, labels, max_per, num_images)
+    # the asynchronous form and the padded-record form publish the same lists
+    h = sharding.gather_keep_lists(dets, labels, max_per, num_images, async_op=True)
+    d2, l2 = h.wait()
+    per_rank = (num_images + world - 1) // world
+    pd = torch.zeros((per_rank, max_per, 6)); pl = torch.zeros((per_rank, max_per), dtype=torch.int64); pc = torch.zeros((per_rank,), dtype=torch.int64)
+    for i, (d, l) in enumerate(zip(dets, labels)):
+        pd[i, :d.size(0)] = d; pl[i, :l.size(0)] = l; pc[i] = d.size(0)
+    d3, l3 = sharding.gather_padded_records(pd, pl, pc, num_images)
+    for a, b_, c in zip(all_dets, d2, d3):
+        assert torch.equal(a, b_) and torch.equal(a, c)
+    for a, b_, c in zip(all_labels, l2, l3):
+        assert torch.equal(a, b_) and torch.equal(a, c)
     q.put((rank, lo, hi, gmax.numpy(), garg.numpy(), npos, nneg, [d.numpy() for d in all_dets], [l.numpy() for l in all_labels]))
     dist.barrier()
     dist.destroy_process_group()
