@@ -93,7 +93,7 @@ struct __attribute__((aligned(16))) WarpSmem {
     unsigned short q2[64];          // separating-axis survivors
 };
 constexpr size_t SMEM_BYTES = sizeof(WarpSmem) * WARPS;
-static_assert(2 * 256 * 8 * 8 + 64 * 8 + 64 <= SMEM_BYTES, "scan buffers alias the per-warp working sets");
+static_assert(2 * 256 * 8 * 8 + 64 * 8 + 64 + 2 * 256 * 2 <= SMEM_BYTES, "scan buffers alias the per-warp working sets");
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
     unsigned v;
@@ -375,24 +375,39 @@ __global__ void __launch_bounds__(THREADS, 2) nms_rounds_kernel(const Args A) {
         int* actn = A.act + (size_t)(par ^ 1) * A.K;
 
         // ---- phase A: every active segment selects its chunk = the next <= B alive positions from its cursor ----
-        for (unsigned i = gwarp; i < n_act; i += nwarps) {
+        // segments are dealt to CTAs first (a segment's position list is 2048 scattered-then-coalesced stores: spread the LSU work)
+        for (unsigned i = blockIdx.x + gridDim.x * warp; i < n_act; i += nwarps) {
             const int s = __ldcg(act + i);
             const int cur = __ldcg(A.seg_cur + s), pe = __ldcg(A.seg_pe + s);
             const int cap = min(B, pe - cur);
             int row_base = 0;
             if (lane == 0) row_base = (int)atomicAdd(&C->rows_used, (unsigned)cap);
-            row_base = __shfl_sync(FULL, row_base, 0);
             int n = 0, cur_new = pe, myfirst = -1;
-            const int wl = (pe - 1) >> 6;
-            for (int w0 = cur >> 6; w0 <= wl; w0 += 32) {
-                const int w = w0 + (int)lane;
-                unsigned long long bits = 0ull;
+            const int wl = (pe - 1) >> 6, wf = cur >> 6;
+            // a lane reads two adjacent alive words per step (one 16-byte load); the next step's words are in flight while
+            // this step's bits are expanded
+            auto load2 = [&](int w0) {
+                const int w = w0 + 2 * (int)lane;
+                ulonglong2 v = make_ulonglong2(0ull, 0ull);
                 if (w <= wl) {
-                    bits = __ldcg(A.alive + w);
-                    if (w == (cur >> 6)) bits &= ~0ull << (cur & 63);
-                    if (w == wl && (pe & 63)) bits &= (1ull << (pe & 63)) - 1ull;
+                    v = __ldcg(reinterpret_cast<const ulonglong2*>(A.alive + w));
+                    if (w < wf) v.x = 0ull;
+                    if (w == wf) v.x &= ~0ull << (cur & 63);
+                    if (w + 1 == wf) v.y &= ~0ull << (cur & 63);
+                    if (w == wl && (pe & 63)) v.x &= (1ull << (pe & 63)) - 1ull;
+                    if (w + 1 == wl && (pe & 63)) v.y &= (1ull << (pe & 63)) - 1ull;
+                    if (w + 1 > wl) v.y = 0ull;
                 }
-                const int cnt = __popcll(bits);
+                return v;
+            };
+            const int wstart = wf & ~1;
+            ulonglong2 nxt = load2(wstart);
+            row_base = __shfl_sync(FULL, row_base, 0);
+            for (int w0 = wstart; w0 <= wl; w0 += 64) {
+                const ulonglong2 v = nxt;
+                if (w0 + 64 <= wl) nxt = load2(w0 + 64);
+                const int w = w0 + 2 * (int)lane;
+                const int c0 = __popcll(v.x), cnt = c0 + __popcll(v.y);
                 int incl = cnt;
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
@@ -401,30 +416,19 @@ __global__ void __launch_bounds__(THREADS, 2) nms_rounds_kernel(const Args A) {
                 }
                 const int total = __shfl_sync(FULL, incl, 31);
                 const int base = n + incl - cnt;
-                // every set bit finds its slot by a population count: no serial chain over the word
-                const unsigned lo32 = (unsigned)bits, hi32 = (unsigned)(bits >> 32);
-                const int clo = __popc(lo32);
-                int mylast = -1;                                   // position of the row that fills slot B - 1 (if this lane holds it)
+                int mylast = -1;                                   // position of the row that fills slot B - 1 (if this lane writes it)
 #pragma unroll
-                for (int j = 0; j < 32; j++) {
-                    if ((lo32 >> j) & 1u) {
-                        const int slot = base + __popc(lo32 & ((1u << j) - 1u));
-                        if (slot < B) {
-                            A.spos[row_base + slot] = w * 64 + j;
-                            if (slot == 0) myfirst = w * 64 + j;
-                            if (slot == B - 1) mylast = w * 64 + j;
-                        }
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < 32; j++) {
-                    if ((hi32 >> j) & 1u) {
-                        const int slot = base + clo + __popc(hi32 & ((1u << j) - 1u));
-                        if (slot < B) {
-                            A.spos[row_base + slot] = w * 64 + 32 + j;
-                            if (slot == 0) myfirst = w * 64 + 32 + j;
-                            if (slot == B - 1) mylast = w * 64 + 32 + j;
-                        }
+                for (int h = 0; h < 2; h++) {
+                    unsigned long long bits = h ? v.y : v.x;
+                    int slot = base + (h ? c0 : 0);
+                    const int p0w = (w + h) * 64;
+                    while (bits && slot < B) {
+                        const int t = __ffsll((long long)bits) - 1;
+                        bits &= bits - 1ull;
+                        A.spos[row_base + slot] = p0w + t;
+                        if (slot == 0) myfirst = p0w + t;
+                        if (slot == B - 1) mylast = p0w + t;
+                        slot++;
                     }
                 }
                 if (n + total >= B) {                              // chunk full: the cursor moves behind its last row
@@ -435,6 +439,7 @@ __global__ void __launch_bounds__(THREADS, 2) nms_rounds_kernel(const Args A) {
                 }
                 n += total;
             }
+            row_base = __shfl_sync(FULL, row_base, 0);            // (idempotent: every lane holds it after the first pass)
             __syncwarp();
             if (n == 1) {
                 if (myfirst >= 0) A.keep_p[myfirst] = 1;                          // alone in its chunk and nothing behind it
@@ -550,7 +555,8 @@ __global__ void __launch_bounds__(THREADS, 2) nms_rounds_kernel(const Args A) {
             WinRow* Wd = reinterpret_cast<WinRow*>(rn_smem);                                      // [2][SBROWS]
             unsigned long long* remv = reinterpret_cast<unsigned long long*>(rn_smem + 2 * SBROWS * WIN * 8);   // [32]
             unsigned long long* keptw = remv + 32;                                                // [32]
-            int* misc = reinterpret_cast<int*>(keptw + 32);
+            int* misc = reinterpret_cast<int*>(keptw + 32);                                       // [16]: 0..2 results, 4..5 kept counts
+            unsigned short* ksb = reinterpret_cast<unsigned short*>(misc + 16);                   // [2][SBROWS] kept rows of a superblock
             const unsigned n_ent = __ldcg(&C->n_ent);
             for (unsigned e = blockIdx.x; e < n_ent; e += gridDim.x) {
                 const int4 e0 = __ldcg(reinterpret_cast<const int4*>(A.ent + e));
@@ -585,50 +591,74 @@ __global__ void __launch_bounds__(THREADS, 2) nms_rounds_kernel(const Args A) {
                     const int bufi = S & 1;
                     __syncthreads();
                     if (warp == 0) {
+                        int nks = 0;                                               // kept rows of this superblock so far
                         for (int q = 0; q < SB; q++) {
                             const int bb = S * SB + q;
                             if (bb >= nb) break;
                             const int rows = min(64, n - bb * 64);
                             const unsigned long long vb = (rows == 64) ? ~0ull : ((1ull << rows) - 1ull);
-                            unsigned long long cur = remv[bb], kept = 0ull, acc = 0ull;
-                            unsigned long long avail = vb & ~cur;
+                            const unsigned long long cur0 = remv[bb];
+                            unsigned long long acc = 0ull;
+                            // the serial chain runs on 32-bit halves (ffs, shift and mask are single instructions there):
+                            // rows 0..31 first — their diagonal words also remove rows 32..63 — then rows 32..63
+                            const unsigned vlo = (unsigned)vb, vhi = (unsigned)(vb >> 32);
+                            unsigned cur_lo = (unsigned)cur0, cur_hi = (unsigned)(cur0 >> 32), kept_lo = 0u, kept_hi = 0u;
+                            const WinRow* wq = Wd + bufi * SBROWS + q * 64;
+                            unsigned avail = vlo & ~cur_lo;
                             while (avail) {                                        // warp-uniform; one kept row per trip
-                                const int t = __ffsll((long long)avail) - 1;
-                                kept |= 1ull << t;
-                                cur |= Wd[bufi * SBROWS + q * 64 + t][q];
-                                if (lane < WIN) acc |= Wd[bufi * SBROWS + q * 64 + t][lane];
-                                const unsigned long long above = (t == 63) ? 0ull : (~0ull << (t + 1));
-                                avail = vb & ~cur & above;
+                                const int t = __ffs((int)avail) - 1;
+                                kept_lo |= 1u << t;
+                                const unsigned long long d = wq[t][q];
+                                if (lane < WIN) acc |= wq[t][lane];
+                                cur_lo |= (unsigned)d; cur_hi |= (unsigned)(d >> 32);
+                                avail = vlo & ~cur_lo & (0xfffffffeu << t);
                             }
+                            avail = vhi & ~cur_hi;
+                            while (avail) {
+                                const int t = __ffs((int)avail) - 1;
+                                kept_hi |= 1u << t;
+                                const unsigned long long d = wq[32 + t][q];
+                                if (lane < WIN) acc |= wq[32 + t][lane];
+                                cur_hi |= (unsigned)(d >> 32);
+                                avail = vhi & ~cur_hi & (0xfffffffeu << t);
+                            }
+                            const unsigned long long kept = ((unsigned long long)kept_hi << 32) | kept_lo;
                             if ((int)lane > q && lane < WIN && S * SB + (int)lane < nb && acc) atomicOr(&remv[S * SB + lane], acc);
                             if (lane == 0) keptw[bb] = kept;
+                            // the block's kept rows, compacted (chunk-local row index), for the warps that apply them next step
+                            const unsigned klo = (unsigned)kept, khi = (unsigned)(kept >> 32);
+                            if ((klo >> lane) & 1u) ksb[bufi * SBROWS + nks + __popc(klo & lt)] = (unsigned short)(bb * 64 + (int)lane);
+                            if ((khi >> lane) & 1u) ksb[bufi * SBROWS + nks + __popc(klo) + __popc(khi & lt)] = (unsigned short)(bb * 64 + 32 + (int)lane);
+                            nks += __popcll(kept);
                             __syncwarp();
                         }
+                        if (lane == 0) misc[4 + bufi] = nks;
                     } else {
                         const int u = (int)tid - 32, nt = THREADS - 32;
                         if (S + 1 < nsb) prefetch(S + 1, bufi ^ 1, u, nt);
-                        const int first = (S - 1) * SB + WIN;                     // first column beyond the window of superblock S-1
+                        // kept rows of superblock S-1 x the columns beyond its window: every (row, column) word is one load,
+                        // a thread owns one column and every `groups`-th kept row, all its loads in flight together
+                        const int first = (S - 1) * SB + WIN;
                         const int ncb = nb - first;
                         if (S > 0 && ncb > 0) {
+                            const int nkp = misc[4 + (bufi ^ 1)];
                             const int groups = nt / ncb;                           // ncb <= 24: every column gets >= 9 threads
                             const int g = u / ncb, c = first + (u - g * ncb);
                             if (g < groups) {
-                                unsigned long long kq[SB];
-#pragma unroll
-                                for (int q = 0; q < SB; q++) kq[q] = ((S - 1) * SB + q < nb) ? keptw[(S - 1) * SB + q] : 0ull;
                                 unsigned long long acc = 0ull;
-                                for (int r0 = g; r0 < SBROWS; r0 += 4 * groups) {  // four independent loads per trip
-                                    unsigned long long v[4];
+                                for (int j0 = g; j0 < nkp; j0 += 8 * groups) {
+                                    unsigned long long v[8];
 #pragma unroll
-                                    for (int j = 0; j < 4; j++) {
-                                        const int r = r0 + j * groups;
+                                    for (int j = 0; j < 8; j++) {
+                                        const int jj = j0 + j * groups;
                                         v[j] = 0ull;
-                                        if (r < SBROWS && ((kq[r >> 6] >> (r & 63)) & 1ull)) {
-                                            const int lr = ((S - 1) * SB + (r >> 6)) * 64 + (r & 63);
+                                        if (jj < nkp) {
+                                            const int lr = ksb[(bufi ^ 1) * SBROWS + jj];
                                             v[j] = __ldcg(A.mask + wbase + (unsigned)(lr * nb + c));
                                         }
                                     }
-                                    acc |= (v[0] | v[1]) | (v[2] | v[3]);
+#pragma unroll
+                                    for (int j = 0; j < 8; j++) acc |= v[j];
                                 }
                                 if (acc) atomicOr(&remv[c], acc);
                             }

@@ -77,9 +77,15 @@ for K in (2000, 8000, 20000, 80000, 200000):
     Lb = torch.from_numpy(np.concatenate([x[2] for x in imgs])).to(dev)
     bid = torch.arange(8, device=dev).repeat_interleave(K)
     scales = torch.tensor([float(x[0].max() + 1) for x in imgs], device=dev)
-    fn = lambda: nms_device(B, S, 0.1, "v1", labels=Lb, class_offset=scales, order_index=True, batch_ids=bid, n_batches=8)
+    fn = lambda: nms_device(B, S, 0.1, "v1", labels=Lb, class_offset=scales, order_index=True, batch_ids=bid, n_batches=8, label_bits=LB)
     keep, num = fn()
-    out["batch8"][str(K)] = {"ms": timeit(fn, 5), "kept": int(num.sum()), "mcands_per_s": 8 * K / timeit(fn, 5) / 1e3}
+    st = {}
+    nms_device(B, S, 0.1, "v1", labels=Lb, class_offset=scales, order_index=True, batch_ids=bid, n_batches=8, stats=st, label_bits=LB)
+    torch.cuda.synchronize()
+    c = st["counters"].cpu().numpy()
+    ms = timeit(fn, 5)
+    out["batch8"][str(K)] = {"ms": ms, "kept": int(num.sum()), "mcands_per_s": 8 * K / ms / 1e3, "rounds": int(c[4]),
+                             "pairs_stage1": int(c[0]), "phase_us": [round(float(x) / 1e3, 1) for x in np.diff(c[9:9 + int(c[8])])]}
     del B, S, Lb, bid
 # worst case for the rounds: sparse small boxes, (almost) nothing suppressed -> the blocked triangular sweep
 for K in (20000, 100000):
