@@ -86,7 +86,7 @@ static NmsWs carve_nms(void* ws, int64_t K) {
     w.flag = (int*)take(4 * K); w.pref = (int*)take(4 * K);
     w.cub_bytes = cub_temp_bytes(K);
     w.cub_tmp = take(w.cub_bytes);
-    w.mask = (unsigned long long*)take((size_t)8 * (size_t)K * (rn::B_MAX / 64 + 1));   // sum over chunks of n * ceil(n / 64)
+    w.mask = (unsigned long long*)take((size_t)8 * (size_t)K * (rn::B_MAX / 64 + 2));   // sum over chunks of n * (ceil(n / 64) rounded up to even)
     w.bytes = off;
     return w;
 }
@@ -413,13 +413,15 @@ static int nms_rounds_stage(NmsWs& w, int Ki, int variant, int inclusive, float 
     }
     static const int chunk_env = nms_env_int("R3G_NMS_CHUNK", rn::B_MAX, 64, rn::B_MAX) / 64 * 64;     // tuning knobs
     static const int grid_env = nms_env_int("R3G_NMS_GRID", 0, 0, 1 << 20);
+    static const int div_env = nms_env_int("R3G_NMS_CHUNK_DIV", 0, 0, 64);
+    static const int min_env = nms_env_int("R3G_NMS_CHUNK_MIN", 512, 64, rn::B_MAX) / 64 * 64;
     rn::Args a;
     a.p0 = w.p0; a.p1 = w.p1; a.p2r = w.p2r; a.p2c = w.p2c; a.raw = w.raw; a.label = w.pos_label; a.K = Ki;
     a.alive = w.alive; a.seg_cur = w.seg_cur; a.seg_pe = w.seg_pe; a.act = w.act; a.ent = w.ent; a.spos = w.spos; a.klist = w.klist;
     a.ownerB = w.ownerB; a.ownerD = w.ownerD; a.mask = w.mask; a.keep_p = w.keep_p;
     a.ctrl = reinterpret_cast<rn::Ctrl*>(w.ctrl); a.bar = reinterpret_cast<unsigned*>(w.ctrl + 128);
     a.dbg = reinterpret_cast<unsigned long long*>(w.ctrl + 512);
-    a.B = chunk_env; a.split = nms_split_of(Ki);
+    a.B = chunk_env; a.split = nms_split_of(Ki); a.chunk_div = div_env; a.chunk_min = min_env;
     a.variant = variant; a.inclusive = inclusive; a.prefilter = prefilter; a.thr = thr; a.tau = tau; a.margin = margin;
     const long long cap = (long long)device_sm_count() * occ;
     long long grid = Ki / 32;

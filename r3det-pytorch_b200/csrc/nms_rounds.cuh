@@ -54,7 +54,7 @@ struct __attribute__((aligned(64))) Ctrl {      // one per round parity; zero at
 
 struct __attribute__((aligned(16))) Entry {     // one segment's chunk in one round (64 bytes, read as four 16-byte words)
     int seg, row_base, n, nb;                   // chunk rows: spos[row_base .. row_base + n), nb = ceil(n / 64)
-    unsigned wbase; int itemB0, cur_new, pe;    // mask words [wbase, wbase + n * nb); columns left to apply to: [cur_new, pe)
+    unsigned wbase; int itemB0, cur_new, pe;    // mask words [wbase, wbase + n * pitch), pitch = nb rounded up to even; columns left to apply to: [cur_new, pe)
     int nk, kbase, itemD0, ncg;                 // kept rows: klist[kbase .. kbase + nk); apply items
     int cg0, pad0, pad1, pad2;                  // first 128-column group of the apply range
 };
@@ -78,6 +78,7 @@ struct Args {
     unsigned long long* dbg;                    // [0] stage-1 pairs [1] separating-axis tests [2] area evaluations [3] restatements
                                                 // [4] rounds [5] mask items [6] apply items [8] n stamps [9..] phase time stamps (ns)
     int B, split;                               // chunk rows (<= B_MAX); row split of a mask item (1, 2, 4, 8)
+    int chunk_div, chunk_min;                   // chunk = clamp(remaining / chunk_div, chunk_min, B) rows (chunk_div = 0: always B)
     int variant, inclusive, prefilter;
     float thr, tau, margin;
 };
@@ -93,7 +94,7 @@ struct __attribute__((aligned(16))) WarpSmem {
     unsigned short q2[64];          // separating-axis survivors
 };
 constexpr size_t SMEM_BYTES = sizeof(WarpSmem) * WARPS;
-static_assert(2 * 256 * 8 * 8 + 64 * 8 + 64 + 2 * 256 * 2 <= SMEM_BYTES, "scan buffers alias the per-warp working sets");
+static_assert(2 * 256 * 8 * 8 + 64 * 8 + 64 + 128 + 2 * 256 * 2 <= SMEM_BYTES, "scan buffers alias the per-warp working sets");
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
     unsigned v;
@@ -364,7 +365,7 @@ __global__ void __launch_bounds__(THREADS, 2) nms_rounds_kernel(const Args A) {
         __syncwarp();
     };
 
-    const int B = A.B;
+    const int Bmax = A.B;
     int par = 0;
     while (true) {
         Ctrl* C = A.ctrl + par;
@@ -379,6 +380,10 @@ __global__ void __launch_bounds__(THREADS, 2) nms_rounds_kernel(const Args A) {
         for (unsigned i = blockIdx.x + gridDim.x * warp; i < n_act; i += nwarps) {
             const int s = __ldcg(act + i);
             const int cur = __ldcg(A.seg_cur + s), pe = __ldcg(A.seg_pe + s);
+            // chunk size of this segment and round: a fraction of what is left of the segment (small chunks waste fewer pair
+            // tests on rows that an earlier row of the same chunk suppresses; each round costs four grid barriers)
+            int B = Bmax;
+            if (A.chunk_div > 0 && pe - cur > A.chunk_min) B = min(Bmax, max(A.chunk_min, ((pe - cur) / A.chunk_div + 63) & ~63));
             const int cap = min(B, pe - cur);
             int row_base = 0;
             if (lane == 0) row_base = (int)atomicAdd(&C->rows_used, (unsigned)cap);
@@ -449,7 +454,7 @@ __global__ void __launch_bounds__(THREADS, 2) nms_rounds_kernel(const Args A) {
                 // the three allocations travel together: lanes 0..2 issue one atomic each
                 unsigned long long got = 0ull;
                 if (lane == 0) got = atomicAdd(&C->n_ent, 1u);
-                else if (lane == 1) got = atomicAdd(&C->words_used, (unsigned long long)n * (unsigned long long)nb);
+                else if (lane == 1) got = atomicAdd(&C->words_used, (unsigned long long)n * (unsigned long long)((nb + 1) & ~1));   // even row pitch
                 else if (lane == 2) got = atomicAdd(&C->itemsB, (unsigned)items);
                 const int e = (int)__shfl_sync(FULL, got, 0);
                 const unsigned wbase = (unsigned)__shfl_sync(FULL, got, 1);
@@ -496,7 +501,7 @@ __global__ void __launch_bounds__(THREADS, 2) nms_rounds_kernel(const Args A) {
                 const int cb0 = rb + 2 * li, ncb = min(2, nb - cb0);
                 const int rows = min(64, n - rb * 64);                        // valid rows of the block
                 const int r_lo = sub * rps, r_hi = min(rows, r_lo + rps);
-                nbw = nb; wb_item = (unsigned)e1.x + (unsigned)(rb * 64) * (unsigned)nb + (unsigned)cb0;
+                nbw = (nb + 1) & ~1; wb_item = (unsigned)e1.x + (unsigned)(rb * 64) * (unsigned)nbw + (unsigned)cb0;
                 // stage rows and columns (gathered through the chunk's position list)
                 __syncwarp();
 #pragma unroll
@@ -533,7 +538,7 @@ __global__ void __launch_bounds__(THREADS, 2) nms_rounds_kernel(const Args A) {
                 __syncwarp();
                 for (int k = r_lo * 2 + (int)lane; k < r_hi * 2; k += 32) {
                     const int il = k >> 1, c = k & 1;
-                    if (c < ncb) A.mask[wb_item + (unsigned)(il * nb + c)] = W.sm[k];
+                    if (c < ncb) A.mask[wb_item + (unsigned)(il * nbw + c)] = W.sm[k];
                 }
                 __syncwarp();
                 while (c3 >= 32) drain_emu(32);
@@ -556,37 +561,49 @@ __global__ void __launch_bounds__(THREADS, 2) nms_rounds_kernel(const Args A) {
             unsigned long long* remv = reinterpret_cast<unsigned long long*>(rn_smem + 2 * SBROWS * WIN * 8);   // [32]
             unsigned long long* keptw = remv + 32;                                                // [32]
             int* misc = reinterpret_cast<int*>(keptw + 32);                                       // [16]: 0..2 results, 4..5 kept counts
-            unsigned short* ksb = reinterpret_cast<unsigned short*>(misc + 16);                   // [2][SBROWS] kept rows of a superblock
+            int* kpre = misc + 16;                                                                // [32] kept rows before each block
+            unsigned short* ksb = reinterpret_cast<unsigned short*>(kpre + 32);                   // [2][SBROWS] kept rows of a superblock
             const unsigned n_ent = __ldcg(&C->n_ent);
             for (unsigned e = blockIdx.x; e < n_ent; e += gridDim.x) {
                 const int4 e0 = __ldcg(reinterpret_cast<const int4*>(A.ent + e));
                 const int4 e1 = __ldcg(reinterpret_cast<const int4*>(A.ent + e) + 1);
                 const int row_base = e0.y, n = e0.z, nb = e0.w, cur_new = e1.z, pe = e1.w;
                 const unsigned wbase = (unsigned)e1.x;
-                const int nsb = (nb + SB - 1) / SB;
-                auto prefetch = [&](int S, int bufi, int u, int nt) {             // all loads of a thread are issued before the first store
-                    constexpr int PAIRS = SBROWS * WIN;
-                    constexpr int PER = (PAIRS + (THREADS - 32) - 1) / (THREADS - 32);
-                    unsigned long long v[PER];
+                const int nsb = (nb + SB - 1) / SB, np = (nb + 1) & ~1;          // np: words per mask row (even: 16-byte loads)
+                constexpr int PAIRS2 = SBROWS * WIN / 2;
+                constexpr int PER = (PAIRS2 + (THREADS - 32) - 1) / (THREADS - 32);
+                // window of superblock S: every row's 8 words are 4 aligned 16-byte loads; all loads of a thread are issued
+                // before anything is stored.  Words left of the diagonal block or right of the chunk were never written: zero.
+                auto pf_load = [&](int S, int u, int nt, ulonglong2 (&v)[PER]) {
 #pragma unroll
                     for (int j = 0; j < PER; j++) {
                         const int idx = u + j * nt;
-                        unsigned long long x = 0ull;
-                        if (idx < PAIRS) {
-                            const int r = idx >> 3, k = idx & (WIN - 1), bb = S * SB + (r >> 6), col = S * SB + k, lr = bb * 64 + (r & 63);
-                            if (bb < nb && col >= bb && col < nb && lr < n) x = __ldcg(A.mask + wbase + (unsigned)(lr * nb + col));
+                        ulonglong2 x = make_ulonglong2(0ull, 0ull);
+                        if (idx < PAIRS2) {
+                            const int r = idx >> 2, k2 = idx & 3, bb = S * SB + (r >> 6), col = S * SB + 2 * k2, lr = bb * 64 + (r & 63);
+                            if (bb < nb && lr < n && col + 1 >= bb && col < nb) {
+                                x = __ldcg(reinterpret_cast<const ulonglong2*>(A.mask + wbase + (unsigned)(lr * np + col)));
+                                if (col < bb) x.x = 0ull;
+                                if (col + 1 >= nb) x.y = 0ull;
+                            }
                         }
                         v[j] = x;
                     }
+                };
+                auto pf_store = [&](int bufi, int u, int nt, const ulonglong2 (&v)[PER]) {
 #pragma unroll
                     for (int j = 0; j < PER; j++) {
                         const int idx = u + j * nt;
-                        if (idx < PAIRS) Wd[bufi * SBROWS + (idx >> 3)][idx & (WIN - 1)] = v[j];
+                        if (idx < PAIRS2) *reinterpret_cast<ulonglong2*>(&Wd[bufi * SBROWS + (idx >> 2)][2 * (idx & 3)]) = v[j];
                     }
                 };
                 __syncthreads();                                                   // the previous chunk is done with shared memory
                 if (tid < 64) remv[tid] = 0ull;                                    // removed[] and keptw[]
-                prefetch(0, 0, (int)tid, THREADS);
+                {
+                    ulonglong2 v[PER];
+                    pf_load(0, (int)tid, THREADS, v);
+                    pf_store(0, (int)tid, THREADS, v);
+                }
                 for (int S = 0; S < nsb; S++) {
                     const int bufi = S & 1;
                     __syncthreads();
@@ -609,7 +626,7 @@ __global__ void __launch_bounds__(THREADS, 2) nms_rounds_kernel(const Args A) {
                                 const int t = __ffs((int)avail) - 1;
                                 kept_lo |= 1u << t;
                                 const unsigned long long d = wq[t][q];
-                                if (lane < WIN) acc |= wq[t][lane];
+                                acc |= wq[t][lane & (WIN - 1)];                    // every lane loads (no divergence on the chain)
                                 cur_lo |= (unsigned)d; cur_hi |= (unsigned)(d >> 32);
                                 avail = vlo & ~cur_lo & (0xfffffffeu << t);
                             }
@@ -618,7 +635,7 @@ __global__ void __launch_bounds__(THREADS, 2) nms_rounds_kernel(const Args A) {
                                 const int t = __ffs((int)avail) - 1;
                                 kept_hi |= 1u << t;
                                 const unsigned long long d = wq[32 + t][q];
-                                if (lane < WIN) acc |= wq[32 + t][lane];
+                                acc |= wq[32 + t][lane & (WIN - 1)];
                                 cur_hi |= (unsigned)(d >> 32);
                                 avail = vhi & ~cur_hi & (0xfffffffeu << t);
                             }
@@ -635,7 +652,8 @@ __global__ void __launch_bounds__(THREADS, 2) nms_rounds_kernel(const Args A) {
                         if (lane == 0) misc[4 + bufi] = nks;
                     } else {
                         const int u = (int)tid - 32, nt = THREADS - 32;
-                        if (S + 1 < nsb) prefetch(S + 1, bufi ^ 1, u, nt);
+                        ulonglong2 pv[PER];
+                        if (S + 1 < nsb) pf_load(S + 1, u, nt, pv);               // in flight together with the loads below
                         // kept rows of superblock S-1 x the columns beyond its window: every (row, column) word is one load,
                         // a thread owns one column and every `groups`-th kept row, all its loads in flight together
                         const int first = (S - 1) * SB + WIN;
@@ -654,7 +672,7 @@ __global__ void __launch_bounds__(THREADS, 2) nms_rounds_kernel(const Args A) {
                                         v[j] = 0ull;
                                         if (jj < nkp) {
                                             const int lr = ksb[(bufi ^ 1) * SBROWS + jj];
-                                            v[j] = __ldcg(A.mask + wbase + (unsigned)(lr * nb + c));
+                                            v[j] = __ldcg(A.mask + wbase + (unsigned)(lr * np + c));
                                         }
                                     }
 #pragma unroll
@@ -663,36 +681,58 @@ __global__ void __launch_bounds__(THREADS, 2) nms_rounds_kernel(const Args A) {
                                 if (acc) atomicOr(&remv[c], acc);
                             }
                         }
+                        if (S + 1 < nsb) pf_store(bufi ^ 1, u, nt, pv);
                     }
                 }
                 __syncthreads();
-                if (tid == 0) {
-                    int nk = 0;
-                    for (int bb = 0; bb < nb; bb++) nk += __popcll(keptw[bb]);
-                    const int kbase = (int)atomicAdd(&C->kept_used, (unsigned)nk);
-                    int itemsD = 0, itemD0 = 0, ncg = 0, cg0 = 0;
+                if (warp == 0) {                                                   // kept counts: prefix over the blocks, allocations
+                    const int cntb = ((int)lane < nb) ? __popcll(keptw[lane]) : 0;
+                    int incl = cntb;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const int t = __shfl_up_sync(FULL, incl, d);
+                        if ((int)lane >= d) incl += t;
+                    }
+                    kpre[lane] = incl - cntb;
+                    const int nk = __shfl_sync(FULL, incl, 31);
+                    int itemsD = 0, ncg = 0, cg0 = 0;
                     if (cur_new < pe && nk > 0) {
                         cg0 = cur_new >> 7;
                         ncg = ((pe - 1) >> 7) - cg0 + 1;
                         itemsD = ((nk + 63) >> 6) * ncg;
-                        itemD0 = (int)atomicAdd(&C->itemsD, (unsigned)itemsD);
                     }
-                    int4* ep = reinterpret_cast<int4*>(A.ent + e);
-                    ep[2] = make_int4(nk, kbase, itemD0, ncg);
-                    ep[3] = make_int4(cg0, 0, 0, 0);
-                    misc[0] = kbase; misc[1] = itemD0; misc[2] = itemsD;
+                    unsigned got = 0u;                                             // the two allocations travel together
+                    if (lane == 0) got = atomicAdd(&C->kept_used, (unsigned)nk);
+                    else if (lane == 1 && itemsD > 0) got = atomicAdd(&C->itemsD, (unsigned)itemsD);
+                    const int kbase = (int)__shfl_sync(FULL, got, 0), itemD0 = (int)__shfl_sync(FULL, got, 1);
+                    if (lane == 0) {
+                        int4* ep = reinterpret_cast<int4*>(A.ent + e);
+                        ep[2] = make_int4(nk, kbase, itemD0, ncg);
+                        ep[3] = make_int4(cg0, 0, 0, 0);
+                        misc[0] = kbase; misc[1] = itemD0; misc[2] = itemsD;
+                    }
                 }
                 __syncthreads();
                 const int kbase = misc[0], itemD0 = misc[1], itemsD = misc[2];
-                for (int lr = tid; lr < n; lr += THREADS) {
-                    const int bb = lr >> 6, t = lr & 63;
-                    const unsigned long long kw = keptw[bb];
-                    if ((kw >> t) & 1ull) {
-                        int idx = __popcll(kw & ((1ull << t) - 1ull));
-                        for (int q = 0; q < bb; q++) idx += __popcll(keptw[q]);
-                        const int p = __ldcg(A.spos + row_base + lr);
-                        A.klist[kbase + idx] = p;
-                        A.keep_p[p] = 1;
+                {
+                    constexpr int RPT = B_MAX / THREADS;                           // rows per thread: all position loads in flight together
+                    int pp[RPT];
+#pragma unroll
+                    for (int i = 0; i < RPT; i++) {
+                        const int lr = (int)tid + i * THREADS;
+                        pp[i] = (lr < n) ? __ldcg(A.spos + row_base + lr) : 0;
+                    }
+#pragma unroll
+                    for (int i = 0; i < RPT; i++) {
+                        const int lr = (int)tid + i * THREADS;
+                        if (lr < n) {
+                            const int bb = lr >> 6, t = lr & 63;
+                            const unsigned long long kw = keptw[bb];
+                            if ((kw >> t) & 1ull) {
+                                A.klist[kbase + kpre[bb] + __popcll(kw & ((1ull << t) - 1ull))] = pp[i];
+                                A.keep_p[pp[i]] = 1;
+                            }
+                        }
                     }
                 }
                 for (int k = tid; k < itemsD; k += THREADS) A.ownerD[itemD0 + k] = (int)e;
