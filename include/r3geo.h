@@ -150,6 +150,17 @@ int r3g_poly_nms_workspace_bytes(int64_t K, size_t* bytes);
 int r3g_poly_nms_f32(const float* polys, int64_t stride, const float* scores, const int64_t* labels, int64_t K, float thr,
                      int64_t* keep_out, int64_t* num_keep_out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- padded keep records ------------------------------------------------------------------------------------
+ * replaces the per-image `dets[keep][:max_num]` slicing after NMS (r3det/core/post_processing/bbox_nms_rotated.py:127-131,
+ * rotate_anchor_head.py:626-673), which needs a host read of the keep count per image.  keep / num_keep are the outputs of
+ * r3g_nms_f32 / r3g_nms_batched_f32 (keep grouped by image).  Image b's first min(num_keep[b] - drop_last, max_per_img)
+ * kept candidates are written to out_dets[b, o, 0..5] = <x, y, w, h, a, score> and out_labels[b, o]; the remaining rows are
+ * zero; out_counts[b] = rows filled.  drop_last = 1 reproduces the `v2` branch's `inds[:-1]` for max_num = -1 (:119-121).
+ * n_batches <= 8192. */
+int r3g_nms_pack_f32(const float* boxes, int64_t stride, const float* scores, const int64_t* labels,
+                     const int64_t* keep, const int64_t* num_keep, const int64_t* batch_ids, int n_batches, int64_t K,
+                     int max_per_img, int drop_last, float* out_dets, int64_t* out_labels, int64_t* out_counts, void* stream);
+
 /* ---- multiclass candidate extraction -----------------------------------------------------------------------
  * replaces the torch prologue of multiclass_nms_rotated (r3det/core/post_processing/bbox_nms_rotated.py:34-41,
  * 98-103): candidates = (box, class) pairs with multi_scores[i, c] > score_thr for c < C (the last, background,

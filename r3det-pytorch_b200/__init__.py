@@ -18,6 +18,7 @@ Module map (reference module -> here):
   r3det/datasets/dota1.py (merge_det, _merge_func, _results2submission; §8f) -> dota_submission
 """
 from . import _lib  # noqa: F401
+from ._nms_core import pack_keep_records  # noqa: F401
 from .assign import FusedMaxIoUAssigner, max_iou_assign, max_iou_assign_batched  # noqa: F401
 from .bbox_nms_rotated import multiclass_nms_rotated, multiclass_nms_rotated_batch  # noqa: F401
 from .box_iou_rotated import obb_overlaps  # noqa: F401

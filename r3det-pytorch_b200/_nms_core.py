@@ -62,6 +62,31 @@ def nms_device(boxes, scores, thr, variant, labels=None, class_offset=None, incl
     return keep, num
 
 
+def pack_keep_records(boxes, scores, labels, keep, num, batch_ids=None, n_batches=1, max_per_img=2000, drop_last=False):
+    """Fixed-size detections from the outputs of `nms_device`, with no host synchronisation: returns
+    (dets (n_batches, max_per_img, 6), labels (n_batches, max_per_img) int64, counts (n_batches,) int64); image b's rows
+    [0, counts[b]) are its kept <x, y, w, h, a, score> in keep order (what `dets[keep][:max_per_img]` gives), the rest zero."""
+    L.require_cuda(boxes, scores, keep, num)
+    boxes, stride = L.as_f32_rows(boxes)
+    scores = scores.float().contiguous()
+    dev = boxes.device
+    K = boxes.size(0)
+    if labels is not None:
+        labels = labels.to(torch.int64).contiguous()
+    if batch_ids is not None:
+        batch_ids = batch_ids.to(torch.int64).contiguous()
+    num = num.reshape(-1).to(torch.int64).contiguous()
+    dets = torch.empty((n_batches, max_per_img, 6), dtype=torch.float32, device=dev)
+    labs = torch.empty((n_batches, max_per_img), dtype=torch.int64, device=dev)
+    counts = torch.empty((n_batches,), dtype=torch.int64, device=dev)
+    with L.device_guard(dev):
+        L.check(L.lib().r3g_nms_pack_f32(L.ptr(boxes), stride, L.ptr(scores), L.ptr(labels), L.ptr(keep), C.c_void_p(num.data_ptr()),
+                                         L.ptr(batch_ids), int(n_batches), K, int(max_per_img), int(bool(drop_last)),
+                                         C.c_void_p(dets.data_ptr()), C.c_void_p(labs.data_ptr()), C.c_void_p(counts.data_ptr()),
+                                         L.stream_ptr(dev)))
+    return dets, labs, counts
+
+
 def to_cuda_input(x, device_id, what):
     """numpy / CPU tensors are uploaded (the reference's convenience path, e.g. rnms_wrapper.py:11-15);
     returns (cuda tensor, is_numpy, was_host).  Host inputs get the reference's CPU rule (IoU >= thr)."""

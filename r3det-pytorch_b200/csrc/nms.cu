@@ -541,6 +541,94 @@ R3G_API int r3g_poly_nms_f32(const float* polys, int64_t stride, const float* sc
     return nms_finish_stage(w, Ki, nullptr, 1, 0, small, keep_out, num_keep_out, st);
 }
 
+// ---- padded keep records -------------------------------------------------------------------------------------------
+// What the callers of NMS do next (rotate_anchor_head.py:626-673, bbox_nms_rotated.py:127-131: `dets[keep][:max_num]`, one
+// Python slice per image after a host read of the keep count) as ONE kernel with fixed-size outputs: image b's first
+// min(num_keep[b], max_per_img) kept candidates -> out_dets[b, o, :] = <x, y, w, h, a, score>, out_labels[b, o]; the rest of
+// the (max_per_img) rows is zero; out_counts[b] = rows filled.  No host synchronisation is needed anywhere downstream.
+namespace r3g {
+
+__global__ void __launch_bounds__(256) nms_pack_kernel(const float* __restrict__ boxes, int64_t stride, const float* __restrict__ scores,
+                                                       const int64_t* __restrict__ labels, const int64_t* __restrict__ keep,
+                                                       const int64_t* __restrict__ num_keep, const int64_t* __restrict__ batch_ids,
+                                                       int n_batches, int64_t K, int max_per_img, int drop_last,
+                                                       float* __restrict__ out_dets, int64_t* __restrict__ out_labels,
+                                                       int64_t* __restrict__ out_counts) {
+    extern __shared__ long long starts[];                        // [n_batches + 1] exclusive prefix of num_keep
+    __shared__ long long carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int b0 = 0; b0 < n_batches; b0 += 256) {               // blocked scan, 256 images at a time
+        const int b = b0 + threadIdx.x;
+        long long v = (b < n_batches) ? num_keep[b] : 0;
+        typedef cub::BlockScan<long long, 256> Scan;
+        __shared__ typename Scan::TempStorage tmp;
+        long long pre, tot;
+        Scan(tmp).ExclusiveSum(v, pre, tot);
+        if (b < n_batches) starts[b] = carry + pre;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) starts[n_batches] = carry;
+    __syncthreads();
+    const long long total = starts[n_batches];
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < (int64_t)n_batches * max_per_img) {                  // padding rows and counts
+        const int b = (int)(t / max_per_img), o = (int)(t - (int64_t)b * max_per_img);
+        long long cnt = num_keep[b] - (drop_last ? 1 : 0);
+        cnt = cnt < 0 ? 0 : (cnt > max_per_img ? max_per_img : cnt);
+        if (o == 0) out_counts[b] = cnt;
+        if (o >= cnt) {
+#pragma unroll
+            for (int q = 0; q < 6; q++) out_dets[t * 6 + q] = 0.0f;
+            out_labels[t] = 0;
+        }
+    }
+    if (t < K && t < total) {                                    // kept entry t of the concatenated keep list
+        const int64_t idx = keep[t];
+        int b = 0;
+        if (batch_ids) {
+            const int64_t bb = batch_ids[idx];
+            b = (bb < 0 || bb >= n_batches) ? -1 : (int)bb;
+        }
+        if (b >= 0) {
+            const long long o = t - starts[b];
+            long long cnt = num_keep[b] - (drop_last ? 1 : 0);
+            cnt = cnt > max_per_img ? max_per_img : cnt;
+            if (o >= 0 && o < cnt) {
+                const int64_t r = (int64_t)b * max_per_img + o;
+                const float* bx = boxes + idx * stride;
+#pragma unroll
+                for (int q = 0; q < 5; q++) out_dets[r * 6 + q] = bx[q];
+                out_dets[r * 6 + 5] = scores[idx];
+                out_labels[r] = labels ? labels[idx] : 0;
+            }
+        }
+    }
+}
+
+}  // namespace r3g
+
+R3G_API int r3g_nms_pack_f32(const float* boxes, int64_t stride, const float* scores, const int64_t* labels,
+                             const int64_t* keep, const int64_t* num_keep, const int64_t* batch_ids, int n_batches, int64_t K,
+                             int max_per_img, int drop_last, float* out_dets, int64_t* out_labels, int64_t* out_counts,
+                             void* stream) {
+    R3G_REQUIRE(K >= 0 && n_batches >= 1 && n_batches <= 8192 && max_per_img >= 1, "r3g_nms_pack_f32: bad sizes (1..8192 images)");
+    R3G_REQUIRE(batch_ids != nullptr || n_batches == 1, "r3g_nms_pack_f32: n_batches > 1 needs batch_ids");
+    R3G_REQUIRE(num_keep && out_dets && out_labels && out_counts, "r3g_nms_pack_f32: null pointer");
+    R3G_REQUIRE(K == 0 || (boxes && scores && keep), "r3g_nms_pack_f32: null pointer");
+    R3G_REQUIRE(stride >= 5, "r3g_nms_pack_f32: box stride must be >= 5 floats");
+    const int64_t slots = (int64_t)n_batches * max_per_img;
+    const int64_t work = slots > K ? slots : K;
+    R3G_REQUIRE(work < (1ll << 31) * 256, "r3g_nms_pack_f32: problem too large");
+    nms_pack_kernel<<<(unsigned)((work + 255) / 256), 256, sizeof(long long) * (size_t)(n_batches + 1), (cudaStream_t)stream>>>(
+        boxes, stride, scores, labels, keep, num_keep, batch_ids, n_batches, K, max_per_img, drop_last ? 1 : 0, out_dets, out_labels,
+        out_counts);
+    R3G_LAUNCH_OK("nms_pack_kernel");
+    return R3G_OK;
+}
+
 // ---- multiclass candidate extraction --------------------------------------------------------------------------------
 // replaces the torch prologue of multiclass_nms_rotated (r3det/core/post_processing/bbox_nms_rotated.py:34-41, 98-103:
 // expand / boolean-mask / nonzero, five kernels and a sync) with ONE pass: candidate k enumerates the (box, class)

@@ -42,13 +42,14 @@ def sharded_assign(gt, anchors, assign_fn, group=None):
     return assign_fn(gt, anchors[lo:hi]), lo, hi
 
 
-def assigner_stats(gt_max_local, gt_argmax_local, max_overlaps_local, lo, pos_iou_thr, neg_iou_thr, group=None):
+def assigner_stats(gt_max_local, gt_argmax_local, max_overlaps_local, lo, pos_iou_thr, neg_iou_thr, group=None, sync=True):
     """Global per-GT best anchor and pos / neg anchor counts from the row-sharded fused assignment.
 
     gt_max_local / gt_argmax_local: (G,) best overlap of each GT inside this rank's anchors [lo, lo + n_local) and its LOCAL
     index; max_overlaps_local: (n_local,) best overlap of each local anchor.  One all_gather of G + 2 int64 per rank.
     Returns (gt_max (G,), gt_argmax (G,) global anchor index, num_pos, num_neg), identical on every rank; ties resolve to
-    the lowest anchor index, like torch.max over the unsharded matrix."""
+    the lowest anchor index, like torch.max over the unsharded matrix.  sync=False returns the two counts as 0-dim device
+    tensors instead of Python ints (no host read at all)."""
     G = gt_max_local.numel()
     dev = gt_max_local.device
     bits = gt_max_local.float().clamp_min(0).contiguous().view(torch.int32).to(torch.int64)    # IoU >= 0: bit order == value order
@@ -67,6 +68,8 @@ def assigner_stats(gt_max_local, gt_argmax_local, max_overlaps_local, lo, pos_io
     tot = buf[:, G:].sum(dim=0)
     gt_max = (best >> 32).to(torch.int32).view(torch.float32)
     gt_argmax = 0xFFFFFFFF - (best & 0xFFFFFFFF)
+    if not sync:
+        return gt_max, gt_argmax, tot[0], tot[1]
     npos, nneg = tot.tolist()                                                                   # the only host read
     return gt_max, gt_argmax, int(npos), int(nneg)
 
@@ -98,6 +101,23 @@ class KeepListGather(object):
         else:
             self.buf = payload[None]
 
+    def wait_padded(self):
+        """(dets (images, max_per_img, 6), labels (images, max_per_img) int64, counts (images,) int64) on the device, images in
+        global order — no host read, no per-image work (ranks hold equal shares when num_images divides by the world size;
+        otherwise the trailing ranks' unused slots are dropped)."""
+        if self.work is not None:
+            self.work.wait()
+            self.work = None
+        m = self.max_per_img
+        per_rank = self.buf.size(1)
+        rows = []
+        for r in range(self.world):
+            lo, hi = shard_range(self.num_images, r, self.world)
+            rows.append(self.buf[r, :hi - lo])
+        flat = torch.cat(rows) if len(rows) > 1 else rows[0]
+        rec = flat[:, :-1].reshape(-1, m, 7)
+        return rec[..., :6], rec[..., 6].to(torch.int64), flat[:, -1].to(torch.int64)
+
     def wait(self):
         if self.work is not None:
             self.work.wait()
@@ -127,11 +147,15 @@ def gather_keep_lists(local_dets, local_labels, max_per_img, num_images, group=N
     return h if async_op else h.wait()
 
 
-def gather_padded_records(dets, labels, counts, num_images, group=None, async_op=False):
+def gather_padded_records(dets, labels, counts, num_images, group=None, async_op=False, padded=False):
     """The same exchange from the padded device outputs of the batched NMS (no per-image Python work, no host read before the
-    collective): dets (per_rank, max_per_img, 6), labels (per_rank, max_per_img) int64, counts (per_rank,) int64."""
+    collective): dets (per_rank, max_per_img, 6), labels (per_rank, max_per_img) int64, counts (per_rank,) int64.
+    padded=True returns the gathered records as padded device tensors (KeepListGather.wait_padded) instead of per-image lists:
+    the whole exchange then runs without a single host synchronisation."""
     per_rank, m = dets.size(0), dets.size(1)
     payload = torch.cat([torch.cat([dets, labels.to(torch.float32)[..., None]], -1).reshape(per_rank, -1),
                          counts.to(torch.float32)[:, None]], 1).contiguous()
     h = KeepListGather(payload, m, num_images, group, async_op)
-    return h if async_op else h.wait()
+    if async_op:
+        return h
+    return h.wait_padded() if padded else h.wait()

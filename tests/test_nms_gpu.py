@@ -292,3 +292,32 @@ def test_randomised_configurations_vs_oracle(cuda_dev):
     spec = importlib.util.spec_from_file_location("fuzz_nms", os.path.join(os.path.dirname(__file__), "probes", "fuzz_nms.py"))
     m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
     assert m.run(seed=5, iters=45, dev=cuda_dev, verbose=True) == 0
+
+
+@pytest.mark.parametrize("by_index", [True, False])
+def test_padded_keep_records(cuda_dev, by_index):
+    """r3g_nms_pack_f32: fixed-size per-image outputs == the per-image `dets[keep][:max_per_img]` slices (no host read)."""
+    import r3det_b200 as R
+    from r3det_b200._nms_core import nms_device
+    sizes = [700, 0, 1500, 40]                                   # one image without candidates
+    parts = [clustered(k, 300 + i, "v1") for i, k in enumerate(sizes) if k]
+    b = np.concatenate([p[0] for p in parts]); s = np.concatenate([p[1] for p in parts]); l = np.concatenate([p[2] for p in parts])
+    bid = np.concatenate([np.full(k, i, np.int64) for i, k in enumerate(sizes)])
+    B, S, Lb, Bi = (_t(x, cuda_dev) for x in (b, s, l, bid))
+    keep, num = nms_device(B, S, 0.1, "v1", labels=Lb, order_index=by_index, batch_ids=Bi, n_batches=len(sizes))
+    for M, drop in ((50, False), (2000, False), (2000, True)):
+        dets, labs, cnt = R.pack_keep_records(B, S, Lb, keep, num, Bi, len(sizes), M, drop_last=drop)
+        nk = num.cpu().numpy(); kk = keep.cpu().numpy(); start = 0
+        for i in range(len(sizes)):
+            c = min(max(int(nk[i]) - (1 if drop else 0), 0), M)
+            idx = kk[start:start + c]
+            assert int(cnt[i]) == c
+            assert np.array_equal(dets[i, :c, :5].cpu().numpy(), b[idx]) and np.array_equal(dets[i, :c, 5].cpu().numpy(), s[idx])
+            assert np.array_equal(labs[i, :c].cpu().numpy(), l[idx])
+            assert float(dets[i, c:].abs().sum()) == 0.0 and int(labs[i, c:].abs().sum()) == 0
+            start += int(nk[i])
+    # single image, no batch ids
+    keep1, num1 = nms_device(B[:700], S[:700], 0.1, "v1", labels=Lb[:700], order_index=by_index)
+    d1, l1, c1 = R.pack_keep_records(B[:700], S[:700], Lb[:700], keep1, num1, None, 1, 100)
+    k1 = keep1[:min(int(num1), 100)].cpu().numpy()
+    assert int(c1[0]) == len(k1) and np.array_equal(d1[0, :len(k1), :5].cpu().numpy(), b[:700][k1])

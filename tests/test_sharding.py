@@ -49,6 +49,12 @@ def _worker(rank, world, port_no, q):
     for i, (d, l) in enumerate(zip(dets, labels)):
         pd[i, :d.size(0)] = d; pl[i, :l.size(0)] = l; pc[i] = d.size(0)
     d3, l3 = sharding.gather_padded_records(pd, pl, pc, num_images)
+    d4, l4, c4 = sharding.gather_padded_records(pd, pl, pc, num_images, padded=True)
+    assert d4.shape == (num_images, max_per, 6) and c4.tolist() == [d.size(0) for d in all_dets]
+    for i, d in enumerate(all_dets):
+        assert torch.equal(d4[i, :d.size(0)], d) and torch.equal(l4[i, :d.size(0)], all_labels[i])
+    g2 = sharding.assigner_stats(out.gt_max_overlaps, out.gt_argmax_overlaps, out.max_overlaps, lo, 0.5, 0.4, sync=False)
+    assert int(g2[2]) == npos and int(g2[3]) == nneg and torch.equal(g2[0], gmax)
     for a, b_, c in zip(all_dets, d2, d3):
         assert torch.equal(a, b_) and torch.equal(a, c)
     for a, b_, c in zip(all_labels, l2, l3):
