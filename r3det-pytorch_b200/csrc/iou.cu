@@ -37,6 +37,15 @@ namespace r3g {
 #ifndef R3G_IOU_TM
 #define R3G_IOU_TM 64
 #endif
+#ifndef R3G_IOU_BATCHLOAD
+#define R3G_IOU_BATCHLOAD 1        // stage 1: the 8 row records of a group are loaded together, ahead of the first use
+#endif
+#ifndef R3G_IOU_UNROLLCOMPACT
+#define R3G_IOU_UNROLLCOMPACT 0    // compaction variant: 32 predicated stores per lane instead of the find-leading-one loop (measured: +0.7 %)
+#endif
+#ifndef R3G_IOU_ZERO_CS
+#define R3G_IOU_ZERO_CS 1          // zero rows leave as streaming (evict-first) stores
+#endif
 constexpr int IOU_THREADS = R3G_IOU_THREADS;
 constexpr int IOU_WARPS = IOU_THREADS / 32;
 constexpr int IOU_CPL = 4;                  // columns per lane
@@ -210,251 +219,279 @@ __global__ void __launch_bounds__(IOU_THREADS, R3G_IOU_MINB) iou_matrix_kernel(c
     if (!isfinite(ox)) ox = 0.0f;
     if (!isfinite(oy)) oy = 0.0f;
 
-    int i0 = 0, j0 = 0, i1 = 0, ig = 0, jb = 0, cshift = 0;
+    int i0 = 0, j0 = 0, i1 = 0, jb = 0, cshift = 0;
     float cx[IOU_CPL], cy[IOU_CPL], cr[IOU_CPL], ck[IOU_CPL];
     unsigned long long CX[IOU_CPL / 2], CY[IOU_CPL / 2], CR[IOU_CPL / 2], CK[IOU_CPL / 2];   // the same, two columns per register pair
     float cm[IOU_CPL] = { 0.f, 0.f, 0.f, 0.f };     // OUT_ASSIGN_TIES: the columns' best overlap (from pass 1)
     float gm_lo = 0.f, gm_hi = 0.f, cmax_item = 0.f;  // OUT_ASSIGN_TIES: row maxima of the item, best column maximum
     bool full4 = false;
     float* orow = A.out;
-    bool flush = true, done = false;       // start by fetching an item
 
-    // One state loop; every stage body exists exactly once in the instruction stream (I-cache), deepest stage first.
+    // ---- stage 4: reference restatement for a batch of flagged pairs (a __noinline__ call: its registers / stack do not
+    //      tax the fast path) ----
+    auto stage4 = [&](int nb) {
+        __syncwarp();
+        if ((int)lane < nb) {
+            uint2 e = W.q3[c3 - nb + lane];
+            ItemCtx ec = { 0, 0, 0, 0 };
+            if (BATCH) {                              // the pair may belong to an earlier image: its id rides in the top bits
+                const AssignProb& pr = A.table->p[e.x >> 26];
+                ec.row0 = pr.row0; ec.col0 = pr.col0; ec.cb_shift = pr.cb_shift;
+                e.x &= 0x3ffffffu;
+            }
+            float r = emu_pair_call(A.raw1 + (int64_t)e.x * A.s1, A.raw2 + (int64_t)e.y * A.s2, A.variant, A.mode);
+            if (A.small_mask) {
+                const float4 a1 = ldg4(A.r1 + e.x), b1 = ldg4(A.c1 + e.y);
+                if (fminf(a1.z, a1.w) * 2.0f < 0.001f || fminf(b1.z, b1.w) * 2.0f < 0.001f) r = 0.0f;
+            }
+            emit_overlap<OUT>(A, (int)e.x, (int)e.y, r, ec);
+        }
+        __syncwarp();
+        c3 -= nb;
+        n_emu += nb;
+    };
+
+    // Items (64 rows x 128 columns) come from a dynamic ticket (the counter is zeroed by the launcher).  Inside an item the
+    // groups of 8 rows run stage 1 and feed the queues; after every group (and once more after the last one, with `fl` set, to
+    // flush what is left) the queue stages run deepest first.  Every stage body exists exactly once in the instruction stream.
     while (true) {
-        if (c3 >= 32 || (done && c3 > 0)) {
-            // ---- stage 4: reference restatement for flagged pairs ----
-            const int nb = min(32, c3);
-            __syncwarp();
-            if ((int)lane < nb) {
-                uint2 e = W.q3[c3 - nb + lane];
-                ItemCtx ec = { 0, 0, 0, 0 };
-                if (BATCH) {                              // the pair may belong to an earlier image: its id rides in the top bits
-                    const AssignProb& pr = A.table->p[e.x >> 26];
-                    ec.row0 = pr.row0; ec.col0 = pr.col0; ec.cb_shift = pr.cb_shift;
-                    e.x &= 0x3ffffffu;
-                }
-                float r = emu_pair_call(A.raw1 + (int64_t)e.x * A.s1, A.raw2 + (int64_t)e.y * A.s2, A.variant, A.mode);
-                if (A.small_mask) {
-                    const float4 a1 = ldg4(A.r1 + e.x), b1 = ldg4(A.c1 + e.y);
-                    if (fminf(a1.z, a1.w) * 2.0f < 0.001f || fminf(b1.z, b1.w) * 2.0f < 0.001f) r = 0.0f;
-                }
-                emit_overlap<OUT>(A, (int)e.x, (int)e.y, r, ec);
+        long long item = 0;
+        if (lane == 0) item = (long long)atomicAdd(A.stats + 4, 1ull);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= total) break;
+        int tiles_n = tiles_n_all, i_end = A.m, j_end = A.n;      // row / column limits of the item's problem
+        if (BATCH) {
+            // image of this item: last p with item0[p] <= item
+            int lo = 0, hi = A.table->nprob;
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (A.table->p[mid].item0 <= item) lo = mid; else hi = mid;
             }
+            const AssignProb pr = A.table->p[lo];
+            item -= pr.item0;
+            tiles_n = (pr.n + IOU_TN - 1) / IOU_TN;
             __syncwarp();
-            c3 -= nb;
-            n_emu += nb;
-            continue;
+            if (lane == 0) { W.ctx[0] = pr.row0; W.ctx[1] = pr.col0; W.ctx[2] = pr.cb_shift; W.ctx[3] = lo; }
+            i_end = pr.row0 + pr.m; j_end = pr.col0 + pr.n;
+            cshift = pr.cb_shift;
+            i0 = pr.row0; j0 = pr.col0;
+        } else {
+            i0 = 0; j0 = 0;
         }
-        if (done) break;
-        if (c2 >= 32 || (flush && c1 == 0 && c2 > 0)) {
-            // ---- stage 3: area integral + epilogue for truly overlapping pairs ----
-            const int nb = min(32, c2);
-            __syncwarp();
-            bool risk = false;
-            int i = 0, j = 0;
-            if ((int)lane < nb) {
-                const unsigned e = W.q2[c2 - nb + lane];
-                const int il = (int)(e >> 7), jl = (int)(e & 127u);
-                i = i0 + il; j = j0 + jl;
-                const BoxP0 A0 = as_p0(W.r0[il]), B0 = as_p0(W.c0[jl]);
-                const BoxP1 A1 = as_p1(W.r1[il]), B1 = as_p1(W.c1[jl]);
-                float r = pair_overlap(A0, A1, B0, B1, A.variant, A.mode, A.tau, risk);
-                if (A.small_mask && (fminf(A1.hw, A1.hh) * 2.0f < 0.001f || fminf(B1.hw, B1.hh) * 2.0f < 0.001f)) r = 0.0f;
-                if (!risk && r != 0.0f) {
-                    ItemCtx ctx = { 0, 0, 0, 0 };
-                    if (BATCH) { ctx.row0 = W.ctx[0]; ctx.col0 = W.ctx[1]; ctx.cb_shift = W.ctx[2]; }
-                    emit_overlap<OUT>(A, i, j, r, ctx);
-                }
-            }
-            __syncwarp();
-            c2 -= nb;
-            n_sat += nb;
-            const unsigned bal = __ballot_sync(0xffffffffu, risk);
-            if (risk) W.q3[c3 + __popc(bal & lt)] = make_uint2((unsigned)i | (BATCH ? ((unsigned)W.ctx[3] << 26) : 0u), (unsigned)j);
-            c3 += __popc(bal);
-            continue;
+        const int tm = (int)(item / tiles_n), tn = (int)(item - (long long)tm * tiles_n);
+        i0 += tm * IOU_TM; j0 += tn * IOU_TN;
+        i1 = min(i_end, i0 + IOU_TM);
+        jb = j0 + (int)lane * IOU_CPL;
+        __syncwarp();
+        // stage the item's prepared boxes: 2 x 64 row records + 2 x 128 column records, 16 bytes each
+        for (int t = lane; t < IOU_TM; t += 32) {
+            const int i = min(i0 + t, i_end - 1);
+            cp_async16(&W.r0[t], A.r0 + i); cp_async16(&W.r1[t], A.r1 + i);
         }
-        if (c1 >= 32 || (flush && c1 > 0)) {
-            // ---- stage 2: separating-axis test ----
-            const int nb = min(32, c1);
-            __syncwarp();
-            bool ok = false;
-            unsigned e = 0;
-            if ((int)lane < nb) {
-                e = W.q1[c1 - nb + lane];
-                const int il = (int)(e >> 7), jl = (int)(e & 127u);
-                ok = pair_sat(as_p0(W.r0[il]), as_p1(W.r1[il]), as_p0(W.c0[jl]), as_p1(W.c1[jl]));
-            }
-            __syncwarp();
-            c1 -= nb;
-            n_circle += nb;
-            const unsigned bal = __ballot_sync(0xffffffffu, ok);
-            if (ok) W.q2[c2 + __popc(bal & lt)] = (unsigned short)e;
-            c2 += __popc(bal);
-            continue;
+        for (int t = lane; t < IOU_TN; t += 32) {
+            const int j = min(j0 + t, j_end - 1);
+            cp_async16(&W.c0[t], A.c0 + j); cp_async16(&W.c1[t], A.c1 + j);
         }
-        if (flush) {
-            // ---- next item (dynamic ticket; the counter is zeroed by the launcher) ----
-            long long item = 0;
-            if (lane == 0) item = (long long)atomicAdd(A.stats + 4, 1ull);
-            item = __shfl_sync(0xffffffffu, item, 0);
-            if (item >= total) { done = true; continue; }
-            int tiles_n = tiles_n_all, i_end = A.m, j_end = A.n;      // row / column limits of the item's problem
-            if (BATCH) {
-                // image of this item: last p with item0[p] <= item
-                int lo = 0, hi = A.table->nprob;
-                while (hi - lo > 1) {
-                    const int mid = (lo + hi) >> 1;
-                    if (A.table->p[mid].item0 <= item) lo = mid; else hi = mid;
-                }
-                const AssignProb pr = A.table->p[lo];
-                item -= pr.item0;
-                tiles_n = (pr.n + IOU_TN - 1) / IOU_TN;
-                __syncwarp();
-                if (lane == 0) { W.ctx[0] = pr.row0; W.ctx[1] = pr.col0; W.ctx[2] = pr.cb_shift; W.ctx[3] = lo; }
-                i_end = pr.row0 + pr.m; j_end = pr.col0 + pr.n;
-                cshift = pr.cb_shift;
-                i0 = pr.row0; j0 = pr.col0;
+        cp_async_wait_all();
+        __syncwarp();
+        // this lane's 4 columns relative to the origin; invalid columns are pushed to +inf (always rejected)
+#pragma unroll
+        for (int k = 0; k < IOU_CPL; k++) {
+            if (jb + k < j_end) {
+                const float4 b = W.c0[lane * IOU_CPL + k];
+                cx[k] = b.x - ox; cy[k] = b.y - oy; cr[k] = b.z;
+                const float q = cx[k] * cx[k] + cy[k] * cy[k], rr = b.z * b.z;
+                ck[k] = (q - rr) - IOU_SLACK * (q + rr);
             } else {
-                i0 = 0; j0 = 0;
+                cx[k] = 0.0f; cy[k] = 0.0f; cr[k] = 0.0f; ck[k] = 3.0e38f;
             }
-            const int tm = (int)(item / tiles_n), tn = (int)(item - (long long)tm * tiles_n);
-            i0 += tm * IOU_TM; j0 += tn * IOU_TN;
-            i1 = min(i_end, i0 + IOU_TM);
-            ig = i0;
-            jb = j0 + (int)lane * IOU_CPL;
-            __syncwarp();
-            // stage the item's prepared boxes: 2 x 64 row records + 2 x 128 column records, 16 bytes each
-            for (int t = lane; t < IOU_TM; t += 32) {
-                const int i = min(i0 + t, i_end - 1);
-                cp_async16(&W.r0[t], A.r0 + i); cp_async16(&W.r1[t], A.r1 + i);
-            }
-            for (int t = lane; t < IOU_TN; t += 32) {
-                const int j = min(j0 + t, j_end - 1);
-                cp_async16(&W.c0[t], A.c0 + j); cp_async16(&W.c1[t], A.c1 + j);
-            }
-            cp_async_wait_all();
-            __syncwarp();
-            // this lane's 4 columns relative to the origin; invalid columns are pushed to +inf (always rejected)
-#pragma unroll
-            for (int k = 0; k < IOU_CPL; k++) {
-                if (jb + k < j_end) {
-                    const float4 b = W.c0[lane * IOU_CPL + k];
-                    cx[k] = b.x - ox; cy[k] = b.y - oy; cr[k] = b.z;
-                    const float q = cx[k] * cx[k] + cy[k] * cy[k], rr = b.z * b.z;
-                    ck[k] = (q - rr) - IOU_SLACK * (q + rr);
-                } else {
-                    cx[k] = 0.0f; cy[k] = 0.0f; cr[k] = 0.0f; ck[k] = 3.0e38f;
-                }
-            }
-            if (OUT == OUT_ASSIGN_MAX) {
-#pragma unroll
-                for (int h = 0; h < IOU_CPL / 2; h++) {
-                    CX[h] = pack2(cx[2 * h], cx[2 * h + 1]); CY[h] = pack2(cy[2 * h], cy[2 * h + 1]);
-                    CR[h] = pack2(cr[2 * h], cr[2 * h + 1]); CK[h] = pack2(ck[2 * h], ck[2 * h + 1]);
-                }
-            }
-            full4 = VEC && (jb + IOU_CPL <= j_end);
-            if (OUT == OUT_MATRIX) orow = A.out + (int64_t)i0 * A.n + jb;
-            if (OUT == OUT_ASSIGN_TIES) {
-#pragma unroll
-                for (int k = 0; k < IOU_CPL; k++)
-                    cm[k] = (jb + k < j_end) ? __uint_as_float((unsigned)(__ldcg(A.col_best + jb + k + cshift) >> 32)) : -1.0f;
-                // row maxima of the item (lane t holds rows t and t+32) and the best column maximum of the item:
-                // a row whose maximum exceeds every column maximum of the item cannot tie here and is skipped whole
-                gm_lo = (i0 + (int)lane < i1) ? __uint_as_float((unsigned)(__ldcg(A.row_best + i0 + lane) >> 32)) : 0.0f;
-                gm_hi = (i0 + 32 + (int)lane < i1) ? __uint_as_float((unsigned)(__ldcg(A.row_best + i0 + 32 + lane) >> 32)) : 0.0f;
-                cmax_item = fmaxf(fmaxf(cm[0], cm[1]), fmaxf(cm[2], cm[3]));
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) cmax_item = fmaxf(cmax_item, __shfl_xor_sync(0xffffffffu, cmax_item, o));
-            }
-            flush = false;
-            continue;
         }
-        if (ig >= i1) { flush = true; continue; }
+        if (OUT == OUT_ASSIGN_MAX) {
+#pragma unroll
+            for (int h = 0; h < IOU_CPL / 2; h++) {
+                CX[h] = pack2(cx[2 * h], cx[2 * h + 1]); CY[h] = pack2(cy[2 * h], cy[2 * h + 1]);
+                CR[h] = pack2(cr[2 * h], cr[2 * h + 1]); CK[h] = pack2(ck[2 * h], ck[2 * h + 1]);
+            }
+        }
+        full4 = VEC && (jb + IOU_CPL <= j_end);
+        if (OUT == OUT_MATRIX) orow = A.out + (int64_t)i0 * A.n + jb;
+        if (OUT == OUT_ASSIGN_TIES) {
+#pragma unroll
+            for (int k = 0; k < IOU_CPL; k++)
+                cm[k] = (jb + k < j_end) ? __uint_as_float((unsigned)(__ldcg(A.col_best + jb + k + cshift) >> 32)) : -1.0f;
+            // row maxima of the item (lane t holds rows t and t+32) and the best column maximum of the item:
+            // a row whose maximum exceeds every column maximum of the item cannot tie here and is skipped whole
+            gm_lo = (i0 + (int)lane < i1) ? __uint_as_float((unsigned)(__ldcg(A.row_best + i0 + lane) >> 32)) : 0.0f;
+            gm_hi = (i0 + 32 + (int)lane < i1) ? __uint_as_float((unsigned)(__ldcg(A.row_best + i0 + 32 + lane) >> 32)) : 0.0f;
+            cmax_item = fmaxf(fmaxf(cm[0], cm[1]), fmaxf(cm[2], cm[3]));
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) cmax_item = fmaxf(cmax_item, __shfl_xor_sync(0xffffffffu, cmax_item, o));
+        }
 
-        // ---- stage 1: one group of 8 rows x (4 columns per lane) ----
-        {
-            const int nr = min(IOU_RG, i1 - ig);
-            unsigned m = 0;
+        for (int ig = i0; ; ig += IOU_RG) {
+            const bool fl = ig >= i1;                  // the flush pass behind the item's last group
+            if (!fl) {
+                // ---- stage 1: one group of 8 rows x (4 columns per lane) ----
+                const int nr = min(IOU_RG, i1 - ig);
+                unsigned m = 0;
+#if R3G_IOU_BATCHLOAD
+                float4 arow[IOU_RG];                   // matrix mode: all row records in flight before the first use
+                if (OUT == OUT_MATRIX) {
 #pragma unroll
-            for (int r = 0; r < IOU_RG; r++) {
-                if (r < nr) {
-                    if (OUT == OUT_ASSIGN_TIES) {
-                        static_assert(IOU_TM <= 64, "row maxima are cached two per lane");
-                        const int rl = ig - i0 + r;
-                        const float gm = __shfl_sync(0xffffffffu, rl < 32 ? gm_lo : gm_hi, rl & 31);
-                        if (!(gm > 0.0f) || gm > cmax_item) { m <<= IOU_CPL; continue; }      // warp-uniform skip
-                        const float4 a = ldg4(A.r2 + ig + r);
+                    for (int r = 0; r < IOU_RG; r++) arow[r] = ldg4(A.r2 + ig + min(r, nr - 1));
+                }
+#endif
 #pragma unroll
-                        for (int k = 0; k < IOU_CPL; k++) {
-                            float s = fmaf(a.x, cx[k], ck[k] + a.w);
-                            s = fmaf(a.y, cy[k], s);
-                            s = fmaf(a.z, cr[k], s);
-                            m = (m << 1) | ((s < 0.0f && cm[k] >= gm) ? 1u : 0u);
+                for (int r = 0; r < IOU_RG; r++) {
+                    if (r < nr) {
+                        if (OUT == OUT_ASSIGN_TIES) {
+                            static_assert(IOU_TM <= 64, "row maxima are cached two per lane");
+                            const int rl = ig - i0 + r;
+                            const float gm = __shfl_sync(0xffffffffu, rl < 32 ? gm_lo : gm_hi, rl & 31);
+                            if (!(gm > 0.0f) || gm > cmax_item) { m <<= IOU_CPL; continue; }      // warp-uniform skip
+                            const float4 a = ldg4(A.r2 + ig + r);
+#pragma unroll
+                            for (int k = 0; k < IOU_CPL; k++) {
+                                float s = fmaf(a.x, cx[k], ck[k] + a.w);
+                                s = fmaf(a.y, cy[k], s);
+                                s = fmaf(a.z, cr[k], s);
+                                m = (m << 1) | ((s < 0.0f && cm[k] >= gm) ? 1u : 0u);
+                            }
+                            continue;
                         }
-                        continue;
-                    }
-                    // s < 0  <=>  centres closer than the sum of the (conservative) circumradii
-                    if (OUT == OUT_MATRIX) {
-                        const float4 a = ldg4(A.r2 + ig + r);
+                        // s < 0  <=>  centres closer than the sum of the (conservative) circumradii
+                        if (OUT == OUT_MATRIX) {
+#if R3G_IOU_BATCHLOAD
+                            const float4 a = arow[r];
+#else
+                            const float4 a = ldg4(A.r2 + ig + r);
+#endif
 #pragma unroll
-                        for (int k = 0; k < IOU_CPL; k++) {
-                            float s = fmaf(a.x, cx[k], ck[k] + a.w);
-                            s = fmaf(a.y, cy[k], s);
-                            s = fmaf(a.z, cr[k], s);
-                            m = __funnelshift_l(__float_as_uint(s), m, 1);
-                        }
-                    } else {
-                        // two columns per instruction, the same operations in the same order (add, then three fused multiply-adds)
-                        const ulonglong2 ra = __ldg(reinterpret_cast<const ulonglong2*>(A.r2d + ig + r));        // {mx, mx}, {my, my}
-                        const ulonglong2 rb = __ldg(reinterpret_cast<const ulonglong2*>(A.r2d + ig + r) + 1);    // {mr, mr}, {k, k}
-#pragma unroll
-                        for (int h = 0; h < IOU_CPL / 2; h++) {
-                            unsigned long long t = add2(CK[h], rb.y);
-                            t = fma2(ra.x, CX[h], t);
-                            t = fma2(ra.y, CY[h], t);
-                            t = fma2(rb.x, CR[h], t);
-                            m = __funnelshift_l((unsigned)t, m, 1);
-                            m = __funnelshift_l((unsigned)(t >> 32), m, 1);
-                        }
-                    }
-                    if (OUT == OUT_MATRIX) {
-                        if (full4) {
-                            st_cs_f4(orow, make_float4(0.f, 0.f, 0.f, 0.f));
+                            for (int k = 0; k < IOU_CPL; k++) {
+                                float s = fmaf(a.x, cx[k], ck[k] + a.w);
+                                s = fmaf(a.y, cy[k], s);
+                                s = fmaf(a.z, cr[k], s);
+                                m = __funnelshift_l(__float_as_uint(s), m, 1);
+                            }
                         } else {
+                            // two columns per instruction, the same operations in the same order (add, then three fused multiply-adds)
+                            const ulonglong2 ra = __ldg(reinterpret_cast<const ulonglong2*>(A.r2d + ig + r));        // {mx, mx}, {my, my}
+                            const ulonglong2 rb = __ldg(reinterpret_cast<const ulonglong2*>(A.r2d + ig + r) + 1);    // {mr, mr}, {k, k}
 #pragma unroll
-                            for (int k = 0; k < IOU_CPL; k++)
-                                if (jb + k < A.n) st_cs_f1(orow + k, 0.f);      // matrix mode only: one problem
+                            for (int h = 0; h < IOU_CPL / 2; h++) {
+                                unsigned long long t = add2(CK[h], rb.y);
+                                t = fma2(ra.x, CX[h], t);
+                                t = fma2(ra.y, CY[h], t);
+                                t = fma2(rb.x, CR[h], t);
+                                m = __funnelshift_l((unsigned)t, m, 1);
+                                m = __funnelshift_l((unsigned)(t >> 32), m, 1);
+                            }
                         }
-                        orow += A.n;
+                        if (OUT == OUT_MATRIX) {
+                            if (full4) {
+#if R3G_IOU_ZERO_CS
+                                st_cs_f4(orow, make_float4(0.f, 0.f, 0.f, 0.f));
+#else
+                                *reinterpret_cast<float4*>(orow) = make_float4(0.f, 0.f, 0.f, 0.f);
+#endif
+                            } else {
+#pragma unroll
+                                for (int k = 0; k < IOU_CPL; k++)
+                                    if (jb + k < A.n) st_cs_f1(orow + k, 0.f);      // matrix mode only: one problem
+                            }
+                            orow += A.n;
+                        }
                     }
                 }
-            }
-            // compact the group's survivors: warp scan of popc, then each lane emits its own bits (row-major order)
-            const int cnt = __popc(m);
-            int incl = cnt;
+                // compact the group's survivors: warp scan of popc, then each lane emits its own bits (row-major order)
+                const int cnt = __popc(m);
+                int incl = cnt;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, incl, d);
-                if ((int)lane >= d) incl += t;
-            }
-            const int tot = __shfl_sync(0xffffffffu, incl, 31);
-            if (tot) {
-                int pos = c1 + incl - cnt;
-                const int nbits = nr * IOU_CPL;
-                const unsigned rowbase = (unsigned)(ig - i0);
-                while (m) {
-                    const int b = 31 - __clz(m);
-                    m ^= 1u << b;
-                    const unsigned idx = (unsigned)(nbits - 1 - b);
-                    W.q1[pos++] = (unsigned short)(((rowbase + (idx >> 2)) << 7) | (lane * IOU_CPL + (idx & 3u)));
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, incl, d);
+                    if ((int)lane >= d) incl += t;
                 }
-                c1 += tot;
+                const int tot = __shfl_sync(0xffffffffu, incl, 31);
+                if (tot) {
+                    int pos = c1 + incl - cnt;
+                    const int nbits = nr * IOU_CPL;
+                    // entry = (row << 7 | column), row = rowbase + idx / 4, column = 4 lane + idx % 4, idx = nbits - 1 - bit
+                    const unsigned ebase = ((unsigned)(ig - i0) << 7) | (lane * IOU_CPL);
+#if R3G_IOU_UNROLLCOMPACT
+                    // 32 predicated stores: no find-leading-one (XU pipe, long dependent chain), no divergent trip counts
+                    m <<= 32 - nbits;                                  // pair t = 4 row + column now sits at bit 31 - t
+                    unsigned short* qp = W.q1 + pos;
+#pragma unroll
+                    for (int t = 0; t < 32; t++) {
+                        if (m & (0x80000000u >> t)) { *qp = (unsigned short)(ebase + (unsigned)(((t & ~3) << 5) + (t & 3))); qp++; }
+                    }
+#else
+                    while (m) {
+                        const int b = 31 - __clz(m);
+                        m ^= 1u << b;
+                        const unsigned idx = (unsigned)(nbits - 1 - b);
+                        W.q1[pos++] = (unsigned short)(ebase + ((idx & ~3u) << 5) + (idx & 3u));
+                    }
+#endif
+                    c1 += tot;
+                }
             }
-            ig += IOU_RG;
+            // ---- queue stages, deepest first ----
+            while (true) {
+                if (c3 >= 32) { stage4(32); continue; }
+                if (c2 >= 32 || (fl && c1 == 0 && c2 > 0)) {
+                    // ---- stage 3: area integral + epilogue for truly overlapping pairs ----
+                    const int nb = min(32, c2);
+                    __syncwarp();
+                    bool risk = false;
+                    int i = 0, j = 0;
+                    if ((int)lane < nb) {
+                        const unsigned e = W.q2[c2 - nb + lane];
+                        const int il = (int)(e >> 7), jl = (int)(e & 127u);
+                        i = i0 + il; j = j0 + jl;
+                        const BoxP0 A0 = as_p0(W.r0[il]), B0 = as_p0(W.c0[jl]);
+                        const BoxP1 A1 = as_p1(W.r1[il]), B1 = as_p1(W.c1[jl]);
+                        float r = pair_overlap(A0, A1, B0, B1, A.variant, A.mode, A.tau, risk);
+                        if (A.small_mask && (fminf(A1.hw, A1.hh) * 2.0f < 0.001f || fminf(B1.hw, B1.hh) * 2.0f < 0.001f)) r = 0.0f;
+                        if (!risk && r != 0.0f) {
+                            ItemCtx ctx = { 0, 0, 0, 0 };
+                            if (BATCH) { ctx.row0 = W.ctx[0]; ctx.col0 = W.ctx[1]; ctx.cb_shift = W.ctx[2]; }
+                            emit_overlap<OUT>(A, i, j, r, ctx);
+                        }
+                    }
+                    __syncwarp();
+                    c2 -= nb;
+                    n_sat += nb;
+                    const unsigned bal = __ballot_sync(0xffffffffu, risk);
+                    if (risk) W.q3[c3 + __popc(bal & lt)] = make_uint2((unsigned)i | (BATCH ? ((unsigned)W.ctx[3] << 26) : 0u), (unsigned)j);
+                    c3 += __popc(bal);
+                    continue;
+                }
+                if (c1 >= 32 || (fl && c1 > 0)) {
+                    // ---- stage 2: separating-axis test ----
+                    const int nb = min(32, c1);
+                    __syncwarp();
+                    bool ok = false;
+                    unsigned e = 0;
+                    if ((int)lane < nb) {
+                        e = W.q1[c1 - nb + lane];
+                        const int il = (int)(e >> 7), jl = (int)(e & 127u);
+                        ok = pair_sat(as_p0(W.r0[il]), as_p1(W.r1[il]), as_p0(W.c0[jl]), as_p1(W.c1[jl]));
+                    }
+                    __syncwarp();
+                    c1 -= nb;
+                    n_circle += nb;
+                    const unsigned bal = __ballot_sync(0xffffffffu, ok);
+                    if (ok) W.q2[c2 + __popc(bal & lt)] = (unsigned short)e;
+                    c2 += __popc(bal);
+                    continue;
+                }
+                break;
+            }
+            if (fl) break;
         }
     }
+    while (c3 > 0) stage4(min(32, c3));     // flagged pairs persist across items (absolute indices): the last ones
 
     if (A.stats) {
         if (blockIdx.x == 0 && threadIdx.x == 0) A.stats[3] = (unsigned long long)A.m * (unsigned long long)A.n;
