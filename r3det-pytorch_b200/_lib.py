@@ -9,7 +9,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libr3geo.so")
+LIB_PATH = os.environ.get("R3G_LIB", os.path.join(_HERE, "libr3geo.so"))      # R3G_LIB: an alternative build (variant timing)
 
 V = {"v1": 1, "v2": 2, "v3": 3}
 MODE = {"iou": 0, "iof": 1}

@@ -23,7 +23,9 @@
 // Sample-point math follows feature_refine_kernel.cu:16-65 (interpolation) and :127-151 (points), including
 // the reference's swap of box x -> row and box y -> column.
 #include <cub/cub.cuh>
+#include <stdlib.h>
 #include "common.cuh"
+#include "frm_tma.cuh"
 
 namespace r3g {
 
@@ -411,6 +413,47 @@ static int frm_plan(const char* who, int L, const float* const* in, const float*
 
 using namespace r3g;
 
+// TMA path of the forward (frm_tma.cuh): every level must be addressable by a tensor map (W % 4 == 0, 16-byte aligned base)
+static bool frm_tma_enabled() {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("R3G_FRM_TMA"); on = (e && e[0] == '0') ? 0 : 1; }
+    return on == 1;
+}
+
+// tensor maps + tile layout of every level; false when a level cannot be addressed by the TMA unit (the gather kernels serve it)
+template <int P, bool BWD>
+static bool frm_tma_levels(const FrmLevels& S, ftma::Levels& T, size_t* blocks_out) {
+    T.L = S.L; T.N = S.N; T.C = S.C;
+    size_t blocks = 0;
+    for (int l = 0; l < S.L; l++) {
+        const FrmLevel& a = S.lv[l];
+        ftma::Level& b = T.lv[l];
+        if (a.H > 32767 || a.W > 32767) return false;
+        if (!ftma::make_map(&b.own, a.feat, S.N * S.C, a.H, a.W, ftma::TW, ftma::TH)) return false;
+        if (!ftma::make_map(&b.win, a.feat, S.N * S.C, a.H, a.W, ftma::Win<P, BWD>::RC, ftma::Win<P, BWD>::RR)) return false;
+        b.feat = a.feat; b.boxes = a.boxes; b.residual = a.residual; b.out = a.out;
+        b.H = a.H; b.W = a.W; b.scale = a.scale;
+        b.tiles_x = (a.W + ftma::TW - 1) / ftma::TW; b.tiles_y = (a.H + ftma::TH - 1) / ftma::TH;
+        b.cchunks = (S.C + ftma::CC - 1) / ftma::CC;
+        b.block0 = (unsigned)blocks; b.loc0 = a.loc0;
+        blocks += (size_t)b.tiles_x * b.tiles_y * b.cchunks * S.N;
+    }
+    *blocks_out = blocks;
+    return blocks < (1ull << 31);
+}
+
+template <int P>
+static int frm_forward_tma(const FrmLevels& S, cudaStream_t st, bool* done) {
+    *done = false;
+    ftma::Levels T;
+    size_t blocks = 0;
+    if (!frm_tma_levels<P, false>(S, T, &blocks)) return R3G_OK;
+    ftma::frm_forward_tma_kernel<P><<<(unsigned)blocks, ftma::THREADS, ftma::STAGES * ftma::Win<P>::STAGE_BYTES, st>>>(T);
+    R3G_LAUNCH_OK("frm_forward_tma_kernel");
+    *done = true;
+    return R3G_OK;
+}
+
 R3G_API int r3g_frm_forward_multi_f32(int L, const float* const* feats, const float* const* boxes, const float* const* residuals,
                                       int N, int C, const int* level_hw, const float* spatial_scales, int points,
                                       float* const* outs, void* stream) {
@@ -421,6 +464,12 @@ R3G_API int r3g_frm_forward_multi_f32(int L, const float* const* feats, const fl
     if (rc < 0) return rc;
     if (rc == 1) return R3G_OK;
     cudaStream_t st = (cudaStream_t)stream;
+    if (frm_tma_enabled()) {
+        bool done = false;
+        rc = (points == 1) ? frm_forward_tma<1>(S, st, &done) : frm_forward_tma<5>(S, st, &done);
+        if (rc != R3G_OK) return rc;
+        if (done) return R3G_OK;
+    }
     if (points == 1) frm_forward_kernel<1><<<(unsigned)blocks, FRM_THREADS, 0, st>>>(S);
     else frm_forward_kernel<5><<<(unsigned)blocks, FRM_THREADS, 0, st>>>(S);
     R3G_LAUNCH_OK("frm_forward_kernel");
@@ -481,6 +530,16 @@ static int frm_bwd_apply(const FrmLevels& S, size_t blocks, int points, void* wo
     if (workspace_bytes < w.bytes) {
         set_error("%s: workspace too small (%zu < %zu)", who, workspace_bytes, w.bytes);
         return R3G_ERR_WORKSPACE;
+    }
+    if (points == 1 && frm_tma_enabled()) {           // points = 5: rows of ~20 entries — the register-resident rows do not pay there
+        ftma::Levels T;
+        size_t tb = 0;
+        if (frm_tma_levels<1, true>(S, T, &tb)) {
+            ftma::frm_backward_tma_kernel<1><<<(unsigned)tb, ftma::THREADS, ftma::STAGES * ftma::Win<1, true>::STAGE_BYTES, st>>>(
+                T, w.row_start, w.src, w.wsorted);
+            R3G_LAUNCH_OK("frm_backward_tma_kernel");
+            return R3G_OK;
+        }
     }
     frm_backward_kernel<<<(unsigned)blocks, FRM_THREADS, 0, st>>>(S, w.row_start, w.src, w.wsorted);
     R3G_LAUNCH_OK("frm_backward_kernel");
