@@ -236,9 +236,13 @@ __global__ void __launch_bounds__(FRM_THREADS, (P == 1) ? 4 : 2) frm_forward_ker
 
 // ---- backward: tap generation -> sort by target -> CSR -> gather ------------------------------------------
 
+// Plan = the taps of the call inverted into a per-target CSR.  The targets of the taps are counted (one integer atomic per tap),
+// an exclusive scan gives the row starts, the taps are dropped into their rows in arrival order and every row (4 entries on
+// average for points = 1) is then sorted by (source location, point, corner) — the order a stable sort of the taps by target
+// would produce — so the summation order of the gather is fixed: bit-reproducible, and no radix sort over all taps.
 template <int P>
-__global__ void frm_bwd_taps_kernel(const __grid_constant__ FrmLevels S, unsigned* __restrict__ keys, unsigned* __restrict__ ids,
-                                    float* __restrict__ wts) {
+__global__ void frm_bwd_count_kernel(const __grid_constant__ FrmLevels S, unsigned* __restrict__ keys, float* __restrict__ wts,
+                                     unsigned* __restrict__ cnt) {
     const size_t nl = S.nl;
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nl) return;
@@ -251,7 +255,7 @@ __global__ void frm_bwd_taps_kernel(const __grid_constant__ FrmLevels S, unsigne
     float b5[5] = { __ldg(bb), __ldg(bb + 1), __ldg(bb + 2), __ldg(bb + 3), __ldg(bb + 4) };
     float px[5], py[5];
     frm_points<P>(b5, scale, px, py);
-    const unsigned sentinel = (unsigned)nl;          // invalid samples sort to the end
+    const unsigned none = 0xffffffffu;                       // invalid samples take no part
 #pragma unroll
     for (int p = 0; p < P; p++) {
         Taps4 t;
@@ -259,34 +263,67 @@ __global__ void frm_bwd_taps_kernel(const __grid_constant__ FrmLevels S, unsigne
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             const size_t e = (i * P + p) * 4 + k;
-            keys[e] = ok ? (lv.loc0 + (unsigned)((size_t)n * HW + t.o[k])) : sentinel;
-            ids[e] = (unsigned)e;
+            const unsigned key = ok ? (lv.loc0 + (unsigned)((size_t)n * HW + t.o[k])) : none;
+            keys[e] = key;
             wts[e] = t.w[k];
+            if (ok) atomicAdd(cnt + key, 1u);
         }
     }
 }
 
-__global__ void frm_bwd_rows_kernel(const unsigned* __restrict__ skeys, size_t E, size_t nl, unsigned* __restrict__ row_start) {
-    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t > nl) return;
-    size_t lo = 0, hi = E;                            // lower_bound(skeys, t)
-    while (lo < hi) {
-        const size_t mid = (lo + hi) >> 1;
-        if (skeys[mid] < (unsigned)t) lo = mid + 1; else hi = mid;
-    }
-    row_start[t] = (unsigned)lo;
+__global__ void frm_bwd_fill_kernel(const __grid_constant__ FrmLevels S, const unsigned* __restrict__ keys, const float* __restrict__ wts,
+                                    size_t E, int P, const unsigned* __restrict__ row_start, unsigned* __restrict__ cnt,
+                                    unsigned* __restrict__ src, float* __restrict__ wsorted) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    const unsigned key = keys[e];
+    if (key == 0xffffffffu) return;
+    const unsigned slot = atomicSub(cnt + key, 1u) - 1u;     // the counters run back down to zero
+    const unsigned pos = row_start[key] + slot;
+    const unsigned loc = (unsigned)(e / (size_t)(4 * P));
+    const unsigned tie = (unsigned)(e - (size_t)loc * (4 * P));                     // point * 4 + corner, < 20
+    const FrmLevel& lv = S.lv[frm_level_of_loc(S, loc)];
+    src[pos] = (((loc - lv.loc0) % (unsigned)(lv.H * lv.W)) << 5) | tie;           // source location inside its image (< 2^24), tie-break
+    wsorted[pos] = wts[e];
 }
 
-__global__ void frm_bwd_materialize_kernel(const __grid_constant__ FrmLevels S, const unsigned* __restrict__ sids,
-                                           const float* __restrict__ wts, size_t E, int P, unsigned* __restrict__ src,
-                                           float* __restrict__ wsorted) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= E) return;
-    const unsigned e = sids[i];
-    const unsigned loc = e / (unsigned)(4 * P);
-    const FrmLevel& lv = S.lv[frm_level_of_loc(S, loc)];
-    src[i] = (loc - lv.loc0) % (unsigned)(lv.H * lv.W);              // source location inside its image
-    wsorted[i] = wts[e];
+// one thread per target: its row sorted by (source, tie), then the tie bits are dropped.  Rows of up to CAP entries are ranked
+// in registers (keys are unique: rank = number of smaller keys; every entry is written straight to its final slot); longer
+// rows — boxes piling onto one pixel — fall back to an insertion sort in global memory.
+template <int CAP>
+__global__ void frm_bwd_sort_rows_kernel(const unsigned* __restrict__ row_start, size_t nl, unsigned* __restrict__ src, float* __restrict__ wsorted) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nl) return;
+    const unsigned a = row_start[t], b = row_start[t + 1];
+    const unsigned n = b - a;
+    if (n <= (unsigned)CAP) {
+        unsigned k[CAP];
+        float w[CAP];
+#pragma unroll
+        for (int i = 0; i < CAP; i++) {
+            k[i] = ((unsigned)i < n) ? src[a + i] : 0xffffffffu;
+            w[i] = ((unsigned)i < n) ? wsorted[a + i] : 0.0f;
+        }
+#pragma unroll
+        for (int i = 0; i < CAP; i++) {
+            if ((unsigned)i < n) {
+                unsigned r = 0;
+#pragma unroll
+                for (int j = 0; j < CAP; j++) r += (k[j] < k[i]) ? 1u : 0u;
+                src[a + r] = k[i] >> 5;
+                wsorted[a + r] = w[i];
+            }
+        }
+        return;
+    }
+    for (unsigned i = a + 1; i < b; i++) {
+        const unsigned kk = src[i];
+        const float ww = wsorted[i];
+        unsigned j = i;
+        while (j > a && src[j - 1] > kk) { src[j] = src[j - 1]; wsorted[j] = wsorted[j - 1]; j--; }
+        src[j] = kk; wsorted[j] = ww;
+    }
+    for (unsigned i = a; i < b; i++) src[i] >>= 5;
 }
 
 __global__ void __launch_bounds__(FRM_THREADS, R3G_FRM_BWD_MINB) frm_backward_kernel(
@@ -353,7 +390,7 @@ __global__ void __launch_bounds__(FRM_THREADS, R3G_FRM_BWD_MINB) frm_backward_ke
 }
 
 struct FrmBwdWs {
-    unsigned *keys, *keys2, *ids, *ids2, *row_start, *src;
+    unsigned *keys, *cnt, *row_start, *src;
     float *wts, *wsorted;
     void* cub_tmp; size_t cub_bytes;
     size_t bytes;
@@ -365,13 +402,13 @@ static FrmBwdWs carve_frm(void* ws, size_t nl, int P) {
     char* p = (char*)ws;
     size_t off = 0;
     auto take = [&](size_t bytes) { char* r = p + off; off += align_up(bytes, 256); return (void*)r; };
-    w.keys = (unsigned*)take(4 * E); w.keys2 = (unsigned*)take(4 * E);
-    w.ids = (unsigned*)take(4 * E); w.ids2 = (unsigned*)take(4 * E);
+    w.keys = (unsigned*)take(4 * E);
     w.wts = (float*)take(4 * E); w.wsorted = (float*)take(4 * E);
     w.src = (unsigned*)take(4 * E);
+    w.cnt = (unsigned*)take(4 * (nl + 1));
     w.row_start = (unsigned*)take(4 * (nl + 1));
     size_t tb = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tb, (unsigned*)nullptr, (unsigned*)nullptr, (unsigned*)nullptr, (unsigned*)nullptr, (int)E);
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, (unsigned*)nullptr, (unsigned*)nullptr, (int)(nl + 1));
     w.cub_bytes = align_up(tb, 256);
     w.cub_tmp = take(w.cub_bytes);
     w.bytes = off;
@@ -511,14 +548,14 @@ static int frm_bwd_plan(const FrmLevels& S, int points, void* workspace, size_t 
         return R3G_ERR_WORKSPACE;
     }
     const int tpb = 256;
-    if (points == 1) frm_bwd_taps_kernel<1><<<(unsigned)((nl + tpb - 1) / tpb), tpb, 0, st>>>(S, w.keys, w.ids, w.wts);
-    else frm_bwd_taps_kernel<5><<<(unsigned)((nl + tpb - 1) / tpb), tpb, 0, st>>>(S, w.keys, w.ids, w.wts);
-    int end_bit = 1;
-    while (((size_t)1 << end_bit) <= nl) end_bit++;            // keys are in [0, nl]
+    R3G_CUDA_OK(cudaMemsetAsync(w.cnt, 0, 4 * (nl + 1), st));
+    if (points == 1) frm_bwd_count_kernel<1><<<(unsigned)((nl + tpb - 1) / tpb), tpb, 0, st>>>(S, w.keys, w.wts, w.cnt);
+    else frm_bwd_count_kernel<5><<<(unsigned)((nl + tpb - 1) / tpb), tpb, 0, st>>>(S, w.keys, w.wts, w.cnt);
     size_t tb = w.cub_bytes;
-    R3G_CUDA_OK(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, w.keys, w.keys2, w.ids, w.ids2, (int)E, 0, end_bit, st));
-    frm_bwd_rows_kernel<<<(unsigned)((nl + 1 + tpb - 1) / tpb), tpb, 0, st>>>(w.keys2, E, nl, w.row_start);
-    frm_bwd_materialize_kernel<<<(unsigned)((E + tpb - 1) / tpb), tpb, 0, st>>>(S, w.ids2, w.wts, E, points, w.src, w.wsorted);
+    R3G_CUDA_OK(cub::DeviceScan::ExclusiveSum(w.cub_tmp, tb, w.cnt, w.row_start, (int)(nl + 1), st));
+    frm_bwd_fill_kernel<<<(unsigned)((E + tpb - 1) / tpb), tpb, 0, st>>>(S, w.keys, w.wts, E, points, w.row_start, w.cnt, w.src, w.wsorted);
+    if (points == 1) frm_bwd_sort_rows_kernel<8><<<(unsigned)((nl + 127) / 128), 128, 0, st>>>(w.row_start, nl, w.src, w.wsorted);
+    else frm_bwd_sort_rows_kernel<32><<<(unsigned)((nl + 127) / 128), 128, 0, st>>>(w.row_start, nl, w.src, w.wsorted);
     R3G_LAUNCH_OK("frm backward plan kernels");
     return R3G_OK;
 }
