@@ -104,6 +104,16 @@ def require_cuda(*tensors):
             raise RuntimeError("r3det_b200 ops run on CUDA tensors only (no CPU fallback); got a CPU tensor")
 
 
+def require_no_grad(op, *tensors):
+    """The kernels behind `op` write into fresh outputs and carry no autograd graph.  Where the reference's implementation is
+    differentiable torch code, silently returning a detached result would zero a gradient: raise instead."""
+    if torch.is_grad_enabled():
+        for t in tensors:
+            if isinstance(t, torch.Tensor) and t.requires_grad:
+                raise RuntimeError(f"r3det_b200.{op}: input requires grad, but this op is not differentiable here "
+                                   "(detach the input, or call it under torch.no_grad())")
+
+
 class device_guard:
     """`with device_guard(dev):` — like torch.cuda.device(dev) but free when dev is already current."""
     __slots__ = ("ctx",)

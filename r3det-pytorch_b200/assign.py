@@ -5,8 +5,10 @@ In the reference, mmdet-2.19's ``MaxIoUAssigner`` calls ``RBboxOverlaps2D_v*`` f
 (caller: r3det/models/dense_heads/rotate_anchor_head.py:220-228; assign_wrt_overlaps semantics recalled in SURVEY.md A6).
 ``max_iou_assign`` does the same assignment in one C call without materialising the matrix; the overlaps it reduces
 are the matrix kernel's values bit for bit.  ``FusedMaxIoUAssigner`` wraps it behind MaxIoUAssigner's constructor and
-``assign`` signature and registers itself in mmdet's BBOX_ASSIGNERS when mmdet is importable.
-Not supported (raise): ``ignore_iof_thr >= 0`` with gt_bboxes_ignore, tuple ``neg_iou_thr``, ``gpu_assign_thr``."""
+``assign`` signature and registers itself in mmdet's BBOX_ASSIGNERS when mmdet is importable: tuple ``neg_iou_thr``, ignore
+regions (``ignore_iof_thr`` > 0 with ``gt_bboxes_ignore``, both ``ignore_wrt_candidates`` settings) and
+``gt_max_assign_all`` / ``match_low_quality`` behave as in mmdet; ``gpu_assign_thr`` (mmdet's CPU off-load for many GTs) is
+accepted and ignored — there is no CPU path here, and the fused kernel never holds the (G, A) matrix it exists to avoid."""
 import ctypes as C
 from collections import namedtuple
 
@@ -119,20 +121,60 @@ class FusedMaxIoUAssigner(object):
                  ignore_wrt_candidates=True, match_low_quality=True, gpu_assign_thr=-1,
                  iou_calculator=dict(type='RBboxOverlaps2D_v1')):
         if isinstance(neg_iou_thr, (tuple, list)):
-            raise NotImplementedError('FusedMaxIoUAssigner: tuple neg_iou_thr is not supported')
+            assert len(neg_iou_thr) == 2
+            neg_iou_thr = (float(neg_iou_thr[0]), float(neg_iou_thr[1]))
         kind = iou_calculator['type'] if isinstance(iou_calculator, dict) else type(iou_calculator).__name__
         self.variant = {'RBboxOverlaps2D_v1': 'v1', 'RBboxOverlaps2D_v2': 'v2', 'RBboxOverlaps2D_v3': 'v3'}[kind]
         self.pos_iou_thr, self.neg_iou_thr, self.min_pos_iou = pos_iou_thr, neg_iou_thr, min_pos_iou
         self.gt_max_assign_all, self.match_low_quality = gt_max_assign_all, match_low_quality
-        self.ignore_iof_thr = ignore_iof_thr
+        self.ignore_iof_thr, self.ignore_wrt_candidates = ignore_iof_thr, ignore_wrt_candidates
+        self.gpu_assign_thr = gpu_assign_thr          # accepted for config compatibility; no CPU off-load exists here
+
+    def _ignored(self, bboxes, gt_bboxes_ignore, flags):
+        """Anchors whose best IoF with an ignore region exceeds ignore_iof_thr (mmdet sets their overlap column to -1)."""
+        from .rbbox_geo import pairwise_iou
+        if self.ignore_wrt_candidates:
+            iof = pairwise_iou(bboxes, gt_bboxes_ignore, self.variant, 'iof', flags).max(dim=1).values
+        else:
+            iof = pairwise_iou(gt_bboxes_ignore, bboxes, self.variant, 'iof', flags).max(dim=0).values
+        return iof > self.ignore_iof_thr
 
     def assign(self, bboxes, gt_bboxes, gt_bboxes_ignore=None, gt_labels=None):
-        if self.ignore_iof_thr > 0 and gt_bboxes_ignore is not None and gt_bboxes_ignore.numel() > 0:
-            raise NotImplementedError('FusedMaxIoUAssigner: ignore regions are not supported')
         strip = lambda b: b[..., :5] if b is not None and b.size(-1) == 6 else b
+        bboxes, gt_bboxes, gt_bboxes_ignore = strip(bboxes), strip(gt_bboxes), strip(gt_bboxes_ignore)
         flags = L.FLAG_STRICT | (L.FLAG_SMALL_MASK if self.variant == 'v3' else 0)
-        out = max_iou_assign(strip(gt_bboxes), strip(bboxes), self.pos_iou_thr, self.neg_iou_thr, self.min_pos_iou,
-                             self.match_low_quality, self.gt_max_assign_all, self.variant, gt_labels, flags)
+        tuple_neg = isinstance(self.neg_iou_thr, tuple)
+        neg = self.neg_iou_thr[1] if tuple_neg else self.neg_iou_thr
+        args = (self.pos_iou_thr, neg, self.min_pos_iou, self.match_low_quality, self.gt_max_assign_all, self.variant)
+        keep = None
+        if (self.ignore_iof_thr > 0 and gt_bboxes_ignore is not None and gt_bboxes_ignore.numel() > 0 and bboxes.numel() > 0
+                and gt_bboxes is not None and gt_bboxes.numel() > 0):
+            ign = self._ignored(bboxes, gt_bboxes_ignore, flags)
+            if bool(ign.any()):
+                keep = (~ign).nonzero(as_tuple=False).squeeze(1)
+        if keep is None:
+            out = max_iou_assign(gt_bboxes, bboxes, *args, gt_labels=None, flags=flags)
+        else:
+            # ignored anchors never enter the sweep: their column is -1 for every GT, so they cannot be a maximum of anything
+            sub = max_iou_assign(gt_bboxes, bboxes[keep], *args, gt_labels=None, flags=flags)
+            A = bboxes.size(0)
+            gt_inds = sub.gt_inds.new_full((A,), -1); gt_inds[keep] = sub.gt_inds
+            max_ov = sub.max_overlaps.new_full((A,), -1.0); max_ov[keep] = sub.max_overlaps
+            argmax = sub.argmax_overlaps.new_zeros((A,)); argmax[keep] = sub.argmax_overlaps
+            gt_arg = keep[sub.gt_argmax_overlaps] if keep.numel() else sub.gt_argmax_overlaps
+            out = AssignOutput(sub.num_gts, gt_inds, max_ov, None, argmax, sub.gt_max_overlaps, gt_arg)
+        gt_inds = out.gt_inds
+        if tuple_neg and out.num_gts > 0:
+            # background only inside [neg_lo, neg_hi): what the kernel marked 0 below neg_lo goes back to -1
+            gt_inds = torch.where((gt_inds == 0) & (out.max_overlaps < self.neg_iou_thr[0]), gt_inds.new_full((), -1), gt_inds)
+        labels = None
+        if gt_labels is not None:
+            labels = gt_inds.new_full((gt_inds.numel(),), -1)
+            pos = gt_inds > 0
+            if out.num_gts:
+                labels[pos] = gt_labels.to(gt_inds.device)[gt_inds[pos] - 1]
+        out = AssignOutput(out.num_gts, gt_inds, out.max_overlaps, labels, out.argmax_overlaps, out.gt_max_overlaps,
+                           out.gt_argmax_overlaps)
         try:  # pragma: no cover - mmdet is not installed in the build image
             from mmdet.core.bbox.assigners import AssignResult
             return AssignResult(out.num_gts, out.gt_inds, out.max_overlaps, labels=out.labels)

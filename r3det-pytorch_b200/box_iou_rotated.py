@@ -3,7 +3,9 @@
 `obb_overlaps(bboxes1, bboxes2, mode, is_aligned, device_id)`: matrix mode goes through the IoU kernel with
 the wrapper's too-small mask (rows/cols with min(w,h) < 1e-3 -> 0, :54-60); empty inputs give zeros (:43-46).
 Aligned mode returns (m, 1); it reuses the matrix geometry core — the reference's pure-torch aligned path
-disagrees with its own matrix op by up to 2.7e-4, so parity is against the matrix op.
+disagrees with its own matrix op by up to 2.7e-4, so parity is against the matrix op.  Like that torch
+path (aligned_obb_overlaps, :67-92) it applies NO too-small mask; unlike it, it is not differentiable: inputs that require
+grad raise (no shipped config differentiates through it).
 numpy inputs are uploaded to cuda:device_id (current device if None) and returned as numpy."""
 import numpy as np
 import torch
@@ -35,7 +37,8 @@ def obb_overlaps(bboxes1, bboxes2, mode='iou', is_aligned=False, device_id=None)
         rows, cols = b1.size(0), b2.size(0)
         outputs = b1.new_zeros(rows, 1) if is_aligned else b1.new_zeros(rows, cols)
     elif is_aligned:
-        outputs = aligned_iou(b1, b2, 'v3', mode, L.FLAG_STRICT | L.FLAG_SMALL_MASK)[:, None]
+        L.require_no_grad('obb_overlaps(is_aligned=True)', b1, b2)
+        outputs = aligned_iou(b1, b2, 'v3', mode, L.FLAG_STRICT)[:, None]
     else:
         outputs = pairwise_iou(b1, b2, 'v3', mode, L.FLAG_STRICT | L.FLAG_SMALL_MASK)
     if isinstance(bboxes1, torch.Tensor) and bboxes1.is_floating_point() and outputs.dtype != bboxes1.dtype:

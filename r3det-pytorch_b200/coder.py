@@ -2,8 +2,15 @@
 
 DeltaXYWHAOBBoxCoder(target_means, target_stds, angle_range, add_ctr_clamp, ctr_clamp) with .encode / .decode, and the
 six module-level functions bbox2delta_v1/v2/v3, delta2bbox_v1/v2/v3 with the reference's signatures.  Each call is one
-CUDA kernel (csrc/coder.cu) instead of ~25 small torch kernels.  CUDA tensors only, no CPU fallback."""
+CUDA kernel (csrc/coder.cu) instead of ~25 small torch kernels.  CUDA tensors only, no CPU fallback.
+
+Autograd: the reference decode is differentiable torch code and rotate_anchor_head.py:418-420 back-propagates through
+`bbox_coder.decode` when `reg_decoded_bbox=True`.  decode is therefore a torch.autograd.Function here: the forward is the CUDA
+kernel, the backward the analytic gradient with respect to the deltas (the boxes being decoded — anchors / rois — get none,
+and raise if they ask for one).  encode produces regression TARGETS; an input that requires grad raises instead of
+returning a silently detached result."""
 import ctypes as C
+import math
 
 import torch
 
@@ -24,6 +31,7 @@ def _encode(proposals, gt, means, stds, version):
     if version not in _VER:
         raise NotImplementedError
     L.require_cuda(proposals, gt)
+    L.require_no_grad('coder.encode', proposals, gt)
     if version == 'v1':
         assert proposals.size() == gt.size()                              # delta_xywha_rbbox_coder.py:123
     p, ps = L.as_f32_rows(proposals.reshape(-1, proposals.size(-1)))
@@ -41,6 +49,15 @@ def _decode(rois, deltas, means, stds, version, max_shape=None, wh_ratio_clip=16
     if version not in _VER:
         raise NotImplementedError
     L.require_cuda(rois, deltas)
+    if torch.is_grad_enabled() and (deltas.requires_grad or rois.requires_grad):
+        L.require_no_grad('coder.decode (rois)', rois)
+        return _DecodeFn.apply(rois, deltas, tuple(float(v) for v in means), tuple(float(v) for v in stds), version,
+                               None if max_shape is None else (int(max_shape[0]), int(max_shape[1])), float(wh_ratio_clip),
+                               bool(add_ctr_clamp), float(ctr_clamp))
+    return _decode_raw(rois, deltas, means, stds, version, max_shape, wh_ratio_clip, add_ctr_clamp, ctr_clamp)
+
+
+def _decode_raw(rois, deltas, means, stds, version, max_shape=None, wh_ratio_clip=16 / 1000, add_ctr_clamp=False, ctr_clamp=32):
     assert rois.dim() == 2 and deltas.dim() == 2 and deltas.size(1) % 5 == 0 and deltas.size(0) == rois.size(0)
     r, rs = L.as_f32_rows(rois)
     d, _ = L.as_f32_rows(deltas)
@@ -55,6 +72,71 @@ def _decode(rois, deltas, means, stds, version, max_shape=None, wh_ratio_clip=16
                                                float(wh_ratio_clip), int(bool(add_ctr_clamp)), float(ctr_clamp), L.ptr(out),
                                                L.stream_ptr(r.device)))
     return out
+
+
+class _DecodeFn(torch.autograd.Function):
+    """delta2bbox_v1/v2/v3 with the gradient of the reference's torch expressions with respect to `deltas`
+    (delta_xywha_rbbox_coder.py:172-211, 283-311, 391-423; torch.clamp passes the gradient inside its closed range)."""
+
+    @staticmethod
+    def forward(ctx, rois, deltas, means, stds, version, max_shape, wh_ratio_clip, add_ctr_clamp, ctr_clamp):
+        out = _decode_raw(rois, deltas.detach(), means, stds, version, max_shape, wh_ratio_clip, add_ctr_clamp, ctr_clamp)
+        ctx.save_for_backward(rois.detach(), deltas.detach())
+        ctx.cfg = (means, stds, version, max_shape, wh_ratio_clip, add_ctr_clamp, ctr_clamp)
+        ctx.in_dtype = deltas.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        rois, deltas = ctx.saved_tensors
+        means, stds, version, max_shape, wh_ratio_clip, add_ctr_clamp, ctr_clamp = ctx.cfg
+        n, g5 = deltas.shape
+        d = deltas.float().reshape(n, g5 // 5, 5)
+        g = grad.float().reshape(n, g5 // 5, 5)
+        std = d.new_tensor(stds)
+        den = d * std + d.new_tensor(means)
+        r = rois.float()
+        pw, ph, pa = r[:, 2, None], r[:, 3, None], r[:, 4, None]
+        max_ratio = abs(math.log(wh_ratio_clip))
+        dx, dy, dw, dh = den[..., 0], den[..., 1], den[..., 2], den[..., 3]
+        if version == 'v1' and add_ctr_clamp:                     # one-sided size clamp, centre shift clamped (:188-192)
+            mw, mh = dw <= max_ratio, dh <= max_ratio
+        else:
+            mw, mh = dw.abs() <= max_ratio, dh.abs() <= max_ratio
+        gw = pw * dw.clamp(min=None if (version == 'v1' and add_ctr_clamp) else -max_ratio, max=max_ratio).exp()
+        gh = ph * dh.clamp(min=None if (version == 'v1' and add_ctr_clamp) else -max_ratio, max=max_ratio).exp()
+        out = torch.empty_like(d)
+        if version == 'v1':
+            sx, sy = pw * dx, ph * dy
+            mx, my = torch.ones_like(mw), torch.ones_like(mh)
+            if add_ctr_clamp:
+                mx, my = sx.abs() <= ctr_clamp, sy.abs() <= ctr_clamp
+                sx, sy = sx.clamp(-ctr_clamp, ctr_clamp), sy.clamp(-ctr_clamp, ctr_clamp)
+            if max_shape is not None:
+                gx, gy = r[:, 0, None] + sx, r[:, 1, None] + sy
+                mx = mx & (gx >= 0) & (gx <= max_shape[1] - 1)
+                my = my & (gy >= 0) & (gy <= max_shape[0] - 1)
+            out[..., 0] = g[..., 0] * pw * mx
+            out[..., 1] = g[..., 1] * ph * my
+            out[..., 2] = g[..., 2] * gw * mw
+            out[..., 3] = g[..., 3] * gh * mh
+            out[..., 4] = g[..., 4]
+        else:
+            ang = pa if version == 'v2' else -pa
+            c, s_ = torch.cos(ang), torch.sin(ang)
+            out[..., 0] = (g[..., 0] * c + g[..., 1] * s_) * pw
+            out[..., 1] = (g[..., 1] * c - g[..., 0] * s_) * ph
+            if version == 'v2':
+                ggw, ggh = g[..., 2], g[..., 3]
+                out[..., 4] = g[..., 4] * math.pi
+            else:                                                  # v3 returns (long edge, short edge): route the gradients back (:414-416)
+                swap = gw > gh
+                ggw = torch.where(swap, g[..., 2], g[..., 3])
+                ggh = torch.where(swap, g[..., 3], g[..., 2])
+                out[..., 4] = g[..., 4]
+            out[..., 2] = ggw * gw * mw
+            out[..., 3] = ggh * gh * mh
+        return None, (out * std).reshape(n, g5).to(ctx.in_dtype), None, None, None, None, None, None, None
 
 
 def bbox2delta_v1(proposals, gt, means=_ZERO5, stds=_ONE5):

@@ -15,6 +15,7 @@ def _run(fn_name, x, version, in_cols, out_cols):
     if version not in _VER:
         raise NotImplementedError
     L.require_cuda(x)
+    L.require_no_grad('rtransforms.' + fn_name.replace('r3g_', '').replace('_f32', ''), x)
     lead = x.shape[:-1]
     xin = x.reshape(-1, in_cols)
     if xin.dtype != torch.float32:

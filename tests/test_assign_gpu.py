@@ -1,5 +1,6 @@
-"""Fused max-IoU assignment vs a torch restatement of mmdet-2.19 MaxIoUAssigner.assign_wrt_overlaps applied to OUR
-overlap matrix (the fused kernel reduces the very same values, so equality is exact, ties included)."""
+"""Fused max-IoU assignment vs the restatement of mmdet-2.19 MaxIoUAssigner (oracle/assign_np.py: provenance and known-answer
+tests there; mmdet itself is unavailable -> parity unpinned upstream) applied to OUR overlap matrix: the fused kernel reduces
+the very same values, so equality is exact, ties included."""
 import numpy as np
 import pytest
 import torch
@@ -10,25 +11,11 @@ pytestmark = pytest.mark.gpu
 
 
 def assign_wrt_overlaps(overlaps, pos_iou_thr, neg_iou_thr, min_pos_iou, match_low_quality, gt_max_assign_all):
-    """mmdet/core/bbox/assigners/max_iou_assigner.py (2.19) — recalled; SURVEY.md A6."""
-    G, A = overlaps.shape
-    assigned = overlaps.new_full((A,), -1, dtype=torch.long)
-    if G == 0:
-        assigned[:] = 0
-        return assigned, overlaps.new_zeros((A,))
-    max_ov, argmax = overlaps.max(dim=0)
-    gt_max, gt_argmax = overlaps.max(dim=1)
-    assigned[(max_ov >= 0) & (max_ov < neg_iou_thr)] = 0
-    pos = max_ov >= pos_iou_thr
-    assigned[pos] = argmax[pos] + 1
-    if match_low_quality:
-        for i in range(G):
-            if gt_max[i] >= min_pos_iou:
-                if gt_max_assign_all:
-                    assigned[overlaps[i, :] == gt_max[i]] = i + 1
-                else:
-                    assigned[gt_argmax[i]] = i + 1
-    return assigned, max_ov
+    """oracle/assign_np.py on the device matrix -> torch tensors on its device"""
+    from oracle import assign_np
+    got, mx = assign_np.assign_wrt_overlaps(overlaps.cpu().numpy(), pos_iou_thr, neg_iou_thr, min_pos_iou, match_low_quality,
+                                            gt_max_assign_all)
+    return torch.from_numpy(got).to(overlaps.device), torch.from_numpy(mx).to(overlaps.device)
 
 
 @pytest.mark.parametrize("v", ["v1", "v3"])
@@ -69,8 +56,42 @@ def test_edge_cases_and_class(cuda_dev):
     res = a.assign(an, gt, gt_labels=labels)
     pos = res.gt_inds > 0
     assert pos.any() and torch.equal(res.labels[pos], labels[res.gt_inds[pos] - 1]) and (res.labels[~pos] == -1).all()
-    with pytest.raises(NotImplementedError):
-        R.FusedMaxIoUAssigner(0.5, (0.1, 0.4))
+
+
+def test_adversarial_cases_vs_oracle(cuda_dev):
+    """Zero rows with min_pos_iou = 0, duplicate anchors (exact ties), gt_max_assign_all False collisions, tuple neg_iou_thr,
+    ignore regions (both ignore_wrt_candidates settings) — FusedMaxIoUAssigner vs oracle/assign_np.py on our own overlaps."""
+    import r3det_b200 as R
+    from oracle import assign_np
+    t = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(cuda_dev)
+    rng = np.random.default_rng(5)
+    gt = rand_obb(12, 21, "v1", 20, 120)
+    gt[3, :2] = [5000, 5000]                                              # a GT far outside: its row is all zeros
+    an = rand_obb(3000, 22, "v1", 10, 150)
+    an[100:140] = an[100]                                                 # 40 identical anchors: exact ties on every GT
+    an[200:203] = gt[5]                                                   # anchors equal to a GT (IoU 1)
+    an[300] = gt[6]; an[301] = gt[6]                                      # two perfect matches for one GT
+    ign = rand_obb(4, 23, "v1", 100, 300)
+    G_, A_, I_ = t(gt), t(an), t(ign)
+    ov = R.pairwise_iou(G_, A_, "v1").cpu().numpy()
+    for assign_all in (True, False):
+        for mlq in (True, False):
+            for neg in (0.4, (0.1, 0.4)):
+                for minpos in (0.0, 0.3):
+                    a = R.FusedMaxIoUAssigner(0.5, neg, min_pos_iou=minpos, gt_max_assign_all=assign_all, match_low_quality=mlq)
+                    res = a.assign(A_, G_)
+                    want, wmax = assign_np.assign_wrt_overlaps(ov, 0.5, neg, minpos, mlq, assign_all)
+                    assert np.array_equal(res.gt_inds.cpu().numpy(), want), (assign_all, mlq, neg, minpos)
+                    assert np.array_equal(res.max_overlaps.cpu().numpy(), wmax)
+    for wrt in (True, False):
+        iof = (R.pairwise_iou(A_, I_, "v1", "iof").max(dim=1).values if wrt else R.pairwise_iou(I_, A_, "v1", "iof").max(dim=0).values).cpu().numpy()
+        assert (iof > 0.5).any() and not (iof > 0.5).all()
+        a = R.FusedMaxIoUAssigner(0.5, 0.4, min_pos_iou=0.0, ignore_iof_thr=0.5, ignore_wrt_candidates=wrt)
+        res = a.assign(A_, G_, gt_bboxes_ignore=I_)
+        want, wmax = assign_np.assign(ov, iof, 0.5, pos_iou_thr=0.5, neg_iou_thr=0.4, min_pos_iou=0.0)
+        assert np.array_equal(res.gt_inds.cpu().numpy(), want) and np.array_equal(res.max_overlaps.cpu().numpy(), wmax)
+    # gpu_assign_thr is accepted (and has no effect: there is no CPU path)
+    assert R.FusedMaxIoUAssigner(0.5, 0.4, gpu_assign_thr=100).assign(A_, G_).gt_inds.shape == (3000,)
 
 
 def test_massive_ties_take_the_sweep(cuda_dev):

@@ -194,3 +194,92 @@ def test_select_decode_many_images_and_ties(cuda_dev):
     out = R.get_bboxes([t(flat[:2] - 20)], [t(reg[:2])], [t(anc)], metas, dict(nms_pre=20, score_thr=0.05, nms=dict(type="v1", iou_thr=0.1),
                                                                                   max_per_img=10), coder)
     assert len(out) == 2 and all(d.shape == (0, 6) and l.shape == (0,) for d, l in out)
+
+
+def _torch_decode(rois, deltas, means, stds, version, max_shape=None, wh_ratio_clip=16 / 1000, add_ctr_clamp=False, ctr_clamp=32):
+    """The reference's torch expressions (delta_xywha_rbbox_coder.py:172-211, 283-311, 391-423), kept differentiable."""
+    import math
+    g = deltas.size(1) // 5
+    den = deltas * deltas.new_tensor(stds).repeat(g)[None] + deltas.new_tensor(means).repeat(g)[None]
+    dx, dy, dw, dh, da = (den[:, i::5] for i in range(5))
+    px, py, pw, ph, pa = (rois[:, i, None].expand_as(dx) for i in range(5))
+    mr = abs(math.log(wh_ratio_clip))
+    if version == 'v1':
+        sx, sy = pw * dx, ph * dy
+        if add_ctr_clamp:
+            sx, sy = sx.clamp(-ctr_clamp, ctr_clamp), sy.clamp(-ctr_clamp, ctr_clamp)
+            dw, dh = dw.clamp(max=mr), dh.clamp(max=mr)
+        else:
+            dw, dh = dw.clamp(-mr, mr), dh.clamp(-mr, mr)
+        gx, gy, gw, gh, ga = px + sx, py + sy, pw * dw.exp(), ph * dh.exp(), pa + da
+        if max_shape is not None:
+            gx, gy = gx.clamp(0, max_shape[1] - 1), gy.clamp(0, max_shape[0] - 1)
+        return torch.stack([gx, gy, gw, gh, ga], -1).view(deltas.size())
+    dw, dh = dw.clamp(-mr, mr), dh.clamp(-mr, mr)
+    ang = pa if version == 'v2' else -pa
+    gx = dx * pw * torch.cos(ang) - dy * ph * torch.sin(ang) + px
+    gy = dx * pw * torch.sin(ang) + dy * ph * torch.cos(ang) + py
+    gw, gh = pw * dw.exp(), ph * dh.exp()
+    if version == 'v2':
+        gt = (da * math.pi + pa + math.pi / 4) % math.pi - math.pi / 4
+        return torch.stack([gx, gy, gw, gh, gt], -1).view_as(deltas)
+    gt = da + pa
+    wr, hr = torch.where(gw > gh, gw, gh), torch.where(gw > gh, gh, gw)
+    tr = (torch.where(gw > gh, gt, gt + math.pi / 2) + math.pi / 2) % math.pi - math.pi / 2
+    return torch.stack([gx, gy, wr, hr, tr], -1).view_as(deltas)
+
+
+@pytest.mark.parametrize("version", ["v1", "v2", "v3"])
+def test_decode_is_differentiable(cuda_dev, version):
+    """rotate_anchor_head.py:418-420 back-propagates through bbox_coder.decode (reg_decoded_bbox=True); the gradient
+    with respect to the deltas must be the reference's (torch autograd over its own expressions), not silently zero."""
+    import r3det_b200 as R
+    rng = np.random.default_rng(3)
+    rois = torch.from_numpy(rand_obb(400, 5, version)).to(cuda_dev)
+    means, stds = (0.01, -0.02, 0.03, 0.0, 0.05), (0.1, 0.2, 0.3, 0.4, 0.5)
+    cases = [dict()]
+    if version == 'v1':
+        cases += [dict(max_shape=(600, 700)), dict(add_ctr_clamp=True, ctr_clamp=8)]
+    for groups in (1, 3):
+        raw = rng.normal(0, 3.0, (400, 5 * groups)).astype(np.float32)          # wide: the size clamps are active for some rows
+        for kw in cases:
+            coder = R.DeltaXYWHAOBBoxCoder(means, stds, angle_range=version, add_ctr_clamp=kw.get('add_ctr_clamp', False),
+                                           ctr_clamp=kw.get('ctr_clamp', 32))
+            d1 = torch.from_numpy(raw).to(cuda_dev).requires_grad_(True)
+            d2 = torch.from_numpy(raw).to(cuda_dev).requires_grad_(True)
+            if groups == 1:
+                out = coder.decode(rois, d1, max_shape=kw.get('max_shape'))
+            else:
+                out = getattr(R, f'delta2bbox_{version}')(rois, d1, means, stds, **({'max_shape': kw.get('max_shape')} if version == 'v1' else {}),
+                                                           **({k: v for k, v in kw.items() if k != 'max_shape'} if version == 'v1' else {}))
+            ref = _torch_decode(rois, d2, means, stds, version, **kw)
+            assert out.requires_grad and out.grad_fn is not None
+            wgt = torch.from_numpy(rng.normal(0, 1, out.shape).astype(np.float32)).to(cuda_dev)
+            (out * wgt).sum().backward()
+            (ref * wgt).sum().backward()
+            scale = float(d2.grad.abs().max())
+            assert float((d1.grad - d2.grad).abs().max()) <= 1e-4 * max(scale, 1.0), (version, groups, kw)
+    # boxes being decoded (anchors) do not get a gradient: asking for one raises instead of returning zero
+    with pytest.raises(RuntimeError):
+        R.DeltaXYWHAOBBoxCoder(angle_range=version).decode(rois.clone().requires_grad_(True), torch.zeros((400, 5), device=cuda_dev))
+    # without grad mode the plain kernel path is taken
+    with torch.no_grad():
+        o = R.DeltaXYWHAOBBoxCoder(angle_range=version).decode(rois, torch.zeros((400, 5), device=cuda_dev, requires_grad=True))
+    assert not o.requires_grad
+
+
+def test_non_differentiable_ops_raise_on_grad_inputs(cuda_dev):
+    import r3det_b200 as R
+    b = torch.from_numpy(rand_obb(16, 1, "v1")).to(cuda_dev)
+    with pytest.raises(RuntimeError):
+        R.obb2poly(b.clone().requires_grad_(True), "v1")
+    with pytest.raises(RuntimeError):
+        R.DeltaXYWHAOBBoxCoder(angle_range="v1").encode(b.clone().requires_grad_(True), b)
+    with pytest.raises(RuntimeError):
+        R.obb_overlaps(b.clone().requires_grad_(True), b, is_aligned=True)
+    with torch.no_grad():
+        R.obb2poly(b.clone().requires_grad_(True), "v1")
+    # aligned v3 overlaps apply no too-small mask (the reference's torch aligned path has none)
+    tiny = b.clone(); tiny[:, 2] = 5e-4
+    assert float(R.obb_overlaps(tiny, tiny, is_aligned=True).min()) > 0.5
+    assert float(R.obb_overlaps(tiny, tiny).max()) == 0.0
