@@ -169,7 +169,8 @@ __global__ void nms_gather_kernel(const float* __restrict__ boxes, int64_t strid
 
 // polygons: corners into the two 16-byte planes, bounding box into the column plane
 __global__ void poly_gather_kernel(const float* __restrict__ polys, int64_t stride, const int* __restrict__ ord_rank,
-                                   const int* __restrict__ pos_rank, int K, float4* p0, float4* p1, float4* p2c, unsigned* alive32) {
+                                   const int* __restrict__ pos_rank, int K, float4* p0, float4* p1, float4* p2r, float4* p2c,
+                                   unsigned* alive32) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p < K) {
         const float* s = polys + (int64_t)ord_rank[pos_rank[p]] * stride;
@@ -181,6 +182,7 @@ __global__ void poly_gather_kernel(const float* __restrict__ polys, int64_t stri
         const float x0 = fminf(fminf(v[0], v[2]), fminf(v[4], v[6])), x1 = fmaxf(fmaxf(v[0], v[2]), fmaxf(v[4], v[6]));
         const float y0 = fminf(fminf(v[1], v[3]), fminf(v[5], v[7])), y1 = fmaxf(fmaxf(v[1], v[3]), fmaxf(v[5], v[7]));
         p2c[p] = make_float4(x0, y0, x1, y1);
+        p2r[2 * (size_t)p] = poly::quad_meta(v);                          // signed area, convexity, coordinate magnitude
     }
     const unsigned bal = __ballot_sync(0xffffffffu, p < K);
     if ((threadIdx.x & 31) == 0 && p < K) alive32[p >> 5] = bal;
@@ -533,7 +535,7 @@ R3G_API int r3g_poly_nms_f32(const float* polys, int64_t stride, const float* sc
     if (rc != R3G_OK) return rc;
     rc = nms_order_stage(w, scores, labels, nullptr, Ki, st, small, 32);
     if (rc != R3G_OK) return rc;
-    poly_gather_kernel<<<gK, tpb, 0, st>>>(polys, stride, w.ord_rank, w.pos_rank, Ki, w.p0, w.p1, w.p2c, (unsigned*)w.alive);
+    poly_gather_kernel<<<gK, tpb, 0, st>>>(polys, stride, w.ord_rank, w.pos_rank, Ki, w.p0, w.p1, w.p2r, w.p2c, (unsigned*)w.alive);
     R3G_LAUNCH_OK("poly_gather_kernel");
     // below 1e-3 the FP32 noise of disjoint pairs could exceed the threshold: test every pair (no bounding-box filter)
     rc = nms_rounds_stage<rn::GEOM_QUAD>(w, Ki, 0, 0, thr, 0.0f, 0.0f, thr >= 1e-3f ? 1 : 0, st);      // poly_nms_cuda.cu:183: IoU > thr

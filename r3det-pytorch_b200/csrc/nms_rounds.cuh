@@ -65,6 +65,7 @@ struct Args {
     const float4* p2r;                          // boxes: row plane, two 16-byte halves per candidate; polygons: unused
     const float4* p2c;                          // boxes: column plane {X, Y, r, k}; polygons: bounding box {x0, y0, x1, y1}
     const float* raw;                           // boxes: (K, 5) tuples with class offsets applied (restatement input)
+                                                // polygons: p2r[2 p] = {signed area, convex, max |coordinate|, -}
     const unsigned* label;                      // segment key per position (sorted ascending)
     int K;
     // state
@@ -204,7 +205,7 @@ __global__ void __launch_bounds__(THREADS, 2) nms_rounds_kernel(const Args A) {
             const uint4 e = W.q3[c3 - nb + lane];
             float r;
             if (GEOM == GEOM_BOX) r = emu_call(A.raw + (int64_t)e.x * 5, A.raw + (int64_t)e.y * 5, A.variant);
-            else r = 0.0f;                                    // polygons never queue here
+            else r = quad_call(__ldg(A.p0 + e.x), __ldg(A.p1 + e.x), __ldg(A.p0 + e.y), __ldg(A.p1 + e.y));   // the reference's own arithmetic
             const bool sup = A.inclusive ? (r >= A.thr) : (r > A.thr);
             if (sup) {
                 const unsigned long long bit = 1ull << (e.w & 63u);
@@ -234,7 +235,12 @@ __global__ void __launch_bounds__(THREADS, 2) nms_rounds_kernel(const Args A) {
                 r = pair_overlap(A0, A1, B0, B1, A.variant, MODE_IOU, A.tau, risk);
                 emu = A.tau > 0.0f && (risk || fabsf(r - A.thr) < A.margin);
             } else {
-                r = quad_call(W.r0[il], W.r1[il], W.c0[jl], W.c1[jl]);
+                // own convex-quadrilateral geometry; concave input and pairs within the reference's noise of the threshold are
+                // left to the restatement
+                float margin;
+                const bool ok = poly::convex_quad_iou(W.r0[il], W.r1[il], __ldg(A.p2r + 2 * (size_t)W.rpos[il]),
+                                                      W.c0[jl], W.c1[jl], __ldg(A.p2r + 2 * (size_t)W.cpos[jl]), r, margin);
+                emu = !ok || fabsf(r - A.thr) < margin;
             }
             if (!emu) {
                 const bool sup = A.inclusive ? (r >= A.thr) : (r > A.thr);
@@ -244,7 +250,7 @@ __global__ void __launch_bounds__(THREADS, 2) nms_rounds_kernel(const Args A) {
         __syncwarp();
         cq -= nb;
         n_area += nb;
-        if (GEOM == GEOM_BOX) {
+        {
             const unsigned bal = __ballot_sync(FULL, emu);
             if (bal) {
                 if (emu) {

@@ -128,10 +128,18 @@ class FrmBackwardPlan:
         need = C.c_size_t(0)
         L.check(lib.r3g_frm_backward_multi_workspace_bytes(nl, self.n, self.hw, self.points, C.byref(need)))
         self.ws = L.workspace(need.value, dev)
+        cur = torch.cuda.current_stream(dev)
+        if torch.cuda.is_current_stream_capturing():
+            # under CUDA-graph capture a forward whose backward never runs would leave side-stream work unjoined: the plan
+            # is captured on the capturing stream itself (it is ~50 us; the overlap is given up, correctness is not)
+            with L.device_guard(dev):
+                L.check(lib.r3g_frm_backward_plan_multi_f32(nl, _ptr_array(self.boxes), self.n, self.hw, self.sc, self.points,
+                                                            L.ptr(self.ws), self.ws.numel(), C.c_void_p(cur.cuda_stream)))
+            self.ready = None
+            return
         side = FrmBackwardPlan._side.get(dev.index)
         if side is None:
             side = FrmBackwardPlan._side[dev.index] = torch.cuda.Stream(device=dev)
-        cur = torch.cuda.current_stream(dev)
         side.wait_stream(cur)                                  # the boxes are produced on the current stream
         with L.device_guard(dev), torch.cuda.stream(side):
             L.check(lib.r3g_frm_backward_plan_multi_f32(nl, _ptr_array(self.boxes), self.n, self.hw, self.sc, self.points,
@@ -144,8 +152,9 @@ class FrmBackwardPlan:
         gs = [g.contiguous() if g.dtype == torch.float32 else g.float().contiguous() for g in grad_outputs]
         gins = [torch.empty_like(g) for g in gs]
         cur = torch.cuda.current_stream(self.dev)
-        cur.wait_event(self.ready)
-        with L.device_guard(self.dev):
+        if self.ready is not None:
+            cur.wait_event(self.ready)
+        with L.device_guard(self.dev):                         # the apply only READS the plan: it can run any number of times
             L.check(L.lib().r3g_frm_backward_apply_multi_f32(self.nl, _ptr_array(gs), _ptr_array(self.boxes), self.n, gs[0].size(1),
                                                              self.hw, self.sc, self.points, _ptr_array(gins), L.ptr(self.ws),
                                                              self.ws.numel(), L.stream_ptr(self.dev)))

@@ -166,3 +166,30 @@ def test_backward_plan_apply_split(cuda_dev):
     torch.autograd.backward(outs, gs)
     want = frm_backward_multi(gs, bs, sc, 5)
     assert all(torch.equal(x.grad, w) for x, w in zip(xs, want))
+
+
+def test_plan_under_capture_and_repeated_backward(cuda_dev):
+    """ADVICE r1: (a) a grad-enabled forward captured in a CUDA graph WITHOUT a backward must not leave side-stream work unjoined;
+    (b) backward twice with retain_graph gives the same gradient (the apply only reads the plan)."""
+    import r3det_b200 as R
+    rng = np.random.default_rng(11)
+    N, C_, H, W, stride = 2, 8, 16, 16, 8
+    ys, xs = np.meshgrid(np.arange(H) * stride, np.arange(W) * stride, indexing="ij")
+    bx = np.zeros((N, H * W, 5), np.float32)
+    bx[:, :, :2] = np.stack([xs, ys], -1).reshape(-1, 2)[None] + rng.normal(0, stride, (N, H * W, 2))
+    bx[:, :, 2:4] = rng.uniform(8, 64, (N, H * W, 2)); bx[:, :, 4] = rng.uniform(-1.5, 0, (N, H * W))
+    boxes = torch.from_numpy(bx.reshape(-1, 5)).to(cuda_dev)
+    x = torch.randn((N, C_, H, W), device=cuda_dev, requires_grad=True)
+    R.feature_refine_multi([x], [boxes], [1.0 / stride], 1)                  # warm-up outside capture
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        y_static = R.feature_refine_multi([x], [boxes], [1.0 / stride], 1)[0]
+    g.replay(); torch.cuda.synchronize()
+    want = R.feature_refine(x.detach(), boxes, 1.0 / stride, 1)
+    assert torch.equal(y_static.detach(), want)
+    y = R.feature_refine_multi([x], [boxes], [1.0 / stride], 1)[0]
+    w = torch.randn_like(y)
+    g1, = torch.autograd.grad((y * w).sum(), x, retain_graph=True)
+    g2, = torch.autograd.grad((y * w).sum(), x)
+    assert torch.equal(g1, g2)
