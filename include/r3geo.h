@@ -115,7 +115,8 @@ int r3g_max_iou_assign_batched_f32(int64_t B, const float* gt, const int64_t* gt
  *           nms_rotated_ext.nms_rotated(dets, scores, thr)     r3det/ops/nms_rotated/src/nms_rotated_ext.cpp:53-56 (variant 3, ORDER_SCORE)
  *           ml_nms_rotated(dets, scores, labels, thr)          r3det/ops/ml_nms_rotated/src/nms_rotated.h:23-38   (variant 2, labels)
  * boxes: (K, stride) floats; scores: (K); labels: (K) int64 in [0, 2^31) or NULL (single class).  A box
- * suppresses a lower-scored box of the same label when IoU > thr (>= with R3G_NMS_INCLUSIVE).
+ * suppresses a lower-scored box of the same label when IoU > thr (>= with R3G_NMS_INCLUSIVE).  Candidates whose score is
+ * -inf or NaN are padding: they take no part and are never kept.
  * keep_out: (K) int64 original indices, first *num_keep_out valid (both device memory).
  * With labels, `class_offset` != NULL points to ONE device float: the reference's per-class coordinate
  * offset scale (rnms_wrapper.py:61-64 / nms_rotated_wrapper.py:84-90); boxes are then evaluated at
@@ -149,6 +150,20 @@ int r3g_nms_batched_f32(const float* boxes, int64_t stride, const float* scores,
 int r3g_poly_nms_workspace_bytes(int64_t K, size_t* bytes);
 int r3g_poly_nms_f32(const float* polys, int64_t stride, const float* scores, const int64_t* labels, int64_t K, float thr,
                      int64_t* keep_out, int64_t* num_keep_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Batched, synchronisation-free form of r3g_mc_candidates_f32 for B <= 64 images of n_per_image boxes each (multi_bboxes /
+ * multi_scores are the (B * n_per_image) concatenated rows).  Outputs have CAPACITY B * n_per_image * C: the candidates are
+ * compacted to the front, the tail is padding with score -inf (r3g_nms_batched_f32 gives such candidates no part), out_batch
+ * holds the image of every candidate and out_src its flat (row * C + class) index (-1 in the padding).  scale_out (B floats) is
+ * the per-image class-offset scale of the reference's batched wrappers — offset_rule 1: max over the candidate boxes + 1
+ * (rnms_wrapper.py:61-64), 2: span of their horizontal bounding boxes + 1 (nms_rotated_wrapper.py:84-90), 0: 1 — so the whole
+ * multiclass NMS of a batch runs without reading anything back to the host.  Workspace: r3g_mc_candidates_workspace_bytes(B *
+ * n_per_image, C) + 512 bytes. */
+int r3g_mc_candidates_batched_f32(const float* multi_bboxes, int box_cols, const float* multi_scores, int64_t score_stride,
+                                  int64_t n_per_image, int B, int C, float score_thr, int offset_rule,
+                                  float* out_boxes, float* out_scores, int64_t* out_labels, int64_t* out_batch,
+                                  int64_t* out_src, int64_t* count_out, float* scale_out,
+                                  void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- padded keep records ------------------------------------------------------------------------------------
  * replaces the per-image `dets[keep][:max_num]` slicing after NMS (r3det/core/post_processing/bbox_nms_rotated.py:127-131,

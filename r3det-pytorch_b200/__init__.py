@@ -20,11 +20,11 @@ Module map (reference module -> here):
 from . import _lib  # noqa: F401
 from ._nms_core import pack_keep_records  # noqa: F401
 from .assign import FusedMaxIoUAssigner, max_iou_assign, max_iou_assign_batched  # noqa: F401
-from .bbox_nms_rotated import multiclass_nms_rotated, multiclass_nms_rotated_batch  # noqa: F401
+from .bbox_nms_rotated import multiclass_nms_rotated, multiclass_nms_rotated_batch, multiclass_nms_rotated_padded  # noqa: F401
 from .box_iou_rotated import obb_overlaps  # noqa: F401
 from .coder import (DeltaXYWHAOBBoxCoder, bbox2delta_v1, bbox2delta_v2, bbox2delta_v3, delta2bbox_v1,  # noqa: F401
                     delta2bbox_v2, delta2bbox_v3)
-from .dense_tail import filter_bboxes, get_bboxes, refine_bboxes, select_decode  # noqa: F401
+from .dense_tail import filter_bboxes, get_bboxes, get_bboxes_padded, refine_bboxes, select_decode  # noqa: F401
 from .fr import (FR, FeatureRefineFunction, FeatureRefineModule, FeatureRefineMultiFunction, feature_refine,  # noqa: F401
                  feature_refine_multi)
 from .iou_calculators import (IOU_CALCULATORS, RBboxOverlaps2D_v1, RBboxOverlaps2D_v2,  # noqa: F401

@@ -20,7 +20,7 @@ import ctypes as C
 import torch
 
 from . import _lib as L
-from ._nms_core import nms_device
+from ._nms_core import nms_device, pack_keep_records
 from .nms_rotated import obb2hbb as _obb2xyxy_v3
 
 #            geometry, ordered by index, drop tiny boxes, offset rule
@@ -160,3 +160,54 @@ def multiclass_nms_rotated_batch(multi_bboxes, multi_scores, score_thr, nms, max
         out.append((dets_kept[start:start + m], labels_kept[start:start + m]))
         start += c
     return out
+
+
+_RULE = {None: 0, 'max': 1, 'hbb_span': 2}
+
+
+def multiclass_nms_rotated_padded(multi_bboxes, multi_scores, score_thr, nms, max_num):
+    """`multiclass_nms_rotated` for a batch with FIXED-SIZE outputs and no host synchronisation anywhere (CUDA-graph
+    capturable): multi_bboxes (B, n, 5), multi_scores (B, n, C + 1) -> dets (B, max_num, 6), labels (B, max_num) int64,
+    counts (B,) int64.  Rows [0, counts[b]) of image b are exactly what the per-image call returns (same order and
+    truncation, reference bbox_nms_rotated.py:98-131); the remaining rows are zero.  Candidate extraction, the per-image
+    class-offset scale, the segmented NMS and the truncation all run on the device: r3g_mc_candidates_batched_f32 ->
+    r3g_nms_batched_f32 -> r3g_nms_pack_f32.  B <= 64; max_num > 0."""
+    kind = _cfg(nms, 'type', 'v1')
+    if kind not in _SPEC:
+        raise KeyError(f'unknown rotated nms type {kind!r}')
+    geometry, by_index, drop_small, offset_rule = _SPEC[kind]
+    L.require_cuda(multi_bboxes, multi_scores)
+    assert multi_bboxes.dim() == 3 and multi_scores.dim() == 3 and multi_bboxes.size(-1) == 5 and max_num > 0
+    B, n, C1 = multi_scores.shape
+    nc = C1 - 1
+    dev = multi_scores.device
+    if B > 64:
+        parts = [multiclass_nms_rotated_padded(multi_bboxes[s:s + 64], multi_scores[s:s + 64], score_thr, nms, max_num)
+                 for s in range(0, B, 64)]
+        return tuple(torch.cat([p[i] for p in parts]) for i in range(3))
+    T = B * n * nc
+    if T == 0:
+        return (multi_bboxes.new_zeros((B, max_num, 6)), torch.zeros((B, max_num), dtype=torch.int64, device=dev),
+                torch.zeros((B,), dtype=torch.int64, device=dev))
+    mb = multi_bboxes.float().contiguous()
+    ms = multi_scores.float().contiguous()
+    boxes = torch.empty((T, 5), dtype=torch.float32, device=dev)
+    scores = torch.empty((T,), dtype=torch.float32, device=dev)
+    labels = torch.empty((T,), dtype=torch.int64, device=dev)
+    bid = torch.empty((T,), dtype=torch.int64, device=dev)
+    src = torch.empty((T,), dtype=torch.int64, device=dev)
+    count = torch.empty((), dtype=torch.int64, device=dev)
+    scale = torch.empty((B,), dtype=torch.float32, device=dev)
+    lib = L.lib()
+    nbytes = C.c_size_t(0)
+    L.check(lib.r3g_mc_candidates_workspace_bytes(B * n, nc, C.byref(nbytes)))
+    ws = L.workspace(nbytes.value + 512, dev)
+    with L.device_guard(dev):
+        L.check(lib.r3g_mc_candidates_batched_f32(L.ptr(mb), 5, L.ptr(ms), C1, n, B, nc, float(score_thr), _RULE[offset_rule],
+                                                  L.ptr(boxes), L.ptr(scores), L.ptr(labels), L.ptr(bid), L.ptr(src),
+                                                  C.c_void_p(count.data_ptr()), L.ptr(scale), L.ptr(ws), ws.numel(),
+                                                  L.stream_ptr(dev)))
+    keep, num = nms_device(boxes, scores, _cfg(nms, 'iou_thr'), geometry, labels=labels,
+                           class_offset=scale if offset_rule is not None else None, order_index=by_index, drop_small=drop_small,
+                           batch_ids=bid, n_batches=B, label_bits=max(1, (nc - 1).bit_length()))
+    return pack_keep_records(boxes, scores, labels, keep, num, bid, B, int(max_num))

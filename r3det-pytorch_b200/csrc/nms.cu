@@ -127,7 +127,7 @@ __global__ void nms_batch_keys_kernel(const int64_t* __restrict__ batch_ids, con
 __global__ void nms_gather_kernel(const float* __restrict__ boxes, int64_t stride, const int* __restrict__ ord_rank,
                                   const int* __restrict__ pos_rank, const unsigned* __restrict__ pos_label, int K,
                                   int variant, int drop_small, const float* __restrict__ class_offset, int has_labels,
-                                  int batched, int n_batches,
+                                  int batched, int n_batches, const float* __restrict__ scores,
                                   float4* p0, float4* p1, float4* p2r, float4* p2c, float* raw, unsigned* alive32) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     bool ok = false;
@@ -136,7 +136,7 @@ __global__ void nms_gather_kernel(const float* __restrict__ boxes, int64_t strid
         const float* b = boxes + (int64_t)idx * stride;
         float x[5] = { b[0], b[1], b[2], b[3], b[4] };
         float off = 0.0f;
-        ok = true;
+        ok = scores[idx] > -INFINITY;                                             // padding candidates (score -inf / NaN) take no part
         if (batched && (pos_label[p] >> 16) >= (unsigned)n_batches) ok = false;    // image id out of range: takes no part
         if (class_offset != nullptr && has_labels) {
             const unsigned key = pos_label[p];
@@ -502,7 +502,7 @@ R3G_API int r3g_nms_batched_f32(const float* boxes, int64_t stride, const float*
     if (rc != R3G_OK) return rc;
     nms_gather_kernel<<<gK, tpb, 0, st>>>(boxes, stride, w.ord_rank, w.pos_rank, w.pos_label, Ki, variant,
                                           (flags & R3G_NMS_DROP_SMALL) ? 1 : 0, class_offset, labels ? 1 : 0,
-                                          batch_ids ? 1 : 0, n_batches, w.p0, w.p1, w.p2r, w.p2c, w.raw, (unsigned*)w.alive);
+                                          batch_ids ? 1 : 0, n_batches, scores, w.p0, w.p1, w.p2r, w.p2c, w.raw, (unsigned*)w.alive);
     R3G_LAUNCH_OK("nms_gather_kernel");
     rc = nms_rounds_stage<rn::GEOM_BOX>(w, Ki, variant, (flags & R3G_NMS_INCLUSIVE) ? 1 : 0, thr,
                                         (flags & R3G_NMS_STRICT) ? 2e-2f : 0.0f, (variant == R3G_V1) ? 1e-3f : 5e-5f, 0, st);
@@ -669,6 +669,117 @@ __global__ void mc_emit_kernel(const float* __restrict__ boxes, int box_cols, co
 }
 
 }  // namespace r3g
+
+// ---- batched, synchronisation-free candidate extraction ----------------------------------------------------------
+// The same enumeration for a whole batch, with everything the batched NMS call needs produced on the device: candidates are
+// compacted to the front of capacity-sized arrays (capacity = B * n * C), the tail is PADDING (score -inf: r3g_nms_batched_f32
+// ignores such candidates), every candidate carries its image id, and the per-image class-offset scale of the reference's
+// batched wrappers is reduced in the same pass (rule 1: max over the candidate boxes' five columns + 1, rnms_wrapper.py:61-64;
+// rule 2: span of their horizontal bounding boxes + 1, nms_rotated_wrapper.py:84-90; images without candidates get 1).
+namespace r3g {
+
+__device__ __forceinline__ int f2ord(float f) { const int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
+__device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+constexpr int MCB_MAX_IMAGES = 64;
+constexpr int MCB_NONE_HI = (int)0x80808080, MCB_NONE_LO = 0x7f7f7f7f;     // memset patterns: "no candidate seen"
+
+__global__ void __launch_bounds__(256) mcb_emit_kernel(const float* __restrict__ boxes, int box_cols, const float* __restrict__ scores,
+                                                       int64_t n_img, int B, int C, int64_t score_stride, const int* __restrict__ flag,
+                                                       const int* __restrict__ pref, int rule, float* __restrict__ out_boxes,
+                                                       float* __restrict__ out_scores, int64_t* __restrict__ out_labels,
+                                                       int64_t* __restrict__ out_batch, int64_t* __restrict__ out_src,
+                                                       int64_t* __restrict__ count, int* __restrict__ ghi, int* __restrict__ glo) {
+    __shared__ int shi[MCB_MAX_IMAGES], slo[MCB_MAX_IMAGES];
+    const int64_t T = (int64_t)B * n_img * C;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (threadIdx.x < MCB_MAX_IMAGES) { shi[threadIdx.x] = MCB_NONE_HI; slo[threadIdx.x] = MCB_NONE_LO; }
+    __syncthreads();
+    const int64_t total = (int64_t)pref[T - 1] + flag[T - 1];
+    if (t == 0) *count = total;
+    if (t < T) {
+        if (flag[t]) {
+            const int64_t i = t / C;
+            const int c = (int)(t - i * C);
+            const int b = (int)(i / n_img);
+            const int64_t k = pref[t];
+            const float* bx = boxes + i * box_cols + (box_cols > 5 ? (int64_t)c * 5 : 0);
+            float v[5];
+#pragma unroll
+            for (int q = 0; q < 5; q++) { v[q] = bx[q]; out_boxes[k * 5 + q] = v[q]; }
+            out_scores[k] = scores[i * score_stride + c];
+            out_labels[k] = c;
+            out_batch[k] = b;
+            out_src[k] = t;
+            if (rule == 1) {
+                atomicMax(&shi[b], f2ord(fmaxf(fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])), v[4])));
+            } else if (rule == 2) {                       // obb2hbb of nms_rotated_wrapper.py:7-20, FP32 like the torch ops
+                const float cs = cosf(v[4]), sn = sinf(v[4]);
+                const float xb = fabsf(v[2] / 2 * cs) + fabsf(v[3] / 2 * sn), yb = fabsf(v[2] / 2 * sn) + fabsf(v[3] / 2 * cs);
+                atomicMax(&shi[b], f2ord(fmaxf(v[0] + xb, v[1] + yb)));
+                atomicMin(&slo[b], f2ord(fminf(v[0] - xb, v[1] - yb)));
+            }
+        }
+        if (t >= total) { out_scores[t] = -INFINITY; out_labels[t] = 0; out_batch[t] = 0; out_src[t] = -1; }
+    }
+    __syncthreads();
+    if (threadIdx.x < B) {
+        if (shi[threadIdx.x] != MCB_NONE_HI) atomicMax(ghi + threadIdx.x, shi[threadIdx.x]);
+        if (slo[threadIdx.x] != MCB_NONE_LO) atomicMin(glo + threadIdx.x, slo[threadIdx.x]);
+    }
+}
+
+__global__ void mcb_scale_kernel(const int* __restrict__ ghi, const int* __restrict__ glo, int B, int rule, float* __restrict__ scale) {
+    const int b = threadIdx.x;
+    if (b >= B) return;
+    float s = 1.0f;
+    if (rule == 1 && ghi[b] != MCB_NONE_HI) s = ord2f(ghi[b]) + 1.0f;
+    if (rule == 2 && ghi[b] != MCB_NONE_HI) s = (ord2f(ghi[b]) - ord2f(glo[b])) + 1.0f;
+    scale[b] = s;
+}
+
+}  // namespace r3g
+
+R3G_API int r3g_mc_candidates_batched_f32(const float* multi_bboxes, int box_cols, const float* multi_scores, int64_t score_stride,
+                                          int64_t n_per_image, int B, int C, float score_thr, int offset_rule,
+                                          float* out_boxes, float* out_scores, int64_t* out_labels, int64_t* out_batch,
+                                          int64_t* out_src, int64_t* count_out, float* scale_out,
+                                          void* workspace, size_t workspace_bytes, void* stream) {
+    R3G_REQUIRE(n_per_image >= 0 && C >= 0 && B >= 1 && B <= MCB_MAX_IMAGES, "r3g_mc_candidates_batched_f32: bad sizes (1..64 images)");
+    const int64_t n = (int64_t)B * n_per_image, T = n * C;
+    R3G_REQUIRE(T < (1ll << 31), "r3g_mc_candidates_batched_f32: too many (box, class) pairs");
+    R3G_REQUIRE(count_out && scale_out && (offset_rule >= 0 && offset_rule <= 2), "r3g_mc_candidates_batched_f32: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (T == 0) {
+        R3G_CUDA_OK(cudaMemsetAsync(count_out, 0, sizeof(int64_t), st));
+        mcb_scale_kernel<<<1, MCB_MAX_IMAGES, 0, st>>>(nullptr, nullptr, B, 0, scale_out);
+        return R3G_OK;
+    }
+    R3G_REQUIRE(box_cols == 5 || box_cols == 5 * C, "r3g_mc_candidates_batched_f32: boxes must be (n, 5) or (n, 5*C)");
+    R3G_REQUIRE(multi_bboxes && multi_scores && out_boxes && out_scores && out_labels && out_batch && out_src && workspace,
+                "r3g_mc_candidates_batched_f32: null pointer");
+    size_t need = 0;
+    r3g_mc_candidates_workspace_bytes(n, C, &need);
+    need += 512;
+    if (workspace_bytes < need) {
+        set_error("r3g_mc_candidates_batched_f32: workspace too small (%zu < %zu)", workspace_bytes, need);
+        return R3G_ERR_WORKSPACE;
+    }
+    char* p = (char*)workspace;
+    int* ghi = (int*)p; int* glo = (int*)(p + 256); p += 512;
+    int* flag = (int*)p; p += align_up(4 * (size_t)T, 256);
+    int* pref = (int*)p; p += align_up(4 * (size_t)T, 256);
+    size_t tb = need - 512 - 2 * align_up(4 * (size_t)T, 256);
+    R3G_CUDA_OK(cudaMemsetAsync(ghi, 0x80, 256, st));
+    R3G_CUDA_OK(cudaMemsetAsync(glo, 0x7f, 256, st));
+    const unsigned grid = (unsigned)((T + 255) / 256);
+    mc_flags_kernel<<<grid, 256, 0, st>>>(multi_scores, n, C, score_stride, score_thr, flag);
+    R3G_CUDA_OK(cub::DeviceScan::ExclusiveSum(p, tb, flag, pref, (int)T, st));
+    mcb_emit_kernel<<<grid, 256, 0, st>>>(multi_bboxes, box_cols, multi_scores, n_per_image, B, C, score_stride, flag, pref, offset_rule,
+                                          out_boxes, out_scores, out_labels, out_batch, out_src, count_out, ghi, glo);
+    mcb_scale_kernel<<<1, MCB_MAX_IMAGES, 0, st>>>(ghi, glo, B, offset_rule, scale_out);
+    R3G_LAUNCH_OK("batched candidate kernels");
+    return R3G_OK;
+}
 
 R3G_API int r3g_mc_candidates_workspace_bytes(int64_t n, int C, size_t* bytes) {
     R3G_REQUIRE(bytes && n >= 0 && C >= 0 && n * (int64_t)C < (1ll << 31), "r3g_mc_candidates_workspace_bytes: bad arguments");

@@ -12,7 +12,7 @@ import ctypes as C
 import torch
 
 from . import _lib as L
-from .bbox_nms_rotated import multiclass_nms_rotated_batch
+from .bbox_nms_rotated import multiclass_nms_rotated_batch, multiclass_nms_rotated_padded
 
 MAX_IMAGES = 64     # per r3g_select_decode_f32 call
 
@@ -97,6 +97,18 @@ def get_bboxes(cls_scores, bbox_preds, mlvl_anchors, img_metas, cfg, coder, resc
     if with_nms:
         return multiclass_nms_rotated_batch(boxes, scores, get('score_thr'), get('nms'), get('max_per_img'))
     return [(boxes[i], scores[i]) for i in range(boxes.size(0))]
+
+
+def get_bboxes_padded(cls_scores, bbox_preds, mlvl_anchors, img_metas, cfg, coder, rescale=False):
+    """`get_bboxes` with fixed-size outputs: dets (B, max_per_img, 6), labels (B, max_per_img), counts (B,) — the first
+    counts[b] rows of image b are what `get_bboxes` returns for it.  Nothing is read back to the host between the network
+    outputs and the detections (select + decode, candidate extraction, class-offset scales, segmented NMS and truncation are
+    device kernels of libr3geo), so the whole tail can be captured in a CUDA graph and replayed."""
+    get = (lambda k, d=None: cfg.get(k, d)) if hasattr(cfg, 'get') else (lambda k, d=None: getattr(cfg, k, d))
+    shapes = [m['img_shape'] for m in img_metas]
+    sfs = [m['scale_factor'] for m in img_metas] if rescale else None
+    boxes, scores = select_decode(cls_scores, bbox_preds, mlvl_anchors, coder, get('nms_pre', -1), shapes, sfs)
+    return multiclass_nms_rotated_padded(boxes, scores, get('score_thr'), get('nms'), get('max_per_img'))
 
 
 def filter_bboxes(cls_scores, bbox_preds, mlvl_anchors, coder, as_batch=False):

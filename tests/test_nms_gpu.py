@@ -321,3 +321,67 @@ def test_padded_keep_records(cuda_dev, by_index):
     d1, l1, c1 = R.pack_keep_records(B[:700], S[:700], Lb[:700], keep1, num1, None, 1, 100)
     k1 = keep1[:min(int(num1), 100)].cpu().numpy()
     assert int(c1[0]) == len(k1) and np.array_equal(d1[0, :len(k1), :5].cpu().numpy(), b[:700][k1])
+
+
+@pytest.mark.parametrize("kind", ["v1", "v3", "v2", "mmcv"])
+def test_multiclass_padded_equals_per_image(cuda_dev, kind):
+    """multiclass_nms_rotated_padded (no host synchronisation, fixed-size outputs) == multiclass_nms_rotated per image."""
+    import r3det_b200 as R
+    rng = np.random.default_rng(31)
+    B, n, nc = 4, 900, 15
+    ver = {"v1": "v1", "v3": "v3", "v2": "v2", "mmcv": "v2"}[kind]
+    boxes = np.stack([clustered(n, 400 + i, ver)[0] for i in range(B)])
+    scores = np.zeros((B, n, nc + 1), np.float32)
+    hot = rng.random((B, n, nc)) < 0.08
+    scores[..., :nc][hot] = rng.uniform(0.05, 1.0, int(hot.sum())).astype(np.float32)
+    scores[2] = 0.0                                                      # an image without candidates
+    Bx, Sc = _t(boxes, cuda_dev), _t(scores, cuda_dev)
+    cfg = dict(type=kind, iou_thr=0.1)
+    for max_num in (50, 2000):
+        dets, labels, counts = R.multiclass_nms_rotated_padded(Bx, Sc, 0.05, cfg, max_num)
+        assert dets.shape == (B, max_num, 6) and labels.shape == (B, max_num)
+        for b in range(B):
+            d, l = R.multiclass_nms_rotated(Bx[b], Sc[b], 0.05, cfg, max_num)
+            c = int(counts[b])
+            assert c == d.size(0), (kind, b, c, d.size(0))
+            assert torch.equal(dets[b, :c], d) and torch.equal(labels[b, :c], l)
+            assert float(dets[b, c:].abs().sum()) == 0.0
+
+
+def test_get_bboxes_padded_graph_capture(cuda_dev):
+    """The whole dense-head tail (select + decode + multiclass NMS + truncation) replays from a CUDA graph on new inputs."""
+    import r3det_b200 as R
+    rng = np.random.default_rng(41)
+    Bn, A, Cn = 2, 9, 15
+    cls, reg, anc = [], [], []
+    for H, stride in ((32, 8), (16, 16), (8, 32)):
+        c = rng.normal(-4.6, 1.0, (Bn, A * Cn, H, H)).astype(np.float32)
+        hot = rng.random(c.shape) < 2e-3
+        c[hot] = rng.normal(1.0, 1.0, int(hot.sum())).astype(np.float32)
+        cls.append(_t(c, cuda_dev)); reg.append(_t(rng.normal(0, 0.2, (Bn, A * 5, H, H)).astype(np.float32), cuda_dev))
+        ys, xs = np.meshgrid(np.arange(H), np.arange(H), indexing="ij")
+        ctr = (np.stack([xs, ys], -1).reshape(-1, 1, 2) * stride + stride / 2).astype(np.float32)
+        wh = np.broadcast_to(np.array([[stride * 4, stride * 4]], np.float32) * np.linspace(1, 2, A, dtype=np.float32)[:, None], (H * H, A, 2))
+        a = np.concatenate([np.broadcast_to(ctr, (H * H, A, 2)), wh, np.zeros((H * H, A, 1), np.float32)], -1)
+        anc.append(_t(a.reshape(-1, 5), cuda_dev))
+    coder = R.DeltaXYWHAOBBoxCoder((0.,) * 5, (1.,) * 5, angle_range="v1")
+    metas = [dict(img_shape=(256, 256, 3), scale_factor=np.ones(4, np.float32))] * Bn
+    cfg = dict(nms_pre=1000, min_bbox_size=0, score_thr=0.05, nms=dict(type="v1", iou_thr=0.1), max_per_img=100)
+    want = R.get_bboxes(cls, reg, anc, metas, cfg, coder)
+    dets, labels, counts = R.get_bboxes_padded(cls, reg, anc, metas, cfg, coder)
+    for b in range(Bn):
+        c = int(counts[b])
+        assert c == want[b][0].size(0) and c > 0
+        assert torch.equal(dets[b, :c], want[b][0]) and torch.equal(labels[b, :c], want[b][1])
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        out = R.get_bboxes_padded(cls, reg, anc, metas, cfg, coder)
+    for t in cls:                                                       # new logits in place, then replay
+        t.copy_(torch.roll(t, 1, dims=0))
+    g.replay(); torch.cuda.synchronize()
+    want2 = R.get_bboxes(cls, reg, anc, metas, cfg, coder)
+    for b in range(Bn):
+        c = int(out[2][b])
+        assert c == want2[b][0].size(0)
+        assert torch.equal(out[0][b, :c], want2[b][0]) and torch.equal(out[1][b, :c], want2[b][1])
