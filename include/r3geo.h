@@ -141,6 +141,15 @@ int r3g_nms_batched_f32(const float* boxes, int64_t stride, const float* scores,
                         int64_t* keep_out, int64_t* num_keep_out,
                         void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same with a device-side candidate count: the K arrays are a CAPACITY, only *count_dev candidates are real and the rest is
+ * padding that must carry score -inf, image id 65535 and label 65535 (what r3g_mc_candidates_batched_f32 writes), so that it
+ * sorts behind every candidate; the selection kernel then never visits it.  count_dev NULL = all K are real. */
+int r3g_nms_batched_counted_f32(const float* boxes, int64_t stride, const float* scores, const int64_t* labels,
+                                const int64_t* batch_ids, int n_batches,
+                                int64_t K, const int64_t* count_dev, float thr, int variant, int flags, const float* class_offset,
+                                int64_t* keep_out, int64_t* num_keep_out,
+                                void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- polygon NMS ----------------------------------------------------------------------
  * replaces nms_rotated_ext.nms_poly   r3det/ops/nms_rotated/src/poly_nms_cuda.cu:122-262 (mask kernel + host scan)
  * polys: K rows of `stride` >= 8 floats [x0, y0, ..., x3, y3] (arbitrary quadrilaterals), scores (K).  Greedy in
@@ -153,8 +162,8 @@ int r3g_poly_nms_f32(const float* polys, int64_t stride, const float* scores, co
 
 /* Batched, synchronisation-free form of r3g_mc_candidates_f32 for B <= 64 images of n_per_image boxes each (multi_bboxes /
  * multi_scores are the (B * n_per_image) concatenated rows).  Outputs have CAPACITY B * n_per_image * C: the candidates are
- * compacted to the front, the tail is padding with score -inf (r3g_nms_batched_f32 gives such candidates no part), out_batch
- * holds the image of every candidate and out_src its flat (row * C + class) index (-1 in the padding).  scale_out (B floats) is
+ * compacted to the front, the tail is padding with score -inf, image id and label 65535 (r3g_nms_batched_f32 gives such candidates
+ * no part; r3g_nms_batched_counted_f32 with count_out does not even visit them), out_batch holds the image of every candidate and out_src its flat (row * C + class) index (-1 in the padding).  scale_out (B floats) is
  * the per-image class-offset scale of the reference's batched wrappers — offset_rule 1: max over the candidate boxes + 1
  * (rnms_wrapper.py:61-64), 2: span of their horizontal bounding boxes + 1 (nms_rotated_wrapper.py:84-90), 0: 1 — so the whole
  * multiclass NMS of a batch runs without reading anything back to the host.  Workspace: r3g_mc_candidates_workspace_bytes(B *

@@ -46,6 +46,7 @@ _SIGNATURES = {
     "r3g_mc_candidates_batched_f32": (_i32, [_vp, _i32, _vp, _i64, _i64, _i32, _i32, _f32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                              _vp, _sz, _vp]),
     "r3g_nms_pack_f32": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "r3g_nms_batched_counted_f32": (_i32, [_vp, _i64, _vp, _vp, _vp, _i32, _i64, _vp, _f32, _i32, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
     "r3g_poly_nms_workspace_bytes": (_i32, [_i64, C.POINTER(_sz)]),
     "r3g_poly_nms_f32": (_i32, [_vp, _i64, _vp, _vp, _i64, _f32, _vp, _vp, _vp, _sz, _vp]),
     "r3g_mc_candidates_workspace_bytes": (_i32, [_i64, _i32, C.POINTER(_sz)]),

@@ -7,7 +7,7 @@ from . import _lib as L
 
 
 def nms_device(boxes, scores, thr, variant, labels=None, class_offset=None, inclusive=False,
-               order_index=False, drop_small=False, strict=True, batch_ids=None, n_batches=1, sort_path=False, stats=None, label_bits=0):
+               order_index=False, drop_small=False, strict=True, batch_ids=None, n_batches=1, sort_path=False, stats=None, label_bits=0, count=None):
     """Rotated NMS on CUDA tensors.
 
     boxes (K, >=5) f32, scores (K,) f32, labels (K,) int64 or None, class_offset: 0-dim CUDA f32 tensor or None.
@@ -19,6 +19,9 @@ def nms_device(boxes, scores, thr, variant, labels=None, class_offset=None, incl
     (n_batches,) int64 tensor and keep is grouped by image (index order or per-image score order).
     In a batch, labels must lie in [0, 65536) (the segment key packs image and label into 32 bits) and candidates whose
     batch id is outside [0, n_batches) take no part.
+
+    count: optional 0-dim int64 CUDA tensor — only the first `count` candidates are real, the rest is padding written by
+    r3g_mc_candidates_batched_f32 (score -inf, image id 65535); needs batch_ids.
 
     label_bits: optional promise that every label is < 2**label_bits (a caller that knows its class count saves radix-sort
     passes above 16384 candidates); 0 = unknown.
@@ -54,9 +57,10 @@ def nms_device(boxes, scores, thr, variant, labels=None, class_offset=None, incl
     L.check(lib.r3g_nms_workspace_bytes(K, C.byref(nbytes)))
     ws = L.workspace(nbytes.value, dev)
     with L.device_guard(dev):
-        L.check(lib.r3g_nms_batched_f32(L.ptr(boxes), stride, L.ptr(scores), L.ptr(labels), L.ptr(batch_ids),
-                                        int(n_batches), K, float(thr), L.V[variant], flags, L.ptr(class_offset),
-                                        L.ptr(keep), C.c_void_p(num.data_ptr()), L.ptr(ws), ws.numel(), L.stream_ptr(dev)))
+        L.check(lib.r3g_nms_batched_counted_f32(L.ptr(boxes), stride, L.ptr(scores), L.ptr(labels), L.ptr(batch_ids),
+                                                int(n_batches), K, None if count is None else C.c_void_p(count.data_ptr()), float(thr),
+                                                L.V[variant], flags, L.ptr(class_offset), L.ptr(keep), C.c_void_p(num.data_ptr()),
+                                                L.ptr(ws), ws.numel(), L.stream_ptr(dev)))
     if stats is not None:
         stats['counters'] = ws[512:1024].view(torch.int64)
     return keep, num

@@ -209,5 +209,5 @@ def multiclass_nms_rotated_padded(multi_bboxes, multi_scores, score_thr, nms, ma
                                                   L.stream_ptr(dev)))
     keep, num = nms_device(boxes, scores, _cfg(nms, 'iou_thr'), geometry, labels=labels,
                            class_offset=scale if offset_rule is not None else None, order_index=by_index, drop_small=drop_small,
-                           batch_ids=bid, n_batches=B, label_bits=max(1, (nc - 1).bit_length()))
+                           batch_ids=bid, n_batches=B, label_bits=max(1, (nc - 1).bit_length()), count=count)
     return pack_keep_records(boxes, scores, labels, keep, num, bid, B, int(max_num))

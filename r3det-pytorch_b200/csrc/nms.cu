@@ -403,7 +403,7 @@ static int nms_env_int(const char* name, int dflt, int lo, int hi) {
 // greedy selection in rounds: one cooperative launch (the grid barrier needs every CTA resident)
 template <int GEOM>
 static int nms_rounds_stage(NmsWs& w, int Ki, int variant, int inclusive, float thr, float tau, float margin, int prefilter,
-                            cudaStream_t st) {
+                            const int64_t* k_valid, cudaStream_t st) {
     static int occ_of[64] = {0};
     int& occ = occ_of[current_device_slot()];
     if (occ == 0) {
@@ -419,6 +419,7 @@ static int nms_rounds_stage(NmsWs& w, int Ki, int variant, int inclusive, float 
     static const int min_env = nms_env_int("R3G_NMS_CHUNK_MIN", 512, 64, rn::B_MAX) / 64 * 64;
     rn::Args a;
     a.p0 = w.p0; a.p1 = w.p1; a.p2r = w.p2r; a.p2c = w.p2c; a.raw = w.raw; a.label = w.pos_label; a.K = Ki;
+    a.k_valid = reinterpret_cast<const long long*>(k_valid);
     a.alive = w.alive; a.seg_cur = w.seg_cur; a.seg_pe = w.seg_pe; a.act = w.act; a.ent = w.ent; a.spos = w.spos; a.klist = w.klist;
     a.ownerB = w.ownerB; a.ownerD = w.ownerD; a.mask = w.mask; a.keep_p = w.keep_p;
     a.ctrl = reinterpret_cast<rn::Ctrl*>(w.ctrl); a.bar = reinterpret_cast<unsigned*>(w.ctrl + 128);
@@ -476,9 +477,19 @@ R3G_API int r3g_nms_batched_f32(const float* boxes, int64_t stride, const float*
                                 int64_t K, float thr, int variant, int flags, const float* class_offset,
                                 int64_t* keep_out, int64_t* num_keep_out,
                                 void* workspace, size_t workspace_bytes, void* stream) {
+    return r3g_nms_batched_counted_f32(boxes, stride, scores, labels, batch_ids, n_batches, K, nullptr, thr, variant, flags, class_offset,
+                                       keep_out, num_keep_out, workspace, workspace_bytes, stream);
+}
+
+R3G_API int r3g_nms_batched_counted_f32(const float* boxes, int64_t stride, const float* scores, const int64_t* labels,
+                                        const int64_t* batch_ids, int n_batches,
+                                        int64_t K, const int64_t* count_dev, float thr, int variant, int flags, const float* class_offset,
+                                        int64_t* keep_out, int64_t* num_keep_out,
+                                        void* workspace, size_t workspace_bytes, void* stream) {
     R3G_REQUIRE(K >= 0 && K <= (1ll << 26), "r3g_nms_f32: bad K (limit 2^26 candidates per call)");
     R3G_REQUIRE(n_batches >= 1 && n_batches <= 65535, "r3g_nms_batched_f32: n_batches must be in [1, 65535]");
     R3G_REQUIRE(batch_ids != nullptr || n_batches == 1, "r3g_nms_batched_f32: n_batches > 1 needs batch_ids");
+    R3G_REQUIRE(count_dev == nullptr || batch_ids != nullptr, "r3g_nms_batched_counted_f32: a device-side count needs batch_ids (padding carries image id 65535)");
     R3G_REQUIRE(variant >= 1 && variant <= 3, "r3g_nms_f32: variant must be 1, 2 or 3 (got %d)", variant);
     R3G_REQUIRE(num_keep_out != nullptr, "r3g_nms_f32: null num_keep_out");
     cudaStream_t st = (cudaStream_t)stream;
@@ -505,7 +516,7 @@ R3G_API int r3g_nms_batched_f32(const float* boxes, int64_t stride, const float*
                                           batch_ids ? 1 : 0, n_batches, scores, w.p0, w.p1, w.p2r, w.p2c, w.raw, (unsigned*)w.alive);
     R3G_LAUNCH_OK("nms_gather_kernel");
     rc = nms_rounds_stage<rn::GEOM_BOX>(w, Ki, variant, (flags & R3G_NMS_INCLUSIVE) ? 1 : 0, thr,
-                                        (flags & R3G_NMS_STRICT) ? 2e-2f : 0.0f, (variant == R3G_V1) ? 1e-3f : 5e-5f, 0, st);
+                                        (flags & R3G_NMS_STRICT) ? 2e-2f : 0.0f, (variant == R3G_V1) ? 1e-3f : 5e-5f, 0, count_dev, st);
     if (rc != R3G_OK) return rc;
     return nms_finish_stage(w, Ki, batch_ids, n_batches, flags, small, keep_out, num_keep_out, st);
 }
@@ -538,7 +549,7 @@ R3G_API int r3g_poly_nms_f32(const float* polys, int64_t stride, const float* sc
     poly_gather_kernel<<<gK, tpb, 0, st>>>(polys, stride, w.ord_rank, w.pos_rank, Ki, w.p0, w.p1, w.p2r, w.p2c, (unsigned*)w.alive);
     R3G_LAUNCH_OK("poly_gather_kernel");
     // below 1e-3 the FP32 noise of disjoint pairs could exceed the threshold: test every pair (no bounding-box filter)
-    rc = nms_rounds_stage<rn::GEOM_QUAD>(w, Ki, 0, 0, thr, 0.0f, 0.0f, thr >= 1e-3f ? 1 : 0, st);      // poly_nms_cuda.cu:183: IoU > thr
+    rc = nms_rounds_stage<rn::GEOM_QUAD>(w, Ki, 0, 0, thr, 0.0f, 0.0f, thr >= 1e-3f ? 1 : 0, nullptr, st);      // poly_nms_cuda.cu:183: IoU > thr
     if (rc != R3G_OK) return rc;
     return nms_finish_stage(w, Ki, nullptr, 1, 0, small, keep_out, num_keep_out, st);
 }
@@ -719,7 +730,9 @@ __global__ void __launch_bounds__(256) mcb_emit_kernel(const float* __restrict__
                 atomicMin(&slo[b], f2ord(fminf(v[0] - xb, v[1] - yb)));
             }
         }
-        if (t >= total) { out_scores[t] = -INFINITY; out_labels[t] = 0; out_batch[t] = 0; out_src[t] = -1; }
+        // padding sorts behind every candidate in both position orders (image-major when ranks are counted, label-major on the
+        // radix path, whose class pass looks at the low label bits only: all ones)
+        if (t >= total) { out_scores[t] = -INFINITY; out_labels[t] = 65535; out_batch[t] = 65535; out_src[t] = -1; }
     }
     __syncthreads();
     if (threadIdx.x < B) {

@@ -68,6 +68,7 @@ struct Args {
                                                 // polygons: p2r[2 p] = {signed area, convex, max |coordinate|, -}
     const unsigned* label;                      // segment key per position (sorted ascending)
     int K;
+    const long long* k_valid;                   // optional (device): only positions < *k_valid hold candidates (padding sorts last)
     // state
     unsigned long long* alive;                  // bit p: candidate p is valid and not suppressed so far
     int* seg_cur; int* seg_pe; int* act;        // per segment: cursor, end; act[2][K]: segment lists of this / the next round
@@ -180,10 +181,11 @@ __global__ void __launch_bounds__(THREADS, 2) nms_rounds_kernel(const Args A) {
     };
 
     // ---- phase 0: class segments of the position space ----
-    for (int p = blockIdx.x * THREADS + (int)tid; p < A.K; p += gridDim.x * THREADS) {
+    const int KV = A.k_valid ? (int)min((long long)A.K, __ldg(A.k_valid)) : A.K;      // padding behind the candidates is never visited
+    for (int p = blockIdx.x * THREADS + (int)tid; p < KV; p += gridDim.x * THREADS) {
         const unsigned L = __ldg(A.label + p);
         if (p == 0 || __ldg(A.label + p - 1) != L) {
-            int lo = p, hi = A.K;
+            int lo = p, hi = KV;
             while (hi - lo > 1) {
                 const int mid = (lo + hi) >> 1;
                 if (__ldg(A.label + mid) == L) lo = mid; else hi = mid;
