@@ -106,8 +106,10 @@ def multiclass_nms_rotated(multi_bboxes, multi_scores, score_thr, nms, max_num=-
 def multiclass_nms_rotated_batch(multi_bboxes, multi_scores, score_thr, nms, max_num=-1):
     """`multiclass_nms_rotated` for a whole batch in one launch sequence: multi_bboxes (B, n, 5), multi_scores
     (B, n, C + 1) CUDA tensors -> list of B (dets (k, 6), labels (k,)) tuples, each identical to what the per-image
-    call returns.  Two host synchronisations per BATCH (candidate count, keep counts) instead of two per image; the
-    reference loops over images (rotate_anchor_head.py:565-588) with ~40 launches and a `nonzero` sync each."""
+    call returns.  With max_num > 0 (every reference config) the batch runs on the fixed-size device path of
+    `multiclass_nms_rotated_padded` and the host reads the B keep counts ONCE, after the detections exist; with
+    max_num <= 0 there are two host synchronisations per BATCH (candidate count, keep counts).  The reference loops
+    over images (rotate_anchor_head.py:565-588) with ~40 launches and a `nonzero` sync each."""
     kind = _cfg(nms, 'type', 'v1')
     if kind not in _SPEC:
         raise KeyError(f'unknown rotated nms type {kind!r}')
@@ -119,6 +121,10 @@ def multiclass_nms_rotated_batch(multi_bboxes, multi_scores, score_thr, nms, max
     empty = (multi_bboxes.new_zeros((0, 6)), multi_bboxes.new_zeros((0,), dtype=torch.long))
     if B == 0:
         return []
+    if max_num > 0 and n * nc > 0:
+        # fixed-size device path (no host read before the detections exist), then ONE read of the B counts to cut the views
+        dets, labels, counts = multiclass_nms_rotated_padded(multi_bboxes, multi_scores, score_thr, nms, max_num)
+        return [(dets[b, :c], labels[b, :c]) for b, c in enumerate(counts.tolist())]
     boxes, scores, labels, src = _candidates(multi_bboxes.reshape(B * n, 5), multi_scores.reshape(B * n, C1), score_thr, None)
     if boxes.size(0) == 0:
         return [empty for _ in range(B)]

@@ -102,23 +102,31 @@ __global__ void nms_keys_kernel(const float* __restrict__ scores, int K, unsigne
     if (i < K) { keyA[i] = score_key_desc(scores[i]); idx[i] = i; }
 }
 
-// segment key of rank r: the label, or (image << 16 | label) for multi-image batches (image-major: an image's
-// segments are contiguous in position space)
+// segment key of candidate i: the label, or (image << 16 | label) for multi-image batches (image-major: an image's
+// segments are contiguous in position space).  In a batch both fields are 16 bits wide: a candidate whose image id is
+// outside [0, 65535) or whose label is outside [0, 65536) gets image 0xffff — never a valid image (n_batches <= 65535), so
+// it takes no part (nms_gather_kernel) instead of aliasing into another image's or class's segment.
+__device__ __forceinline__ unsigned seg_key_of(const int64_t* labels, const int64_t* batch_ids, int i) {
+    const int64_t lab = labels ? labels[i] : 0;
+    if (!batch_ids) return (unsigned)lab;
+    const int64_t img = batch_ids[i];
+    const bool bad = img < 0 || img >= 0xffff || lab < 0 || lab > 0xffff;
+    return ((bad ? 0xffffu : (unsigned)img) << 16) | ((unsigned)lab & 0xffffu);
+}
+
 __global__ void nms_label_keys_kernel(const int64_t* __restrict__ labels, const int64_t* __restrict__ batch_ids,
                                       const int* __restrict__ ord_rank, int K, unsigned* keyB, int* rank_iota) {
     int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r < K) {
-        const int idx = ord_rank[r];
-        unsigned key = labels ? (unsigned)labels[idx] : 0u;
-        if (batch_ids) key = (((unsigned)batch_ids[idx] & 0xffffu) << 16) | (key & 0xffffu);
-        keyB[r] = key;
+        keyB[r] = seg_key_of(labels, batch_ids, ord_rank[r]);
         rank_iota[r] = r;
     }
 }
 
-__global__ void nms_batch_keys_kernel(const int64_t* __restrict__ batch_ids, const int* __restrict__ order, int K, unsigned* key) {
+__global__ void nms_batch_keys_kernel(const int64_t* __restrict__ labels, const int64_t* __restrict__ batch_ids, const int* __restrict__ order,
+                                      int K, unsigned* key) {
     int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r < K) key[r] = (unsigned)batch_ids[order[r]] & 0xffffu;
+    if (r < K) key[r] = seg_key_of(labels, batch_ids, order[r]) >> 16;
 }
 
 // Gather + prepare boxes in position order; class offsets in FP32 as the reference wrappers compute them:
@@ -219,12 +227,6 @@ __global__ void nms_emit_kernel(const int* __restrict__ flag, const int* __restr
 //   pos(i)  = #{ j : (segment_j, score_key_j, j) < (segment_i, score_key_i, i) }       (segment-major position order)
 // O(K^2) compares spread over (K/256) x slices CTAs — a few microseconds — and exactly the permutations the stable
 // radix sorts produce.  The final compaction becomes one single-CTA kernel.
-
-__device__ __forceinline__ unsigned seg_key_of(const int64_t* labels, const int64_t* batch_ids, int i) {
-    unsigned key = labels ? (unsigned)labels[i] : 0u;
-    if (batch_ids) key = (((unsigned)batch_ids[i] & 0xffffu) << 16) | (key & 0xffffu);
-    return key;
-}
 
 template <bool BATCHED>
 __global__ void __launch_bounds__(256) nms_rank_count_kernel(const float* __restrict__ scores, const int64_t* __restrict__ labels,
@@ -365,7 +367,7 @@ static int nms_order_stage(NmsWs& w, const float* scores, const int64_t* labels,
     R3G_CUDA_OK(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, w.keyA, w.keyA2, w.ord_tmp, w.ord_rank, Ki, 0, 32, st));
     if (batch_ids) {
         // multi-image batch: rank order becomes (image asc, score desc) by a stable 16-bit pass over the image id
-        nms_batch_keys_kernel<<<gK, tpb, 0, st>>>(batch_ids, w.ord_rank, Ki, w.keyA);
+        nms_batch_keys_kernel<<<gK, tpb, 0, st>>>(labels, batch_ids, w.ord_rank, Ki, w.keyA);
         R3G_CUDA_OK(cudaMemcpyAsync(w.ord_tmp, w.ord_rank, 4 * (size_t)Ki, cudaMemcpyDeviceToDevice, st));
         tb = w.cub_bytes;
         R3G_CUDA_OK(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, w.keyA, w.keyA2, w.ord_tmp, w.ord_rank, Ki, 0, 16, st));

@@ -44,7 +44,11 @@ def collect_patches(results, img_ids):
 def merge_image(label_dets, num_classes, iou_thr=0.1, version='v1', merge_nms='obb', device=None):
     """_merge_func (dota1.py:632-667) for one image: (N, 7) rows -> list over classes of kept (k, 6) detections.
     merge_nms 'poly' -> polygon NMS of obb2poly_np(dets, version) (rule >); otherwise rnms (v1: rule >=, kept rows in
-    ascending index) or obb_nms (v2 / v3: rule >=, descending score) exactly as the reference's numpy calls resolve."""
+    ascending index) or obb_nms (v2 / v3: rule >=, descending score) exactly as the reference's numpy calls resolve.
+    PRECISION: the reference passes these float64 rows to its CPU ops (double templates) and rotates obb2poly_np in float64;
+    here the rows are cast to float32 for the device kernels.  On full-image coordinates (~1e4 px, FP32 ulp 1e-3 px) the IoU of a
+    pair can move by ~1e-4, so a pair whose float64 IoU lies that close to iou_thr may be decided differently; the returned rows
+    themselves are the caller's float64 rows, untouched (tests/test_nms_gpu.py::test_dota_merge_float64_full_image_coordinates)."""
     device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
     label_dets = np.asarray(label_dets)
     labels, dets = label_dets[:, 0], label_dets[:, 1:]

@@ -85,9 +85,11 @@ def poly_nms(dets, iou_thr, device_id=None):
 
 
 def obb_batched_nms(bboxes, scores, inds, nms_thr, class_agnostic=False):
-    """Compute the NMS of oriented bboxes in batches (per class id `inds`)."""
+    """Compute the NMS of oriented bboxes in batches (per class id `inds`).
+    (N, 4) horizontal boxes: the reference adds the offsets and then calls obb_nms on an (N, 5) tensor, whose
+    `dets_th[:, 5]` raises IndexError (nms_rotated_wrapper.py:47, 92-97) — there is no working behaviour to mirror."""
     if bboxes.size(-1) != 5:
-        raise NotImplementedError("obb_batched_nms: only (N, 5) oriented boxes are supported")
+        raise NotImplementedError("obb_batched_nms: only (N, 5) oriented boxes are supported (the reference raises IndexError on (N, 4))")
     if class_agnostic or bboxes.shape[0] == 0:
         dets, keep = obb_nms(torch.cat([bboxes, scores[:, None]], -1), nms_thr)
         return torch.cat([bboxes[keep], dets[:, -1:]], -1), keep

@@ -67,5 +67,26 @@ q = np.concatenate([T.obb2poly(c, 'v1') + rng.normal(0, 2, (1500, 8)).astype(np.
 for K in (1, 64, 65, 1500):
     R.poly_nms(t(q[:K]), 0.1)
 R.poly_nms(t(q[:300]), 0.0)
+# round-2 additions: NMS rounds kernel with several rounds per segment (K above the chunk size), polygon NMS on the rounds
+# kernel, padded keep records / padded multiclass NMS / padded dense tail (device-side counts), TMA FRM (W % 4 == 0 levels,
+# windows crossing every map edge) forward + backward
+cb2, sb2, lb2 = clustered(6000, 21, 'v1')
+bid2 = torch.arange(2, device=dev).repeat_interleave(3000)
+kp, nm = nms_device(t(cb2), t(sb2), 0.1, 'v1', labels=t(lb2), class_offset=torch.tensor([1025.0, 900.0], device=dev), order_index=True,
+                    batch_ids=bid2, n_batches=2)
+from r3det_b200 import pack_keep_records
+pack_keep_records(t(cb2), t(sb2), t(lb2), kp, nm, bid2, 2, 100)
+nms_device(t(cb2), t(sb2), 0.3, 'v3')                         # one segment, K > chunk: several rounds
+R.poly_nms(t(np.concatenate([T.obb2poly(cb2, 'v1'), sb2[:, None]], 1).astype(np.float32)), 0.1)
+for v in ('v1', 'v2', 'v3'):
+    R.multiclass_nms_rotated_padded(t(c[:900]).reshape(3, 300, 5), torch.rand(3, 300, 16, device=dev) ** 4, 0.05, dict(type=v, iou_thr=0.1), 50)
+    coder = R.DeltaXYWHAOBBoxCoder((0.,) * 5, (0.5,) * 5, angle_range=v)
+    R.get_bboxes_padded(cls, reg, anc, metas, dict(nms_pre=50, score_thr=0.05, nms=dict(type=v, iou_thr=0.1), max_per_img=20), coder, rescale=True)
+for (N, Cc, H, W, stride) in ((2, 32, 12, 16, 8), (1, 64, 40, 44, 8), (2, 16, 4, 4, 64)):
+    feat = t(rng.standard_normal((N, Cc, H, W)).astype(np.float32))
+    boxes = np.concatenate([rng.uniform(-80, W * stride + 80, (N * H * W, 1)), rng.uniform(-80, H * stride + 80, (N * H * W, 1)),
+                            rng.uniform(1, 12 * stride, (N * H * W, 2)), rng.uniform(-1.6, 0, (N * H * W, 1))], 1).astype(np.float32)
+    for P in (1, 5):
+        frm_forward(feat, t(boxes), 1.0 / stride, P); frm_backward(feat, t(boxes), 1.0 / stride, P)
 torch.cuda.synchronize()
 print('sanitize smoke ok')

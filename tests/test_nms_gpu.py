@@ -104,6 +104,31 @@ def test_multi_image_batch_equals_per_image_calls(cuda_dev, v):
         start += num[i]; off += len(b)
 
 
+@pytest.mark.parametrize("K", [900, 40000])          # counted-rank path / radix path
+def test_batch_out_of_range_ids_take_no_part(cuda_dev, K):
+    """image ids outside [0, n_batches) and labels outside [0, 65536) must not alias into another segment (the key packs
+    16 + 16 bits): such candidates take no part and the result equals the call without them"""
+    from r3det_b200._nms_core import nms_device
+    b, s, l = clustered(K, 77, "v1")
+    bid = (np.arange(K) % 3).astype(np.int64)
+    bad = np.zeros(K, bool); bad[5::7] = True
+    l2, bid2 = l.copy(), bid.copy()
+    sel = np.nonzero(bad)[0]
+    l2[sel[0::4]] += 65536                      # would alias into the same label
+    bid2[sel[1::4]] += 65536                    # would alias into the same image
+    bid2[sel[2::4]] = -1
+    bid2[sel[3::4]] = 3                         # == n_batches
+    scales = _t(np.full(3, b.max() + 1, np.float32), cuda_dev)
+    keep, num = nms_device(_t(b, cuda_dev), _t(s, cuda_dev), 0.1, "v1", labels=_t(l2, cuda_dev), class_offset=scales,
+                           order_index=True, batch_ids=_t(bid2, cuda_dev), n_batches=3)
+    good = np.nonzero(~bad)[0]
+    k0, n0 = nms_device(_t(b[good], cuda_dev), _t(s[good], cuda_dev), 0.1, "v1", labels=_t(l[good], cuda_dev), class_offset=scales,
+                        order_index=True, batch_ids=_t(bid[good], cuda_dev), n_batches=3)
+    assert np.array_equal(num.cpu().numpy(), n0.cpu().numpy())
+    tot = int(n0.sum())
+    assert np.array_equal(keep[:tot].cpu().numpy(), good[k0[:tot].cpu().numpy()])
+
+
 def test_edge_cases(cuda_dev):
     import r3det_b200 as R
     from r3det_b200._nms_core import nms_device
@@ -254,6 +279,41 @@ def test_dota_patch_merge(cuda_dev, version, merge_nms):
     ids, merged = R.dota_submission.merge_det([[rows[l == c][:, 1:].astype(np.float32) for c in range(ncls)]], ["P1__1__100___200"],
                                               ["a", "b", "c", "d", "e"], 0.1, version, merge_nms, cuda_dev)
     assert ids == ["P1"] and [m.shape for m in merged[0]] == [g.shape for g in got]
+
+
+def test_dota_merge_float64_full_image_coordinates(cuda_dev):
+    """The reference's _merge_func hands FLOAT64 rows to the CPU rnms (double template, rule >=; dota1.py:660-666);
+    merge_image computes in FP32.  At full-image coordinates (~1e4 px: FP32 ulp 1e-3 px) the two may part only on a pair
+    whose float64 IoU lies within 1e-3 of the threshold (documented deviation, dota_submission.py): walk the greedy order
+    and check that the FIRST differing decision of every class is such a pair."""
+    import r3det_b200 as R
+    from oracle import ref
+    ncls, thr, delta = 5, 0.1, 1e-3
+    b, s, l = clustered(2500, 93, "v1", ncls=ncls)
+    rng = np.random.default_rng(5)
+    b64 = b.astype(np.float64)
+    b64[:, :2] += np.array([11000.0, 7000.0]) + rng.uniform(0, 1, (len(b), 2))       # sub-ulp(FP32) fractions on purpose
+    rows = np.concatenate([l[:, None].astype(np.float64), b64, s[:, None].astype(np.float64)], 1)
+    got = R.dota_submission.merge_image(rows, ncls, thr, "v1", "obb", cuda_dev)
+    exact = 0
+    for c in range(ncls):
+        cls = rows[l == c][:, 1:]
+        iou = ref.v1_iou(cls[:, :5], cls[:, :5], dtype=np.float64)
+        order = np.argsort(-cls[:, 5], kind="stable")
+        ours = {tuple(r) for r in np.asarray(got[c])}
+        kept = []
+        for i in order:
+            worst = max((iou[i, k] for k in kept), default=0.0)
+            ref_keeps = not (worst >= thr)
+            if ref_keeps != (tuple(cls[i]) in ours):
+                assert abs(worst - thr) < delta, (c, i, worst)        # a near-threshold pair decided differently in FP32
+                break
+            if ref_keeps:
+                kept.append(i)
+        else:
+            exact += 1
+            assert len(ours) == len(kept)
+    assert exact >= ncls - 1                                             # and such pairs are rare
 
 
 @pytest.mark.parametrize("v", ["v1", "v3"])
