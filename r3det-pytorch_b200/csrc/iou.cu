@@ -40,6 +40,9 @@ namespace r3g {
 #ifndef R3G_IOU_BATCHLOAD
 #define R3G_IOU_BATCHLOAD 1        // stage 1: the 8 row records of a group are loaded together, ahead of the first use
 #endif
+#ifndef R3G_IOU_FASTGROUP
+#define R3G_IOU_FASTGROUP 1        // stage 1, matrix mode: straight-line path for full 8-row groups of full tiles
+#endif
 #ifndef R3G_IOU_UNROLLCOMPACT
 #define R3G_IOU_UNROLLCOMPACT 0    // compaction variant: 32 predicated stores per lane instead of the find-leading-one loop (measured: +0.7 %)
 #endif
@@ -314,6 +317,7 @@ __global__ void __launch_bounds__(IOU_THREADS, R3G_IOU_MINB) iou_matrix_kernel(c
             }
         }
         full4 = VEC && (jb + IOU_CPL <= j_end);
+        const bool full_tile = VEC && (j0 + IOU_TN <= j_end);        // warp-uniform: every lane owns four valid columns
         if (OUT == OUT_MATRIX) orow = A.out + (int64_t)i0 * A.n + jb;
         if (OUT == OUT_ASSIGN_TIES) {
 #pragma unroll
@@ -334,6 +338,31 @@ __global__ void __launch_bounds__(IOU_THREADS, R3G_IOU_MINB) iou_matrix_kernel(c
                 // ---- stage 1: one group of 8 rows x (4 columns per lane) ----
                 const int nr = min(IOU_RG, i1 - ig);
                 unsigned m = 0;
+#if R3G_IOU_FASTGROUP
+                // matrix mode, a full group inside a full tile (all but the edge items): straight-line code — no per-row bounds
+                // or tail tests, one base address for the row records, rows loaded four at a time
+                if (OUT == OUT_MATRIX && nr == IOU_RG && full_tile) {
+                    const RowP2* __restrict__ rp = A.r2 + ig;
+#pragma unroll
+                    for (int h = 0; h < IOU_RG; h += 4) {
+                        float4 a[4];
+#pragma unroll
+                        for (int r = 0; r < 4; r++) a[r] = ldg4(rp + h + r);
+#pragma unroll
+                        for (int r = 0; r < 4; r++) {
+#pragma unroll
+                            for (int k = 0; k < IOU_CPL; k++) {
+                                float s = fmaf(a[r].x, cx[k], ck[k] + a[r].w);
+                                s = fmaf(a[r].y, cy[k], s);
+                                s = fmaf(a[r].z, cr[k], s);
+                                m = __funnelshift_l(__float_as_uint(s), m, 1);
+                            }
+                            st_cs_f4(orow, make_float4(0.f, 0.f, 0.f, 0.f));
+                            orow += A.n;
+                        }
+                    }
+                } else {
+#endif
 #if R3G_IOU_BATCHLOAD
                 float4 arow[IOU_RG];                   // matrix mode: all row records in flight before the first use
                 if (OUT == OUT_MATRIX) {
@@ -403,6 +432,9 @@ __global__ void __launch_bounds__(IOU_THREADS, R3G_IOU_MINB) iou_matrix_kernel(c
                         }
                     }
                 }
+#if R3G_IOU_FASTGROUP
+                }
+#endif
                 // compact the group's survivors: warp scan of popc, then each lane emits its own bits (row-major order)
                 const int cnt = __popc(m);
                 int incl = cnt;
