@@ -99,8 +99,10 @@ struct PairFrame {
     float cd, sd, dbx, dby;   // relative rotation and centre offset in B's frame (for the degeneracy test)
 };
 
-// Returns false when a separating axis exists (boxes disjoint -> intersection exactly 0).
-R3G_HD bool pair_frame(const BoxP0& A0, const BoxP1& A1, const BoxP0& B0, const BoxP1& B1, PairFrame& f) {
+// Returns false when a separating axis exists (boxes disjoint -> intersection exactly 0).  `sat_passed`: the caller has
+// already run pair_sat() on this pair (the kernels' queue stage), so the test is skipped — for a pair that pair_sat lets
+// through by a rounding of the last bit the integral below returns the (continuous) ~0 area instead of an exact 0.
+R3G_HD bool pair_frame(const BoxP0& A0, const BoxP1& A1, const BoxP0& B0, const BoxP1& B1, PairFrame& f, bool sat_passed = false) {
     float dx = B0.cx - A0.cx, dy = B0.cy - A0.cy;
     float a = A1.hw, b = A1.hh;
     // relative rotation (cos, sin of thetaB - thetaA)
@@ -114,9 +116,11 @@ R3G_HD bool pair_frame(const BoxP0& A0, const BoxP1& A1, const BoxP0& B0, const 
     float ux = B1.hw * cd, uy = B1.hw * sd;
     float vx = -B1.hh * sd, vy = B1.hh * cd;
     // separating axes: A's two, then B's two
-    bool sep = (fabsf(dlx) > a + fabsf(ux) + fabsf(vx)) | (fabsf(dly) > b + fabsf(uy) + fabsf(vy)) |
-               (fabsf(dbx) > B1.hw + a * acd + b * asd) | (fabsf(dby) > B1.hh + a * asd + b * acd);
-    if (sep) return false;
+    if (!sat_passed) {
+        bool sep = (fabsf(dlx) > a + fabsf(ux) + fabsf(vx)) | (fabsf(dly) > b + fabsf(uy) + fabsf(vy)) |
+                   (fabsf(dbx) > B1.hw + a * acd + b * asd) | (fabsf(dby) > B1.hh + a * asd + b * acd);
+        if (sep) return false;
+    }
     float ex = dlx - vx, ey = dly - vy, gx = dlx + vx, gy = dly + vy;
     f.qx[0] = ex - ux; f.qy[0] = ey - uy;
     f.qx[1] = ex + ux; f.qy[1] = ey + uy;
@@ -221,10 +225,10 @@ R3G_HD float overlap_ratio(float inter, float s1, float s2, int variant, int mod
 // Fast-path overlap of one prepared pair.  `risk` is set for pairs the caller must re-evaluate with the
 // variant's restatement in emu.cuh (strict reference parity); tau = 0 disables the test.
 R3G_HD float pair_overlap(const BoxP0& A0, const BoxP1& A1, const BoxP0& B0, const BoxP1& B1,
-                          int variant, int mode, float tau, bool& risk) {
+                          int variant, int mode, float tau, bool& risk, bool sat_passed = false) {
     risk = false;
     PairFrame f;
-    if (!pair_frame(A0, A1, B0, B1, f)) return 0.0f;
+    if (!pair_frame(A0, A1, B0, B1, f, sat_passed)) return 0.0f;
     float inter = frame_area(f);
     if (tau > 0.0f) {
         // Thin boxes go to the restatement as well: below tau every vertex is "near" another one, and for v1

@@ -43,6 +43,9 @@ namespace r3g {
 #ifndef R3G_IOU_FASTGROUP
 #define R3G_IOU_FASTGROUP 1        // stage 1, matrix mode: straight-line path for full 8-row groups of full tiles
 #endif
+#ifndef R3G_IOU_TABCOMPACT
+#define R3G_IOU_TABCOMPACT 1       // compaction loop: leading-zero count + offset table instead of per-entry index arithmetic
+#endif
 #ifndef R3G_IOU_UNROLLCOMPACT
 #define R3G_IOU_UNROLLCOMPACT 0    // compaction variant: 32 predicated stores per lane instead of the find-leading-one loop (measured: +0.7 %)
 #endif
@@ -210,6 +213,11 @@ __global__ void __launch_bounds__(IOU_THREADS, R3G_IOU_MINB) iou_matrix_kernel(c
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const unsigned warp = threadIdx.x >> 5, lane = lane_id();
     WarpSmem& W = reinterpret_cast<WarpSmem*>(smem_raw)[warp];
+#if R3G_IOU_TABCOMPACT
+    __shared__ unsigned q1_offset[32];          // queue entry of pair t = 4 row + column of a group, relative to (row base << 7 | 4 lane)
+    if (threadIdx.x < 32) { const unsigned t = 31u - threadIdx.x; q1_offset[threadIdx.x] = ((t & ~3u) << 5) + (t & 3u); }   // bit b holds pair t = 31 - b
+    __syncthreads();
+#endif
     int c1 = 0, c2 = 0, c3 = 0;
     const unsigned lt = lanemask_lt();
     // matrix mode: one (m, n) problem.  Assigner modes: the images of the batch, items enumerated image by image.
@@ -440,8 +448,9 @@ __global__ void __launch_bounds__(IOU_THREADS, R3G_IOU_MINB) iou_matrix_kernel(c
                 int incl = cnt;
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
-                    const int t = __shfl_up_sync(0xffffffffu, incl, d);
-                    if ((int)lane >= d) incl += t;
+                    // the shuffle's own predicate (source lane in range) guards the add: two instructions per step
+                    asm volatile("{ .reg .pred p; .reg .s32 t; shfl.sync.up.b32 t|p, %0, %1, 0, 0xffffffff; @p add.s32 %0, %0, t; }"
+                                 : "+r"(incl) : "r"(d));
                 }
                 const int tot = __shfl_sync(0xffffffffu, incl, 31);
                 if (tot) {
@@ -458,12 +467,24 @@ __global__ void __launch_bounds__(IOU_THREADS, R3G_IOU_MINB) iou_matrix_kernel(c
                         if (m & (0x80000000u >> t)) { *qp = (unsigned short)(ebase + (unsigned)(((t & ~3) << 5) + (t & 3))); qp++; }
                     }
 #else
+#if R3G_IOU_TABCOMPACT
+                    // pair t = 4 row + column moved to bit 31 - t; the entry offset of a bit comes from a 32-entry table
+                    m <<= 32 - nbits;
+                    unsigned short* qp = W.q1 + pos;
+                    while (m) {
+                        unsigned b;
+                        asm("bfind.u32 %0, %1;" : "=r"(b) : "r"(m));   // one find-leading-one; the table is indexed by the bit
+                        m ^= 1u << b;
+                        *qp++ = (unsigned short)(ebase + q1_offset[b]);
+                    }
+#else
                     while (m) {
                         const int b = 31 - __clz(m);
                         m ^= 1u << b;
                         const unsigned idx = (unsigned)(nbits - 1 - b);
                         W.q1[pos++] = (unsigned short)(ebase + ((idx & ~3u) << 5) + (idx & 3u));
                     }
+#endif
 #endif
                     c1 += tot;
                 }
@@ -483,7 +504,7 @@ __global__ void __launch_bounds__(IOU_THREADS, R3G_IOU_MINB) iou_matrix_kernel(c
                         i = i0 + il; j = j0 + jl;
                         const BoxP0 A0 = as_p0(W.r0[il]), B0 = as_p0(W.c0[jl]);
                         const BoxP1 A1 = as_p1(W.r1[il]), B1 = as_p1(W.c1[jl]);
-                        float r = pair_overlap(A0, A1, B0, B1, A.variant, A.mode, A.tau, risk);
+                        float r = pair_overlap(A0, A1, B0, B1, A.variant, A.mode, A.tau, risk, true);      // survivors of stage 2
                         if (A.small_mask && (fminf(A1.hw, A1.hh) * 2.0f < 0.001f || fminf(B1.hw, B1.hh) * 2.0f < 0.001f)) r = 0.0f;
                         if (!risk && r != 0.0f) {
                             ItemCtx ctx = { 0, 0, 0, 0 };

@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(THREADS, 2) nms_rounds_kernel(const Args A) {
                 const BoxP0 A0 = { a0.x, a0.y, a0.z, a0.w }; const BoxP1 A1 = { a1.x, a1.y, a1.z, a1.w };
                 const BoxP0 B0 = { b0.x, b0.y, b0.z, b0.w }; const BoxP1 B1 = { b1.x, b1.y, b1.z, b1.w };
                 bool risk;
-                r = pair_overlap(A0, A1, B0, B1, A.variant, MODE_IOU, A.tau, risk);
+                r = pair_overlap(A0, A1, B0, B1, A.variant, MODE_IOU, A.tau, risk, true);       // survivors of the separating-axis stage
                 emu = A.tau > 0.0f && (risk || fabsf(r - A.thr) < A.margin);
             } else {
                 // own convex-quadrilateral geometry; concave input and pairs within the reference's noise of the threshold are

@@ -2,12 +2,12 @@
 built from: joins the SASS page with nvdisasm line info like ncu_lines.py, then maps source lines to stages through the stage
 markers in iou.cu (comments "---- stage N", "compact the group's survivors", ...) and the functions of geom.cuh / emu.cuh.
 Instructions attributed to CUDA headers (intrinsics) inherit the stage of the preceding instruction.
-usage: iou_stage_table.py <ncu-rep> <iou.cu.o> [kernel-symbol-substring]"""
+usage: iou_stage_table.py <ncu-rep> <iou.cu.o> [kernel-symbol-substring] [iou.cu as it was when the object was built]"""
 import collections, csv, io, os, re, subprocess, sys, tempfile
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 rep, obj = sys.argv[1:3]
 sym = sys.argv[3] if len(sys.argv) > 3 else "iou_matrix_kernelILb1ELi0ELb0"
-src = open(os.path.join(ROOT, "r3det-pytorch_b200", "csrc", "iou.cu")).read().splitlines()
+src = open(sys.argv[4] if len(sys.argv) > 4 else os.path.join(ROOT, "r3det-pytorch_b200", "csrc", "iou.cu")).read().splitlines()
 
 
 def line_of(marker, start=0):
