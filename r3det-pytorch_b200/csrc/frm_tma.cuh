@@ -26,6 +26,12 @@ constexpr int THREADS = 256;
 constexpr int STAGES = 4;
 constexpr int CC = 32;                           // channels per CTA
 constexpr int MAXL = 8;
+#ifndef R3G_FRM_EMPTY_BARRIER
+#define R3G_FRM_EMPTY_BARRIER 0                  // 1: slot release through per-slot mbarriers (one arrival per warp, delayed refill by the
+                                                 // producer thread) instead of __syncthreads.  MEASURED SLOWER (forward 0.102 vs 0.091 ms, backward
+                                                 // apply 0.210 vs 0.162 ms): the producer's warp stalls on the slowest warp and the ring runs one
+                                                 // slot shallower; kept as a build variant for the record
+#endif
 
 template <int P, bool BWD = false> struct Win {  // window of the taps: rows [w0 - HR, w0 + TW + HR), columns [h0 - HC, h0 - HC + RC)
     // the TMA unit wants the first column of a box on a 16-byte boundary: the left halo HC is a multiple of 4 floats.
@@ -68,6 +74,9 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
         "D_%=:\n"
         "}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, unsigned long long* bar) {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
                  :: "r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
@@ -106,6 +115,7 @@ __global__ void __launch_bounds__(THREADS, (P == 1) ? 5 : 2) frm_forward_tma_ker
     typedef Win<P> Wn;
     extern __shared__ __align__(128) unsigned char fsm[];
     __shared__ __align__(8) unsigned long long full[STAGES];
+    __shared__ __align__(8) unsigned long long empty[STAGES];     // one arrival per warp that has finished reading the slot
     int li = 0;
 #pragma unroll
     for (int i = 1; i < MAXL; i++) if (i < S.L && blockIdx.x >= S.lv[i].block0) li = i;
@@ -126,7 +136,7 @@ __global__ void __launch_bounds__(THREADS, (P == 1) ? 5 : 2) frm_forward_tma_ker
 
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < STAGES; s++) mbar_init(&full[s], 1);
+        for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], THREADS / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -220,8 +230,24 @@ __global__ void __launch_bounds__(THREADS, (P == 1) ? 5 : 2) frm_forward_tma_ker
                 if (valid[0]) __stcs(optr, v[0]);
                 if (valid[1]) __stcs(optr + 8, v[1]);
                 optr += HW; plane += HW;
+#if R3G_FRM_EMPTY_BARRIER
+                // consumer release: no block-wide barrier — a warp signals that it is done with the slot and moves on; the
+                // producer thread refills the PREVIOUS slot (whose readers have normally all passed by now) once its eight
+                // arrivals are in, so the warps of a CTA drift apart and hide each other's shared-memory latency
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[slot]);
+                if (tid == 0) {
+                    const int pslot = (slot + STAGES - 1) % STAGES;
+                    const int pc = cbase + slot - 1;                               // channel the previous slot held
+                    if (pc >= ca && pc + STAGES < cb) {
+                        mbar_wait(&empty[pslot], (unsigned)(((pc - ca) / STAGES) & 1));
+                        issue(pslot, pc + STAGES);
+                    }
+                }
+#else
                 __syncthreads();                                   // every thread is done with this slot: the TMA unit may refill it
                 if (tid == 0 && cbase + slot + STAGES < cb) issue(slot, cbase + slot + STAGES);
+#endif
             }
         }
     }
@@ -246,6 +272,7 @@ __global__ void __launch_bounds__(THREADS, R3G_FRM_BWD_TMA_MINB) frm_backward_tm
     typedef Win<P, true> Wn;
     extern __shared__ __align__(128) unsigned char fsm[];
     __shared__ __align__(8) unsigned long long full[STAGES];
+    __shared__ __align__(8) unsigned long long empty[STAGES];
     int li = 0;
 #pragma unroll
     for (int i = 1; i < MAXL; i++) if (i < S.L && blockIdx.x >= S.lv[i].block0) li = i;
@@ -266,7 +293,7 @@ __global__ void __launch_bounds__(THREADS, R3G_FRM_BWD_TMA_MINB) frm_backward_tm
 
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < STAGES; s++) mbar_init(&full[s], 1);
+        for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], THREADS / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -360,8 +387,21 @@ __global__ void __launch_bounds__(THREADS, R3G_FRM_BWD_TMA_MINB) frm_backward_tm
                 if (valid[0]) __stcs(optr, v0);
                 if (valid[1]) __stcs(optr + 8, v1);
                 optr += HW; plane += HW;
+#if R3G_FRM_EMPTY_BARRIER
+                __syncwarp();                                      // consumer release + delayed refill, as in the forward kernel
+                if (lane == 0) mbar_arrive(&empty[slot]);
+                if (tid == 0) {
+                    const int pslot = (slot + STAGES - 1) % STAGES;
+                    const int pc = cbase + slot - 1;
+                    if (pc >= ca && pc + STAGES < cb) {
+                        mbar_wait(&empty[pslot], (unsigned)(((pc - ca) / STAGES) & 1));
+                        issue(pslot, pc + STAGES);
+                    }
+                }
+#else
                 __syncthreads();
                 if (tid == 0 && cbase + slot + STAGES < cb) issue(slot, cbase + slot + STAGES);
+#endif
             }
         }
     }

@@ -43,6 +43,9 @@ namespace r3g {
 #ifndef R3G_IOU_FASTGROUP
 #define R3G_IOU_FASTGROUP 1        // stage 1, matrix mode: straight-line path for full 8-row groups of full tiles
 #endif
+#ifndef R3G_IOU_PREFETCH_BEST
+#define R3G_IOU_PREFETCH_BEST 1    // assigner sweep: read the two running maxima of a pair before its area is computed
+#endif
 #ifndef R3G_IOU_TABCOMPACT
 #define R3G_IOU_TABCOMPACT 1       // compaction loop: leading-zero count + offset table instead of per-entry index arithmetic
 #endif
@@ -158,14 +161,20 @@ __device__ __forceinline__ void update_best(unsigned long long* slot, unsigned l
     if (cand > __ldcg(slot)) atomicMax(slot, cand);
 }
 
+// `pre` (assigner pass 1): the two running maxima of the pair, read BEFORE its overlap was computed (the L2 latency hides under
+// the area stage).  They can only be older, i.e. smaller, than the slots are now: an atomic may be issued that no longer
+// changes its slot, a tie record may be appended that the check kernel drops again — never the other way round.
+struct BestPre { unsigned long long col, row; bool have; };
+
 template <int OUT>
-__device__ __forceinline__ void emit_overlap(const IouArgs& A, int i, int j, float r, const ItemCtx& c) {
+__device__ __forceinline__ void emit_overlap(const IouArgs& A, int i, int j, float r, const ItemCtx& c, BestPre pre = BestPre{ 0ull, 0ull, false }) {
     if (OUT == OUT_MATRIX) {
         A.out[(int64_t)i * A.n + j] = r;
     } else if (OUT == OUT_ASSIGN_MAX) {
         if (r > 0.0f) {
-            update_best(A.col_best + j + c.cb_shift, pack_best(r, i - c.row0));
-            const unsigned long long cand = pack_best(r, j - c.col0), cur = __ldcg(A.row_best + i);
+            const unsigned long long ccand = pack_best(r, i - c.row0);
+            if (ccand > (pre.have ? pre.col : __ldcg(A.col_best + j + c.cb_shift))) atomicMax(A.col_best + j + c.cb_shift, ccand);
+            const unsigned long long cand = pack_best(r, j - c.col0), cur = pre.have ? pre.row : __ldcg(A.row_best + i);
             if (cand > cur) atomicMax(A.row_best + i, cand);
             if (A.ties != nullptr && r >= __uint_as_float((unsigned)(cur >> 32)) && r >= A.min_pos_iou) {
                 const unsigned long long t = atomicAdd(A.stats + 5, 1ull);
@@ -369,6 +378,28 @@ __global__ void __launch_bounds__(IOU_THREADS, R3G_IOU_MINB) iou_matrix_kernel(c
                             orow += A.n;
                         }
                     }
+                } else if (OUT == OUT_ASSIGN_MAX && nr == IOU_RG && full_tile) {
+                    // the assigner sweep's full groups: the same straight-line form in packed f32x2 arithmetic (two columns
+                    // per instruction; add, then three fused multiply-adds, exactly as in the general path below)
+                    const ulonglong2* __restrict__ rp = reinterpret_cast<const ulonglong2*>(A.r2d + ig);
+#pragma unroll
+                    for (int h = 0; h < IOU_RG; h += 4) {
+                        ulonglong2 ra[4], rb[4];
+#pragma unroll
+                        for (int r = 0; r < 4; r++) { ra[r] = __ldg(rp + 2 * (h + r)); rb[r] = __ldg(rp + 2 * (h + r) + 1); }
+#pragma unroll
+                        for (int r = 0; r < 4; r++) {
+#pragma unroll
+                            for (int q = 0; q < IOU_CPL / 2; q++) {
+                                unsigned long long t = add2(CK[q], rb[r].y);
+                                t = fma2(ra[r].x, CX[q], t);
+                                t = fma2(ra[r].y, CY[q], t);
+                                t = fma2(rb[r].x, CR[q], t);
+                                m = __funnelshift_l((unsigned)t, m, 1);
+                                m = __funnelshift_l((unsigned)(t >> 32), m, 1);
+                            }
+                        }
+                    }
                 } else {
 #endif
 #if R3G_IOU_BATCHLOAD
@@ -502,15 +533,17 @@ __global__ void __launch_bounds__(IOU_THREADS, R3G_IOU_MINB) iou_matrix_kernel(c
                         const unsigned e = W.q2[c2 - nb + lane];
                         const int il = (int)(e >> 7), jl = (int)(e & 127u);
                         i = i0 + il; j = j0 + jl;
+                        ItemCtx ctx = { 0, 0, 0, 0 };
+                        if (BATCH) { ctx.row0 = W.ctx[0]; ctx.col0 = W.ctx[1]; ctx.cb_shift = W.ctx[2]; }
+                        BestPre pre = { 0ull, 0ull, false };
+#if R3G_IOU_PREFETCH_BEST
+                        if (OUT == OUT_ASSIGN_MAX) { pre.col = __ldcg(A.col_best + j + ctx.cb_shift); pre.row = __ldcg(A.row_best + i); pre.have = true; }
+#endif
                         const BoxP0 A0 = as_p0(W.r0[il]), B0 = as_p0(W.c0[jl]);
                         const BoxP1 A1 = as_p1(W.r1[il]), B1 = as_p1(W.c1[jl]);
                         float r = pair_overlap(A0, A1, B0, B1, A.variant, A.mode, A.tau, risk, true);      // survivors of stage 2
                         if (A.small_mask && (fminf(A1.hw, A1.hh) * 2.0f < 0.001f || fminf(B1.hw, B1.hh) * 2.0f < 0.001f)) r = 0.0f;
-                        if (!risk && r != 0.0f) {
-                            ItemCtx ctx = { 0, 0, 0, 0 };
-                            if (BATCH) { ctx.row0 = W.ctx[0]; ctx.col0 = W.ctx[1]; ctx.cb_shift = W.ctx[2]; }
-                            emit_overlap<OUT>(A, i, j, r, ctx);
-                        }
+                        if (!risk && r != 0.0f) emit_overlap<OUT>(A, i, j, r, ctx, pre);
                     }
                     __syncwarp();
                     c2 -= nb;
