@@ -6,7 +6,7 @@
 
 A "step" is one pass of the hot path over one batch: BASELINE.json configs[2], the rotated-IoU microbench —
 RBboxOverlaps2D_v1 on 1,000 GT x 200,000 anchors per GPU (synthetic rotated boxes), through
-the C ABI (r3g_iou_matrix_f32: 2 prep kernels + the pair kernel).  The anchor axis is the shard axis: every
+the C ABI (r3g_iou_matrix_f32: one prepare kernel + the pair kernel).  The anchor axis is the shard axis: every
 rank owns 200k anchors (weak scaling), GT replicated, no data-path collective.
   value     Gpairs/s, inputs resident in HBM, K steps timed with CUDA events between barriers, max over ranks
   e2e       same metric through the Python plugin API with HOST buffers: pinned H2D of both box sets + D2H of the
@@ -343,7 +343,7 @@ def run_gpu(args):
                             "d2h_gbs_all_ranks": world * d2h / ms_copy / 1e6,
                             "what": "the same pinned H2D + D2H copies with no kernel in between, all ranks at once: the "
                                     "PCIe / host-memory limit of returning the dense matrix"}},
-        "gpu_launches": 3 * args.steps,
+        "gpu_launches": 2 * args.steps,          # per step: prep_pair_kernel + iou_matrix_kernel
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
                      "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": "iou_matrix_kernel<true, 0, false>",
                      "kernel_ms": ms_kernel, "algorithmic_bytes_per_launch": 4 * pairs,

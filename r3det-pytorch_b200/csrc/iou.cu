@@ -110,6 +110,33 @@ __global__ void prep_boxes_kernel(const float* __restrict__ boxes, int64_t n, in
     }
 }
 
+// rows and columns of one problem in ONE launch (blocks [0, row_blocks) prepare the rows, the rest the columns); block 0 also
+// zeroes the sweep's counters, so that the matrix op is two stream operations: this kernel and the pair kernel
+__global__ void prep_pair_kernel(const float* __restrict__ boxes1, int64_t m, int64_t stride1, const float* __restrict__ boxes2, int64_t n,
+                                 int64_t stride2, int variant, unsigned row_blocks, BoxP0* __restrict__ r0, BoxP1* __restrict__ r1,
+                                 RowP2* __restrict__ r2, RowP2D* __restrict__ r2d, BoxP0* __restrict__ c0, BoxP1* __restrict__ c1,
+                                 unsigned long long* __restrict__ stats) {
+    if (blockIdx.x == 0 && threadIdx.x < 32) stats[threadIdx.x] = 0ull;
+    const bool rows = blockIdx.x < row_blocks;
+    const int64_t i = (int64_t)(rows ? blockIdx.x : blockIdx.x - row_blocks) * blockDim.x + threadIdx.x;
+    if (i >= (rows ? m : n)) return;
+    const float* b = rows ? boxes1 + i * stride1 : boxes2 + i * stride2;
+    float raw[5] = { b[0], b[1], b[2], b[3], b[4] };
+    BoxP0 a; BoxP1 c;
+    emu::prep_box_strict(raw, variant, a, c);
+    if (!rows) { c0[i] = a; c1[i] = c; return; }
+    r0[i] = a; r1[i] = c;
+    const float ox = isfinite(boxes1[0]) ? boxes1[0] : 0.0f, oy = isfinite(boxes1[1]) ? boxes1[1] : 0.0f;
+    const float x = a.cx - ox, y = a.cy - oy;
+    const float q = x * x + y * y, rr = a.r * a.r;
+    RowP2 r;
+    r.mx = -2.0f * x; r.my = -2.0f * y; r.mr = -2.0f * a.r;
+    r.k = (q - rr) - IOU_SLACK * (q + rr) - 1e-6f;
+    r2[i] = r;
+    RowP2D d = { r.mx, r.mx, r.my, r.my, r.mr, r.mr, r.k, r.k };
+    r2d[i] = d;
+}
+
 __device__ __noinline__ float emu_pair_call(const float* b1, const float* b2, int variant, int mode) {
     float x[5] = { b1[0], b1[1], b1[2], b1[3], b1[4] };
     float y[5] = { b2[0], b2[1], b2[2], b2[3], b2[4] };
@@ -690,16 +717,15 @@ R3G_API int r3g_iou_prepare_f32(const float* boxes1, int64_t m, int64_t stride1,
         return R3G_ERR_WORKSPACE;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    prep_boxes_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(boxes1, m, stride1, variant, boxes1, w.r0, w.r1, w.r2, w.r2d);
-    prep_boxes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(boxes2, n, stride2, variant, boxes1, w.c0, w.c1, nullptr, nullptr);
-    R3G_LAUNCH_OK("prep_boxes_kernel");
+    const unsigned rb = (unsigned)((m + 255) / 256), cbk = (unsigned)((n + 255) / 256);
+    prep_pair_kernel<<<rb + cbk, 256, 0, st>>>(boxes1, m, stride1, boxes2, n, stride2, variant, rb, w.r0, w.r1, w.r2, w.r2d, w.c0, w.c1, w.stats);
+    R3G_LAUNCH_OK("prep_pair_kernel");
     return R3G_OK;
 }
 
-R3G_API int r3g_iou_matrix_prepared_f32(const float* boxes1, int64_t m, int64_t stride1,
-                                        const float* boxes2, int64_t n, int64_t stride2,
-                                        int variant, int mode, int flags, float* out,
-                                        void* workspace, size_t workspace_bytes, void* stream) {
+static int iou_matrix_prepared(const float* boxes1, int64_t m, int64_t stride1, const float* boxes2, int64_t n, int64_t stride2,
+                               int variant, int mode, int flags, float* out, void* workspace, size_t workspace_bytes, void* stream,
+                               bool counters_zeroed) {
     int rc = iou_check_common("r3g_iou_matrix_prepared_f32", m, n, variant, mode);
     if (rc != R3G_OK) return rc;
     if (m == 0 || n == 0) return R3G_OK;
@@ -710,7 +736,7 @@ R3G_API int r3g_iou_matrix_prepared_f32(const float* boxes1, int64_t m, int64_t 
         return R3G_ERR_WORKSPACE;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    R3G_CUDA_OK(cudaMemsetAsync(w.stats, 0, 256, st));
+    if (!counters_zeroed) R3G_CUDA_OK(cudaMemsetAsync(w.stats, 0, 256, st));       // (the prepare kernel of the same call has done it)
     IouArgs a = {};
     a.r0 = w.r0; a.r1 = w.r1; a.r2 = w.r2; a.r2d = w.r2d; a.m = (int)m; a.c0 = w.c0; a.c1 = w.c1; a.n = (int)n;
     a.raw1 = boxes1; a.s1 = stride1; a.raw2 = boxes2; a.s2 = stride2; a.origin_box = boxes1;
@@ -726,6 +752,13 @@ R3G_API int r3g_iou_matrix_prepared_f32(const float* boxes1, int64_t m, int64_t 
     return R3G_OK;
 }
 
+R3G_API int r3g_iou_matrix_prepared_f32(const float* boxes1, int64_t m, int64_t stride1,
+                                        const float* boxes2, int64_t n, int64_t stride2,
+                                        int variant, int mode, int flags, float* out,
+                                        void* workspace, size_t workspace_bytes, void* stream) {
+    return iou_matrix_prepared(boxes1, m, stride1, boxes2, n, stride2, variant, mode, flags, out, workspace, workspace_bytes, stream, false);
+}
+
 R3G_API int r3g_iou_matrix_f32(const float* boxes1, int64_t m, int64_t stride1,
                                const float* boxes2, int64_t n, int64_t stride2,
                                int variant, int mode, int flags, float* out,
@@ -734,8 +767,8 @@ R3G_API int r3g_iou_matrix_f32(const float* boxes1, int64_t m, int64_t stride1,
     if (rc != R3G_OK) return rc;
     rc = r3g_iou_prepare_f32(boxes1, m, stride1, boxes2, n, stride2, variant, workspace, workspace_bytes, stream);
     if (rc != R3G_OK) return rc;
-    return r3g_iou_matrix_prepared_f32(boxes1, m, stride1, boxes2, n, stride2, variant, mode, flags, out,
-                                       workspace, workspace_bytes, stream);
+    return iou_matrix_prepared(boxes1, m, stride1, boxes2, n, stride2, variant, mode, flags, out, workspace, workspace_bytes, stream,
+                               m > 0 && n > 0);
 }
 
 R3G_API int r3g_iou_aligned_f32(const float* boxes1, int64_t n1, int64_t stride1,

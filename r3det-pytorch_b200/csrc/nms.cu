@@ -123,10 +123,16 @@ __global__ void nms_label_keys_kernel(const int64_t* __restrict__ labels, const 
     }
 }
 
+// image key of rank r for the stable image-major pass: ids that take no part (reserved 0xffff) sort behind the last image, so
+// the key needs only bit_length(n_batches) bits — one radix digit pass for up to 255 images; the rank order is copied alongside
 __global__ void nms_batch_keys_kernel(const int64_t* __restrict__ labels, const int64_t* __restrict__ batch_ids, const int* __restrict__ order,
-                                      int K, unsigned* key) {
+                                      int K, unsigned n_batches, unsigned* key, int* order_copy) {
     int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r < K) key[r] = seg_key_of(labels, batch_ids, order[r]) >> 16;
+    if (r < K) {
+        const int o = order[r];
+        key[r] = min(seg_key_of(labels, batch_ids, o) >> 16, n_batches);
+        order_copy[r] = o;
+    }
 }
 
 // Gather + prepare boxes in position order; class offsets in FP32 as the reference wrappers compute them:
@@ -342,7 +348,7 @@ using namespace r3g;
 
 // ---- host stages shared by the rotated-box and the polygon entry points ------------------------------------------
 static int nms_order_stage(NmsWs& w, const float* scores, const int64_t* labels, const int64_t* batch_ids, int Ki, cudaStream_t st,
-                           bool small, int label_bits) {
+                           bool small, int label_bits, int n_batches = 1) {
     const int tpb = 256, gK = (Ki + tpb - 1) / tpb;
     if (small) {
         // counted ranks: keyA / keyA2 double as the two count arrays
@@ -366,11 +372,12 @@ static int nms_order_stage(NmsWs& w, const float* scores, const int64_t* labels,
     size_t tb = w.cub_bytes;
     R3G_CUDA_OK(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, w.keyA, w.keyA2, w.ord_tmp, w.ord_rank, Ki, 0, 32, st));
     if (batch_ids) {
-        // multi-image batch: rank order becomes (image asc, score desc) by a stable 16-bit pass over the image id
-        nms_batch_keys_kernel<<<gK, tpb, 0, st>>>(labels, batch_ids, w.ord_rank, Ki, w.keyA);
-        R3G_CUDA_OK(cudaMemcpyAsync(w.ord_tmp, w.ord_rank, 4 * (size_t)Ki, cudaMemcpyDeviceToDevice, st));
+        // multi-image batch: rank order becomes (image asc, score desc) by a stable pass over the image id
+        nms_batch_keys_kernel<<<gK, tpb, 0, st>>>(labels, batch_ids, w.ord_rank, Ki, (unsigned)n_batches, w.keyA, w.ord_tmp);
+        int img_bits = 1;
+        while ((1 << img_bits) <= n_batches) img_bits++;
         tb = w.cub_bytes;
-        R3G_CUDA_OK(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, w.keyA, w.keyA2, w.ord_tmp, w.ord_rank, Ki, 0, 16, st));
+        R3G_CUDA_OK(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, w.keyA, w.keyA2, w.ord_tmp, w.ord_rank, Ki, 0, img_bits, st));
     }
     // 2. position order: stable by segment key (label, or label and image) on top of the rank order
     nms_label_keys_kernel<<<gK, tpb, 0, st>>>(labels, batch_ids, w.ord_rank, Ki, w.keyB, w.pos_tmp);
@@ -511,7 +518,7 @@ R3G_API int r3g_nms_batched_counted_f32(const float* boxes, int64_t stride, cons
     if (rc != R3G_OK) return rc;
     int label_bits = (flags >> 8) & 63;                 // R3G_NMS_LABEL_BITS(n): labels < 2^n; 0 = unknown
     if (label_bits == 0 || label_bits > 32) label_bits = 32;
-    rc = nms_order_stage(w, scores, labels, batch_ids, Ki, st, small, label_bits);
+    rc = nms_order_stage(w, scores, labels, batch_ids, Ki, st, small, label_bits, n_batches);
     if (rc != R3G_OK) return rc;
     nms_gather_kernel<<<gK, tpb, 0, st>>>(boxes, stride, w.ord_rank, w.pos_rank, w.pos_label, Ki, variant,
                                           (flags & R3G_NMS_DROP_SMALL) ? 1 : 0, class_offset, labels ? 1 : 0,
