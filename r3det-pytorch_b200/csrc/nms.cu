@@ -103,22 +103,24 @@ __global__ void nms_keys_kernel(const float* __restrict__ scores, int K, unsigne
 }
 
 // segment key of candidate i: the label, or (image << 16 | label) for multi-image batches (image-major: an image's
-// segments are contiguous in position space).  In a batch both fields are 16 bits wide: a candidate whose image id is
-// outside [0, 65535) or whose label is outside [0, 65536) gets image 0xffff — never a valid image (n_batches <= 65535), so
-// it takes no part (nms_gather_kernel) instead of aliasing into another image's or class's segment.
-__device__ __forceinline__ unsigned seg_key_of(const int64_t* labels, const int64_t* batch_ids, int i) {
+// segments are contiguous in position space).  In a batch both fields are 16 bits wide.  A candidate that cannot take part —
+// image id outside [0, n_batches), label outside [0, 65536); the padding of r3g_mc_candidates_batched_f32 is of this kind —
+// gets the ONE reserved key 0xffffffff instead of aliasing into another image's or class's segment.  One key for all of them
+// matters: the rounds kernel (phase 0) relies on every key occupying exactly ONE run of the position order.
+constexpr unsigned NMS_DEAD_KEY = 0xffffffffu;
+__device__ __forceinline__ unsigned seg_key_of(const int64_t* labels, const int64_t* batch_ids, int i, int n_batches) {
     const int64_t lab = labels ? labels[i] : 0;
     if (!batch_ids) return (unsigned)lab;
     const int64_t img = batch_ids[i];
-    const bool bad = img < 0 || img >= 0xffff || lab < 0 || lab > 0xffff;
-    return ((bad ? 0xffffu : (unsigned)img) << 16) | ((unsigned)lab & 0xffffu);
+    const bool bad = img < 0 || img >= n_batches || lab < 0 || lab > 0xffff;
+    return bad ? NMS_DEAD_KEY : (((unsigned)img << 16) | (unsigned)lab);
 }
 
 __global__ void nms_label_keys_kernel(const int64_t* __restrict__ labels, const int64_t* __restrict__ batch_ids,
-                                      const int* __restrict__ ord_rank, int K, unsigned* keyB, int* rank_iota) {
+                                      const int* __restrict__ ord_rank, int K, int n_batches, unsigned* keyB, int* rank_iota) {
     int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r < K) {
-        keyB[r] = seg_key_of(labels, batch_ids, ord_rank[r]);
+        keyB[r] = seg_key_of(labels, batch_ids, ord_rank[r], n_batches);
         rank_iota[r] = r;
     }
 }
@@ -130,7 +132,7 @@ __global__ void nms_batch_keys_kernel(const int64_t* __restrict__ labels, const 
     int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r < K) {
         const int o = order[r];
-        key[r] = min(seg_key_of(labels, batch_ids, o) >> 16, n_batches);
+        key[r] = min(seg_key_of(labels, batch_ids, o, (int)n_batches) >> 16, n_batches);
         order_copy[r] = o;
     }
 }
@@ -236,14 +238,14 @@ __global__ void nms_emit_kernel(const int* __restrict__ flag, const int* __restr
 
 template <bool BATCHED>
 __global__ void __launch_bounds__(256) nms_rank_count_kernel(const float* __restrict__ scores, const int64_t* __restrict__ labels,
-                                                             const int64_t* __restrict__ batch_ids, int K, int slice_len,
+                                                             const int64_t* __restrict__ batch_ids, int K, int n_batches, int slice_len,
                                                              int* __restrict__ rcnt, int* __restrict__ pcnt) {
     __shared__ uint4 tile[256];                              // {key low (index), key high (score key), segment key, -}
     __shared__ unsigned img_lo, img_hi;                      // BATCHED: image range of the tile
     const int i = blockIdx.x * 256 + threadIdx.x;
     const bool iv = i < K;
     const unsigned long long ai = iv ? (((unsigned long long)score_key_desc(scores[i]) << 32) | (unsigned)i) : 0ull;
-    const unsigned si = iv ? seg_key_of(labels, batch_ids, i) : 0u;
+    const unsigned si = iv ? seg_key_of(labels, batch_ids, i, n_batches) : 0u;
     const unsigned mi = si >> 16;                            // BATCHED: the image (segment keys are image-major)
     const int j_begin = blockIdx.y * slice_len, j_end = min(K, j_begin + slice_len);
     int r = 0, p = 0, r1 = 0, p1 = 0, r2 = 0, p2 = 0, r3 = 0, p3 = 0;
@@ -254,7 +256,7 @@ __global__ void __launch_bounds__(256) nms_rank_count_kernel(const float* __rest
         __syncthreads();
         unsigned lo = 0xffffffffu, hi = 0u;
         if (j < j_end) {
-            const unsigned sj = seg_key_of(labels, batch_ids, j);
+            const unsigned sj = seg_key_of(labels, batch_ids, j, n_batches);
             tile[threadIdx.x] = make_uint4((unsigned)j, score_key_desc(scores[j]), sj, 0u);
             lo = hi = sj >> 16;
         }
@@ -296,7 +298,7 @@ __global__ void __launch_bounds__(256) nms_rank_count_kernel(const float* __rest
     if (iv) { atomicAdd(rcnt + i, r); atomicAdd(pcnt + i, p); }
 }
 
-__global__ void nms_rank_scatter_kernel(const int64_t* __restrict__ labels, const int64_t* __restrict__ batch_ids, int K,
+__global__ void nms_rank_scatter_kernel(const int64_t* __restrict__ labels, const int64_t* __restrict__ batch_ids, int K, int n_batches,
                                         const int* __restrict__ rcnt, const int* __restrict__ pcnt,
                                         int* __restrict__ ord_rank, int* __restrict__ pos_rank, unsigned* __restrict__ pos_label) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -304,7 +306,7 @@ __global__ void nms_rank_scatter_kernel(const int64_t* __restrict__ labels, cons
     const int r = rcnt[i], p = pcnt[i];
     ord_rank[r] = i;
     pos_rank[p] = r;
-    pos_label[p] = seg_key_of(labels, batch_ids, i);
+    pos_label[p] = seg_key_of(labels, batch_ids, i, n_batches);
 }
 
 // nms_flags_kernel + exclusive sum + nms_emit_kernel in one CTA
@@ -361,9 +363,9 @@ static int nms_order_stage(NmsWs& w, const float* scores, const int64_t* labels,
         if (slices < 1) slices = 1;
         const int slice_len = ((Ki + slices - 1) / slices + 255) / 256 * 256;
         slices = (Ki + slice_len - 1) / slice_len;
-        if (batch_ids) nms_rank_count_kernel<true><<<dim3(gK, slices), 256, 0, st>>>(scores, labels, batch_ids, Ki, slice_len, rcnt, pcnt);
-        else nms_rank_count_kernel<false><<<dim3(gK, slices), 256, 0, st>>>(scores, labels, batch_ids, Ki, slice_len, rcnt, pcnt);
-        nms_rank_scatter_kernel<<<gK, tpb, 0, st>>>(labels, batch_ids, Ki, rcnt, pcnt, w.ord_rank, w.pos_rank, w.pos_label);
+        if (batch_ids) nms_rank_count_kernel<true><<<dim3(gK, slices), 256, 0, st>>>(scores, labels, batch_ids, Ki, n_batches, slice_len, rcnt, pcnt);
+        else nms_rank_count_kernel<false><<<dim3(gK, slices), 256, 0, st>>>(scores, labels, batch_ids, Ki, n_batches, slice_len, rcnt, pcnt);
+        nms_rank_scatter_kernel<<<gK, tpb, 0, st>>>(labels, batch_ids, Ki, n_batches, rcnt, pcnt, w.ord_rank, w.pos_rank, w.pos_label);
         R3G_LAUNCH_OK("nms rank kernels");
         return R3G_OK;
     }
@@ -380,7 +382,7 @@ static int nms_order_stage(NmsWs& w, const float* scores, const int64_t* labels,
         R3G_CUDA_OK(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, w.keyA, w.keyA2, w.ord_tmp, w.ord_rank, Ki, 0, img_bits, st));
     }
     // 2. position order: stable by segment key (label, or label and image) on top of the rank order
-    nms_label_keys_kernel<<<gK, tpb, 0, st>>>(labels, batch_ids, w.ord_rank, Ki, w.keyB, w.pos_tmp);
+    nms_label_keys_kernel<<<gK, tpb, 0, st>>>(labels, batch_ids, w.ord_rank, Ki, n_batches, w.keyB, w.pos_tmp);
     if (labels || batch_ids) {
         tb = w.cub_bytes;
         // in a batch the rank order is already image-major: sorting on the 16 label bits alone keeps every (image, label)

@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(THREADS, 2) nms_rounds_kernel(const Args A) {
         stamp();
     };
 
-    // ---- phase 0: class segments of the position space ----
+    // ---- phase 0: class segments of the position space (a run start finds its end by bisection: every key occupies one run) ----
     const int KV = A.k_valid ? (int)min((long long)A.K, __ldg(A.k_valid)) : A.K;      // padding behind the candidates is never visited
     for (int p = blockIdx.x * THREADS + (int)tid; p < KV; p += gridDim.x * THREADS) {
         const unsigned L = __ldg(A.label + p);
@@ -395,6 +395,11 @@ __global__ void __launch_bounds__(THREADS, 2) nms_rounds_kernel(const Args A) {
             const int cap = min(B, pe - cur);
             int row_base = 0;
             if (lane == 0) row_base = (int)atomicAdd(&C->rows_used, (unsigned)cap);
+            row_base = __shfl_sync(FULL, row_base, 0);
+            // segments are disjoint runs of the position order (every key occupies ONE run: nms.cu, seg_key_of), so the caps sum
+            // to <= K.  Malformed keys (a caller whose labels exceed its R3G_NMS_LABEL_BITS promise) could break that: such a
+            // segment is dropped rather than allowed to write beyond the position list
+            if ((long long)row_base + cap > (long long)A.K) continue;
             int n = 0, cur_new = pe, myfirst = -1;
             const int wl = (pe - 1) >> 6, wf = cur >> 6;
             // a lane reads two adjacent alive words per step (one 16-byte load); the next step's words are in flight while
