@@ -143,17 +143,24 @@ __global__ void nms_batch_keys_kernel(const int64_t* __restrict__ labels, const 
 __global__ void nms_gather_kernel(const float* __restrict__ boxes, int64_t stride, const int* __restrict__ ord_rank,
                                   const int* __restrict__ pos_rank, const unsigned* __restrict__ pos_label, int K,
                                   int variant, int drop_small, const float* __restrict__ class_offset, int has_labels,
-                                  int batched, int n_batches, const float* __restrict__ scores,
+                                  int batched, int n_batches, const float* __restrict__ scores, const long long* __restrict__ k_valid,
                                   float4* p0, float4* p1, float4* p2r, float4* p2c, float* raw, unsigned* alive32) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    // counted call: positions behind the device-side candidate count hold padding (it sorts last) — nothing reads their planes
+    // and their alive words are already zero (reset stage); whole warps leave
+    if (k_valid != nullptr && (long long)(p & ~31) >= __ldg(k_valid)) return;
     bool ok = false;
     if (p < K) {
         const int idx = ord_rank[pos_rank[p]];
         const float* b = boxes + (int64_t)idx * stride;
-        float x[5] = { b[0], b[1], b[2], b[3], b[4] };
         float off = 0.0f;
         ok = scores[idx] > -INFINITY;                                             // padding candidates (score -inf / NaN) take no part
         if (batched && (pos_label[p] >> 16) >= (unsigned)n_batches) ok = false;    // image id out of range: takes no part
+        float x[5] = { 0.0f, 0.0f, 1.0f, 1.0f, 0.0f };                            // (their boxes may be unwritten memory: not read)
+        if (ok) {
+#pragma unroll
+            for (int k = 0; k < 5; k++) x[k] = b[k];
+        }
         if (class_offset != nullptr && has_labels) {
             const unsigned key = pos_label[p];
             const float scale = batched ? class_offset[min(key >> 16, (unsigned)n_batches - 1u)] : class_offset[0];   // per-image offset scale
@@ -524,7 +531,8 @@ R3G_API int r3g_nms_batched_counted_f32(const float* boxes, int64_t stride, cons
     if (rc != R3G_OK) return rc;
     nms_gather_kernel<<<gK, tpb, 0, st>>>(boxes, stride, w.ord_rank, w.pos_rank, w.pos_label, Ki, variant,
                                           (flags & R3G_NMS_DROP_SMALL) ? 1 : 0, class_offset, labels ? 1 : 0,
-                                          batch_ids ? 1 : 0, n_batches, scores, w.p0, w.p1, w.p2r, w.p2c, w.raw, (unsigned*)w.alive);
+                                          batch_ids ? 1 : 0, n_batches, scores, (const long long*)count_dev, w.p0, w.p1, w.p2r, w.p2c, w.raw,
+                                          (unsigned*)w.alive);
     R3G_LAUNCH_OK("nms_gather_kernel");
     rc = nms_rounds_stage<rn::GEOM_BOX>(w, Ki, variant, (flags & R3G_NMS_INCLUSIVE) ? 1 : 0, thr,
                                         (flags & R3G_NMS_STRICT) ? 2e-2f : 0.0f, (variant == R3G_V1) ? 1e-3f : 5e-5f, 0, count_dev, st);

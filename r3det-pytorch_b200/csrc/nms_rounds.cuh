@@ -29,6 +29,10 @@
 #include "geom.cuh"
 #include "poly.cuh"
 
+#ifndef R3G_NMS_INITCHECK_CLEAN
+#define R3G_NMS_INITCHECK_CLEAN 0
+#endif
+
 namespace r3g {
 namespace rn {
 
@@ -595,9 +599,15 @@ __global__ void __launch_bounds__(THREADS, 2) nms_rounds_kernel(const Args A) {
                         if (idx < PAIRS2) {
                             const int r = idx >> 2, k2 = idx & 3, bb = S * SB + (r >> 6), col = S * SB + 2 * k2, lr = bb * 64 + (r & 63);
                             if (bb < nb && lr < n && col + 1 >= bb && col < nb) {
+#if R3G_NMS_INITCHECK_CLEAN
+                                // (diagnostic build for compute-sanitizer --tool initcheck: never touch the unwritten word of a pair)
+                                if (col >= bb) x.x = __ldcg(A.mask + wbase + (unsigned)(lr * np + col));
+                                if (col + 1 < nb) x.y = __ldcg(A.mask + wbase + (unsigned)(lr * np + col + 1));
+#else
                                 x = __ldcg(reinterpret_cast<const ulonglong2*>(A.mask + wbase + (unsigned)(lr * np + col)));
                                 if (col < bb) x.x = 0ull;
                                 if (col + 1 >= nb) x.y = 0ull;
+#endif
                             }
                         }
                         v[j] = x;

@@ -76,6 +76,14 @@ kp, nm = nms_device(t(cb2), t(sb2), 0.1, 'v1', labels=t(lb2), class_offset=torch
                     batch_ids=bid2, n_batches=2)
 from r3det_b200 import pack_keep_records
 pack_keep_records(t(cb2), t(sb2), t(lb2), kp, nm, bid2, 2, 100)
+# invalid image ids / labels of every kind, interleaved (they share one reserved segment key), on both ordering paths
+for Kx in (900, 6000):
+    lbx, bdx = lb2[:Kx].copy(), (np.arange(Kx) % 2).astype(np.int64)
+    lbx[5::28] += 65536; bdx[12::28] += 65536; bdx[19::28] = -1; bdx[26::28] = 2
+    nms_device(t(cb2[:Kx]), t(sb2[:Kx]), 0.1, 'v1', labels=t(lbx), class_offset=torch.tensor([1025.0, 900.0], device=dev), order_index=True,
+               batch_ids=t(bdx), n_batches=2)
+    nms_device(t(cb2[:Kx]), t(sb2[:Kx]), 0.1, 'v1', labels=t(lbx), class_offset=torch.tensor([1025.0, 900.0], device=dev), order_index=True,
+               batch_ids=t(bdx), n_batches=2, sort_path=True)
 nms_device(t(cb2), t(sb2), 0.3, 'v3')                         # one segment, K > chunk: several rounds
 R.poly_nms(t(np.concatenate([T.obb2poly(cb2, 'v1'), sb2[:, None]], 1).astype(np.float32)), 0.1)
 for v in ('v1', 'v2', 'v3'):
