@@ -9,13 +9,13 @@ from ._nms_core import nms_device, to_cuda_input
 
 
 def obb2hbb(obboxes):
-    """[x_ctr,y_ctr,w,h,angle] -> [x_lt,y_lt,x_rb,y_rb] (nms_rotated_wrapper.py:7-20)."""
-    center, w, h, theta = torch.split(obboxes, [2, 1, 1, 1], dim=1)
-    Cos, Sin = torch.cos(theta), torch.sin(theta)
-    x_bias = torch.abs(w / 2 * Cos) + torch.abs(h / 2 * Sin)
-    y_bias = torch.abs(w / 2 * Sin) + torch.abs(h / 2 * Cos)
-    bias = torch.cat([x_bias, y_bias], dim=1)
-    return torch.cat([center - bias, center + bias], dim=1)
+    """[x_ctr, y_ctr, w, h, angle] -> [x_lt, y_lt, x_rb, y_rb] (nms_rotated_wrapper.py:7-20; the same expression as
+    rtransforms.obb2xyxy_v3, which is the kernel that runs here)."""
+    from .rtransforms import obb2xyxy
+    if obboxes.is_cuda:
+        return obb2xyxy(obboxes.float(), 'v3').to(obboxes.dtype)
+    dev = torch.device('cuda', torch.cuda.current_device())
+    return obb2xyxy(obboxes.float().to(dev), 'v3').to(obboxes.dtype).cpu()
 
 
 def obb_nms(dets, iou_thr, device_id=None):
