@@ -410,7 +410,7 @@ def _graph_time(torch, fn, iters=20):
 
 def bench_iou_variants(torch, R, dev):
     """configs[2] names all three angle conventions: the same 1000 x 200000 matrix for v1 / v2 / v3 (device-resident inputs,
-    strict reference parity, whole op = two prepare launches + the pair kernel) and the IoF mode of v1."""
+    strict reference parity, whole op = one prepare launch + the pair kernel) and the IoF mode of v1."""
     out = {}
     for v, mode in (("v1", "iou"), ("v2", "iou"), ("v3", "iou"), ("v1", "iof")):
         gt = torch.from_numpy(rand_obb(GT, 1, v)).to(dev)
@@ -508,7 +508,11 @@ def bench_nms_batch(torch, R, dev, rk):
                                 label_bits=4)
         keep, num = fn()
         ms = rk.time(fn, 5 if K >= 80000 else 10)
-        out["sweep"][str(K)] = {"ms": ms, "mcands_per_s": rk.world * 8 * K / ms / 1e3, "kept_rank0": int(num.sum())}
+        rec = {"ms": ms, "mcands_per_s": rk.world * 8 * K / ms / 1e3, "kept_rank0": int(num.sum())}
+        gms = _graph_time(torch, fn)                          # the same launch sequence replayed from a CUDA graph (rank-local)
+        if isinstance(gms, float):
+            rec["graph_ms_rank"] = gms
+        out["sweep"][str(K)] = rec
         del B, S, Lb, bid
     return out
 

@@ -181,6 +181,34 @@ def test_full_size_properties(cuda_dev):
         assert (cover.max(dim=1)[0] > thr - 1e-5).all()
 
 
+def test_full_size_batch_8x200k_equals_per_image_calls(cuda_dev):
+    """BASELINE configs[3] at its upper size: 8 images x 200k candidates x 15 classes in ONE batched call (round 1 could not
+    allocate its quadratic mask for this) equals the eight per-image calls; the workspace is linear in K."""
+    import ctypes as C
+    from r3det_b200 import _lib as L
+    from r3det_b200._nms_core import nms_device
+    K, nimg = 200000, 8
+    nb = C.c_size_t(0)
+    L.check(L.lib().r3g_nms_workspace_bytes(K, C.byref(nb)))
+    one = nb.value
+    L.check(L.lib().r3g_nms_workspace_bytes(K * nimg, C.byref(nb)))
+    assert one < 0.5e9 and nb.value < 1.05 * nimg * one                    # < 0.5 GB for 200k, and linear
+    imgs = [clustered(K, 300 + i, "v1") for i in range(nimg)]
+    B = _t(np.concatenate([x[0] for x in imgs]), cuda_dev); S = _t(np.concatenate([x[1] for x in imgs]), cuda_dev)
+    Lb = _t(np.concatenate([x[2] for x in imgs]), cuda_dev)
+    bid = torch.arange(nimg, device=cuda_dev).repeat_interleave(K)
+    scales = torch.tensor([float(x[0].max() + 1) for x in imgs], device=cuda_dev)
+    keep, num = nms_device(B, S, 0.1, "v1", labels=Lb, class_offset=scales, order_index=True, batch_ids=bid, n_batches=nimg,
+                           label_bits=4)
+    num = num.cpu().numpy(); keep = keep.cpu().numpy()
+    start = 0
+    for i, (b, s, l) in enumerate(imgs):
+        k1, n1 = nms_device(_t(b, cuda_dev), _t(s, cuda_dev), 0.1, "v1", labels=_t(l, cuda_dev), class_offset=scales[i], order_index=True)
+        want = k1[:int(n1)].cpu().numpy() + i * K
+        assert num[i] == len(want) and np.array_equal(keep[start:start + num[i]], want), i
+        start += num[i]
+
+
 @pytest.mark.parametrize("kind", ["v1", "v2", "v3", "mmcv"])
 def test_multiclass_batch_equals_per_image(cuda_dev, kind):
     """multiclass_nms_rotated_batch == the per-image wrapper, image by image (including an image with no candidate)."""
