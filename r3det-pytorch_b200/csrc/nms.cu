@@ -224,16 +224,29 @@ __global__ void nms_emit_kernel(const int* __restrict__ flag, const int* __restr
                                 const int64_t* __restrict__ batch_ids, int n_batches, int K, int order_index, int64_t* keep_out,
                                 unsigned long long* num_keep) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= K) return;
-    if (flag[s]) {
+    int img = -1;                                                          // image of a kept candidate (batched calls)
+    if (s < K && flag[s]) {
         const int idx = order_index ? s : ord_rank[s];
         keep_out[pref[s]] = (int64_t)idx;
-        if (batch_ids) {                                                  // per-image counts (zeroed by the launcher)
+        if (batch_ids) {
             const int64_t b = batch_ids[idx];
-            if (b >= 0 && b < n_batches) atomicAdd(num_keep + b, 1ull);
+            if (b >= 0 && b < n_batches) img = (int)b;
         }
     }
-    if (!batch_ids && s == K - 1) *num_keep = (unsigned long long)(pref[s] + flag[s]);
+    if (batch_ids) {
+        // per-image counts (zeroed by the launcher): one atomic per image and warp — neighbours in the keep order are mostly
+        // of one image, and thousands of single increments on a handful of addresses serialise in L2
+        unsigned todo = __ballot_sync(0xffffffffu, img >= 0);
+        while (todo) {
+            const int lead = __ffs((int)todo) - 1;
+            const int li = __shfl_sync(0xffffffffu, img, lead);
+            const unsigned peers = __ballot_sync(0xffffffffu, img == li);
+            if ((int)(threadIdx.x & 31) == lead) atomicAdd(num_keep + li, (unsigned long long)__popc(peers));
+            todo &= ~peers;
+        }
+    } else if (s == K - 1) {
+        *num_keep = (unsigned long long)(pref[s] + flag[s]);
+    }
 }
 
 // ---- small-K path (K <= NMS_SMALL_K): the sorts, the structure scans and the compaction are launch latency there ----
@@ -433,7 +446,8 @@ static int nms_rounds_stage(NmsWs& w, int Ki, int variant, int inclusive, float 
     }
     static const int chunk_env = nms_env_int("R3G_NMS_CHUNK", rn::B_MAX, 64, rn::B_MAX) / 64 * 64;     // tuning knobs
     static const int grid_env = nms_env_int("R3G_NMS_GRID", 0, 0, 1 << 20);
-    static const int div_env = nms_env_int("R3G_NMS_CHUNK_DIV", 0, 0, 64);
+    static const int div_env = nms_env_int("R3G_NMS_CHUNK_DIV", 0, -1, 64);           // 0: decided on the device from the segment lengths
+    static const int work_env = nms_env_int("R3G_NMS_WORK_THR_M", 24, 0, 1 << 20);     // ... threshold, in millions of pair tests
     static const int min_env = nms_env_int("R3G_NMS_CHUNK_MIN", 512, 64, rn::B_MAX) / 64 * 64;
     rn::Args a;
     a.p0 = w.p0; a.p1 = w.p1; a.p2r = w.p2r; a.p2c = w.p2c; a.raw = w.raw; a.label = w.pos_label; a.K = Ki;
@@ -442,7 +456,7 @@ static int nms_rounds_stage(NmsWs& w, int Ki, int variant, int inclusive, float 
     a.ownerB = w.ownerB; a.ownerD = w.ownerD; a.mask = w.mask; a.keep_p = w.keep_p;
     a.ctrl = reinterpret_cast<rn::Ctrl*>(w.ctrl); a.bar = reinterpret_cast<unsigned*>(w.ctrl + 128);
     a.dbg = reinterpret_cast<unsigned long long*>(w.ctrl + 512);
-    a.B = chunk_env; a.split = nms_split_of(Ki); a.chunk_div = div_env; a.chunk_min = min_env;
+    a.B = chunk_env; a.split = nms_split_of(Ki); a.chunk_div = div_env; a.chunk_min = min_env; a.work_thr = (unsigned long long)work_env * 1000000ull;
     a.variant = variant; a.inclusive = inclusive; a.prefilter = prefilter; a.thr = thr; a.tau = tau; a.margin = margin;
     const long long cap = (long long)device_sm_count() * occ;
     long long grid = Ki / 32;

@@ -53,7 +53,8 @@ struct __attribute__((aligned(64))) Ctrl {      // one per round parity; zero at
     unsigned kept_used;    // kept-list slots handed out
     unsigned itemsB, itemsD, ticketB, ticketD;
     unsigned long long words_used;
-    unsigned long long pad[3];
+    unsigned long long work;   // ctrl[0] only: sum over segments of min(length, B)^2 / 2 — the pair tests of a first round of full chunks
+    unsigned long long pad[2];
 };
 
 struct __attribute__((aligned(16))) Entry {     // one segment's chunk in one round (64 bytes, read as four 16-byte words)
@@ -84,7 +85,10 @@ struct Args {
     unsigned long long* dbg;                    // [0] stage-1 pairs [1] separating-axis tests [2] area evaluations [3] restatements
                                                 // [4] rounds [5] mask items [6] apply items [8] n stamps [9..] phase time stamps (ns)
     int B, split;                               // chunk rows (<= B_MAX); row split of a mask item (1, 2, 4, 8)
-    int chunk_div, chunk_min;                   // chunk = clamp(remaining / chunk_div, chunk_min, B) rows (chunk_div = 0: always B)
+    int chunk_div, chunk_min;                   // chunk = clamp(remaining / chunk_div, chunk_min, B) rows; chunk_div = 0: the kernel decides
+                                                // (4 when the first round of full chunks would cost more than work_thr pair tests, else
+                                                // full chunks), < 0: always full chunks
+    unsigned long long work_thr;
     int variant, inclusive, prefilter;
     float thr, tau, margin;
 };
@@ -196,6 +200,8 @@ __global__ void __launch_bounds__(THREADS, 2) nms_rounds_kernel(const Args A) {
             }
             const unsigned s = atomicAdd(&A.ctrl[0].n_act, 1u);
             A.seg_cur[s] = p; A.seg_pe[s] = lo + 1; A.act[s] = (int)s;
+            const unsigned long long len = (unsigned long long)min(lo + 1 - p, A.B);
+            if (len >= 128) atomicAdd(&A.ctrl[0].work, len * len / 2ull);
         }
     }
     grid_barrier();
@@ -378,6 +384,10 @@ __global__ void __launch_bounds__(THREADS, 2) nms_rounds_kernel(const Args A) {
     };
 
     const int Bmax = A.B;
+    // chunk policy.  Full chunks need the fewest rounds (each costs four grid barriers and a serial resolve); when the in-chunk
+    // triangles alone are a throughput problem (many long segments: batches), chunks of a quarter of what is left of a segment
+    // test ~5x fewer pairs — rows that an earlier chunk's kept rows suppress are never paired with each other — for 1-2 rounds more
+    const int chunk_div = A.chunk_div > 0 ? A.chunk_div : ((A.chunk_div == 0 && __ldcg(&A.ctrl[0].work) > A.work_thr) ? 4 : 0);
     int par = 0;
     while (true) {
         Ctrl* C = A.ctrl + par;
@@ -395,7 +405,7 @@ __global__ void __launch_bounds__(THREADS, 2) nms_rounds_kernel(const Args A) {
             // chunk size of this segment and round: a fraction of what is left of the segment (small chunks waste fewer pair
             // tests on rows that an earlier row of the same chunk suppresses; each round costs four grid barriers)
             int B = Bmax;
-            if (A.chunk_div > 0 && pe - cur > A.chunk_min) B = min(Bmax, max(A.chunk_min, ((pe - cur) / A.chunk_div + 63) & ~63));
+            if (chunk_div > 0 && pe - cur > A.chunk_min) B = min(Bmax, max(A.chunk_min, ((pe - cur) / chunk_div + 63) & ~63));
             const int cap = min(B, pe - cur);
             int row_base = 0;
             if (lane == 0) row_base = (int)atomicAdd(&C->rows_used, (unsigned)cap);
