@@ -131,8 +131,9 @@ int r3g_nms_f32(const float* boxes, int64_t stride, const float* scores, const i
 
 /* Multi-image form of r3g_nms_f32: one launch sequence for a whole batch of images (BASELINE configs[3]: images are
  * independent, so (image, class) pairs are simply more segments).  batch_ids: (K) int64 in [0, n_batches) or NULL
- * (n_batches = 1; candidates with an id outside the range take no part); labels < 65536 when batch_ids is given (the
- * segment key packs image and label into 32 bits); class_offset: n_batches device floats (per-image scale) or
+ * (n_batches = 1); labels in [0, 65536) when batch_ids is given (the segment key packs image and label into 32 bits) —
+ * candidates with an image id outside [0, n_batches) or a label outside [0, 65536) take no part and are never kept;
+ * class_offset: n_batches device floats (per-image scale) or
  * NULL.  keep_out: kept original indices grouped by image — ascending index (R3G_NMS_ORDER_INDEX; candidates are
  * expected to be concatenated image by image) or descending score within each image; num_keep_out: n_batches int64. */
 int r3g_nms_batched_f32(const float* boxes, int64_t stride, const float* scores, const int64_t* labels,
