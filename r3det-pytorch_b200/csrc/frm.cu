@@ -290,6 +290,7 @@ __global__ void frm_bwd_fill_kernel(const __grid_constant__ FrmLevels S, const u
 // one thread per target: its row sorted by (source, tie), then the tie bits are dropped.  Rows of up to CAP entries are ranked
 // in registers (keys are unique: rank = number of smaller keys; every entry is written straight to its final slot); longer
 // rows — boxes piling onto one pixel — fall back to an insertion sort in global memory.
+constexpr unsigned FRM_SORT_MAX_ROW = 512;
 template <int CAP>
 __global__ void frm_bwd_sort_rows_kernel(const unsigned* __restrict__ row_start, size_t nl, unsigned* __restrict__ src, float* __restrict__ wsorted) {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -316,6 +317,9 @@ __global__ void frm_bwd_sort_rows_kernel(const unsigned* __restrict__ row_start,
         }
         return;
     }
+    // pathological pile-ups (hundreds of boxes sampling one pixel) stay in arrival order: still correct — the reference sums with
+    // float atomics in arbitrary order — but not bit-reproducible, instead of a quadratic serial sort that could run for seconds
+    if (n > FRM_SORT_MAX_ROW) { for (unsigned i = a; i < b; i++) src[i] >>= 5; return; }
     for (unsigned i = a + 1; i < b; i++) {
         const unsigned kk = src[i];
         const float ww = wsorted[i];

@@ -258,6 +258,9 @@ __global__ void __launch_bounds__(THREADS, (P == 1) ? 5 : 2) frm_forward_tma_ker
 // again.  A thread owns two targets and keeps the first EMAX entries of each CSR row in registers (window offset + weight);
 // longer rows (rare for points = 1, where the mean row has 4 entries) finish from global memory in CSR order, so the
 // summation order — and the result, bit for bit — is that of the gather kernel in frm.cu.
+#ifndef R3G_FRM_BWD_GROUP
+#define R3G_FRM_BWD_GROUP 4                      // backward apply: entries of a row per warp-uniform test (measured: 1 -> 0.161, 2-4 -> 0.151, 6-12 -> 0.161 ms)
+#endif
 #ifndef R3G_FRM_EMAX
 #define R3G_FRM_EMAX 12
 #endif
@@ -361,11 +364,24 @@ __global__ void __launch_bounds__(THREADS, R3G_FRM_BWD_TMA_MINB) frm_backward_tm
                 const unsigned char* st = fsm + slot * Wn::STAGE_BYTES;
                 float v0 = *reinterpret_cast<const float*>(st + ownoff), v1 = *reinterpret_cast<const float*>(st + ownoff + 32);
                 if (!slow) {
+                    // entries in groups of R3G_FRM_BWD_GROUP: one warp-uniform test per group, the group's loads issued together
+                    // (slots past a row's end point at the zero word with weight 0: reading them is harmless); the summation order
+                    // of a row is unchanged
 #pragma unroll
-                    for (int e = 0; e < EMAX; e++) {
-                        if ((unsigned)e >= wmax) break;
-                        v0 = fmaf(ew[0][e], *reinterpret_cast<const float*>(st + eo[0][e]), v0);
-                        v1 = fmaf(ew[1][e], *reinterpret_cast<const float*>(st + eo[1][e]), v1);
+                    for (int e0g = 0; e0g < EMAX; e0g += R3G_FRM_BWD_GROUP) {
+                        if ((unsigned)e0g >= wmax) break;
+                        float g0[R3G_FRM_BWD_GROUP], g1[R3G_FRM_BWD_GROUP];
+#pragma unroll
+                        for (int k = 0; k < R3G_FRM_BWD_GROUP; k++) {
+                            if (e0g + k < EMAX) {
+                                g0[k] = *reinterpret_cast<const float*>(st + eo[0][e0g + k]);
+                                g1[k] = *reinterpret_cast<const float*>(st + eo[1][e0g + k]);
+                            }
+                        }
+#pragma unroll
+                        for (int k = 0; k < R3G_FRM_BWD_GROUP; k++) {
+                            if (e0g + k < EMAX) { v0 = fmaf(ew[0][e0g + k], g0[k], v0); v1 = fmaf(ew[1][e0g + k], g1[k], v1); }
+                        }
                     }
                 } else {
 #pragma unroll

@@ -51,6 +51,25 @@ def test_oracle(cuda_dev, shape, P):
     assert np.array_equal(got, frm_backward(g, b, 1.0 / stride, P).cpu().numpy())       # bit-reproducible (no atomics)
 
 
+@pytest.mark.parametrize("P", [1, 5])
+def test_pile_up_every_box_on_one_pixel(cuda_dev, P):
+    """every location's box sits on the same point: four target pixels receive one tap from EVERY source (rows of 4096+ entries,
+    far beyond the register-resident rows and beyond the sorted-row bound).  The gather must stay correct — order of summation
+    is then arrival order, as with the reference's atomics — and finish promptly."""
+    from r3det_b200.fr import frm_backward, frm_forward
+    rng = np.random.default_rng(11)
+    N, Cc, H, W, stride = 2, 8, 64, 64, 8
+    feat = rng.standard_normal((N, Cc, H, W)).astype(np.float32)
+    gout = rng.standard_normal((N, Cc, H, W)).astype(np.float32)
+    boxes = np.zeros((N * H * W, 5), np.float32)
+    boxes[:, 0] = 200.3; boxes[:, 1] = 117.6; boxes[:, 2] = 4.0; boxes[:, 3] = 3.0; boxes[:, 4] = -0.3
+    f, go, b = (torch.from_numpy(x).to(cuda_dev) for x in (feat, gout, boxes))
+    assert _rel(frm_forward(f, b, 1.0 / stride, P).cpu().numpy(), port.frm_forward(feat, boxes, 1.0 / stride, P)) <= RTOL
+    got = frm_backward(go, b, 1.0 / stride, P).cpu().numpy()
+    want = port.frm_backward(gout, boxes, 1.0 / stride, P, acc64=True)
+    assert _rel(got, want) <= 1e-4            # thousands of FP32 terms per target in a different order than the oracle's
+
+
 def test_autograd_function_and_module(cuda_dev):
     import r3det_b200 as R
     feat, gout, boxes = _case(np.random.default_rng(5), 2, 16, 16, 16, 8)
