@@ -489,7 +489,9 @@ static int frm_forward_tma(const FrmLevels& S, cudaStream_t st, bool* done) {
     ftma::Levels T;
     size_t blocks = 0;
     if (!frm_tma_levels<P, false>(S, T, &blocks)) return R3G_OK;
-    ftma::frm_forward_tma_kernel<P><<<(unsigned)blocks, ftma::THREADS, ftma::STAGES * ftma::Win<P>::STAGE_BYTES, st>>>(T);
+    constexpr int smem = ftma::STAGES * ftma::Win<P>::STAGE_BYTES;
+    if (smem > 48 * 1024) R3G_CUDA_OK(cudaFuncSetAttribute(ftma::frm_forward_tma_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    ftma::frm_forward_tma_kernel<P><<<(unsigned)blocks, ftma::THREADS, smem, st>>>(T);
     R3G_LAUNCH_OK("frm_forward_tma_kernel");
     *done = true;
     return R3G_OK;

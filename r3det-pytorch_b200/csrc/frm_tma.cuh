@@ -23,7 +23,10 @@ namespace ftma {
 
 constexpr int TH = 32, TW = 16;                  // location tile: 32 rows (h) x 16 columns (w); a thread owns (h, w) and (h, w + 8)
 constexpr int THREADS = 256;
-constexpr int STAGES = 4;
+#ifndef R3G_FRM_STAGES
+#define R3G_FRM_STAGES 4                           // ring depth (measured: 3 / 4 / 5 / 6)
+#endif
+constexpr int STAGES = R3G_FRM_STAGES;
 constexpr int CC = 32;                           // channels per CTA
 constexpr int MAXL = 8;
 #ifndef R3G_FRM_EMPTY_BARRIER
