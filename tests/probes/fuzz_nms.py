@@ -5,11 +5,13 @@ import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from r3det_b200._nms_core import nms_device
 from oracle import port
-from tests.util import clustered
+from tests.util import clustered, rand_obb
 
 
-def run(seed=0, iters=60, dev=None, verbose=True):
-    """Returns the number of images whose keep list differs from the oracle's."""
+def run(seed=0, iters=60, dev=None, verbose=True, large=False):
+    """Returns the number of images whose keep list differs from the oracle's.  large=True: few classes and thousands of
+    candidates per class, so that segments need several rounds of chunks (> 2048 rows) and batches cross the work threshold
+    above which the rounds kernel switches to quarter chunks."""
     dev = torch.device('cuda:0') if dev is None else dev
     rng = np.random.default_rng(seed)
     t = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)
@@ -17,10 +19,12 @@ def run(seed=0, iters=60, dev=None, verbose=True):
     t0 = time.time()
     for it in range(iters):
         v = ['v1', 'v2', 'v3'][it % 3]
-        nimg = int(rng.choice([1, 1, 2, 5, 9]))
-        ncls = int(rng.choice([1, 2, 15, 40]))
-        sizes = [int(rng.choice([0, 1, 63, 64, 65, 300, 1000, 2500])) for _ in range(nimg)]
+        nimg = int(rng.choice([1, 3, 6])) if large else int(rng.choice([1, 1, 2, 5, 9]))
+        ncls = int(rng.choice([1, 2, 4])) if large else int(rng.choice([1, 2, 15, 40]))
+        sizes = [int(rng.choice([2100, 9000, 30000] if large else [0, 1, 63, 64, 65, 300, 1000, 2500])) for _ in range(nimg)]
         parts = [clustered(max(k, 1), int(rng.integers(1 << 30)), v, ncls=ncls) for k in sizes]
+        if large and rng.random() < 0.25:                     # sparse small boxes: (almost) nothing is suppressed, the worst case of the rounds
+            parts = [(rand_obb(max(k, 1), int(rng.integers(1 << 30)), v, 2, 6), p[1], p[2]) for p, k in zip(parts, sizes)]
         parts = [(b[:k], s[:k], l[:k]) for (b, s, l), k in zip(parts, sizes)]
         b = np.concatenate([p[0] for p in parts]); s = np.concatenate([p[1] for p in parts]); l = np.concatenate([p[2] for p in parts])
         if len(b) == 0:
@@ -70,4 +74,5 @@ def run(seed=0, iters=60, dev=None, verbose=True):
 
 
 if __name__ == '__main__':
-    run(int(sys.argv[1]) if len(sys.argv) > 1 else 0, int(sys.argv[2]) if len(sys.argv) > 2 else 60)
+    sys.exit(1 if run(int(sys.argv[1]) if len(sys.argv) > 1 else 0, int(sys.argv[2]) if len(sys.argv) > 2 else 60,
+                      large=len(sys.argv) > 3 and sys.argv[3] == 'large') else 0)
