@@ -70,6 +70,15 @@ def test_pile_up_every_box_on_one_pixel(cuda_dev, P):
     assert _rel(got, want) <= 1e-4            # thousands of FP32 terms per target in a different order than the oracle's
 
 
+def test_randomised_shapes_vs_oracle(cuda_dev):
+    """80 random (levels, N, C, H, W, stride, points, box jitter) cases, forward and backward, against the oracle
+    (tests/probes/fuzz_frm.py; 1500 further cases were run once on the final round-2 build)."""
+    import importlib.util, os
+    spec = importlib.util.spec_from_file_location("fuzz_frm", os.path.join(os.path.dirname(__file__), "probes", "fuzz_frm.py"))
+    m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
+    assert m.run(seed=2, iters=80, dev=cuda_dev, verbose=True) == 0
+
+
 def test_autograd_function_and_module(cuda_dev):
     import r3det_b200 as R
     feat, gout, boxes = _case(np.random.default_rng(5), 2, 16, 16, 16, 8)
