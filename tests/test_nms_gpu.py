@@ -392,6 +392,16 @@ def test_randomised_large_segments_vs_oracle(cuda_dev):
     assert m.run(seed=11, iters=4, dev=cuda_dev, verbose=True, large=True) == 0
 
 
+def test_randomised_padded_multiclass_vs_per_image(cuda_dev):
+    """60 random (nms.type, batch incl. > 64, rows, classes, thresholds, max_num, images without candidates) cases of the
+    synchronisation-free padded chain against the per-image reference-API call (tests/probes/fuzz_tail.py; 1000 further cases
+    were run once on the final round-2 build)."""
+    import importlib.util, os
+    spec = importlib.util.spec_from_file_location("fuzz_tail", os.path.join(os.path.dirname(__file__), "probes", "fuzz_tail.py"))
+    m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
+    assert m.run(seed=4, iters=60, dev=cuda_dev, verbose=True) == 0
+
+
 @pytest.mark.parametrize("by_index", [True, False])
 def test_padded_keep_records(cuda_dev, by_index):
     """r3g_nms_pack_f32: fixed-size per-image outputs == the per-image `dets[keep][:max_per_img]` slices (no host read)."""
