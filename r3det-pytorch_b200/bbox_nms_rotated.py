@@ -177,7 +177,7 @@ def multiclass_nms_rotated_padded(multi_bboxes, multi_scores, score_thr, nms, ma
     counts (B,) int64.  Rows [0, counts[b]) of image b are exactly what the per-image call returns (same order and
     truncation, reference bbox_nms_rotated.py:98-131); the remaining rows are zero.  Candidate extraction, the per-image
     class-offset scale, the segmented NMS and the truncation all run on the device: r3g_mc_candidates_batched_f32 ->
-    r3g_nms_batched_f32 -> r3g_nms_pack_f32.  B <= 64; max_num > 0."""
+    r3g_nms_batched_counted_f32 -> r3g_nms_pack_f32.  max_num > 0; large batches are processed in slices (see below)."""
     kind = _cfg(nms, 'type', 'v1')
     if kind not in _SPEC:
         raise KeyError(f'unknown rotated nms type {kind!r}')
@@ -187,9 +187,12 @@ def multiclass_nms_rotated_padded(multi_bboxes, multi_scores, score_thr, nms, ma
     B, n, C1 = multi_scores.shape
     nc = C1 - 1
     dev = multi_scores.device
-    if B > 64:
-        parts = [multiclass_nms_rotated_padded(multi_bboxes[s:s + 64], multi_scores[s:s + 64], score_thr, nms, max_num)
-                 for s in range(0, B, 64)]
+    # the candidate buffers and the NMS workspace (~0.5 KB per slot) are sized for the CAPACITY B * n * C of the call, not for
+    # the candidates that exist: batches are cut so that one call stays at <= 2^21 slots (~1 GB of workspace) and <= 64 images
+    step = min(64, max(1, (1 << 21) // max(n * nc, 1)))
+    if B > step:
+        parts = [multiclass_nms_rotated_padded(multi_bboxes[s:s + step], multi_scores[s:s + step], score_thr, nms, max_num)
+                 for s in range(0, B, step)]
         return tuple(torch.cat([p[i] for p in parts]) for i in range(3))
     T = B * n * nc
     if T == 0:
