@@ -246,18 +246,32 @@ __global__ void __launch_bounds__(256) select_hist_kernel(const __grid_constant_
     for (int t = threadIdx.x; t < SEL_BINS; t += 256) h[t] = 0;
     __syncthreads();
     const int local = (blockIdx.x - lv.blk0) * 256 + threadIdx.x;        // anchor-major, location-minor
+    int bin = -1;
     if (local < lv.n) {
         const int a = local / lv.HW, hw = local - a * lv.HW;
         const float* cb = lv.cls + ((int64_t)b * S.A * S.C + (int64_t)a * S.C) * lv.HW + hw;
         float m = __ldg(cb);
-        for (int c = 1; c < S.C; c++) {
+        int c = 1;
+        for (; c + 4 <= S.C; c += 4) {                      // four class planes in flight per step
+            float v[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) v[k] = __ldg(cb + (int64_t)(c + k) * lv.HW);
+#pragma unroll
+            for (int k = 0; k < 4; k++) m = (v[k] > m || v[k] != v[k]) ? v[k] : m;     // torch.max propagates NaN
+        }
+        for (; c < S.C; c++) {
             const float v = __ldg(cb + (int64_t)c * lv.HW);
-            m = (v > m || v != v) ? v : m;                  // torch.max propagates NaN
+            m = (v > m || v != v) ? v : m;
         }
         unsigned u = ~__float_as_uint(sigmoidf(m));
         u = u < 0xC0000000u ? 0xC0000000u : u;             // NaN scores rank first, as torch.topk ranks them
         ukey[(int64_t)b * S.n_total + lv.row0 + hw * S.A + a] = u;       // at the row's own slot
-        atomicAdd(&h[u >> (32 - SEL_BIN_BITS)], 1);
+        bin = (int)(u >> (32 - SEL_BIN_BITS));
+    }
+    // background rows crowd into a handful of bins: one shared-memory atomic per distinct bin and warp instead of one per row
+    {
+        const unsigned peers = __match_any_sync(0xffffffffu, bin);
+        if (bin >= 0 && (int)(threadIdx.x & 31) == __ffs((int)peers) - 1) atomicAdd(&h[bin], __popc(peers));
     }
     __syncthreads();
     int* g = hist + (int64_t)(b * S.L + l) * SEL_BINS;
