@@ -409,11 +409,6 @@ __global__ void __launch_bounds__(THREADS, 2) nms_rounds_kernel(const Args A) {
             const int cap = min(B, pe - cur);
             int row_base = 0;
             if (lane == 0) row_base = (int)atomicAdd(&C->rows_used, (unsigned)cap);
-            row_base = __shfl_sync(FULL, row_base, 0);
-            // segments are disjoint runs of the position order (every key occupies ONE run: nms.cu, seg_key_of), so the caps sum
-            // to <= K.  Malformed keys (a caller whose labels exceed its R3G_NMS_LABEL_BITS promise) could break that: such a
-            // segment is dropped rather than allowed to write beyond the position list
-            if ((long long)row_base + cap > (long long)A.K) continue;
             int n = 0, cur_new = pe, myfirst = -1;
             const int wl = (pe - 1) >> 6, wf = cur >> 6;
             // a lane reads two adjacent alive words per step (one 16-byte load); the next step's words are in flight while
@@ -435,6 +430,10 @@ __global__ void __launch_bounds__(THREADS, 2) nms_rounds_kernel(const Args A) {
             const int wstart = wf & ~1;
             ulonglong2 nxt = load2(wstart);
             row_base = __shfl_sync(FULL, row_base, 0);
+            // segments are disjoint runs of the position order (every key occupies ONE run: nms.cu, seg_key_of), so the caps sum
+            // to <= K.  Malformed keys (a caller whose labels exceed its R3G_NMS_LABEL_BITS promise) could break that: such a
+            // segment is dropped rather than allowed to write beyond the position list
+            if ((long long)row_base + cap > (long long)A.K) continue;
             for (int w0 = wstart; w0 <= wl; w0 += 64) {
                 const ulonglong2 v = nxt;
                 if (w0 + 64 <= wl) nxt = load2(w0 + 64);
@@ -775,6 +774,12 @@ __global__ void __launch_bounds__(THREADS, 2) nms_rounds_kernel(const Args A) {
         grid_barrier();
 
         // ---- phase D: the chunk's kept rows x the later alive candidates of the segment ----
+        // (the common small call — every segment fits one chunk — has nothing to apply and no next round: every CTA reads the
+        //  same two counters here and leaves without the apply phase's barrier)
+        if (__ldcg(&C->itemsD) == 0u && __ldcg(&Cn->n_act) == 0u) {
+            if (blockIdx.x == 0 && tid == 0) { A.dbg[4] += 1ull; A.dbg[5] += __ldcg(&C->itemsB); stamp(); }
+            break;
+        }
         pd = true;
         {
             const unsigned total = __ldcg(&C->itemsD);
