@@ -84,6 +84,8 @@ for Kx in (900, 6000):
                batch_ids=t(bdx), n_batches=2)
     nms_device(t(cb2[:Kx]), t(sb2[:Kx]), 0.1, 'v1', labels=t(lbx), class_offset=torch.tensor([1025.0, 900.0], device=dev), order_index=True,
                batch_ids=t(bdx), n_batches=2, sort_path=True)
+# a broken R3G_NMS_LABEL_BITS promise (labels up to 14 with 2 bits): unspecified result, but no access outside the workspace
+nms_device(t(cb2), t(sb2), 0.1, 'v1', labels=t(lb2), class_offset=torch.tensor(1025.0, device=dev), order_index=True, label_bits=2, sort_path=True)
 nms_device(t(cb2), t(sb2), 0.3, 'v3')                         # one segment, K > chunk: several rounds
 R.poly_nms(t(np.concatenate([T.obb2poly(cb2, 'v1'), sb2[:, None]], 1).astype(np.float32)), 0.1)
 for v in ('v1', 'v2', 'v3'):

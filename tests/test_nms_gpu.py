@@ -129,6 +129,22 @@ def test_batch_out_of_range_ids_take_no_part(cuda_dev, K):
     assert np.array_equal(keep[:tot].cpu().numpy(), good[k0[:tot].cpu().numpy()])
 
 
+def test_broken_label_bits_promise_is_memory_safe(cuda_dev):
+    """R3G_NMS_LABEL_BITS(n) is the caller's promise that labels < 2^n (it saves radix passes).  A broken promise makes the
+    label sort merge classes, so a segment key can occupy several runs of the position order; the result is then unspecified,
+    but the call must stay inside its workspace (the chunk selection drops what does not fit) and the next call must be right."""
+    from r3det_b200._nms_core import nms_device
+    b, s, l = clustered(40000, 88, "v1")                                   # labels 0..14, sort path
+    B, S, Lb = _t(b, cuda_dev), _t(s, cuda_dev), _t(l, cuda_dev)
+    scale = torch.tensor(float(b.max() + 1), device=cuda_dev)
+    keep, num = nms_device(B, S, 0.1, "v1", labels=Lb, class_offset=scale, order_index=True, label_bits=2)      # broken promise
+    torch.cuda.synchronize()
+    assert 0 <= int(num) <= 40000
+    k1, n1 = nms_device(B, S, 0.1, "v1", labels=Lb, class_offset=scale, order_index=True, label_bits=4)
+    k2, n2 = nms_device(B, S, 0.1, "v1", labels=Lb, class_offset=scale, order_index=True)
+    assert int(n1) == int(n2) and torch.equal(k1[:int(n1)], k2[:int(n2)])
+
+
 def test_edge_cases(cuda_dev):
     import r3det_b200 as R
     from r3det_b200._nms_core import nms_device
